@@ -1,0 +1,264 @@
+"""
+Host-side packing: (reads, variants) of one gene -> arrays the CUDA kernels eat.
+
+This is the exact, integer part of ``AlleleTyping.__init__`` restated on flat
+arrays (reference: graphkir/typing_mulit_allele.py:229-269):
+
+* column order = sorted allele names collected from ``variant.allele``
+  (:249-255, :283-285);
+* ``errorCorrection`` (:302-338): per variant id count positive / negative
+  observations over both mates; total < 3 drops the id from both polarities,
+  a polarity whose share is < 0.2 is dropped;
+* ``removeEmptyReads`` (:274-281);
+* the likelihood of a read for an allele only depends on K_r (number of
+  observations, duplicates across mates counted) and m[r, a] (how many of them
+  disagree with the allele) (:294-300, :363-375), so the kernels get
+    - ``mem_words[w, a]``: bit b set  <=>  allele a carries variant 32*w + b
+      (word-major so that a warp reading 32 consecutive alleles of one word is
+      one coalesced 128-byte access),
+    - per read a short list of entries ``(word, pos_bits, neg_bits)``;
+      ``m[r, a] = sum_e popc((pos_e & ~mem[word_e, a]) | (neg_e & mem[word_e, a]))``.
+      An id observed c times in one polarity is spread over c entries, so
+      multiplicities (a variant seen by both mates counts twice, :363-368) are
+      exact.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from itertools import chain
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from .synthetic import LIST_NAMES, ReadCSR, SyntheticGene
+
+MAX_OBS_PER_READ = 255  # m[r, a] is stored as one byte on the device
+
+
+@dataclass
+class GenePack:
+    """Everything the device needs for one (sample, gene) typing problem."""
+
+    gene: str
+    allele_names: list[str]          # column id -> name (sorted)
+    variant_ids: list[str]           # variant index -> id
+    mem_words: np.ndarray            # uint32 [W, A]
+    ent_off: np.ndarray              # int32 [R+1]
+    ent_word: np.ndarray             # int32 [E]
+    ent_pos: np.ndarray              # uint32 [E]
+    ent_neg: np.ndarray              # uint32 [E]
+    k_obs: np.ndarray                # int32 [R]   observations per read (K_r)
+    kept_reads: np.ndarray           # int64 [R]   index of each packed read in the caller's list
+    csr: ReadCSR | None = None       # post-correction lists (for homozygosity / EM / oracle)
+
+    @property
+    def n_alleles(self) -> int:
+        return len(self.allele_names)
+
+    @property
+    def n_variants(self) -> int:
+        return len(self.variant_ids)
+
+    @property
+    def n_words(self) -> int:
+        return self.mem_words.shape[0]
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.k_obs)
+
+    @property
+    def n_entries(self) -> int:
+        return len(self.ent_word)
+
+
+# ---------------------------------------------------------------------------
+# object lists  <->  CSR
+# ---------------------------------------------------------------------------
+def csr_from_reads(reads: Sequence, vid_to_idx: dict[str, int]) -> ReadCSR:
+    """Flatten ``read.lpv/rpv/lnv/rnv`` (lists of variant ids) into CSR arrays.
+
+    Raises KeyError for an id that is not in the variant table, like the
+    reference's ``self.variants[i]`` lookup (typing_mulit_allele.py:364).
+    """
+    n = len(reads)
+    offsets, indices = {}, {}
+    for name in LIST_NAMES:
+        lens = np.fromiter((len(getattr(r, name)) for r in reads), dtype=np.int64, count=n)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        flat = np.fromiter(
+            (vid_to_idx[str(v)] for v in chain.from_iterable(getattr(r, name) for r in reads)),
+            dtype=np.int32, count=int(off[-1]))
+        offsets[name] = off
+        indices[name] = flat
+    return ReadCSR(n, offsets, indices)
+
+
+def error_correction_masks(csr: ReadCSR, n_variants: int) -> tuple[np.ndarray, np.ndarray]:
+    """Variant indices to drop from the positive / negative lists.
+
+    reference: graphkir/typing_mulit_allele.py:304-325 (thresholds 3 and 0.2).
+    """
+    pos = (np.bincount(csr.indices["lpv"], minlength=n_variants)
+           + np.bincount(csr.indices["rpv"], minlength=n_variants)).astype(np.int64)
+    neg = (np.bincount(csr.indices["lnv"], minlength=n_variants)
+           + np.bincount(csr.indices["rnv"], minlength=n_variants)).astype(np.int64)
+    total = pos + neg
+    seen = total > 0
+    shallow = seen & (total < 3)
+    safe_total = np.where(seen, total, 1)
+    minor_pos = seen & ~shallow & ((pos / safe_total) < 0.2)
+    minor_neg = seen & ~shallow & ((neg / safe_total) < 0.2)
+    return shallow | minor_pos, shallow | minor_neg
+
+
+def filter_csr(csr: ReadCSR, drop_pos: np.ndarray, drop_neg: np.ndarray) -> ReadCSR:
+    """Remove dropped variant indices from each list, keeping list order."""
+    offsets, indices = {}, {}
+    for name in LIST_NAMES:
+        drop = drop_pos if name in ("lpv", "rpv") else drop_neg
+        idx = csr.indices[name]
+        keep = ~drop[idx]
+        off = csr.offsets[name]
+        row = np.repeat(np.arange(csr.n_reads), off[1:] - off[:-1])
+        lens = np.bincount(row[keep], minlength=csr.n_reads)
+        new_off = np.zeros(csr.n_reads + 1, dtype=np.int64)
+        np.cumsum(lens, out=new_off[1:])
+        offsets[name] = new_off
+        indices[name] = idx[keep]
+    return ReadCSR(csr.n_reads, offsets, indices)
+
+
+def nonempty_reads(csr: ReadCSR) -> np.ndarray:
+    """Boolean mask of reads with at least one id in any list (:274-281)."""
+    lens = np.zeros(csr.n_reads, dtype=np.int64)
+    for name in LIST_NAMES:
+        off = csr.offsets[name]
+        lens += off[1:] - off[:-1]
+    return lens > 0
+
+
+# ---------------------------------------------------------------------------
+# bit packing
+# ---------------------------------------------------------------------------
+def pack_membership(member: np.ndarray) -> np.ndarray:
+    """bool [V, A] -> uint32 [ceil(V/32), A], bit b of word w = variant 32w+b."""
+    n_var, n_allele = member.shape
+    n_words = max(1, (n_var + 31) // 32)
+    padded = np.zeros((n_words * 32, n_allele), dtype=np.uint32)
+    padded[:n_var] = member
+    shifts = (np.arange(32, dtype=np.uint32))[None, :, None]
+    words = (padded.reshape(n_words, 32, n_allele) << shifts).sum(axis=1, dtype=np.uint64)
+    return words.astype(np.uint32)
+
+
+def pack_entries(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """CSR lists -> (ent_off, ent_word, ent_pos, ent_neg, k_obs)."""
+    n = csr.n_reads
+    rows, pols, vids = [], [], []
+    for name in LIST_NAMES:
+        off = csr.offsets[name]
+        rows.append(np.repeat(np.arange(n, dtype=np.int64), off[1:] - off[:-1]))
+        idx = csr.indices[name].astype(np.int64)
+        vids.append(idx)
+        pols.append(np.full(len(idx), 1 if name in ("lpv", "rpv") else 0, dtype=np.int64))
+    row = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    pol = np.concatenate(pols) if pols else np.zeros(0, np.int64)
+    vid = np.concatenate(vids) if vids else np.zeros(0, np.int64)
+    k_obs = np.bincount(row, minlength=n).astype(np.int32)
+    if len(row) == 0:
+        return (np.zeros(n + 1, np.int32), np.zeros(0, np.int32),
+                np.zeros(0, np.uint32), np.zeros(0, np.uint32), k_obs)
+
+    # occurrence rank of identical (read, polarity, variant) observations
+    order = np.lexsort((vid, pol, row))
+    row, pol, vid = row[order], pol[order], vid[order]
+    new_run = np.ones(len(row), dtype=bool)
+    new_run[1:] = (row[1:] != row[:-1]) | (pol[1:] != pol[:-1]) | (vid[1:] != vid[:-1])
+    run_start = np.maximum.accumulate(np.where(new_run, np.arange(len(row)), 0))
+    rank = np.arange(len(row)) - run_start
+
+    word = vid >> 5
+    bit = (np.uint32(1) << (vid & 31).astype(np.uint32)).astype(np.uint32)
+    order = np.lexsort((word, rank, row))
+    row, rank, word, bit, pol = row[order], rank[order], word[order], bit[order], pol[order]
+    new_ent = np.ones(len(row), dtype=bool)
+    new_ent[1:] = (row[1:] != row[:-1]) | (rank[1:] != rank[:-1]) | (word[1:] != word[:-1])
+    starts = np.flatnonzero(new_ent)
+    ent_pos = np.bitwise_or.reduceat(np.where(pol == 1, bit, np.uint32(0)), starts).astype(np.uint32)
+    ent_neg = np.bitwise_or.reduceat(np.where(pol == 0, bit, np.uint32(0)), starts).astype(np.uint32)
+    ent_word = word[starts].astype(np.int32)
+    ent_row = row[starts]
+    ent_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(ent_row, minlength=n), out=ent_off[1:])
+    return ent_off.astype(np.int32), ent_word, ent_pos, ent_neg, k_obs
+
+
+def _finish(gene: str, allele_names: list[str], variant_ids: list[str], member: np.ndarray,
+            csr: ReadCSR, variant_correction: bool, no_empty: bool) -> tuple[GenePack, tuple]:
+    drop = (np.zeros(len(variant_ids), bool), np.zeros(len(variant_ids), bool))
+    if variant_correction:
+        drop = error_correction_masks(csr, len(variant_ids))
+        csr = filter_csr(csr, *drop)
+    kept = np.arange(csr.n_reads, dtype=np.int64)
+    if no_empty:
+        mask = nonempty_reads(csr)
+        kept = np.flatnonzero(mask)
+        csr = csr.take(kept)
+    ent_off, ent_word, ent_pos, ent_neg, k_obs = pack_entries(csr)
+    if len(k_obs) and int(k_obs.max()) > MAX_OBS_PER_READ:
+        raise ValueError(
+            f"a read pair carries {int(k_obs.max())} variant observations; the device "
+            f"mismatch matrix is one byte per cell (limit {MAX_OBS_PER_READ})")
+    pack = GenePack(gene, allele_names, variant_ids, pack_membership(member),
+                    ent_off, ent_word, ent_pos, ent_neg, k_obs, kept, csr)
+    return pack, drop
+
+
+def pack_gene(reads: Sequence, variants: Iterable, variant_correction: bool = True,
+              no_empty: bool = True, mutate_reads: bool = True, gene: str = "") -> GenePack:
+    """Object-level entry: the work of ``AlleleTyping.__init__`` up to the likelihood.
+
+    With ``mutate_reads`` the surviving ids are written back into the caller's
+    read objects, reproducing the in-place side effect of the reference's
+    ``errorCorrection`` (typing_mulit_allele.py:333-338).
+    """
+    variants = list(variants)
+    by_id: dict[str, object] = {str(v.id): v for v in variants}      # later duplicates win (:253)
+    variant_ids = list(by_id.keys())
+    vid_to_idx = {vid: i for i, vid in enumerate(variant_ids)}
+    allele_names = sorted(set(chain.from_iterable(v.allele for v in variants)))   # (:254, :283-285)
+    col = {name: i for i, name in enumerate(allele_names)}
+    member = np.zeros((len(variant_ids), len(allele_names)), dtype=bool)
+    for vid, i in vid_to_idx.items():
+        for name in by_id[vid].allele:
+            member[i, col[name]] = True
+    if not gene and variants:
+        gene = str(variants[0].ref)
+
+    csr = csr_from_reads(reads, vid_to_idx)
+    pack, (drop_pos, drop_neg) = _finish(gene, allele_names, variant_ids, member, csr,
+                                         variant_correction, no_empty)
+    if variant_correction and mutate_reads:
+        bad_pos = {variant_ids[i] for i in np.flatnonzero(drop_pos)}
+        bad_neg = {variant_ids[i] for i in np.flatnonzero(drop_neg)}
+        for read in reads:
+            read.lpv = [v for v in read.lpv if v not in bad_pos]
+            read.rpv = [v for v in read.rpv if v not in bad_pos]
+            read.lnv = [v for v in read.lnv if v not in bad_neg]
+            read.rnv = [v for v in read.rnv if v not in bad_neg]
+    return pack
+
+
+def pack_synthetic(gene: SyntheticGene, variant_correction: bool = True,
+                   no_empty: bool = True) -> GenePack:
+    """Array-level entry for :mod:`kir_graph_b200.synthetic` problems (no Python objects)."""
+    has_variant = gene.member.any(axis=0)
+    cols = [a for a in np.argsort(np.array(gene.allele_names, dtype=object), kind="stable")
+            if has_variant[a]]
+    names = [gene.allele_names[a] for a in cols]
+    member = gene.member[:, cols]
+    pack, _ = _finish(gene.gene, names, list(gene.variant_ids), member, gene.reads,
+                      variant_correction, no_empty)
+    return pack

@@ -1,0 +1,82 @@
+"""Host packing (kir_graph_b200/packing.py) against the oracle's set logic."""
+import copy
+
+import numpy as np
+import pytest
+
+from kir_graph_b200 import packing, synthetic
+from oracle import typing_oracle as orc
+from tests.helpers import golden_names, load_golden, objects_from_input
+
+
+def counts_from_pack(pack: packing.GenePack) -> np.ndarray:
+    """NumPy emulation of the likelihood kernel's formula on the packed arrays."""
+    m = np.zeros((pack.n_reads, pack.n_alleles), dtype=np.int64)
+    row = np.repeat(np.arange(pack.n_reads), np.diff(pack.ent_off))
+    mem = pack.mem_words[pack.ent_word]                      # [E, A]
+    x = (pack.ent_pos[:, None] & ~mem) | (pack.ent_neg[:, None] & mem)
+    pop = np.zeros(x.shape, dtype=np.int64)
+    for b in range(32):
+        pop += (x >> np.uint32(b)) & np.uint32(1)
+    np.add.at(m, row, pop)
+    return m
+
+
+@pytest.mark.parametrize("name", golden_names("typing"))
+def test_pack_matches_oracle_and_reference(name):
+    case = load_golden(name)
+    reads, variants = objects_from_input(case["input"])
+    reads_o = copy.deepcopy(reads)
+    pack = packing.pack_gene(reads, variants, variant_correction=case["variant_correction"])
+    assert pack.allele_names == case["allele_names"]
+    assert pack.n_reads == case["n_reads"]
+    # in-place side effect of errorCorrection on the caller's reads
+    kept = [reads[i] for i in pack.kept_reads]
+    after = [{"lpv": r.lpv, "rpv": r.rpv, "lnv": r.lnv, "rnv": r.rnv} for r in kept]
+    assert after == case["reads_after"]
+    # oracle path
+    if case["variant_correction"]:
+        reads_o = orc.error_correction(reads_o)
+    reads_o = orc.remove_empty_reads(reads_o)
+    by_id = {str(v.id): v for v in variants}
+    col = {n: i for i, n in enumerate(pack.allele_names)}
+    m, k = orc.mismatch_counts(reads_o, by_id, col)
+    assert np.array_equal(pack.k_obs, k)
+    assert np.array_equal(counts_from_pack(pack), m)
+
+
+def test_pack_synthetic_equals_object_path():
+    gene = synthetic.make_gene([5, 1], "KIRQ*BACKBONE", 33, 264, 3, 500, hierarchical=True)
+    a = packing.pack_synthetic(gene, variant_correction=True)
+    reads, variants = gene.to_objects()
+    b = packing.pack_gene(reads, variants, variant_correction=True)
+    assert a.allele_names == b.allele_names
+    for f in ("mem_words", "ent_off", "ent_word", "ent_pos", "ent_neg", "k_obs", "kept_reads"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
+def test_duplicates_and_conflicts():
+    from kir_graph_b200.hisat2 import PairRead
+    from kir_graph_b200.msa2hisat import Variant
+    g = "X*BACKBONE"
+    variants = [Variant(pos=i, typ="single", ref=g, val="A", id=f"hv{i}",
+                        allele=[f"X*{j}" for j in range(3) if (i + j) % 2]) for i in range(40)]
+    variants.append(Variant(pos=99, typ="single", ref=g, val="C", id="nv0", allele=[]))
+    reads = [PairRead(backbone=g, lpv=["hv1", "hv1", "hv33"], rpv=["hv1", "nv0"], lnv=["hv1", "hv2"], rnv=["hv2", "hv2", "hv39"]),
+             PairRead(backbone=g),
+             PairRead(backbone=g, rnv=["hv0"])]
+    pack = packing.pack_gene(reads, variants, variant_correction=False)
+    assert pack.kept_reads.tolist() == [0, 2]
+    by_id = {v.id: v for v in variants}
+    col = {n: i for i, n in enumerate(pack.allele_names)}
+    m, k = orc.mismatch_counts([reads[0], reads[2]], by_id, col)
+    assert np.array_equal(pack.k_obs, k) and k.tolist() == [10, 1]
+    assert np.array_equal(counts_from_pack(pack), m)
+    full = packing.pack_gene(reads, variants, variant_correction=False, no_empty=False)
+    assert full.n_reads == 3 and full.k_obs.tolist() == [10, 0, 1]
+
+
+def test_too_many_observations_is_loud():
+    gene = synthetic.make_gene([5, 2], "KIRW*BACKBONE", 8, 600, 1, 4, w=140)
+    with pytest.raises(ValueError):
+        packing.pack_synthetic(gene, variant_correction=False)
