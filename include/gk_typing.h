@@ -1,0 +1,145 @@
+/*
+ * gk_typing.h -- C ABI of the B200 allele-typing core (libgk_typing.so).
+ *
+ * The reference (linnil1/KIR_graph) has no FFI layer: its typing core is NumPy
+ * code inside graphkir/typing_mulit_allele.py and graphkir/typing_em.py.  Each
+ * entry point below names the reference expression it replaces; a reference
+ * maintainer binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name starts with h_;
+ *   - every launcher takes the CUDA stream (cudaStream_t passed as void*) and
+ *     is asynchronous on it; return value 0 = ok, negative = error, message via
+ *     gk_last_error() (thread local);
+ *   - "matrix"  = the likelihood data of one (sample, gene): mismatch counts
+ *     m[r, a] in two layouts plus per-allele column sums;
+ *     "search"  = the state of one greedy top-N search over a matrix (several
+ *     searches may share a matrix: exon-first runs one per tied exon result);
+ *   - all per-problem arrays live in pooled device buffers; the descriptor
+ *     tables hold element offsets into those pools.
+ *
+ * Integer formulation: log10 P(read r | allele a) = (K_r - m) log10(.999) +
+ * m log10(.001) with m[r, a] the number of the read pair's K_r variant
+ * observations that disagree with allele a, so every score below is an exact
+ * integer count of mismatches; conversion to log10 units happens on the host.
+ */
+#ifndef GK_TYPING_H
+#define GK_TYPING_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GK_MAX_CN 8        /* alleles per set (copy number) supported by the search kernels */
+#define GK_KB 128          /* kept-set block: P is stored [k_block][read][GK_KB]             */
+#define GK_RT 16           /* read rows per shared-memory stage of the scoring kernel        */
+#define GK_LIK_READS 64    /* read rows per CTA of the likelihood kernel                     */
+
+/* Likelihood data of one gene problem.  Offsets are in elements of the pool type. */
+typedef struct GkMatrix {
+    int64_t mem_off;     /* uint32 pool: mem[w * n_alleles + a], bit b = allele a carries variant 32w+b */
+    int64_t entoff_off;  /* int32 pool : n_reads+1 entry offsets (absolute indices into the entry pools) */
+    int64_t L_off;       /* float pool : L[(a_blk * r_pad + r) * a_tile + a % a_tile] = m[r, a]          */
+    int64_t LT_off;      /* uint8 pool : LT[a * r_pad + r] = m[r, a]                                     */
+    int64_t col_off;     /* uint64 pool: colsum[a] = sum_r m[r, a]                                       */
+    int32_t n_reads;
+    int32_t n_alleles;
+    int32_t n_words;
+    int32_t r_pad;       /* multiple of 128; rows >= n_reads are zero                                    */
+    int32_t a_tile;      /* 16, 32, 64 or 128                                                            */
+    int32_t n_ablk;      /* ceil(n_alleles / a_tile)                                                     */
+} GkMatrix;
+
+/* State of one search.  Strides are fixed by (top_n, GK_MAX_CN). */
+typedef struct GkSearch {
+    int64_t P_off;       /* float pool : P[(k_blk * r_pad + r) * GK_KB + k % GK_KB] = min over members   */
+    int64_t S_off;       /* uint32 pool: S[k * s_stride + a]                                             */
+    int64_t cand_off;    /* int32 pool : candidate allele ids of the current step                        */
+    int64_t flag_off;    /* uint8 pool : first-occurrence flag per flat candidate k * n_cand + j         */
+    int64_t alive_off;   /* int32 pool : flat candidates that can still reach the final top_n            */
+    int64_t cnt_off;     /* uint32 pool: cnt[(f * n + t) * n + (q-1)] tie-split counts per alive set     */
+    int32_t matrix;      /* index into the GkMatrix table                                                */
+    int32_t n_cand;
+    int32_t s_stride;    /* n_ablk * a_tile of the matrix                                                */
+    int32_t alive_cap;
+} GkSearch;
+
+/* Work items (built by the host per launch). */
+typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* r0 multiple of GK_LIK_READS */
+typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, pad; } GkScoreItem; /* [r0, r1) multiple of GK_RT   */
+typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16 */
+typedef struct GkPItem { int32_t search, k_blk, r0, pad; } GkPItem;                  /* 128 reads from r0           */
+
+/* Per-search step outputs (device arrays indexed [search]). */
+typedef struct GkStepInfo {
+    int32_t n_kept;      /* sets kept after this step (<= top_n)                                         */
+    int32_t n_unique;    /* distinct candidate sets (N_uniq of typing_mulit_allele.py:561-567)           */
+    int32_t n_alive;     /* sets rescored                                                                */
+    int32_t cut;         /* M = max(top_n, n_unique / 5)                                                 */
+    uint32_t bar;        /* score of the top_n-th unique candidate                                       */
+    int32_t tie_flags;   /* bit0: tie group straddles the M cut, bit1: straddles the final top_n cut,
+                            bit2: rank 0 and rank 1 share score / column sums / evenness                 */
+    int32_t pad0, pad1;
+} GkStepInfo;
+
+const char* gk_last_error(void);
+int gk_abi_version(void);
+int gk_sizeof(const char* struct_name);     /* sizeof(GkMatrix) etc., for binding self-checks */
+
+/* (a) likelihood build: replaces AlleleTyping.reads2AlleleProb + np.log10
+ *     (graphkir/typing_mulit_allele.py:340-381, :263), fed by hisat2.py's per-read
+ *     positive/negative variant ids.  Writes L, LT and accumulates colsum
+ *     (colsum must be zeroed by the caller). */
+int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, int n_items,
+                  const uint32_t* mem_pool, const int32_t* entoff_pool,
+                  const int32_t* ent_word, const uint32_t* ent_pos, const uint32_t* ent_neg,
+                  float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, void* stream);
+
+/* CN = 1 step: replaces log_probs[:, idx].sum(0) + argsort()[::-1][:top_n]
+ *     (typing_mulit_allele.py:512-532).  One CTA per search.  Order: (colsum, position). */
+int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n,
+                  const unsigned long long* col_pool, const int32_t* cand_pool,
+                  int32_t* ids_out, uint32_t* score_out, uint32_t* cnt_out, int32_t* flat_out,
+                  GkStepInfo* info, int32_t* kept_count, void* stream);
+
+/* (b) max-then-sum candidate scoring: replaces
+ *     np.maximum(log_probs[:, idx], prev.T[:, :, None]).sum(axis=1)   (:540-542)
+ *     as S[k, a] += sum_{r in item} min(L[r, a], P[r, k])  (S zeroed by the caller). */
+int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,
+             const float* L_pool, const float* P_pool, uint32_t* S_pool, void* stream);
+
+/* (c) segmented selection, part 1: canonical-key dedup (uniqueAllele, :456-476, :551-563),
+ *     N_uniq, the cut max(top_n, N_uniq // 5) (:567) and the list of candidates that can
+ *     still reach the final top_n.  One CTA per search. */
+int gk_select(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n, int n_prev,
+              int max_alleles, const int32_t* kept_count, const int32_t* ids_prev, const int32_t* cand_pool,
+              const uint32_t* S_pool, uint8_t* flag_pool, int32_t* alive_pool,
+              GkStepInfo* info, void* stream);
+
+/*     rescoring of the alive sets: replaces log_probs[:, ids].max(2) / np.equal / belong_norm
+ *     (:569-580) with integer tie-split counts (cnt zeroed by the caller). */
+int gk_rescore_count(const GkMatrix* matrices, const GkSearch* searches, const GkCountItem* items,
+                     int n_items, int top_n, int n_set, const GkStepInfo* info,
+                     const int32_t* ids_prev, const int32_t* cand_pool, const int32_t* alive_pool,
+                     const uint8_t* LT_pool, uint32_t* cnt_pool, void* stream);
+
+/*     part 2: 3-key ranking (rankScore / sortByScoreAndEveness, :156-171, :202-214) on exact
+ *     integers (score, sum of member column sums, unevenness, flat index); keeps top_n. */
+int gk_rank(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n, int n_set,
+            const int32_t* ids_prev, const int32_t* cand_pool, const int32_t* alive_pool,
+            const uint32_t* S_pool, const uint32_t* cnt_pool, const unsigned long long* col_pool,
+            unsigned long long* key_pool /* 3 words per alive slot */, int32_t* ids_out, uint32_t* score_out, uint32_t* cnt_out, int32_t* flat_out,
+            GkStepInfo* info, int32_t* kept_count_out, void* stream);
+
+/*     P for the next step: P[r, k] = min over members of m[r, id]  (allele_prob, :569). */
+int gk_write_p(const GkMatrix* matrices, const GkSearch* searches, const GkPItem* items, int n_items,
+               int top_n, int n_set, const int32_t* kept_count, const int32_t* ids,
+               const uint8_t* LT_pool, float* P_pool, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GK_TYPING_H */

@@ -1,0 +1,116 @@
+// Kernel (a): likelihood build.
+//
+// Replaces AlleleTyping.reads2AlleleProb + np.log10 (reference:
+// graphkir/typing_mulit_allele.py:340-381, :263).  For a tile of 64 reads x one
+// allele block, every lane owns up to four alleles (lane, lane+32, ...) and walks
+// the read's packed observation entries:
+//     m[r, a] += popc((pos & ~mem[word, a]) | (neg & mem[word, a]))
+// The membership row mem[word, :] is word-major, so the 32 lanes of a warp read
+// 128 consecutive bytes (coalesced; a gene's table is <= 1 MB and stays in L1/L2).
+// Outputs, both written with full 128-byte lines:
+//     L  float32, blocked [a_blk][r][a_tile]  -> operand of the scoring kernel (TMA bulk tiles)
+//     LT uint8,   allele-major [a][r]         -> rescoring / P kernels stream along reads
+// and the per-allele column sums (CN=1 scores) via one 64-bit atomic per allele per CTA.
+//
+// Bound: HBM writes, 5 B per cell (4 B L + 1 B LT); POPC issue is the secondary limit.
+#include "gk_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTilePitch = GK_LIK_READS + 16;  // bytes; keeps rows 16-byte aligned
+
+__global__ void __launch_bounds__(kThreads)
+gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __restrict__ items,
+                     const uint32_t* __restrict__ mem_pool, const int32_t* __restrict__ entoff_pool,
+                     const int32_t* __restrict__ ent_word, const uint32_t* __restrict__ ent_pos,
+                     const uint32_t* __restrict__ ent_neg, float* __restrict__ L_pool,
+                     uint8_t* __restrict__ LT_pool, unsigned long long* __restrict__ col_pool) {
+    __shared__ __align__(16) uint8_t tile[128 * kTilePitch];
+    __shared__ unsigned int colpart[kWarps][128];
+
+    const GkLikItem item = items[blockIdx.x];
+    const GkMatrix M = matrices[item.matrix];
+    const int a_tile = M.a_tile;
+    const int a0 = item.a_blk * a_tile;
+    const int r0 = item.r0;
+    const int lane = gk_lane();
+    const int warp = gk_warp();
+
+    const uint32_t* mem = mem_pool + M.mem_off;
+    const int32_t* eoff = entoff_pool + M.entoff_off;
+    float* L = L_pool + M.L_off + (int64_t)item.a_blk * M.r_pad * a_tile;
+
+    bool live[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) live[g] = (lane + 32 * g < a_tile) && (a0 + lane + 32 * g < M.n_alleles);
+
+    unsigned int csum[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+    for (int i = 0; i < GK_LIK_READS / kWarps; ++i) {
+        const int rl = warp + kWarps * i;
+        const int r = r0 + rl;
+        unsigned int cnt[4] = {0u, 0u, 0u, 0u};
+        if (r < M.n_reads) {
+            const int e0 = __ldg(eoff + r);
+            const int e1 = __ldg(eoff + r + 1);
+            for (int e = e0; e < e1; ++e) {
+                const int w = __ldg(ent_word + e);
+                const uint32_t p = __ldg(ent_pos + e);
+                const uint32_t n = __ldg(ent_neg + e);
+                const uint32_t* row = mem + (int64_t)w * M.n_alleles + a0 + lane;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (live[g]) {
+                        const uint32_t mw = __ldg(row + 32 * g);
+                        cnt[g] += __popc((p & ~mw) | (n & mw));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int a = lane + 32 * g;
+            if (a < a_tile) {
+                L[(int64_t)r * a_tile + a] = (float)cnt[g];
+                tile[a * kTilePitch + rl] = (uint8_t)cnt[g];
+                csum[g] += cnt[g];
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) colpart[warp][lane + 32 * g] = csum[g];
+    __syncthreads();
+
+    unsigned long long* col = col_pool + M.col_off;
+    for (int a = threadIdx.x; a < a_tile; a += kThreads) {
+        unsigned int s = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += colpart[w][a];
+        if (a0 + a < M.n_alleles && s) atomicAdd(col + a0 + a, (unsigned long long)s);
+    }
+
+    uint8_t* LT = LT_pool + M.LT_off;
+    for (int idx = threadIdx.x; idx < a_tile * (GK_LIK_READS / 16); idx += kThreads) {
+        const int a = idx / (GK_LIK_READS / 16);
+        const int seg = idx % (GK_LIK_READS / 16);
+        if (a0 + a < M.n_alleles) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + a * kTilePitch + seg * 16);
+            *reinterpret_cast<uint4*>(LT + (int64_t)(a0 + a) * M.r_pad + r0 + seg * 16) = v;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, int n_items,
+                             const uint32_t* mem_pool, const int32_t* entoff_pool,
+                             const int32_t* ent_word, const uint32_t* ent_pos, const uint32_t* ent_neg,
+                             float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, void* stream) {
+    if (n_items <= 0) return 0;
+    gk_likelihood_kernel<<<n_items, kThreads, 0, (cudaStream_t)stream>>>(
+        matrices, items, mem_pool, entoff_pool, ent_word, ent_pos, ent_neg, L_pool, LT_pool, col_pool);
+    GK_CHECK_LAUNCH("gk_likelihood");
+    return 0;
+}

@@ -1,0 +1,182 @@
+// Rescoring kernels: stream the allele-major byte matrix LT[a][r] along reads.
+//
+//   gk_rescore_count   for every alive candidate set: per member t and tie size q, the
+//                      number of reads where member t attains the set's minimum mismatch
+//                      count together with q-1 other members.  Replaces
+//                      log_probs[:, ids].max(2), np.equal(...), belong / belong.sum(2)
+//                      (reference: typing_mulit_allele.py:569, :575-580) with exact integer
+//                      counts; fraction[t] = sum_q cnt[t][q] / q / R is formed later.
+//   gk_write_p         P[r, k] = min over the members of kept set k of m[r, id]
+//                      (allele_prob for the next step, :569) in the blocked float layout
+//                      the scoring kernel's TMA stages expect; columns k >= n_kept are zero.
+//
+// Both are HBM-bound: per (read, set) they read n bytes (16-byte vector loads, coalesced
+// along reads) and write 0 resp. 4 bytes.
+#include "gk_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+template <int N>
+__device__ __forceinline__ void count_set(const uint8_t* const (&rows)[N], int r0, int r1, int n_reads,
+                                          uint32_t* __restrict__ out) {
+    const int lane = gk_lane();
+    uint32_t cnt[N][N];
+#pragma unroll
+    for (int t = 0; t < N; ++t)
+#pragma unroll
+        for (int q = 0; q < N; ++q) cnt[t][q] = 0u;
+
+    for (int r = r0 + lane * 16; r < r1; r += 32 * 16) {
+        uint4 x[N];
+#pragma unroll
+        for (int t = 0; t < N; ++t) x[t] = __ldg(reinterpret_cast<const uint4*>(rows[t] + r));
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t v[N];
+#pragma unroll
+            for (int t = 0; t < N; ++t) v[t] = w == 0 ? x[t].x : w == 1 ? x[t].y : w == 2 ? x[t].z : x[t].w;
+            uint32_t mn = v[0];
+#pragma unroll
+            for (int t = 1; t < N; ++t) mn = __vminu4(mn, v[t]);
+            int left = n_reads - (r + 4 * w);
+            left = left < 0 ? 0 : (left > 4 ? 4 : left);
+            const uint32_t valid = left == 4 ? 0xffffffffu : ((1u << (8 * left)) - 1u);
+            uint32_t eq[N];
+            uint32_t q = 0u;
+#pragma unroll
+            for (int t = 0; t < N; ++t) {
+                eq[t] = __vcmpeq4(v[t], mn) & valid;
+                q += eq[t] & 0x01010101u;
+            }
+#pragma unroll
+            for (int qq = 0; qq < N; ++qq) {
+                const uint32_t sel = __vcmpeq4(q, 0x01010101u * (uint32_t)(qq + 1));
+#pragma unroll
+                for (int t = 0; t < N; ++t) cnt[t][qq] += __popc(eq[t] & sel) >> 3;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            uint32_t c = cnt[t][q];
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0 && c) atomicAdd(out + t * N + q, c);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kThreads)
+gk_rescore_count_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
+                        const GkCountItem* __restrict__ items, int top_n, const GkStepInfo* __restrict__ info,
+                        const int32_t* __restrict__ ids_prev, const int32_t* __restrict__ cand_pool,
+                        const int32_t* __restrict__ alive_pool, const uint8_t* __restrict__ LT_pool,
+                        uint32_t* __restrict__ cnt_pool) {
+    const GkCountItem item = items[blockIdx.x];
+    const GkSearch X = searches[item.search];
+    const GkMatrix M = matrices[X.matrix];
+    const int f = item.f0 + gk_warp();
+    const int n_alive = info[item.search].n_alive < X.alive_cap ? info[item.search].n_alive : X.alive_cap;
+    if (f >= n_alive) return;
+    const int i = alive_pool[X.alive_off + f];
+    const int k = i / X.n_cand;
+    const int a = cand_pool[X.cand_off + (i - k * X.n_cand)];
+    const int32_t* prev = ids_prev + ((int64_t)item.search * top_n + k) * GK_MAX_CN;
+    const uint8_t* LT = LT_pool + M.LT_off;
+    const uint8_t* rows[N];
+#pragma unroll
+    for (int t = 0; t < N - 1; ++t) rows[t] = LT + (int64_t)prev[t] * M.r_pad;
+    rows[N - 1] = LT + (int64_t)a * M.r_pad;
+    count_set<N>(rows, item.r0, item.r1, M.n_reads, cnt_pool + X.cnt_off + (int64_t)f * N * N);
+}
+
+// P tile: 128 kept sets x 128 reads per CTA.
+constexpr int kPitch = 132;  // bytes per set row in shared memory (33 words: conflict-free transposed reads)
+
+__global__ void __launch_bounds__(kThreads)
+gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
+                  const GkPItem* __restrict__ items, int top_n, int n_set, const int32_t* __restrict__ kept_count,
+                  const int32_t* __restrict__ ids, const uint8_t* __restrict__ LT_pool,
+                  float* __restrict__ P_pool) {
+    __shared__ __align__(16) uint8_t tile[GK_KB * kPitch];
+    const GkPItem item = items[blockIdx.x];
+    const GkSearch X = searches[item.search];
+    const GkMatrix M = matrices[X.matrix];
+    const int K = kept_count[item.search];
+    const int lane = gk_lane();
+    const int warp = gk_warp();
+    const uint8_t* LT = LT_pool + M.LT_off + item.r0;
+
+    // phase 1: one warp per set row, one 4-byte word (4 reads) per lane
+    for (int kl = warp; kl < GK_KB; kl += kWarps) {
+        const int k = item.k_blk * GK_KB + kl;
+        uint32_t mn = 0u;
+        if (k < K) {
+            const int32_t* set = ids + ((int64_t)item.search * top_n + k) * GK_MAX_CN;
+            mn = 0xffffffffu;
+            for (int t = 0; t < n_set; ++t) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(LT + (int64_t)set[t] * M.r_pad) + lane);
+                mn = __vminu4(mn, v);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(tile + kl * kPitch + lane * 4) = mn;
+    }
+    __syncthreads();
+
+    // phase 2: one warp per read row, four consecutive sets per lane -> 512-byte row stores
+    float* P = P_pool + X.P_off + ((int64_t)item.k_blk * M.r_pad + item.r0) * GK_KB;
+    for (int rl = warp; rl < 128; rl += kWarps) {
+        float4 out;
+        out.x = (float)tile[(lane * 4 + 0) * kPitch + rl];
+        out.y = (float)tile[(lane * 4 + 1) * kPitch + rl];
+        out.z = (float)tile[(lane * 4 + 2) * kPitch + rl];
+        out.w = (float)tile[(lane * 4 + 3) * kPitch + rl];
+        *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + lane * 4) = out;
+    }
+}
+
+}  // namespace
+
+extern "C" int gk_rescore_count(const GkMatrix* matrices, const GkSearch* searches, const GkCountItem* items,
+                                int n_items, int top_n, int n_set, const GkStepInfo* info,
+                                const int32_t* ids_prev, const int32_t* cand_pool, const int32_t* alive_pool,
+                                const uint8_t* LT_pool, uint32_t* cnt_pool, void* stream) {
+    if (n_items <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define GK_COUNT_CASE(N)                                                                                   \
+    case N:                                                                                                \
+        gk_rescore_count_kernel<N><<<n_items, kThreads, 0, st>>>(matrices, searches, items, top_n, info,   \
+                                                                 ids_prev, cand_pool, alive_pool, LT_pool, \
+                                                                 cnt_pool);                                \
+        break;
+    switch (n_set) {
+        GK_COUNT_CASE(2)
+        GK_COUNT_CASE(3)
+        GK_COUNT_CASE(4)
+        GK_COUNT_CASE(5)
+        GK_COUNT_CASE(6)
+        GK_COUNT_CASE(7)
+        GK_COUNT_CASE(8)
+        default:
+            GK_REQUIRE(false, "gk_rescore_count: set size %d outside 2..%d", n_set, GK_MAX_CN);
+    }
+#undef GK_COUNT_CASE
+    GK_CHECK_LAUNCH("gk_rescore_count");
+    return 0;
+}
+
+extern "C" int gk_write_p(const GkMatrix* matrices, const GkSearch* searches, const GkPItem* items, int n_items,
+                          int top_n, int n_set, const int32_t* kept_count, const int32_t* ids,
+                          const uint8_t* LT_pool, float* P_pool, void* stream) {
+    if (n_items <= 0) return 0;
+    GK_REQUIRE(n_set >= 1 && n_set <= GK_MAX_CN, "gk_write_p: set size %d outside 1..%d", n_set, GK_MAX_CN);
+    gk_write_p_kernel<<<n_items, kThreads, 0, (cudaStream_t)stream>>>(matrices, searches, items, top_n, n_set,
+                                                                      kept_count, ids, LT_pool, P_pool);
+    GK_CHECK_LAUNCH("gk_write_p");
+    return 0;
+}

@@ -1,0 +1,311 @@
+"""
+TEST DOUBLE -- a NumPy statement of what each CUDA launcher of libgk_typing.so must
+compute on the pooled buffers, item by item.  It lives in tests/ only:
+
+* `-m "not gpu"` tests run the engine's host orchestration (work-item lists, pool
+  offsets, step sequencing) against it and compare with the oracle;
+* `-m gpu` kernel tests run the same launch on the GPU and on this double and compare
+  the output pools byte for byte.
+
+``kir_graph_b200`` never imports it; the product path has no CPU implementation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from kir_graph_b200._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, LIK_ITEM_DTYPE,
+                                  MATRIX_DTYPE, P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE)
+
+LCM = [1, 1, 2, 6, 12, 60, 60, 420, 840]
+
+
+def popcount32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint32)
+    out = np.zeros(x.shape, dtype=np.int64)
+    for b in range(32):
+        out += (x >> np.uint32(b)) & np.uint32(1)
+    return out
+
+
+class FakeBackend:
+    def __init__(self):
+        self.launches = 0
+        self.timing = None
+        self.log: list[str] = []
+
+    # --- memory ---------------------------------------------------------------
+    def zeros(self, n, dtype):
+        return np.zeros(max(int(n), 1), dtype=dtype)
+
+    def empty(self, n, dtype):
+        # poison so that reads of never-written memory show up in tests
+        arr = np.zeros(max(int(n), 1), dtype=dtype)
+        arr.view(np.uint8)[:] = 0xA5
+        return arr
+
+    def upload(self, array):
+        array = np.ascontiguousarray(array)
+        if array.size == 0:
+            return np.zeros(1, dtype=array.dtype)
+        return array.reshape(-1).copy()
+
+    def download(self, tensor, dtype=None, count=None):
+        if count is not None:
+            tensor = tensor[:count]
+        out = np.array(tensor, copy=True)
+        return out.view(dtype) if dtype is not None else out
+
+    def zero_(self, tensor):
+        tensor.view(np.uint8)[:] = 0
+
+    def sync(self):
+        pass
+
+    def launch(self, name, *args, work=0.0):
+        self.launches += 1
+        self.log.append(name)
+        getattr(self, name)(*args)
+
+    # --- kernel (a) --------------------------------------------------------------
+    def gk_likelihood(self, table, items, n_items, mem, entoff, ent_word, ent_pos, ent_neg, L, LT, col):
+        table = table.view(MATRIX_DTYPE)
+        items = items.view(LIK_ITEM_DTYPE)[:n_items]
+        for it in items:
+            M = table[it["matrix"]]
+            A, a_tile, rp, R = int(M["n_alleles"]), int(M["a_tile"]), int(M["r_pad"]), int(M["n_reads"])
+            a0 = int(it["a_blk"]) * a_tile
+            r0 = int(it["r0"])
+            a_hi = min(a0 + a_tile, A)
+            eo = entoff[M["entoff_off"]: M["entoff_off"] + R + 1]
+            memv = mem[M["mem_off"]: M["mem_off"] + int(M["n_words"]) * A].reshape(int(M["n_words"]), A)
+            tile = np.zeros((GK_LIK_READS, a_tile), dtype=np.int64)
+            for rl in range(GK_LIK_READS):
+                r = r0 + rl
+                if r >= R:
+                    continue
+                for e in range(eo[r], eo[r + 1]):
+                    mw = memv[ent_word[e], a0:a_hi]
+                    x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
+                    tile[rl, : a_hi - a0] += popcount32(x)
+            base = int(M["L_off"]) + (int(it["a_blk"]) * rp + r0) * a_tile
+            L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
+            for a in range(a0, a_hi):
+                o = int(M["LT_off"]) + a * rp + r0
+                LT[o: o + GK_LIK_READS] = tile[:, a - a0].astype(np.uint8)
+                col[int(M["col_off"]) + a] += np.uint64(tile[:, a - a0].sum())
+
+    # --- helpers -------------------------------------------------------------------
+    @staticmethod
+    def _L_view(M, L):
+        nb, rp, tile = int(M["n_ablk"]), int(M["r_pad"]), int(M["a_tile"])
+        o = int(M["L_off"])
+        return L[o: o + nb * rp * tile].reshape(nb, rp, tile)
+
+    @staticmethod
+    def _LT_view(M, LT):
+        A, rp = int(M["n_alleles"]), int(M["r_pad"])
+        o = int(M["LT_off"])
+        return LT[o: o + A * rp].reshape(A, rp)
+
+    # --- CN = 1 -----------------------------------------------------------------------
+    def gk_first_step(self, table, stab, n_search, top_n, col, cand_pool, ids_out, score_out, cnt_out,
+                      flat_out, info, kept):
+        table = table.view(MATRIX_DTYPE)
+        stab = stab.view(SEARCH_DTYPE)
+        info = info.view(STEP_INFO_DTYPE)
+        ids_out = ids_out.reshape(n_search, top_n, GK_MAX_CN)
+        score_out = score_out.reshape(n_search, top_n)
+        cnt_out = cnt_out.reshape(n_search, top_n, GK_MAX_CN * GK_MAX_CN)
+        flat_out = flat_out.reshape(n_search, top_n)
+        for s in range(n_search):
+            X = stab[s]
+            M = table[X["matrix"]]
+            C = int(X["n_cand"])
+            cand = cand_pool[X["cand_off"]: X["cand_off"] + C]
+            sc = col[int(M["col_off"]) + cand].astype(np.uint64)
+            order = np.lexsort((np.arange(C), sc))
+            k = min(C, top_n)
+            for rank in range(k):
+                j = order[rank]
+                ids_out[s, rank, 0] = cand[j]
+                score_out[s, rank] = sc[j]
+                cnt_out[s, rank, 0] = M["n_reads"]
+                flat_out[s, rank] = j
+            flags = 0
+            if C > top_n and sc[order[top_n - 1]] == sc[order[top_n]]:
+                flags |= 2
+            if C > 1 and sc[order[0]] == sc[order[1]]:
+                flags |= 4
+            bar = sc[order[top_n - 1]] if C >= top_n else 0xFFFFFFFF
+            info[s] = (k, C, k, top_n, np.uint32(bar & 0xFFFFFFFF), flags, 0, 0)
+            kept[s] = k
+
+    # --- kernel (b) ---------------------------------------------------------------------
+    def gk_score(self, table, stab, items, n_items, L, P, S):
+        table = table.view(MATRIX_DTYPE)
+        stab = stab.view(SEARCH_DTYPE)
+        items = items.view(SCORE_ITEM_DTYPE)[:n_items]
+        for it in items:
+            X = stab[it["search"]]
+            M = table[X["matrix"]]
+            rp, tile = int(M["r_pad"]), int(M["a_tile"])
+            r0, r1 = int(it["r0"]), int(it["r1"])
+            assert r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
+            Lt = self._L_view(M, L)[it["a_blk"], r0:r1, :]                     # [r, tile]
+            po = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
+            Pt = P[po: po + (r1 - r0) * GK_KB].reshape(r1 - r0, GK_KB)          # [r, 128]
+            part = np.minimum(Lt[:, None, :], Pt[:, :, None]).sum(axis=0)       # [128, tile]
+            assert part.max(initial=0) < 2 ** 24
+            stride = int(X["s_stride"])
+            for kl in range(GK_KB):
+                o = int(X["S_off"]) + (int(it["k_blk"]) * GK_KB + kl) * stride + int(it["a_blk"]) * tile
+                S[o: o + tile] += part[kl].astype(np.uint32)
+
+    # --- kernel (c), part 1 ----------------------------------------------------------------
+    def gk_select(self, table, stab, n_search, top_n, n_prev, max_alleles, kept, ids_prev, cand_pool, S,
+                  flag, alive, info):
+        table = table.view(MATRIX_DTYPE)
+        stab = stab.view(SEARCH_DTYPE)
+        info = info.view(STEP_INFO_DTYPE)
+        ids_prev = ids_prev.reshape(n_search, top_n, GK_MAX_CN)
+        for s in range(n_search):
+            X = stab[s]
+            K, C = int(kept[s]), int(X["n_cand"])
+            N = K * C
+            cand = cand_pool[X["cand_off"]: X["cand_off"] + C]
+            stride = int(X["s_stride"])
+            seen = {}
+            uniq = np.zeros(N, dtype=bool)
+            score = np.zeros(N, dtype=np.uint32)
+            for i in range(N):
+                k, j = divmod(i, C)
+                key = tuple(sorted(list(ids_prev[s, k, :n_prev]) + [cand[j]]))
+                if key not in seen:
+                    seen[key] = i
+                    uniq[i] = True
+                score[i] = S[int(X["S_off"]) + k * stride + cand[j]]
+            flag[X["flag_off"]: X["flag_off"] + N] = uniq
+            n_unique = int(uniq.sum())
+            cut = max(top_n, n_unique // 5)
+            us = np.flatnonzero(uniq)
+            if n_unique > top_n:
+                bar = np.sort(score[us])[top_n - 1]
+                c_less = int((score[us] < bar).sum())
+                c_eq = int((score[us] == bar).sum())
+            else:
+                bar, c_less, c_eq = np.uint32(0xFFFFFFFF), n_unique, 0
+            take_eq = max(0, min(cut - c_less, c_eq))
+            out, taken = [], 0
+            for i in us:
+                if score[i] < bar:
+                    out.append(i)
+                elif score[i] == bar and taken < take_eq:
+                    out.append(i)
+                    taken += 1
+            out = out[: int(X["alive_cap"])]
+            alive[X["alive_off"]: X["alive_off"] + len(out)] = out
+            info[s] = (0, n_unique, len(out), cut, bar, 1 if c_eq > take_eq else 0, 0, 0)
+
+    # --- rescoring ------------------------------------------------------------------------
+    def _alive_sets(self, X, s, n, top_n, ids_prev, cand_pool, alive, n_alive):
+        C = int(X["n_cand"])
+        cand = cand_pool[X["cand_off"]: X["cand_off"] + C]
+        flat = alive[X["alive_off"]: X["alive_off"] + n_alive]
+        k, j = flat // max(C, 1), flat % max(C, 1)
+        ids = np.concatenate([ids_prev[s, k, : n - 1], cand[j][:, None]], axis=1) if n_alive else np.zeros((0, n), int)
+        return flat, ids
+
+    def gk_rescore_count(self, table, stab, items, n_items, top_n, n_set, info, ids_prev, cand_pool, alive,
+                         LT, cnt):
+        table = table.view(MATRIX_DTYPE)
+        stab = stab.view(SEARCH_DTYPE)
+        info = info.view(STEP_INFO_DTYPE)
+        items = items.view(COUNT_ITEM_DTYPE)[:n_items]
+        ids_prev = ids_prev.reshape(len(stab), top_n, GK_MAX_CN)
+        n = n_set
+        for it in items:
+            s = int(it["search"])
+            X = stab[s]
+            M = table[X["matrix"]]
+            n_alive = min(int(info[s]["n_alive"]), int(X["alive_cap"]))
+            _, ids = self._alive_sets(X, s, n, top_n, ids_prev, cand_pool, alive, n_alive)
+            r0, r1 = int(it["r0"]), min(int(it["r1"]), int(M["n_reads"]))
+            assert int(it["r0"]) % 16 == 0 and int(it["r1"]) % 16 == 0
+            if r1 <= r0:
+                continue
+            m = self._LT_view(M, LT)
+            for f in range(int(it["f0"]), min(int(it["f0"]) + 8, n_alive)):
+                g = m[ids[f], r0:r1].astype(np.int64)              # [n, r]
+                mn = g.min(axis=0)
+                eq = g == mn[None, :]
+                q = eq.sum(axis=0)
+                for t in range(n):
+                    for qq in range(1, n + 1):
+                        cnt[int(X["cnt_off"]) + (f * n + t) * n + qq - 1] += np.uint32((eq[t] & (q == qq)).sum())
+
+    # --- kernel (c), part 2 -----------------------------------------------------------------
+    def gk_rank(self, table, stab, n_search, top_n, n_set, ids_prev, cand_pool, alive, S, cnt, col, keys,
+                ids_out, score_out, cnt_out, flat_out, info, kept_out):
+        table = table.view(MATRIX_DTYPE)
+        stab = stab.view(SEARCH_DTYPE)
+        info = info.view(STEP_INFO_DTYPE)
+        ids_prev = ids_prev.reshape(n_search, top_n, GK_MAX_CN)
+        ids_out = ids_out.reshape(n_search, top_n, GK_MAX_CN)
+        score_out = score_out.reshape(n_search, top_n)
+        cnt_out = cnt_out.reshape(n_search, top_n, GK_MAX_CN * GK_MAX_CN)
+        flat_out = flat_out.reshape(n_search, top_n)
+        n = n_set
+        for s in range(n_search):
+            X = stab[s]
+            M = table[X["matrix"]]
+            F = min(int(info[s]["n_alive"]), int(X["alive_cap"]))
+            flat, ids = self._alive_sets(X, s, n, top_n, ids_prev, cand_pool, alive, F)
+            C = int(X["n_cand"])
+            stride = int(X["s_stride"])
+            colv = col[int(M["col_off"]): int(M["col_off"]) + int(M["n_alleles"])].astype(np.int64)
+            cn = cnt[int(X["cnt_off"]): int(X["cnt_off"]) + F * n * n].astype(np.int64).reshape(F, n, n)
+            w = np.array([LCM[n] // q for q in range(1, n + 1)], dtype=np.int64)
+            num = (cn * w[None, None, :]).sum(axis=2)
+            even = int(M["n_reads"]) * LCM[n] // n
+            uneven = np.abs(num - even).sum(axis=1)
+            sc = np.array([S[int(X["S_off"]) + (i // C) * stride + ids[f, -1]] for f, i in enumerate(flat)],
+                          dtype=np.int64)
+            cs = colv[ids].sum(axis=1) if F else np.zeros(0, np.int64)
+            order = np.lexsort((np.arange(F), uneven, cs, sc))
+            k = min(F, top_n)
+            for rank in range(k):
+                f = order[rank]
+                ids_out[s, rank, :n] = ids[f]
+                score_out[s, rank] = sc[f]
+                cnt_out[s, rank, : n * n] = cn[f].reshape(-1)
+                flat_out[s, rank] = flat[f]
+            flags = int(info[s]["tie_flags"])
+            if F > top_n and sc[order[top_n - 1]] == sc[order[top_n]]:
+                flags |= 2
+            if F > 1 and sc[order[0]] == sc[order[1]]:
+                flags |= 4
+            info[s]["n_kept"] = k
+            info[s]["tie_flags"] = flags
+            kept_out[s] = k
+
+    def gk_write_p(self, table, stab, items, n_items, top_n, n_set, kept, ids, LT, P):
+        table = table.view(MATRIX_DTYPE)
+        stab = stab.view(SEARCH_DTYPE)
+        items = items.view(P_ITEM_DTYPE)[:n_items]
+        ids = ids.reshape(-1, top_n, GK_MAX_CN)
+        for it in items:
+            s = int(it["search"])
+            X = stab[s]
+            M = table[X["matrix"]]
+            rp = int(M["r_pad"])
+            K = int(kept[s])
+            m = self._LT_view(M, LT)
+            r0 = int(it["r0"])
+            assert r0 % 128 == 0 and r0 + 128 <= rp
+            tile = np.zeros((128, GK_KB), dtype=np.float32)
+            for kl in range(GK_KB):
+                k = int(it["k_blk"]) * GK_KB + kl
+                if k < K:
+                    tile[:, kl] = m[ids[s, k, :n_set], r0:r0 + 128].min(axis=0)
+            o = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
+            P[o: o + 128 * GK_KB] = tile.reshape(-1)

@@ -1,0 +1,169 @@
+"""Host orchestration (kir_graph_b200/engine.py + typing classes) on the NumPy test double.
+
+These tests cover everything around the kernels -- pool layout, work-item lists, step
+sequencing, result conversion -- without a GPU; the kernels themselves are checked by the
+-m gpu tests against the same oracle.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from kir_graph_b200 import engine, packing, synthetic
+from kir_graph_b200.typing_mulit_allele import AlleleTyping, AlleleTypingExonFirst
+from oracle import typing_oracle as orc
+from tests.fake_backend import FakeBackend
+from tests.helpers import (assert_same_modulo_ties, golden_names, int_scores_from_values, load_golden,
+                           objects_from_input)
+
+
+def oracle_for_pack(pack, reads, variants, top_n):
+    by_id = {str(v.id): v for v in variants}
+    col = {n: i for i, n in enumerate(pack.allele_names)}
+    kept = [reads[i] for i in pack.kept_reads]
+    m, k = orc.mismatch_counts(kept, by_id, col)
+    return m, k, orc.IntSearch(m, k, top_n=top_n)
+
+
+def check_steps(group_out, ref):
+    assert np.array_equal(group_out.ids, ref.allele_id)
+    assert np.array_equal(group_out.score, ref.score)
+    n = group_out.n
+    w = np.array([orc.lcm_upto(n) // q for q in range(1, n + 1)])
+    assert np.array_equal((group_out.cnt * w[None, None, :]).sum(axis=2), ref.frac_num)
+    assert group_out.n_unique == ref.n_unique
+
+
+@pytest.mark.parametrize("spec", [
+    dict(seed=[7, 0], n_allele=20, n_var=96, cn=3, n_reads=260, top_n=25),
+    dict(seed=[7, 1], n_allele=5, n_var=64, cn=4, n_reads=150, top_n=300),
+    dict(seed=[7, 2], n_allele=70, n_var=560, cn=2, n_reads=300, top_n=40),
+    dict(seed=[7, 3], n_allele=150, n_var=600, cn=2, n_reads=140, top_n=130),
+])
+def test_search_group_equals_int_oracle(spec):
+    top_n = spec.pop("top_n")
+    cn = spec["cn"]
+    gene = synthetic.make_gene(gene="KIRT*BACKBONE", **spec)
+    reads, variants = gene.to_objects()
+    pack = packing.pack_gene(reads, variants, variant_correction=True)
+    m, k, search = oracle_for_pack(pack, reads, variants, top_n)
+    be = FakeBackend()
+    batch = engine.MatrixBatch([pack], backend=be)
+    assert np.array_equal(batch.mismatch_counts(0), m)
+    assert np.array_equal(batch.blocked_counts(0), m)
+    assert np.array_equal(batch.colsum(0), m.sum(axis=0))
+    group = engine.SearchGroup(batch, [0], top_n)
+    for step in range(cn):
+        out = group.step(need_next=[step + 1 < cn])[0]
+        ref = search.add_candidate()
+        check_steps(out, ref)
+    p = group.materialize_p(0, out.ids)
+    assert np.array_equal(p, ref.allele_prob)
+
+
+def test_batch_of_genes_with_different_cn_and_restricted_candidates():
+    genes = [synthetic.make_gene([9, i], f"KIRU{i}*BACKBONE", a, max(64, 8 * a), c, r)
+             for i, (a, c, r) in enumerate([(12, 2, 130), (40, 3, 200), (6, 1, 90), (33, 2, 170)])]
+    packs, oracles = [], []
+    for g in genes:
+        reads, variants = g.to_objects()
+        p = packing.pack_gene(reads, variants)
+        packs.append(p)
+        oracles.append(oracle_for_pack(p, reads, variants, 30)[2])
+    be = FakeBackend()
+    batch = engine.MatrixBatch(packs, backend=be)
+    group = engine.SearchGroup(batch, [0, 1, 2, 3, 1], 30)      # search 4 shares matrix 1, restricted candidates
+    oracles.append(orc.IntSearch(oracles[1].m, np.array([oracles[1].k_total]), top_n=30))
+    cns = [2, 3, 1, 2, 3]
+    rng = np.random.default_rng(0)
+    for step in range(3):
+        active = np.array([c > step for c in cns])
+        need = np.array([c > step + 1 for c in cns])
+        cands = [None, None, None, None, rng.choice(packs[1].n_alleles, size=7, replace=False)]
+        outs = group.step(cands=cands, active=active, need_next=need)
+        for s in np.flatnonzero(active):
+            ref = oracles[s].add_candidate(cands[s])
+            check_steps(outs[s], ref)
+    assert set(be.log) >= {"gk_likelihood", "gk_first_step", "gk_score", "gk_select", "gk_rescore_count",
+                           "gk_rank", "gk_write_p"}
+
+
+@pytest.mark.parametrize("name", golden_names("typing"))
+def test_allele_typing_class_against_reference(name):
+    case = load_golden(name)
+    reads, variants = objects_from_input(case["input"])
+    typ = AlleleTyping(reads, variants, force_homo=case["force_homo"], top_n=case["top_n"],
+                       variant_correction=case["variant_correction"], _backend=FakeBackend())
+    assert [typ.id_to_allele[i] for i in range(len(typ.id_to_allele))] == case["allele_names"]
+    assert typ.getReadsNum() == case["n_reads"]
+    after = [{"lpv": r.lpv, "rpv": r.rpv, "lnv": r.lnv, "rnv": r.rnv} for r in typ.reads]
+    assert after == case["reads_after"]
+    np.testing.assert_allclose(typ.log_probs, np.array(case["log_probs"]), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(typ.probs, np.array(case["probs"]), rtol=1e-9)
+    res = typ.typing(case["cn"])
+    assert len(typ.result) == len(case["steps"])
+    for got, ref in zip(typ.result, case["steps"]):
+        assert got.n == ref["n"]
+        np.testing.assert_allclose(got.value, np.sort(ref["value"])[::-1], rtol=1e-11)
+        if got.frac_num is None:        # homozygous shortcut
+            assert got.allele_id.tolist() == ref["allele_id"] or got.tie_flags
+            continue
+        ref_scores = int_scores_from_values(ref["value"], typ._k_total)
+        assert_same_modulo_ties(ref["allele_id"], ref_scores, got.allele_id, got.score,
+                                kept_all=got.n_unique <= case["top_n"])
+    best = res.selectBest()
+    assert best == case["best"] or res.tie_flags, (best, case["best"])
+    # lazy allele_prob equals max over members of log_probs
+    last = typ.result[-1]
+    if last.frac_num is not None:
+        lp = typ.log_probs
+        want = lp[:, last.allele_id].max(axis=2)
+        np.testing.assert_allclose(np.asarray(last.allele_prob), want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", golden_names("exonfirst"))
+def test_exon_first_class_against_reference(name):
+    case = load_golden(name)
+    reads, variants = objects_from_input(case["input"])
+    typ = AlleleTypingExonFirst(reads, variants, force_homo=False, top_n=case["top_n"],
+                                candidate_set_threshold=case["threshold"], _backend=FakeBackend())
+    assert {k: sorted(v) for k, v in typ.allele_group.items()} == \
+           {k: sorted(v) for k, v in case["allele_group"].items()}
+    assert [typ.id_to_allele[i] for i in range(len(typ.id_to_allele))] == case["exon_allele_names"]
+    assert typ.getReadsNum() == case["exon_n_reads"]
+    res = typ.typing(case["cn"])
+    for got, ref in zip(typ.result[: case["cn"]], case["exon_steps"]):
+        np.testing.assert_allclose(got.value, np.sort(ref["value"])[::-1], rtol=1e-11)
+    assert len(typ.result) == case["n_results"] or any(r.tie_flags for r in typ.result)
+    np.testing.assert_allclose(res.value[:5], np.sort(case["final"]["value"])[::-1][:5], rtol=1e-11)
+    best = res.selectBest()
+    assert best == case["best"] or res.tie_flags, (best, case["best"])
+
+
+def test_deepcopy_continues_search():
+    gene = synthetic.make_gene([3, 3], "KIRV*BACKBONE", 18, 144, 3, 220)
+    reads, variants = gene.to_objects()
+    be = FakeBackend()
+    a = AlleleTyping(copy.deepcopy(reads), variants, force_homo=False, top_n=20, _backend=be)
+    a.addCandidate()
+    b = copy.deepcopy(a)
+    assert b._batch is a._batch
+    a.addCandidate()
+    b.addCandidate()
+    assert np.array_equal(a.result[-1].allele_id, b.result[-1].allele_id)
+    assert np.array_equal(a.result[-1].score, b.result[-1].score)
+    assert len(a.result) == len(b.result) == 2
+
+
+def test_errors_and_empty():
+    gene = synthetic.make_gene([3, 4], "KIRY*BACKBONE", 8, 64, 2, 50)
+    reads, variants = gene.to_objects()
+    typ = AlleleTyping(reads, variants, force_homo=False, top_n=10, _backend=FakeBackend())
+    with pytest.raises(ValueError):
+        typ.typing(0)
+    with pytest.raises(ValueError):
+        AlleleTyping.createHomoResult(typ.addCandidate(), 1)
+    empty = AlleleTyping([], variants, force_homo=False, top_n=10, _backend=FakeBackend())
+    res = empty.typing(2)
+    assert res.isFail() and res.selectBest() == ["fail", "fail"] and empty.getReadsNum() == 0
+    assert empty.probs.shape == (0,)

@@ -1,0 +1,140 @@
+"""CUDA kernels against (1) the NumPy launch-by-launch statement in tests/fake_backend.py,
+(2) the oracle's exact integer search, (3) golden outputs of the reference itself.
+All calls go through the C ABI (ctypes -> libgk_typing.so)."""
+import numpy as np
+import pytest
+
+from kir_graph_b200 import engine, packing, synthetic
+from kir_graph_b200._cabi import GK_KB, STEP_INFO_DTYPE
+from oracle import typing_oracle as orc
+from tests.fake_backend import FakeBackend
+from tests.helpers import (assert_same_modulo_ties, golden_names, int_scores_from_values, load_golden,
+                           objects_from_input)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    return engine.CudaBackend()
+
+
+def _packs(specs, seed):
+    packs = []
+    for i, (a, c, r) in enumerate(specs):
+        g = synthetic.make_gene([seed, i], f"KIRK{i}*BACKBONE", a, max(64, 8 * a), c, r)
+        packs.append(packing.pack_synthetic(g))
+    return packs
+
+
+def _compare_outputs(a, b):
+    assert set(a) == set(b)
+    for s in a:
+        x, y = a[s], b[s]
+        assert np.array_equal(x.ids, y.ids), f"search {s}: ids"
+        assert np.array_equal(x.score, y.score), f"search {s}: score"
+        assert np.array_equal(x.cnt, y.cnt), f"search {s}: cnt"
+        assert np.array_equal(x.flat, y.flat), f"search {s}: flat"
+        assert (x.n_unique, x.n_alive, x.cut, x.tie_flags) == (y.n_unique, y.n_alive, y.cut, y.tie_flags)
+
+
+@pytest.mark.parametrize("specs,top_n,cns", [
+    ([(12, 2, 130), (40, 3, 700), (6, 1, 90), (150, 2, 400), (3, 4, 260)], 30, [2, 3, 1, 2, 4]),
+    ([(70, 3, 1500), (33, 2, 90)], 300, [3, 2]),
+])
+def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns):
+    packs = _packs(specs, 101)
+    fake = FakeBackend()
+    bg, bf = engine.MatrixBatch(packs, backend=cuda), engine.MatrixBatch(packs, backend=fake)
+    assert np.array_equal(cuda.download(bg.d_LT, np.uint8), bf.d_LT), "LT"
+    assert np.array_equal(cuda.download(bg.d_L, np.float32), bf.d_L), "L"
+    assert np.array_equal(cuda.download(bg.d_col, np.uint64), bf.d_col), "colsum"
+    ids = list(range(len(packs))) + [1]
+    cns = cns + [cns[1]]
+    gg, gf = engine.SearchGroup(bg, ids, top_n), engine.SearchGroup(bf, ids, top_n)
+    rng = np.random.default_rng(5)
+    for step in range(max(cns)):
+        active = np.array([c > step for c in cns])
+        need = np.array([c > step + 1 for c in cns])
+        cands = [None] * len(packs) + [rng.choice(packs[1].n_alleles, size=9, replace=False)]
+        og = gg.step(cands=cands, active=active, need_next=need)
+        of = gf.step(cands=cands, active=active, need_next=need)
+        if step:
+            assert np.array_equal(cuda.download(gg.d_S, np.uint32), gf.d_S), f"S at step {step + 1}"
+        _compare_outputs(og, of)
+        if need.any():
+            pg = cuda.download(gg.d_P, np.float32)
+            for s in np.flatnonzero(need):
+                rp = int(gg.mt["r_pad"][s])
+                n = -(-int(gg.kept[s]) // GK_KB) * rp * GK_KB
+                o = int(gg.tab["P_off"][s])
+                assert np.array_equal(pg[o:o + n], gf.d_P[o:o + n]), f"P of search {s}"
+
+
+@pytest.mark.parametrize("a,cn,r,top_n", [(120, 3, 6000, 300), (200, 2, 12000, 300), (45, 4, 3000, 64)])
+def test_search_equals_oracle(cuda, a, cn, r, top_n):
+    gene = synthetic.make_gene([77, a], "KIRO*BACKBONE", a, 8 * a, cn, r)
+    pack = packing.pack_synthetic(gene)
+    batch = engine.MatrixBatch([pack], backend=cuda)
+    m = batch.mismatch_counts(0)
+    # independent m from the CSR lists by set logic
+    want = np.zeros_like(m, dtype=np.int64)
+    member = gene.member[:, [gene.allele_names.index(n) for n in pack.allele_names]]
+    for name in ("lpv", "rpv", "lnv", "rnv"):
+        off, idx = pack.csr.offsets[name], pack.csr.indices[name]
+        row = np.repeat(np.arange(pack.n_reads), np.diff(off))
+        contrib = ~member[idx] if name in ("lpv", "rpv") else member[idx]
+        np.add.at(want, row, contrib.astype(np.int64))
+    assert np.array_equal(m, want)
+    search = orc.IntSearch(m.astype(np.int64), pack.k_obs, top_n=top_n)
+    group = engine.SearchGroup(batch, [0], top_n)
+    for step in range(cn):
+        out = group.step(need_next=[step + 1 < cn])[0]
+        ref = search.add_candidate()
+        assert np.array_equal(out.ids, ref.allele_id)
+        assert np.array_equal(out.score, ref.score)
+        w = np.array([orc.lcm_upto(out.n) // q for q in range(1, out.n + 1)])
+        assert np.array_equal((out.cnt * w[None, None, :]).sum(axis=2), ref.frac_num)
+    assert np.array_equal(group.materialize_p(0, out.ids), ref.allele_prob)
+
+
+@pytest.mark.parametrize("name", golden_names("typing"))
+def test_reference_golden(cuda, name):
+    from kir_graph_b200.typing_mulit_allele import AlleleTyping
+    case = load_golden(name)
+    reads, variants = objects_from_input(case["input"])
+    typ = AlleleTyping(reads, variants, force_homo=case["force_homo"], top_n=case["top_n"],
+                       variant_correction=case["variant_correction"], _backend=cuda)
+    np.testing.assert_allclose(typ.log_probs, np.array(case["log_probs"]), rtol=1e-5, atol=1e-12)
+    res = typ.typing(case["cn"])
+    for got, ref in zip(typ.result, case["steps"]):
+        np.testing.assert_allclose(got.value, np.sort(ref["value"])[::-1], rtol=1e-5)
+        if got.frac_num is None:
+            continue
+        ref_scores = int_scores_from_values(ref["value"], typ._k_total)
+        assert_same_modulo_ties(ref["allele_id"], ref_scores, got.allele_id, got.score,
+                                kept_all=got.n_unique <= case["top_n"])
+    best = res.selectBest()
+    assert best == case["best"] or res.tie_flags, (best, case["best"])
+
+
+def test_split_invariance_and_idempotence(cuda, monkeypatch):
+    """Scores do not depend on how reads are chunked into work items, and reruns are bit-identical."""
+    gene = synthetic.make_gene([88, 0], "KIRP*BACKBONE", 130, 1040, 3, 20000)
+    pack = packing.pack_synthetic(gene)
+    outs = []
+    for chunk in (8192, 2048, 8192):
+        monkeypatch.setattr(engine, "SCORE_READ_CHUNK", chunk)
+        batch = engine.MatrixBatch([pack], backend=cuda)
+        group = engine.SearchGroup(batch, [0], 300)
+        steps = [group.step(need_next=[i < 2])[0] for i in range(3)]
+        outs.append(steps)
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a.ids, b.ids) and np.array_equal(a.score, b.score) and np.array_equal(a.cnt, b.cnt)
+    for a, b in zip(outs[0], outs[2]):
+        assert np.array_equal(a.ids, b.ids) and np.array_equal(a.score, b.score) and np.array_equal(a.cnt, b.cnt)
+    last = outs[0][-1]
+    assert np.all(np.diff(last.score) >= 0)
+    assert np.all(last.cnt.sum(axis=(1, 2)) >= pack.n_reads)          # every read counted for >= 1 member
+    w = np.array([orc.lcm_upto(3) // q for q in (1, 2, 3)])
+    assert np.all((last.cnt * w).sum(axis=(1, 2)) == pack.n_reads * orc.lcm_upto(3))   # fractions sum to 1
