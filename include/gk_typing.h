@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define GK_MAX_CN 8        /* alleles per set (copy number) supported by the search kernels */
-#define GK_KB 128          /* kept-set block: P is stored [k_block][read][GK_KB]             */
+#define GK_KB 64           /* kept-set block: P is stored [k_block][read][GK_KB]             */
 #define GK_RT 16           /* read rows per shared-memory stage of the scoring kernel        */
 #define GK_LIK_READS 64    /* read rows per CTA of the likelihood kernel                     */
 
@@ -49,7 +49,7 @@ typedef struct GkMatrix {
     int32_t n_alleles;
     int32_t n_words;
     int32_t r_pad;       /* multiple of 128; rows >= n_reads are zero                                    */
-    int32_t a_tile;      /* 16, 32, 64 or 128                                                            */
+    int32_t a_tile;      /* allele block width of L: 16 (genes with <= 16 alleles) or 32                 */
     int32_t n_ablk;      /* ceil(n_alleles / a_tile)                                                     */
 } GkMatrix;
 
@@ -68,10 +68,11 @@ typedef struct GkSearch {
 } GkSearch;
 
 /* Work items (built by the host per launch). */
-typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* r0 multiple of GK_LIK_READS */
-typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, pad; } GkScoreItem; /* [r0, r1) multiple of GK_RT   */
+typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS */
+typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
+    shape = k-blocks (1|2) | a-blocks (1|2|4) << 8 covered by the CTA tile */
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16 */
-typedef struct GkPItem { int32_t search, k_blk, r0, pad; } GkPItem;                  /* 128 reads from r0           */
+typedef struct GkPItem { int32_t search, k_blk, r0, pad; } GkPItem;                  /* one k-block x 128 reads from r0 */
 
 /* Per-search step outputs (device arrays indexed [search]). */
 typedef struct GkStepInfo {

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 GK_MAX_CN = 8
-GK_KB = 128
+GK_KB = 64
 GK_RT = 16
 GK_LIK_READS = 64
 
@@ -34,7 +34,7 @@ SEARCH_DTYPE = np.dtype([
 
 LIK_ITEM_DTYPE = np.dtype([("matrix", "<i4"), ("a_blk", "<i4"), ("r0", "<i4"), ("pad", "<i4")])
 SCORE_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("a_blk", "<i4"),
-                             ("r0", "<i4"), ("r1", "<i4"), ("pad", "<i4")])
+                             ("r0", "<i4"), ("r1", "<i4"), ("shape", "<i4")])
 COUNT_ITEM_DTYPE = np.dtype([("search", "<i4"), ("f0", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
 P_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("r0", "<i4"), ("pad", "<i4")])
 STEP_INFO_DTYPE = np.dtype([("n_kept", "<i4"), ("n_unique", "<i4"), ("n_alive", "<i4"), ("cut", "<i4"),

@@ -1,9 +1,9 @@
 // Kernel (a): likelihood build.
 //
 // Replaces AlleleTyping.reads2AlleleProb + np.log10 (reference:
-// graphkir/typing_mulit_allele.py:340-381, :263).  For a tile of 64 reads x one
-// allele block, every lane owns up to four alleles (lane, lane+32, ...) and walks
-// the read's packed observation entries:
+// graphkir/typing_mulit_allele.py:340-381, :263).  For a tile of 64 reads x up to four
+// allele blocks (128 alleles), every lane owns up to four alleles (lane, lane+32, ...) and
+// walks the read's packed observation entries:
 //     m[r, a] += popc((pos & ~mem[word, a]) | (neg & mem[word, a]))
 // The membership row mem[word, :] is word-major, so the 32 lanes of a warp read
 // 128 consecutive bytes (coalesced; a gene's table is <= 1 MB and stays in L1/L2).
@@ -32,19 +32,24 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
-    const int a_tile = M.a_tile;
+    const int a_tile = M.a_tile;           // 16 (single block) or 32
     const int a0 = item.a_blk * a_tile;
     const int r0 = item.r0;
+    int n_blk = M.n_ablk - item.a_blk;     // allele blocks covered by this CTA (<= 4)
+    n_blk = n_blk > 4 ? 4 : n_blk;
+    const int a_span = n_blk * a_tile;     // <= 128
     const int lane = gk_lane();
     const int warp = gk_warp();
 
     const uint32_t* mem = mem_pool + M.mem_off;
     const int32_t* eoff = entoff_pool + M.entoff_off;
+    // group g of this lane is column (lane + 32 g) of the span = block (a_blk + g) when a_tile == 32
     float* L = L_pool + M.L_off + (int64_t)item.a_blk * M.r_pad * a_tile;
+    const int64_t blk_stride = (int64_t)M.r_pad * a_tile;
 
     bool live[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) live[g] = (lane + 32 * g < a_tile) && (a0 + lane + 32 * g < M.n_alleles);
+    for (int g = 0; g < 4; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
 
     unsigned int csum[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
@@ -72,8 +77,8 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int a = lane + 32 * g;
-            if (a < a_tile) {
-                L[(int64_t)r * a_tile + a] = (float)cnt[g];
+            if (a < a_span) {
+                L[(a / a_tile) * blk_stride + (int64_t)r * a_tile + (a % a_tile)] = (float)cnt[g];
                 tile[a * kTilePitch + rl] = (uint8_t)cnt[g];
                 csum[g] += cnt[g];
             }
@@ -84,7 +89,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     __syncthreads();
 
     unsigned long long* col = col_pool + M.col_off;
-    for (int a = threadIdx.x; a < a_tile; a += kThreads) {
+    for (int a = threadIdx.x; a < a_span; a += kThreads) {
         unsigned int s = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += colpart[w][a];
@@ -92,7 +97,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     }
 
     uint8_t* LT = LT_pool + M.LT_off;
-    for (int idx = threadIdx.x; idx < a_tile * (GK_LIK_READS / 16); idx += kThreads) {
+    for (int idx = threadIdx.x; idx < a_span * (GK_LIK_READS / 16); idx += kThreads) {
         const int a = idx / (GK_LIK_READS / 16);
         const int seg = idx % (GK_LIK_READS / 16);
         if (a0 + a < M.n_alleles) {

@@ -95,8 +95,8 @@ gk_rescore_count_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* _
     count_set<N>(rows, item.r0, item.r1, M.n_reads, cnt_pool + X.cnt_off + (int64_t)f * N * N);
 }
 
-// P tile: 128 kept sets x 128 reads per CTA.
-constexpr int kPitch = 132;  // bytes per set row in shared memory (33 words: conflict-free transposed reads)
+// P tile: one k-block (GK_KB = 64 kept sets) x 128 reads per CTA.
+constexpr int kPitch = 132;  // bytes per set row in shared memory (33 words)
 
 __global__ void __launch_bounds__(kThreads)
 gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
@@ -128,15 +128,17 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
     }
     __syncthreads();
 
-    // phase 2: one warp per read row, four consecutive sets per lane -> 512-byte row stores
+    // phase 2: half a warp per read row, four consecutive sets per lane -> 256-byte row stores
     float* P = P_pool + X.P_off + ((int64_t)item.k_blk * M.r_pad + item.r0) * GK_KB;
-    for (int rl = warp; rl < 128; rl += kWarps) {
+    const int half = lane >> 4;
+    const int kq = (lane & 15) * 4;
+    for (int rl = warp * 2 + half; rl < 128; rl += kWarps * 2) {
         float4 out;
-        out.x = (float)tile[(lane * 4 + 0) * kPitch + rl];
-        out.y = (float)tile[(lane * 4 + 1) * kPitch + rl];
-        out.z = (float)tile[(lane * 4 + 2) * kPitch + rl];
-        out.w = (float)tile[(lane * 4 + 3) * kPitch + rl];
-        *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + lane * 4) = out;
+        out.x = (float)tile[(kq + 0) * kPitch + rl];
+        out.y = (float)tile[(kq + 1) * kPitch + rl];
+        out.z = (float)tile[(kq + 2) * kPitch + rl];
+        out.w = (float)tile[(kq + 3) * kPitch + rl];
+        *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = out;
     }
 }
 

@@ -31,17 +31,11 @@ from .packing import GenePack
 SCORE_READ_CHUNK = 8192     # reads per scoring work item: 8192 * 255 < 2^24 keeps float32 sums exact
 COUNT_READ_CHUNK = 16384    # reads per rescoring work item
 MAX_TOP_N = 2048
+MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
 
 
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
-
-
-def pick_a_tile(n_alleles: int) -> int:
-    for tile in (16, 32, 64):
-        if n_alleles <= tile:
-            return tile
-    return 128
 
 
 # ---------------------------------------------------------------------------
@@ -60,6 +54,8 @@ class CudaBackend:
         self.device = torch.device(device if isinstance(device, str) else f"cuda:{device}")
         _cabi.load()
         self.launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
         self.timing: dict[str, list] | None = None   # name -> [(start_event, end_event, work)]
 
     # --- memory ---------------------------------------------------------------
@@ -85,12 +81,14 @@ class CudaBackend:
             array = array.view(np.int64)
         if array.size == 0:
             return self.zeros(1, array.dtype)
-        return self.torch.from_numpy(array.reshape(-1)).to(self.device, non_blocking=False)
+        self.h2d_bytes += array.nbytes
+        return self.torch.from_numpy(array.reshape(-1)).to(self.device, non_blocking=True)
 
     def download(self, tensor, dtype=None, count: int | None = None) -> np.ndarray:
         if count is not None:
             tensor = tensor[:count]
         out = tensor.cpu().numpy()
+        self.d2h_bytes += out.nbytes
         return out.view(dtype) if dtype is not None else out
 
     def zero_(self, tensor) -> None:
@@ -98,6 +96,29 @@ class CudaBackend:
 
     def sync(self) -> None:
         self.torch.cuda.synchronize(self.device)
+
+    def gather_rows(self, tensor, row_len: int, rows: np.ndarray, cols: int | None = None) -> np.ndarray:
+        """Download tensor.view(-1, row_len)[rows, :cols] (device-side gather, one copy)."""
+        if len(rows) == 0:
+            return np.zeros((0, cols or row_len), dtype=np.dtype(str(tensor.dtype).split(".")[-1]))
+        idx = self.torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device)
+        view = tensor.view(-1, row_len).index_select(0, idx)
+        if cols is not None:
+            view = view[:, :cols].contiguous()
+        out = view.cpu().numpy()
+        self.d2h_bytes += out.nbytes
+        return out
+
+    def pin(self, array: np.ndarray) -> np.ndarray:
+        """Copy a host array into page-locked memory (for timed host->device copies)."""
+        flat = np.ascontiguousarray(array).reshape(-1)
+        raw = flat.view(np.uint8)
+        t = self.torch.empty(max(raw.size, 1), dtype=self.torch.uint8).pin_memory()
+        out = t.numpy()[: raw.size]
+        out[:] = raw
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(t)
+        return out.view(flat.dtype)
 
     # --- kernels ----------------------------------------------------------------
     def launch(self, name: str, *args, work: float = 0.0) -> None:
@@ -118,11 +139,11 @@ class CudaBackend:
 # ---------------------------------------------------------------------------
 # matrices
 # ---------------------------------------------------------------------------
-class MatrixBatch:
-    """Likelihood data of a batch of gene problems, resident on one GPU."""
+class HostBatch:
+    """Packed problems of a batch concatenated into host pools (the "packed host arrays"
+    that the end-to-end path copies to the device)."""
 
-    def __init__(self, packs: list[GenePack], backend=None, run: bool = True):
-        self.be = backend if backend is not None else CudaBackend()
+    def __init__(self, packs: list[GenePack]):
         self.packs = packs
         n = len(packs)
         table = np.zeros(n, dtype=MATRIX_DTYPE)
@@ -131,7 +152,7 @@ class MatrixBatch:
         for i, p in enumerate(packs):
             if p.n_reads and int(p.k_obs.astype(np.int64).sum()) >= 2 ** 32 - 1:
                 raise ValueError("sum of observations per problem must stay below 2^32 (32-bit score atomics)")
-            a_tile = pick_a_tile(p.n_alleles)
+            a_tile = 16 if p.n_alleles <= 16 else 32
             n_ablk = max(1, -(-p.n_alleles // a_tile))
             r_pad = max(128, _round_up(p.n_reads, 128))
             table[i] = (mem_off, entoff_off, L_off, LT_off, col_off, p.n_reads, p.n_alleles, p.n_words,
@@ -145,54 +166,90 @@ class MatrixBatch:
             col_off += max(p.n_alleles, 1)
         if ent_base >= 2 ** 31:
             raise ValueError("entry pool exceeds 2^31 entries; split the batch")
-        self.table = table
-        self.max_alleles = int(table["n_alleles"].max()) if n else 0
-        be = self.be
         cat = lambda xs, dt: (np.concatenate(xs).astype(dt, copy=False) if xs else np.zeros(0, dt))
-        self.d_table = be.upload(table)
-        self.d_mem = be.upload(cat([p.mem_words.reshape(-1) for p in packs], np.uint32))
-        self.d_entoff = be.upload(cat(entoffs, np.int32))
-        self.d_ent_word = be.upload(cat([p.ent_word for p in packs], np.int32))
-        self.d_ent_pos = be.upload(cat([p.ent_pos for p in packs], np.uint32))
-        self.d_ent_neg = be.upload(cat([p.ent_neg for p in packs], np.uint32))
-        self.d_L = be.empty(L_off, np.float32)
-        self.d_LT = be.empty(LT_off, np.uint8)
-        self.d_col = be.zeros(col_off, np.uint64)
-        self.n_cells = int((table["n_reads"].astype(np.int64) * table["n_alleles"]).sum())
-        self.bytes_out = int(L_off) * 4 + int(LT_off)
+        self.table = table
+        self.mem = cat([p.mem_words.reshape(-1) for p in packs], np.uint32)
+        self.entoff = cat(entoffs, np.int32)
+        self.ent_word = cat([p.ent_word for p in packs], np.int32)
+        self.ent_pos = cat([p.ent_pos for p in packs], np.uint32)
+        self.ent_neg = cat([p.ent_neg for p in packs], np.uint32)
+        self.k_total = np.array([int(np.where(p.k_obs == 0, 1, p.k_obs).astype(np.int64).sum()) for p in packs],
+                                dtype=np.int64)
+        self.L_size, self.LT_size, self.col_size = int(L_off), int(LT_off), int(col_off)
+
+    def pin(self, backend) -> "HostBatch":
+        for name in ("mem", "entoff", "ent_word", "ent_pos", "ent_neg"):
+            setattr(self, name, backend.pin(getattr(self, name)))
+        return self
+
+    @property
+    def nbytes(self) -> int:
+        return sum(getattr(self, n).nbytes for n in ("mem", "entoff", "ent_word", "ent_pos", "ent_neg")) \
+            + self.table.nbytes
+
+
+class MatrixBatch:
+    """Likelihood data of a batch of gene problems, resident on one GPU."""
+
+    def __init__(self, packs, backend=None, run: bool = True):
+        self.be = backend if backend is not None else CudaBackend()
+        host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
+        self.host = host
+        self.packs = host.packs
+        self.table = host.table
+        self.max_alleles = int(host.table["n_alleles"].max()) if len(host.table) else 0
+        be = self.be
+        self.d_table = be.upload(host.table)
+        self.d_mem = be.upload(host.mem)
+        self.d_entoff = be.upload(host.entoff)
+        self.d_ent_word = be.upload(host.ent_word)
+        self.d_ent_pos = be.upload(host.ent_pos)
+        self.d_ent_neg = be.upload(host.ent_neg)
+        self.d_L = be.empty(host.L_size, np.float32)
+        self.d_LT = be.empty(host.LT_size, np.uint8)
+        self.d_col = be.zeros(host.col_size, np.uint64)
+        t = host.table
+        self.n_cells = int((t["n_reads"].astype(np.int64) * t["n_alleles"]).sum())
+        self.bytes_out = host.L_size * 4 + host.LT_size
         self._colsum_host: np.ndarray | None = None
+        self.d_lik_items = None
         if run:
             self.run_likelihood()
 
     def lik_items(self) -> np.ndarray:
         t = self.table
-        tiles = t["r_pad"] // GK_LIK_READS
-        per = tiles * t["n_ablk"]
+        tiles = (t["r_pad"] // GK_LIK_READS).astype(np.int64)
+        groups = -(-t["n_ablk"].astype(np.int64) // 4)          # 4 allele blocks per CTA
+        per = tiles * groups
         total = int(per.sum())
         items = np.zeros(total, dtype=LIK_ITEM_DTYPE)
-        mat = np.repeat(np.arange(len(t), dtype=np.int32), per)
-        start = np.repeat(np.cumsum(per) - per, per)
-        local = np.arange(total) - start
+        mat = np.repeat(np.arange(len(t), dtype=np.int64), per)
+        local = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(per) - per, per)
         items["matrix"] = mat
-        items["a_blk"] = local // tiles[mat]
+        items["a_blk"] = (local // tiles[mat]) * 4
         items["r0"] = (local % tiles[mat]) * GK_LIK_READS
         return items
 
     def run_likelihood(self) -> None:
-        items = self.lik_items()
+        if self.d_lik_items is None:
+            items = self.lik_items()
+            self.n_lik_items = len(items)
+            self.d_lik_items = self.be.upload(items)
         self.be.zero_(self.d_col)
-        self.d_lik_items = self.be.upload(items)
-        self.be.launch("gk_likelihood", self.d_table, self.d_lik_items, len(items), self.d_mem, self.d_entoff,
-                       self.d_ent_word, self.d_ent_pos, self.d_ent_neg, self.d_L, self.d_LT, self.d_col,
-                       work=float(self.n_cells))
+        self.be.launch("gk_likelihood", self.d_table, self.d_lik_items, self.n_lik_items, self.d_mem,
+                       self.d_entoff, self.d_ent_word, self.d_ent_pos, self.d_ent_neg, self.d_L, self.d_LT,
+                       self.d_col, work=float(self.n_cells))
         self._colsum_host = None
 
     # --- read-backs ------------------------------------------------------------
-    def colsum(self, i: int) -> np.ndarray:
+    def colsum_all(self) -> np.ndarray:
         if self._colsum_host is None:
             self._colsum_host = self.be.download(self.d_col, np.uint64).astype(np.int64)
+        return self._colsum_host
+
+    def colsum(self, i: int) -> np.ndarray:
         o = int(self.table["col_off"][i])
-        return self._colsum_host[o:o + int(self.table["n_alleles"][i])]
+        return self.colsum_all()[o:o + int(self.table["n_alleles"][i])]
 
     def mismatch_counts(self, i: int) -> np.ndarray:
         """m[r, a] as uint8 [R, A], read back from the allele-major device copy."""
@@ -228,10 +285,44 @@ class StepOutput:
     tie_flags: int
 
 
+class StepBatch:
+    """Results of one step for every collected search, as bulk arrays."""
+
+    def __init__(self, n: int, searches: np.ndarray, info: np.ndarray, ids, score, cnt, flat):
+        self.n = n
+        self.searches = searches                     # search index of each row below
+        self.info = info                             # GkStepInfo [n_search]
+        self.ids, self.score, self.cnt, self.flat = ids, score, cnt, flat
+        self._row = {int(s): i for i, s in enumerate(searches)}
+
+    def __contains__(self, s: int) -> bool:
+        return int(s) in self._row
+
+    def __getitem__(self, s: int) -> StepOutput:
+        i = self._row[int(s)]
+        n, inf = self.n, self.info[int(s)]
+        k = int(inf["n_kept"])
+        return StepOutput(
+            n=n, ids=self.ids[i, :k, :n].copy(), score=self.score[i, :k].astype(np.int64),
+            cnt=self.cnt[i, :k].astype(np.int64).reshape(k, n, n), flat=self.flat[i, :k].copy(),
+            n_unique=int(inf["n_unique"]), n_alive=int(inf["n_alive"]), cut=int(inf["cut"]),
+            tie_flags=int(inf["tie_flags"]))
+
+    def keys(self):
+        return self._row.keys()
+
+    def __iter__(self):
+        return iter(self._row)
+
+
+# greedy cover of the last (n_ablk % 4) allele blocks by CTA tiles of width 2 and 1
+_A_REM = {0: [], 1: [(0, 1)], 2: [(0, 2)], 3: [(0, 2), (2, 1)]}
+
+
 class SearchGroup:
     """Greedy searches (one per entry of ``matrix_ids``) advancing in lock step."""
 
-    def __init__(self, batch: MatrixBatch, matrix_ids, top_n: int, max_cn: int = GK_MAX_CN):
+    def __init__(self, batch: MatrixBatch, matrix_ids, top_n: int):
         if not 1 <= top_n <= MAX_TOP_N:
             raise ValueError(f"top_n must be in 1..{MAX_TOP_N}")
         self.batch = batch
@@ -242,15 +333,17 @@ class SearchGroup:
         self.n_search = ns
         mt = batch.table[self.matrix_ids]
         self.mt = mt
+        self.R = mt["n_reads"].astype(np.int64)
+        self.r_pad = mt["r_pad"].astype(np.int64)
+        self.A = mt["n_alleles"].astype(np.int64)
+        self.n_ablk = mt["n_ablk"].astype(np.int64)
+        self.a_tile = mt["a_tile"].astype(np.int64)
         self.n_kblk_max = -(-self.top_n // GK_KB)
-        self.n = 0
-        self.kept = np.zeros(ns, dtype=np.int32)
-        self.score_cells = 0
 
         tab = np.zeros(ns, dtype=SEARCH_DTYPE)
-        cand_cap = np.maximum(mt["n_alleles"], 1).astype(np.int64)
-        p_size = self.n_kblk_max * mt["r_pad"].astype(np.int64) * GK_KB
-        s_stride = (mt["n_ablk"] * mt["a_tile"]).astype(np.int64)
+        cand_cap = np.maximum(self.A, 1)
+        p_size = self.n_kblk_max * self.r_pad * GK_KB
+        s_stride = self.n_ablk * self.a_tile
         s_size = self.n_kblk_max * GK_KB * s_stride
         flag_size = _round_up_arr(self.top_n * cand_cap, 16)
         alive_cap = np.maximum(self.top_n, (self.top_n * cand_cap) // 5)
@@ -268,7 +361,6 @@ class SearchGroup:
         self.d_P = None
         self._p_size = int(p_size.sum())
         self.d_S = be.zeros(int(s_size.sum()), np.uint32)
-        self.d_cand = be.zeros(int(cand_cap.sum()), np.int32)
         self.d_flag = be.empty(int(flag_size.sum()), np.uint8)
         self.d_alive = be.empty(int(alive_cap.sum()), np.int32)
         self.d_keys = be.empty(3 * int(alive_cap.sum()), np.uint64)
@@ -279,89 +371,176 @@ class SearchGroup:
         self.d_flat = be.zeros(out_rows, np.int32)
         self.d_info = be.zeros(ns * (STEP_INFO_DTYPE.itemsize // 4), np.int32)
         self.d_kept = be.zeros(ns, np.int32)
-        self.cur = 0  # index of the ids buffer holding the current kept sets
-        self.cands: list[np.ndarray] = [np.zeros(0, np.int32)] * ns
+        # default candidates: every allele of the gene
+        total = int(cand_cap.sum())
+        self._default_pool = (np.arange(total, dtype=np.int64)
+                              - np.repeat(tab["cand_off"], cand_cap)).astype(np.int32)
+        self._pool = self._default_pool.copy()
+        self.d_cand = be.upload(self._pool)
+        self._pool_dirty = False
+        self.reset()
 
-    # --- helpers -----------------------------------------------------------------
+    def reset(self) -> None:
+        """Start all searches over (buffers are reused)."""
+        self.n = 0
+        self.cur = 0
+        self.kept = np.zeros(self.n_search, dtype=np.int32)
+        self.score_cells = 0
+        self.n_cand = self.A.copy()                       # current candidate count per search
+        self.restricted: dict[int, np.ndarray] = {}       # search -> explicit candidate ids
+        if self._pool_dirty:
+            self._pool = self._default_pool.copy()
+            self.d_cand = self.be.upload(self._pool)
+            self._pool_dirty = False
+
+    # --- candidates ------------------------------------------------------------------
     def _set_candidates(self, cands, active: np.ndarray) -> None:
-        pool = np.zeros(int(self.cand_cap.sum()), dtype=np.int32)
-        for s in range(self.n_search):
-            if not active[s]:
-                self.tab["n_cand"][s] = 0
-                continue
-            c = cands[s]
-            a = int(self.mt["n_alleles"][s])
-            c = np.arange(a, dtype=np.int32) if c is None else np.asarray(c, dtype=np.int32)
-            if len(c) > self.cand_cap[s]:
-                raise ValueError("more candidates than alleles in the gene")
-            if len(c) and (c.min() < 0 or c.max() >= a):
-                raise ValueError("candidate allele id out of range")
-            o = int(self.tab["cand_off"][s])
-            pool[o:o + len(c)] = c
-            self.tab["n_cand"][s] = len(c)
-            self.cands[s] = c
-        self.d_cand = self.be.upload(pool)
+        changed = False
+        if cands is not None:
+            for s, c in enumerate(cands):
+                if not active[s]:
+                    continue
+                o = int(self.tab["cand_off"][s])
+                a = int(self.A[s])
+                if c is None:
+                    if s in self.restricted:
+                        del self.restricted[s]
+                        self._pool[o:o + a] = np.arange(a, dtype=np.int32)
+                        self.n_cand[s] = a
+                        changed = True
+                    continue
+                c = np.asarray(c, dtype=np.int32)
+                if len(c) > self.cand_cap[s]:
+                    raise ValueError("more candidates than alleles in the gene")
+                if len(c) and (c.min() < 0 or c.max() >= a):
+                    raise ValueError("candidate allele id out of range")
+                self._pool[o:o + len(c)] = c
+                self.n_cand[s] = len(c)
+                self.restricted[s] = c
+                changed = True
+        if changed:
+            self.d_cand = self.be.upload(self._pool)
+            self._pool_dirty = True
+        self.tab["n_cand"] = np.where(active, self.n_cand, 0)
 
-    def _read_chunks(self, s_idx: np.ndarray, chunk: int, align: int):
-        """(search, r0, r1) triples covering [0, round_up(R, align)) per search."""
-        out_s, out_r0, out_r1 = [], [], []
-        r_end = _round_up_arr(self.mt["n_reads"][s_idx].astype(np.int64), align)
-        n_chunk = np.maximum(1, -(-r_end // chunk))
-        for s, re, nc in zip(s_idx, r_end, n_chunk):
-            r0 = np.arange(nc, dtype=np.int64) * chunk
-            out_s.append(np.full(nc, s, dtype=np.int64))
-            out_r0.append(r0)
-            out_r1.append(np.minimum(r0 + chunk, re))
-        if not out_s:
-            z = np.zeros(0, np.int64)
-            return z, z, z
-        return np.concatenate(out_s), np.concatenate(out_r0), np.concatenate(out_r1)
+    # --- work items ---------------------------------------------------------------------
+    @staticmethod
+    def _product_items(counts_per_search: list[np.ndarray]):
+        """Decode a flat index over the per-search product of several counts."""
+        total_per = np.ones_like(counts_per_search[0])
+        for c in counts_per_search:
+            total_per = total_per * c
+        total = int(total_per.sum())
+        search = np.repeat(np.arange(len(total_per), dtype=np.int64), total_per)
+        local = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(total_per) - total_per, total_per)
+        parts = []
+        for c in reversed(counts_per_search):
+            cs = c[search]
+            parts.append(local % np.maximum(cs, 1))
+            local = local // np.maximum(cs, 1)
+        return search, list(reversed(parts))
+
+    def _a_tiles(self, s: int) -> list[tuple[int, int]]:
+        """(a_blk, width-in-blocks) CTA tiles covering the candidate columns of search ``s``."""
+        nb = int(self.n_ablk[s])
+        if self.a_tile[s] == 16:
+            return [(0, 1)]
+        if s in self.restricted:
+            blocks = np.unique(self.restricted[s] // 32)
+        else:
+            blocks = np.arange(nb)
+        tiles, i = [], 0
+        while i < len(blocks):
+            run = 1
+            while i + run < len(blocks) and blocks[i + run] == blocks[i] + run and run < 4:
+                run += 1
+            w = 4 if run == 4 else (2 if run >= 2 else 1)
+            tiles.append((int(blocks[i]), w))
+            i += w
+        return tiles
 
     def _score_items(self, active_idx: np.ndarray) -> np.ndarray:
-        rows = []
-        cells = 0
-        for s in active_idx:
-            k = int(self.kept[s])
-            c = self.cands[s]
-            if k == 0 or len(c) == 0:
-                continue
-            a_tile = int(self.mt["a_tile"][s])
-            ablks = np.unique(c // a_tile)
-            n_kblk = -(-k // GK_KB)
-            cs, r0, r1 = self._read_chunks(np.array([s]), SCORE_READ_CHUNK, _cabi.GK_RT)
-            kb, ab, ch = np.meshgrid(np.arange(n_kblk), ablks, np.arange(len(r0)), indexing="ij")
-            item = np.zeros(kb.size, dtype=SCORE_ITEM_DTYPE)
-            item["search"] = s
-            item["k_blk"] = kb.reshape(-1)
-            item["a_blk"] = ab.reshape(-1)
-            item["r0"] = r0[ch.reshape(-1)]
-            item["r1"] = r1[ch.reshape(-1)]
-            rows.append(item)
-            cells += k * len(c) * int(self.mt["n_reads"][s])
-        self._step_cells = cells
-        if not rows:
+        kept = self.kept.astype(np.int64)
+        live = active_idx[(kept[active_idx] > 0) & (self.n_cand[active_idx] > 0)]
+        self._step_cells = int((kept[live] * self.n_cand[live] * self.R[live]).sum())
+        if not len(live):
             return np.zeros(0, dtype=SCORE_ITEM_DTYPE)
-        items = np.concatenate(rows)
-        # longest items first
-        order = np.argsort(-(items["r1"] - items["r0"]).astype(np.int64) * self.mt["a_tile"][items["search"]],
-                           kind="stable")
+        n_k64 = -(-kept[live] // GK_KB)
+        n_kt = -(-n_k64 // 2)
+        r16 = _round_up_arr(self.R[live], _cabi.GK_RT)
+        # a-tiles as CSR
+        is_restricted = np.array([int(s) in self.restricted for s in live])
+        nb = self.n_ablk[live]
+        n_at = np.where(self.a_tile[live] == 16, 1, nb // 4 + np.array([len(_A_REM[int(x) % 4]) for x in nb]))
+        custom = {}
+        for j in np.flatnonzero(is_restricted):
+            custom[j] = self._a_tiles(int(live[j]))
+            n_at[j] = len(custom[j])
+        # chunk size: large chunks unless that leaves the GPU underfilled
+        chunk = SCORE_READ_CHUNK
+        for cand_chunk in (8192, 4096, 2048, 1024):
+            if cand_chunk > SCORE_READ_CHUNK:
+                continue
+            chunk = cand_chunk
+            if int((n_kt * n_at * np.maximum(1, -(-r16 // cand_chunk))).sum()) >= MIN_SCORE_ITEMS:
+                break
+        n_ch = np.maximum(1, -(-r16 // chunk))
+        search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
+        items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
+        items["search"] = live[search]
+        full_k = ikt < (n_k64[search] // 2)
+        items["k_blk"] = np.where(full_k, 2 * ikt, n_k64[search] - 1)
+        kw = np.where(full_k, 2, 1)
+        nbs = nb[search]
+        quad = iat < nbs // 4
+        rem_idx = np.maximum(iat - nbs // 4, 0)
+        rem = nbs % 4
+        rem_blk = np.where(rem_idx == 0, 0, 2)                       # second remainder tile starts 2 blocks in
+        rem_w = np.where(rem == 1, 1, np.where(rem == 2, 2, np.where(rem_idx == 0, 2, 1)))
+        a_blk = np.where(quad, 4 * iat, (nbs // 4) * 4 + rem_blk)
+        aw = np.where(quad, 4, rem_w)
+        aw = np.where(self.a_tile[live][search] == 16, 1, aw)
+        for j, tiles in custom.items():
+            sel = np.flatnonzero(search == j)
+            t = np.array(tiles, dtype=np.int64)
+            a_blk[sel] = t[iat[sel], 0]
+            aw[sel] = t[iat[sel], 1]
+        items["a_blk"] = a_blk
+        items["r0"] = ich * chunk
+        items["r1"] = np.minimum((ich + 1) * chunk, r16[search])
+        items["shape"] = kw | (aw << 8)
+        order = np.argsort(-((items["r1"] - items["r0"]).astype(np.int64) * kw * aw
+                             * self.a_tile[live][search]), kind="stable")
         return items[order]
 
     def _p_items(self, idx: np.ndarray) -> np.ndarray:
-        rows = []
-        for s in idx:
-            k = int(self.kept[s])
-            if k == 0:
-                continue
-            n_kblk = -(-k // GK_KB)
-            r0 = np.arange(0, int(self.mt["r_pad"][s]), 128)
-            kb, rr = np.meshgrid(np.arange(n_kblk), r0, indexing="ij")
-            item = np.zeros(kb.size, dtype=P_ITEM_DTYPE)
-            item["search"] = s
-            item["k_blk"] = kb.reshape(-1)
-            item["r0"] = rr.reshape(-1)
-            rows.append(item)
-        return np.concatenate(rows) if rows else np.zeros(0, dtype=P_ITEM_DTYPE)
+        kept = self.kept.astype(np.int64)
+        idx = idx[kept[idx] > 0]
+        if not len(idx):
+            return np.zeros(0, dtype=P_ITEM_DTYPE)
+        n_k64 = -(-kept[idx] // GK_KB)
+        n_rt = self.r_pad[idx] // 128
+        search, (ik, ir) = self._product_items([n_k64, n_rt])
+        items = np.zeros(len(search), dtype=P_ITEM_DTYPE)
+        items["search"] = idx[search]
+        items["k_blk"] = ik
+        items["r0"] = ir * 128
+        return items
+
+    def _count_items(self, active_idx: np.ndarray, n_alive: np.ndarray) -> np.ndarray:
+        idx = active_idx[n_alive[active_idx] > 0]
+        if not len(idx):
+            return np.zeros(0, dtype=COUNT_ITEM_DTYPE)
+        n_f = -(-n_alive[idx] // 8)
+        r16 = _round_up_arr(self.R[idx], 16)
+        n_ch = np.maximum(1, -(-r16 // COUNT_READ_CHUNK))
+        search, (jf, ich) = self._product_items([n_f, n_ch])
+        items = np.zeros(len(search), dtype=COUNT_ITEM_DTYPE)
+        items["search"] = idx[search]
+        items["f0"] = jf * 8
+        items["r0"] = ich * COUNT_READ_CHUNK
+        items["r1"] = np.minimum((ich + 1) * COUNT_READ_CHUNK, r16[search])
+        return items
 
     def _write_p(self, idx: np.ndarray, n_set: int) -> None:
         items = self._p_items(idx)
@@ -372,39 +551,30 @@ class SearchGroup:
         d_items = self.be.upload(items)
         self.be.launch("gk_write_p", self.batch.d_table, self.d_tab, d_items, len(items), self.top_n, n_set,
                        self.d_kept, self.d_ids[self.cur], self.batch.d_LT, self.d_P,
-                       work=float(len(items)) * 128 * 128)
+                       work=float(len(items)) * 128 * GK_KB)
 
-    def _collect(self, active_idx: np.ndarray, n: int) -> dict[int, StepOutput]:
-        be = self.be
-        ns, tn = self.n_search, self.top_n
-        info = be.download(self.d_info, None).view(STEP_INFO_DTYPE)
-        ids = be.download(self.d_ids[self.cur], np.int32).reshape(ns, tn, GK_MAX_CN)
-        score = be.download(self.d_score, np.uint32).reshape(ns, tn)
-        cnt = be.download(self.d_cnt_out, np.uint32).reshape(ns, tn, GK_MAX_CN * GK_MAX_CN)
-        flat = be.download(self.d_flat, np.int32).reshape(ns, tn)
-        out = {}
-        for s in active_idx:
-            k = int(info["n_kept"][s])
-            self.kept[s] = k
-            out[int(s)] = StepOutput(
-                n=n, ids=ids[s, :k, :n].copy(), score=score[s, :k].astype(np.int64),
-                cnt=cnt[s, :k, :n * n].astype(np.int64).reshape(k, n, n), flat=flat[s, :k].copy(),
-                n_unique=int(info["n_unique"][s]), n_alive=int(info["n_alive"][s]),
-                cut=int(info["cut"][s]), tie_flags=int(info["tie_flags"][s]))
-        return out
+    def _collect(self, rows: np.ndarray, n: int, info: np.ndarray) -> StepBatch:
+        be, tn = self.be, self.top_n
+        ids = be.gather_rows(self.d_ids[self.cur], tn * GK_MAX_CN, rows).reshape(len(rows), tn, GK_MAX_CN)
+        score = be.gather_rows(self.d_score, tn, rows).view(np.uint32)
+        cnt = be.gather_rows(self.d_cnt_out, tn * GK_MAX_CN * GK_MAX_CN, rows) \
+            .view(np.uint32).reshape(len(rows), tn, GK_MAX_CN * GK_MAX_CN)[:, :, :n * n]
+        flat = be.gather_rows(self.d_flat, tn, rows)
+        return StepBatch(n, rows, info, ids, score, cnt, flat)
 
     # --- one copy-number step ---------------------------------------------------------
-    def step(self, cands=None, active=None, need_next=None) -> dict[int, StepOutput]:
+    def step(self, cands=None, active=None, need_next=None, collect=None) -> StepBatch:
         """Advance the active searches by one allele.
 
         cands      per-search candidate allele ids (None = every allele of the gene)
         active     bool per search (default all)
         need_next  bool per search: will be stepped again (P is only written for those)
+        collect    bool per search: download the full step output (default: the active ones)
         """
         ns = self.n_search
         active = np.ones(ns, bool) if active is None else np.asarray(active, bool)
         need_next = active.copy() if need_next is None else (np.asarray(need_next, bool) & active)
-        cands = [None] * ns if cands is None else cands
+        collect = active if collect is None else (np.asarray(collect, bool) & active)
         be, bt = self.be, self.batch
         n = self.n + 1
         if n > GK_MAX_CN:
@@ -433,35 +603,22 @@ class SearchGroup:
             self.tab["cnt_off"] = _excl_cumsum(n_alive * n * n)
             self.d_tab = be.upload(self.tab)
             d_cnt = be.zeros(int((n_alive * n * n).sum()), np.uint32)
-            rows = []
-            for s in active_idx:
-                f = int(n_alive[s])
-                if f == 0:
-                    continue
-                _, r0, r1 = self._read_chunks(np.array([s]), COUNT_READ_CHUNK, 16)
-                f0 = np.arange(0, f, 8)
-                ff, ch = np.meshgrid(f0, np.arange(len(r0)), indexing="ij")
-                item = np.zeros(ff.size, dtype=COUNT_ITEM_DTYPE)
-                item["search"] = s
-                item["f0"] = ff.reshape(-1)
-                item["r0"] = r0[ch.reshape(-1)]
-                item["r1"] = r1[ch.reshape(-1)]
-                rows.append(item)
-            c_items = np.concatenate(rows) if rows else np.zeros(0, dtype=COUNT_ITEM_DTYPE)
+            c_items = self._count_items(active_idx, n_alive)
             d_citems = be.upload(c_items)
             be.launch("gk_rescore_count", bt.d_table, self.d_tab, d_citems, len(c_items), self.top_n, n,
                       self.d_info, self.d_ids[self.cur], self.d_cand, self.d_alive, bt.d_LT, d_cnt,
-                      work=float((n_alive * self.mt["n_reads"]).sum()) * n)
+                      work=float((n_alive * self.R).sum()) * n)
             be.launch("gk_rank", bt.d_table, self.d_tab, ns, self.top_n, n, self.d_ids[self.cur], self.d_cand,
                       self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_keys, self.d_ids[new], self.d_score,
                       self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
         self.cur = new
-        out = self._collect(active_idx, n)                                    # sync 2: step results
+        info = be.download(self.d_info, None).view(STEP_INFO_DTYPE).copy()   # sync 2: kept counts
+        self.kept[active_idx] = info["n_kept"][active_idx]
         self.n = n
         nxt = np.flatnonzero(need_next)
         if len(nxt):
             self._write_p(nxt, n)
-        return out
+        return self._collect(np.flatnonzero(collect), n, info)
 
     def restore(self, s: int, ids: np.ndarray) -> None:
         """Re-seed search ``s`` with kept sets ``ids`` [K, n] (device state is a pure function
@@ -477,6 +634,7 @@ class SearchGroup:
         self.kept[s] = k
         self.d_kept = self.be.upload(self.kept)
         self.n = n
+        self.tab["n_cand"] = self.n_cand
         self.d_tab = self.be.upload(self.tab)
         self._write_p(np.array([s]), n)
 
@@ -490,7 +648,7 @@ class SearchGroup:
         if k > self.top_n:
             raise ValueError("more sets than top_n")
         n_kblk = max(1, -(-k // GK_KB))
-        r_pad, r = int(self.mt["r_pad"][s]), int(self.mt["n_reads"][s])
+        r_pad, r = int(self.r_pad[s]), int(self.R[s])
         tab = self.tab[s:s + 1].copy()
         tab["P_off"] = 0
         buf = np.zeros((self.top_n, GK_MAX_CN), dtype=np.int32)

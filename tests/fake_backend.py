@@ -30,6 +30,8 @@ def popcount32(x: np.ndarray) -> np.ndarray:
 class FakeBackend:
     def __init__(self):
         self.launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
         self.timing = None
         self.log: list[str] = []
 
@@ -61,6 +63,13 @@ class FakeBackend:
     def sync(self):
         pass
 
+    def gather_rows(self, tensor, row_len, rows, cols=None):
+        view = tensor.reshape(-1, row_len)[np.asarray(rows, dtype=np.int64)]
+        return np.array(view[:, :cols] if cols is not None else view, copy=True)
+
+    def pin(self, array):
+        return np.ascontiguousarray(array).reshape(-1)
+
     def launch(self, name, *args, work=0.0):
         self.launches += 1
         self.log.append(name)
@@ -73,26 +82,27 @@ class FakeBackend:
         for it in items:
             M = table[it["matrix"]]
             A, a_tile, rp, R = int(M["n_alleles"]), int(M["a_tile"]), int(M["r_pad"]), int(M["n_reads"])
-            a0 = int(it["a_blk"]) * a_tile
             r0 = int(it["r0"])
-            a_hi = min(a0 + a_tile, A)
             eo = entoff[M["entoff_off"]: M["entoff_off"] + R + 1]
             memv = mem[M["mem_off"]: M["mem_off"] + int(M["n_words"]) * A].reshape(int(M["n_words"]), A)
-            tile = np.zeros((GK_LIK_READS, a_tile), dtype=np.int64)
-            for rl in range(GK_LIK_READS):
-                r = r0 + rl
-                if r >= R:
-                    continue
-                for e in range(eo[r], eo[r + 1]):
-                    mw = memv[ent_word[e], a0:a_hi]
-                    x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
-                    tile[rl, : a_hi - a0] += popcount32(x)
-            base = int(M["L_off"]) + (int(it["a_blk"]) * rp + r0) * a_tile
-            L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
-            for a in range(a0, a_hi):
-                o = int(M["LT_off"]) + a * rp + r0
-                LT[o: o + GK_LIK_READS] = tile[:, a - a0].astype(np.uint8)
-                col[int(M["col_off"]) + a] += np.uint64(tile[:, a - a0].sum())
+            for blk in range(int(it["a_blk"]), min(int(it["a_blk"]) + 4, int(M["n_ablk"]))):
+                a0 = blk * a_tile
+                a_hi = min(a0 + a_tile, A)
+                tile = np.zeros((GK_LIK_READS, a_tile), dtype=np.int64)
+                for rl in range(GK_LIK_READS):
+                    r = r0 + rl
+                    if r >= R:
+                        continue
+                    for e in range(eo[r], eo[r + 1]):
+                        mw = memv[ent_word[e], a0:a_hi]
+                        x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
+                        tile[rl, : a_hi - a0] += popcount32(x)
+                base = int(M["L_off"]) + (blk * rp + r0) * a_tile
+                L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
+                for a in range(a0, a_hi):
+                    o = int(M["LT_off"]) + a * rp + r0
+                    LT[o: o + GK_LIK_READS] = tile[:, a - a0].astype(np.uint8)
+                    col[int(M["col_off"]) + a] += np.uint64(tile[:, a - a0].sum())
 
     # --- helpers -------------------------------------------------------------------
     @staticmethod
@@ -150,16 +160,21 @@ class FakeBackend:
             M = table[X["matrix"]]
             rp, tile = int(M["r_pad"]), int(M["a_tile"])
             r0, r1 = int(it["r0"]), int(it["r1"])
+            kw, aw = int(it["shape"]) & 0xFF, (int(it["shape"]) >> 8) & 0xFF
             assert r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
-            Lt = self._L_view(M, L)[it["a_blk"], r0:r1, :]                     # [r, tile]
-            po = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
-            Pt = P[po: po + (r1 - r0) * GK_KB].reshape(r1 - r0, GK_KB)          # [r, 128]
-            part = np.minimum(Lt[:, None, :], Pt[:, :, None]).sum(axis=0)       # [128, tile]
-            assert part.max(initial=0) < 2 ** 24
+            assert kw in (1, 2) and aw in (1, 2, 4) and (tile == 32 or aw == 1)
+            assert int(it["a_blk"]) + aw <= int(M["n_ablk"])
             stride = int(X["s_stride"])
-            for kl in range(GK_KB):
-                o = int(X["S_off"]) + (int(it["k_blk"]) * GK_KB + kl) * stride + int(it["a_blk"]) * tile
-                S[o: o + tile] += part[kl].astype(np.uint32)
+            for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw):
+                po = int(X["P_off"]) + (kb * rp + r0) * GK_KB
+                Pt = P[po: po + (r1 - r0) * GK_KB].reshape(r1 - r0, GK_KB)
+                for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw):
+                    Lt = self._L_view(M, L)[ab, r0:r1, :]
+                    part = np.minimum(Lt[:, None, :], Pt[:, :, None]).sum(axis=0)   # [GK_KB, tile]
+                    assert part.max(initial=0) < 2 ** 24
+                    for kl in range(GK_KB):
+                        o = int(X["S_off"]) + (kb * GK_KB + kl) * stride + ab * tile
+                        S[o: o + tile] += part[kl].astype(np.uint32)
 
     # --- kernel (c), part 1 ----------------------------------------------------------------
     def gk_select(self, table, stab, n_search, top_n, n_prev, max_alleles, kept, ids_prev, cand_pool, S,
