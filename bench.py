@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""
+Benchmark of the allele-typing hot path (BASELINE.json metric: read x candidate GCells/s and
+samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cohort|wgs30x|deep]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm: the oracle's float64 NumPy restatement
+
+One step = one pass of the hot path over the whole batch: likelihood build (kernel a), every
+copy-number step of the greedy search (kernels b, c) and the allele calls.
+
+  value   whole-job scoring GCells/s with the packed inputs already resident in HBM
+  e2e     the same pass through the public host API (``BatchTyper.upload() + run()``): packed host
+          arrays in pinned memory -> device, results back to the host, every step
+  roofline        dominant kernel (gk_score), CUDA events around every launch in the timed region
+  cpu_baseline    the oracle (kind "port": reference NumPy expressions, read-chunked) on host cores
+
+Workloads: cohort = cfg5 (96 x cfg3, sample-sharded over the ranks, strong
+scaling), wgs30x = cfg3 (one sample, 17 genes), deep = cfg4 (2M reads x 1000 alleles, CN 6).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SM_COUNT = 148
+FP32_LANES_PER_SM = 128
+
+
+# ---------------------------------------------------------------------------
+# workload construction (host, before CUDA is touched so that fork is safe)
+# ---------------------------------------------------------------------------
+def _make_sample(args):
+    seed, scale = args
+    from kir_graph_b200 import packing, synthetic
+    genes = synthetic.make_wgs30x_sample(seed=seed, scale=scale)
+    packs = [packing.pack_synthetic(g) for g in genes]
+    return packs, [g.cn for g in genes], [sorted(g.allele_names[t] for t in g.truth) for g in genes]
+
+
+def build_cohort(seeds, scale, workers):
+    jobs = [(s, scale) for s in seeds]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            out = pool.map(_make_sample, jobs)
+    else:
+        out = [_make_sample(j) for j in jobs]
+    packs, cns, truth = [], [], []
+    for p, c, t in out:
+        packs += p
+        cns += c
+        truth += t
+    return packs, cns, truth
+
+
+def build_deep(n_reads, n_allele, cn):
+    from kir_graph_b200 import packing, synthetic
+    gene = synthetic.make_deep_sample(n_reads=n_reads, n_allele=n_allele, n_var=8 * n_allele, cn=cn)
+    pack = packing.pack_synthetic(gene)
+    return [pack], [cn], [sorted(gene.allele_names[t] for t in gene.truth)]
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle's float64 restatement of the reference path
+# ---------------------------------------------------------------------------
+def _cpu_type_sample(args):
+    """Type one synthetic cfg3 sample (read-scaled) with the reference's NumPy expressions."""
+    seed, scale, top_n = args
+    from kir_graph_b200 import packing, synthetic
+    from oracle import typing_oracle as orc
+    genes = synthetic.make_wgs30x_sample(seed=seed, scale=scale)
+    prepared = []
+    for g in genes:
+        pack = packing.pack_synthetic(g)
+        member = g.member[:, [g.allele_names.index(n) for n in pack.allele_names]]
+        m = np.zeros((pack.n_reads, pack.n_alleles), dtype=np.int64)
+        for name in ("lpv", "rpv", "lnv", "rnv"):
+            off, idx = pack.csr.offsets[name], pack.csr.indices[name]
+            row = np.repeat(np.arange(pack.n_reads), np.diff(off))
+            np.add.at(m, row, (~member[idx] if name in ("lpv", "rpv") else member[idx]).astype(np.int64))
+        prepared.append((orc.log_probs_from_counts(m, pack.k_obs.astype(np.int64)), g.cn))
+    t0 = time.perf_counter()
+    cells = 0
+    for lp, cn in prepared:
+        search = orc.F64Search(lp, top_n=top_n, read_chunk=1024)
+        for step in range(cn):
+            if step:
+                cells += len(search.result[-1].value) * lp.shape[1] * lp.shape[0]
+            search.add_candidate()
+    return cells, time.perf_counter() - t0
+
+
+def cpu_reference_step(cores, scale, top_n, first_seed=100):
+    """``cores`` worker processes each type one read-scaled sample; returns (cells, wall seconds, samples)."""
+    jobs = [(first_seed + i, scale, top_n) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores > 1:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(cores) as pool:      # CUDA may already be initialised: no fork
+            out = pool.map(_cpu_type_sample, jobs)
+    else:
+        out = [_cpu_type_sample(jobs[0])]
+    wall = max(t for _, t in out)      # typing time only (generation excluded), slowest worker
+    _ = time.perf_counter() - t0
+    return sum(c for c, _ in out), wall, len(jobs)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
+    scale = args.cpu_scale
+    for _ in range(args.warmup):
+        pass                                   # nothing to warm: fresh processes every step
+    cells = wall = 0.0
+    samples = 0
+    for _ in range(max(1, args.steps)):
+        c, w, n = cpu_reference_step(cores, scale, args.top_n)
+        cells += c
+        wall += w
+        samples += n
+    value = cells / wall / 1e9
+    sample_desc = (f"{cores} processes x 1 synthetic cfg3 sample each at {scale:g} of the reads "
+                   f"({int(200000 * scale)} read pairs, 17 genes, top_n={args.top_n}), oracle F64Search "
+                   f"(reference NumPy expressions, 1024-read chunks); typing time only")
+    line = {
+        "impl": "reference", "metric": "allele-typing read x candidate GCells/s", "value": value,
+        "unit": "GCells/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cohort (cfg5: 96 x cfg3 synthetic 30x WGS samples), bounded sample", "top_n": args.top_n},
+        "samples_per_s": samples * scale / wall,
+        "cpu_baseline": {"value": value, "unit": "GCells/s", "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "GCells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cohort", choices=["cohort", "wgs30x", "deep"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=96)
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the reads per sample (tests)")
+    ap.add_argument("--top-n", type=int, default=300)
+    ap.add_argument("--deep-reads", type=int, default=2_000_000)
+    ap.add_argument("--deep-alleles", type=int, default=1000)
+    ap.add_argument("--deep-cn", type=int, default=6)
+    ap.add_argument("--cpu-scale", type=float, default=0.25)
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    # ---- host: build this rank's share of the workload -------------------------
+    t_build = time.perf_counter()
+    workers = max(1, (os.cpu_count() or 1) // max(world, 1))
+    if args.workload == "cohort":
+        seeds = list(range(100, 100 + args.samples))[rank::world]
+        packs, cns, truth = build_cohort(seeds, args.scale, workers)
+        n_samples_total, n_samples_local = args.samples, len(seeds)
+        desc = (f"cfg5 cohort: {args.samples} synthetic 30x WGS samples x {int(200000 * args.scale)} read pairs x 900 "
+                f"alleles / 17 genes, CN<=4, top_n={args.top_n}, sample-sharded")
+    elif args.workload == "wgs30x":
+        packs, cns, truth = build_cohort([3], args.scale, 1)
+        n_samples_total = n_samples_local = 1
+        desc = f"cfg3: one synthetic 30x WGS sample, {int(200000 * args.scale)} read pairs x 900 alleles / 17 genes"
+    else:
+        packs, cns, truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
+        n_samples_total = n_samples_local = 1
+        desc = (f"cfg4 deep: {args.deep_reads} read pairs x {args.deep_alleles} alleles, CN {args.deep_cn}, "
+                f"top_n={args.top_n}")
+    t_build = time.perf_counter() - t_build
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    from kir_graph_b200 import cohort, engine
+    be = engine.CudaBackend(local_rank)
+    typer = cohort.BatchTyper(packs, cns, top_n=args.top_n, backend=be)
+    typer.host.pin(be)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA events on the launching stream around `steps` calls; max over ranks."""
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            fn()
+        end.record()
+        torch.cuda.synchronize()
+        ms = start.elapsed_time(end)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item())
+
+    # ---- resident: inputs already in HBM ---------------------------------------------
+    typer.upload()
+    calls = None
+    for _ in range(args.warmup):
+        calls = typer.run()
+    cells_per_step = typer.score_cells
+    lik_cells = typer.batch.n_cells
+    lik_bytes = typer.batch.bytes_out
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    be.timing = {}
+    launches0 = be.launches
+    ms_total = timed(typer.run, args.steps)
+    launches = be.launches - launches0
+    timing = be.timing
+    be.timing = None
+    clocks = sampler.stop()
+
+    # ---- end to end: pinned host arrays -> device -> calls on the host ------------------
+    def e2e_step():
+        typer.upload()
+        typer.run()
+    for _ in range(2):
+        e2e_step()
+    h0, d0 = be.h2d_bytes, be.d2h_bytes
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = (be.h2d_bytes - h0) / args.steps
+    d2h = (be.d2h_bytes - d0) / args.steps
+
+    # ---- aggregate over ranks --------------------------------------------------------------
+    agg = torch.tensor([cells_per_step, lik_cells, launches, h2d, d2h, n_samples_local], dtype=torch.float64,
+                       device="cuda")
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    cells_all, lik_all, launches_all, h2d_all, d2h_all, samples_all = [float(x) for x in agg.tolist()]
+
+    def kernel_stats(name):
+        evs = timing.get(name, [])
+        ms = sum(s.elapsed_time(e) for s, e, _ in evs)
+        work = sum(w for _, _, w in evs)
+        return ms, work, len(evs)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        fp32_peak = SM_COUNT * FP32_LANES_PER_SM * sm_max * 1e6 / 1e12          # T lane-ops/s
+        ms_s, work_s, n_s = kernel_stats("gk_score")
+        ms_l, work_l, n_l = kernel_stats("gk_likelihood")
+        score_ops = 2.0 * work_s / (ms_s * 1e-3) / 1e12 if ms_s else 0.0        # FMNMX + FADD per cell
+        hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
+        lik_gbs = (lik_bytes * n_l) / (ms_l * 1e-3) / 1e9 if ms_l else 0.0
+        step_ms = ms_total / args.steps
+        value = cells_all / (step_ms * 1e-3) / 1e9
+        e2e_ms = ms_e2e / args.steps
+        truth_ok = sum(sorted(c.alleles) == t for c, t in zip(calls, truth)) if calls else 0
+        line = {
+            "metric": "allele-typing read x candidate GCells/s", "value": value, "unit": "GCells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong" if args.workload == "cohort" else "replicas",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "top_n": args.top_n, "l2": "inputs larger than L2 (no flush needed)",
+                       "timed_region": "likelihood build + all CN steps + calls, packed inputs resident in HBM"},
+            "samples_per_s": samples_all / (step_ms * 1e-3),
+            "e2e": {"value": cells_all / (e2e_ms * 1e-3) / 1e9, "unit": "GCells/s",
+                    "samples_per_s": samples_all / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "gk_score_kernel", "bound": "fp32_nontensor",
+                "achieved": score_ops, "peak": fp32_peak, "unit": "T FP32 ops/s (1 FMNMX + 1 FADD per cell)",
+                "frac": score_ops / fp32_peak if fp32_peak else None, "traffic": None,
+                "cells_per_s": work_s / (ms_s * 1e-3) if ms_s else 0.0, "launches": n_s,
+                "kernel_ms_per_step": ms_s / args.steps, "share_of_step": ms_s / ms_total if ms_total else None,
+                "peak_source": f"148 SM x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
+                               "not in MEASURED_PEAKS.json, which only holds HBM and bf16 tensor peaks",
+            },
+            "roofline_likelihood": {
+                "kernel": "gk_likelihood_kernel", "bound": "hbm", "achieved": lik_gbs, "peak": hbm_peak,
+                "unit": "GB/s", "frac": lik_gbs / hbm_peak if hbm_peak else None, "traffic": None,
+                "cells_per_s": work_l / (ms_l * 1e-3) if ms_l else 0.0, "bytes_per_cell": 5,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+            },
+            "kernel_ms_per_step": {k: kernel_stats(k)[0] / args.steps for k in timing},
+            "parity": {"genes_matching_generator_truth": truth_ok, "genes": len(truth)},
+            "build_s": t_build,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
+            c_cells, c_wall, c_n = cpu_reference_step(cores, args.cpu_scale, args.top_n)
+            line["cpu_baseline"] = {
+                "value": c_cells / c_wall / 1e9, "unit": "GCells/s", "cores": cores, "kind": "port",
+                "samples_per_s": c_n * args.cpu_scale / c_wall,
+                "sample": f"{cores} processes x 1 synthetic cfg3 sample each at {args.cpu_scale:g} of the reads, "
+                          "oracle F64Search (reference NumPy expressions, 1024-read chunks), typing time only"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

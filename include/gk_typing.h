@@ -72,7 +72,7 @@ typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;         
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
     shape = k-blocks (1|2) | a-blocks (1|2|4) << 8 covered by the CTA tile */
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16 */
-typedef struct GkPItem { int32_t search, k_blk, r0, pad; } GkPItem;                  /* one k-block x 128 reads from r0 */
+typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 
 /* Per-search step outputs (device arrays indexed [search]). */
 typedef struct GkStepInfo {
@@ -107,8 +107,10 @@ int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_sear
                   GkStepInfo* info, int32_t* kept_count, void* stream);
 
 /* (b) max-then-sum candidate scoring: replaces
- *     np.maximum(log_probs[:, idx], prev.T[:, :, None]).sum(axis=1)   (:540-542)
- *     as S[k, a] += sum_{r in item} min(L[r, a], P[r, k])  (S zeroed by the caller). */
+ *     np.maximum(log_probs[:, idx], prev.T[:, :, None]).sum(axis=1)   (:540-542).
+ *     Accumulates D[k, a] += sum_{r in item} |L[r, a] - P[r, k]| into S_pool (zeroed by the
+ *     caller); the min-sum score is (colsum[a] + score_prev[k] - D[k, a]) / 2, formed by
+ *     gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]). */
 int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,
              const float* L_pool, const float* P_pool, uint32_t* S_pool, void* stream);
 
@@ -117,8 +119,8 @@ int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreIt
  *     still reach the final top_n.  One CTA per search. */
 int gk_select(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n, int n_prev,
               int max_alleles, const int32_t* kept_count, const int32_t* ids_prev, const int32_t* cand_pool,
-              const uint32_t* S_pool, uint8_t* flag_pool, int32_t* alive_pool,
-              GkStepInfo* info, void* stream);
+              const uint32_t* S_pool, const unsigned long long* col_pool, const uint32_t* score_prev,
+              uint8_t* flag_pool, int32_t* alive_pool, GkStepInfo* info, void* stream);
 
 /*     rescoring of the alive sets: replaces log_probs[:, ids].max(2) / np.equal / belong_norm
  *     (:569-580) with integer tie-split counts (cnt zeroed by the caller). */
@@ -132,7 +134,7 @@ int gk_rescore_count(const GkMatrix* matrices, const GkSearch* searches, const G
 int gk_rank(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n, int n_set,
             const int32_t* ids_prev, const int32_t* cand_pool, const int32_t* alive_pool,
             const uint32_t* S_pool, const uint32_t* cnt_pool, const unsigned long long* col_pool,
-            unsigned long long* key_pool /* 3 words per alive slot */, int32_t* ids_out, uint32_t* score_out, uint32_t* cnt_out, int32_t* flat_out,
+            const uint32_t* score_prev, unsigned long long* key_pool /* 3 words per alive slot */, int32_t* ids_out, uint32_t* score_out, uint32_t* cnt_out, int32_t* flat_out,
             GkStepInfo* info, int32_t* kept_count_out, void* stream);
 
 /*     P for the next step: P[r, k] = min over members of m[r, id]  (allele_prob, :569). */

@@ -1,0 +1,225 @@
+"""
+Batched typing of many (sample, gene) problems on one GPU, and sharding of a
+cohort over the GPUs of one box.
+
+The reference types samples and genes one after the other in Python
+(graphkir/main.py:171-220 -> kir_typing.py:42-62, :103-132).  Here every problem
+of a batch advances through the copy-number steps together, so each step is a
+handful of grouped kernel launches over all problems; samples are independent,
+so a cohort shards across ranks with no communication on the data path (one
+process per GPU; rank r takes samples r, r + world, ...).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import engine
+from .packing import GenePack, site_tallies
+from .typing_mulit_allele import C_HIT, C_MISS, _lcm_upto, _no_hetero_site, isHetrozygous
+
+
+@dataclass
+class GeneCall:
+    """Typing outcome of one gene problem."""
+
+    gene: str
+    cn: int
+    alleles: list[str]            # called allele names (len == cn); "fail" entries when no reads
+    n_reads: int
+    homozygous: bool
+    best_rank: int = 0
+    value: float = float("nan")   # log10 likelihood of the called set
+    tie_flags: int = 0
+    score: int = 0                # integer mismatch score of the called set
+    ids: list[int] = field(default_factory=list)
+
+
+def decide_homozygous(pack: GenePack, cn: int) -> bool:
+    """force_homo rule of kir_typing.py:106 + isHomozygous (typing_mulit_allele.py:807-857)."""
+    if isHetrozygous(pack.gene):
+        return False
+    if cn <= 1:
+        return False
+    return _no_hetero_site(site_tallies(pack), cn)
+
+
+class HomozygosityIndex:
+    """isHomozygous (typing_mulit_allele.py:807-857) for a whole batch at once.
+
+    Static per-variant arrays are concatenated when the batch is created; ``decide`` is pure
+    array arithmetic over all variants of all problems (no per-read work: the per-variant
+    observation counts are part of the packed input)."""
+
+    def __init__(self, packs: list[GenePack]):
+        site, key, pos, neg, owner = [], [], [], [], []
+        base = 0
+        for i, p in enumerate(packs):
+            keep = ~p.var_is_del
+            _, site_id = np.unique(p.var_pos, return_inverse=True)
+            _, val_code = np.unique(np.array(p.var_val, dtype=object).astype(str), return_inverse=True)
+            site.append(site_id[keep] + base)
+            key.append(val_code[keep])
+            pos.append(p.obs_pos[keep])
+            neg.append(p.obs_neg[keep])
+            n_site = int(site_id.max()) + 1 if len(site_id) else 0
+            owner.append(np.full(n_site, i, dtype=np.int64))
+            base += n_site
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)
+        site, key, pos, neg = cat(site), cat(key), cat(pos), cat(neg)
+        self.site_owner = cat(owner)
+        self.n_pack = len(packs)
+        self.forced_hetero = np.array([isHetrozygous(p.gene) for p in packs], dtype=bool)
+        # one entry per (site, value, polarity) with a non-zero count; equal keys at a site add up
+        ent_site = np.concatenate([site, site])
+        ent_key = np.concatenate([key * 2, key * 2 + 1])
+        ent_cnt = np.concatenate([pos, neg])
+        nz = ent_cnt > 0
+        ent_site, ent_key, ent_cnt = ent_site[nz], ent_key[nz], ent_cnt[nz]
+        combo = ent_site * (int(ent_key.max(initial=0)) + 2) + ent_key
+        uniq, inv = np.unique(combo, return_inverse=True)
+        e_cnt = np.bincount(inv, weights=ent_cnt, minlength=len(uniq)).astype(np.int64)
+        first = np.zeros(len(uniq), dtype=np.int64)
+        first[inv] = np.arange(len(inv))
+        e_site = ent_site[first]
+        e_negative = (ent_key[first] % 2) == 1
+
+        # per-site summary; everything except the final 1/(2 cn) comparison is independent of cn
+        n_site = len(self.site_owner)
+        n_keys = np.bincount(e_site, minlength=n_site)
+        any_pos = np.bincount(e_site, weights=(~e_negative).astype(np.float64), minlength=n_site) > 0
+        big = e_cnt > 3                                                  # drop low coverage (:844)
+        depth = np.bincount(e_site[big], weights=e_cnt[big], minlength=n_site).astype(np.int64)
+        share = e_cnt / np.maximum(depth[e_site], 1)
+        strong = big & (share > 0.1)                                     # (:850)
+        n_strong = np.bincount(e_site[strong], minlength=n_site)
+        order = np.lexsort((-e_cnt, e_site))
+        s_sorted, strong_sorted, share_sorted = e_site[order], strong[order], share[order]
+        s_strong, sh_strong = s_sorted[strong_sorted], share_sorted[strong_sorted]
+        start = np.searchsorted(s_strong, np.arange(n_site), side="left")
+        has2 = n_strong >= 2
+        self.second = np.zeros(n_site)                                   # runner-up share per site
+        self.second[has2] = sh_strong[start[has2] + 1]
+        considered = (n_keys > 1) & any_pos & (depth >= 20)
+        self.broken = bool(np.any(considered & (n_strong == 0)))
+        self.candidate = considered & has2
+
+    def decide(self, cns: np.ndarray) -> np.ndarray:
+        if self.broken:
+            raise IndexError("list index out of range")                  # the reference fails here too
+        cn_site = cns[self.site_owner]
+        hetero_site = self.candidate & (self.second > 1 / (np.maximum(cn_site, 1) * 2))
+        hits = np.bincount(self.site_owner[hetero_site], minlength=self.n_pack)
+        return (hits == 0) & (cns > 1) & ~self.forced_hetero
+
+
+def _select_best(frac_num: np.ndarray, n_reads: int, n: int) -> int:
+    """First rank whose every fraction >= 1/(2n), else 0 (TypingResult.selectBest)."""
+    fraction = frac_num / float(n_reads * _lcm_upto(n))
+    ok = np.all(fraction >= (1 / n) / 2, axis=1)
+    hits = np.flatnonzero(ok)
+    return int(hits[0]) if len(hits) else 0
+
+
+class BatchTyper:
+    """Types a fixed batch of gene problems; device buffers are reused across ``run`` calls."""
+
+    def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
+                 host_batch: engine.HostBatch | None = None):
+        self.be = backend if backend is not None else engine.CudaBackend()
+        self.packs = packs
+        self.cns = np.asarray(cns, dtype=np.int64)
+        self.top_n = top_n
+        self.host = host_batch if host_batch is not None else engine.HostBatch(packs)
+        self.homo_index = HomozygosityIndex(packs)
+        typable = np.array([p.n_reads > 0 and p.n_alleles > 0 for p in packs], dtype=bool)
+        self.live = np.flatnonzero((self.cns > 0) & typable)
+        self.n_reads = np.array([p.n_reads for p in packs], dtype=np.int64)
+        self.batch: engine.MatrixBatch | None = None
+        self.group: engine.SearchGroup | None = None
+        self.score_cells = 0
+        self.homo = np.zeros(len(packs), dtype=bool)
+
+    def upload(self) -> None:
+        """Host pools -> device (the end-to-end path times this; the resident path does it once)."""
+        self.batch = engine.MatrixBatch(self.host, backend=self.be, run=False)
+        if self.group is not None:
+            self.group.batch = self.batch      # same tables and offsets: search buffers are reused
+
+    def run(self) -> list[GeneCall]:
+        """Likelihood build + greedy search + calls for every problem of the batch."""
+        if self.batch is None:
+            self.upload()
+        batch = self.batch
+        batch.run_likelihood()
+        if self.group is None:
+            self.group = engine.SearchGroup(batch, self.live, self.top_n)
+        else:
+            self.group.reset()
+        group = self.group
+        self.homo = self.homo_index.decide(self.cns) & (self.n_reads > 0)
+        cn_live = self.cns[self.live]
+        homo_live = self.homo[self.live]
+        steps = np.where(homo_live, 1, cn_live)
+
+        # per search: (best rank, ids of the called set, score, tie flags)
+        n_live = len(self.live)
+        best = np.zeros(n_live, dtype=np.int64)
+        score = np.zeros(n_live, dtype=np.int64)
+        flags = np.zeros(n_live, dtype=np.int64)
+        called = np.full((n_live, max(int(cn_live.max(initial=1)), 1)), -1, dtype=np.int64)
+        for step in range(1, int(steps.max(initial=0)) + 1):
+            out = group.step(active=steps >= step, need_next=steps > step, collect=steps == step)
+            rows = out.searches
+            if not len(rows):
+                continue
+            n, tn = out.n, self.top_n
+            kept = out.info["n_kept"][rows].astype(np.int64)
+            weights = np.array([_lcm_upto(n) // q for q in range(1, n + 1)], dtype=np.int64)
+            frac_num = (out.cnt.reshape(len(rows), tn, n, n).astype(np.int64) * weights).sum(axis=3)
+            denom = (group.R[rows] * _lcm_upto(n)).astype(np.float64)
+            fraction = frac_num / denom[:, None, None]
+            ok = np.all(fraction >= (1 / n) / 2, axis=2) & (np.arange(tn)[None, :] < kept[:, None])
+            pick = np.where(ok.any(axis=1), ok.argmax(axis=1), 0)            # selectBest (:63-103)
+            pick = np.where(homo_live[rows], 0, pick)
+            ar = np.arange(len(rows))
+            best[rows] = pick
+            score[rows] = out.score[ar, pick].astype(np.int64)
+            flags[rows] = out.info["tie_flags"][rows]
+            ids = out.ids[ar, pick, :n].astype(np.int64)
+            ids[kept == 0] = -1
+            if n == 1:                                                       # homozygous shortcut (:423-454)
+                called[rows] = ids[:, :1]
+            else:
+                called[rows, :n] = ids
+        self.score_cells = group.score_cells
+
+        where = np.full(len(self.packs), -1, dtype=np.int64)
+        where[self.live] = np.arange(n_live)
+        mult = np.where(self.homo, self.cns, 1)
+        sc_all = np.zeros(len(self.packs), dtype=np.int64)
+        sc_all[self.live] = score
+        value = (self.host.k_total * C_HIT + sc_all * (C_MISS - C_HIT)) * mult
+        sc_all = sc_all * mult
+        calls: list[GeneCall] = []
+        called_l, best_l, flags_l = called.tolist(), best.tolist(), flags.tolist()
+        value_l, sc_l, homo_l, where_l = value.tolist(), sc_all.tolist(), self.homo.tolist(), where.tolist()
+        for i, pack in enumerate(self.packs):
+            cn = int(self.cns[i])
+            if cn == 0:
+                continue
+            s = where_l[i]
+            if s < 0 or called_l[s][0] < 0:
+                calls.append(GeneCall(pack.gene, cn, ["fail"] * cn, pack.n_reads, False))
+                continue
+            ids = called_l[s][:cn]
+            names = pack.allele_names
+            calls.append(GeneCall(pack.gene, cn, [names[a] for a in ids], len(pack.k_obs), homo_l[i],
+                                  best_l[s], value_l[i], flags_l[s], sc_l[i], ids))
+        return calls
+
+
+def shard(items: list, rank: int, world: int) -> list:
+    """Round-robin assignment of cohort samples to ranks (no data-path communication)."""
+    return items[rank::world]

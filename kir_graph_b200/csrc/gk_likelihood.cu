@@ -20,6 +20,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTilePitch = GK_LIK_READS + 16;  // bytes; keeps rows 16-byte aligned
+constexpr int kEntCap = 1024;                  // observation entries of the read tile staged in shared memory
 
 __global__ void __launch_bounds__(kThreads)
 gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __restrict__ items,
@@ -29,6 +30,10 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
                      uint8_t* __restrict__ LT_pool, unsigned long long* __restrict__ col_pool) {
     __shared__ __align__(16) uint8_t tile[128 * kTilePitch];
     __shared__ unsigned int colpart[kWarps][128];
+    __shared__ int s_eoff[GK_LIK_READS + 1];
+    __shared__ int s_word[kEntCap];
+    __shared__ uint32_t s_pos[kEntCap];
+    __shared__ uint32_t s_neg[kEntCap];
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
@@ -47,6 +52,21 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     float* L = L_pool + M.L_off + (int64_t)item.a_blk * M.r_pad * a_tile;
     const int64_t blk_stride = (int64_t)M.r_pad * a_tile;
 
+    // stage the tile's entry offsets and entries with coalesced loads (they are shared by all lanes)
+    for (int i = threadIdx.x; i <= GK_LIK_READS; i += kThreads) {
+        const int r = r0 + i;
+        s_eoff[i] = __ldg(eoff + (r < M.n_reads ? r : M.n_reads));
+    }
+    __syncthreads();
+    const int e_lo = s_eoff[0];
+    const int e_n = s_eoff[GK_LIK_READS] - e_lo;
+    for (int i = threadIdx.x; i < e_n && i < kEntCap; i += kThreads) {
+        s_word[i] = __ldg(ent_word + e_lo + i);
+        s_pos[i] = __ldg(ent_pos + e_lo + i);
+        s_neg[i] = __ldg(ent_neg + e_lo + i);
+    }
+    __syncthreads();
+
     bool live[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
@@ -58,12 +78,20 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
         const int r = r0 + rl;
         unsigned int cnt[4] = {0u, 0u, 0u, 0u};
         if (r < M.n_reads) {
-            const int e0 = __ldg(eoff + r);
-            const int e1 = __ldg(eoff + r + 1);
+            const int e0 = s_eoff[rl] - e_lo;
+            const int e1 = s_eoff[rl + 1] - e_lo;
             for (int e = e0; e < e1; ++e) {
-                const int w = __ldg(ent_word + e);
-                const uint32_t p = __ldg(ent_pos + e);
-                const uint32_t n = __ldg(ent_neg + e);
+                int w;
+                uint32_t p, n;
+                if (e < kEntCap) {
+                    w = s_word[e];
+                    p = s_pos[e];
+                    n = s_neg[e];
+                } else {
+                    w = __ldg(ent_word + e_lo + e);
+                    p = __ldg(ent_pos + e_lo + e);
+                    n = __ldg(ent_neg + e_lo + e);
+                }
                 const uint32_t* row = mem + (int64_t)w * M.n_alleles + a0 + lane;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {

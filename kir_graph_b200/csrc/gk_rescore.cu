@@ -95,7 +95,7 @@ gk_rescore_count_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* _
     count_set<N>(rows, item.r0, item.r1, M.n_reads, cnt_pool + X.cnt_off + (int64_t)f * N * N);
 }
 
-// P tile: one k-block (GK_KB = 64 kept sets) x 128 reads per CTA.
+// P tiles: one k-block (GK_KB = 64 kept sets) x 128 reads at a time, over the item's read range.
 constexpr int kPitch = 132;  // bytes per set row in shared memory (33 words)
 
 __global__ void __launch_bounds__(kThreads)
@@ -110,35 +110,37 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
     const int K = kept_count[item.search];
     const int lane = gk_lane();
     const int warp = gk_warp();
-    const uint8_t* LT = LT_pool + M.LT_off + item.r0;
-
-    // phase 1: one warp per set row, one 4-byte word (4 reads) per lane
-    for (int kl = warp; kl < GK_KB; kl += kWarps) {
-        const int k = item.k_blk * GK_KB + kl;
-        uint32_t mn = 0u;
-        if (k < K) {
-            const int32_t* set = ids + ((int64_t)item.search * top_n + k) * GK_MAX_CN;
-            mn = 0xffffffffu;
-            for (int t = 0; t < n_set; ++t) {
-                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(LT + (int64_t)set[t] * M.r_pad) + lane);
-                mn = __vminu4(mn, v);
-            }
-        }
-        *reinterpret_cast<uint32_t*>(tile + kl * kPitch + lane * 4) = mn;
-    }
-    __syncthreads();
-
-    // phase 2: half a warp per read row, four consecutive sets per lane -> 256-byte row stores
-    float* P = P_pool + X.P_off + ((int64_t)item.k_blk * M.r_pad + item.r0) * GK_KB;
     const int half = lane >> 4;
     const int kq = (lane & 15) * 4;
-    for (int rl = warp * 2 + half; rl < 128; rl += kWarps * 2) {
-        float4 out;
-        out.x = (float)tile[(kq + 0) * kPitch + rl];
-        out.y = (float)tile[(kq + 1) * kPitch + rl];
-        out.z = (float)tile[(kq + 2) * kPitch + rl];
-        out.w = (float)tile[(kq + 3) * kPitch + rl];
-        *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = out;
+    for (int r0 = item.r0; r0 < item.r1; r0 += 128) {
+        const uint8_t* LT = LT_pool + M.LT_off + r0;
+        // phase 1: one warp per set row, one 4-byte word (4 reads) per lane
+        for (int kl = warp; kl < GK_KB; kl += kWarps) {
+            const int k = item.k_blk * GK_KB + kl;
+            uint32_t mn = 0u;
+            if (k < K) {
+                const int32_t* set = ids + ((int64_t)item.search * top_n + k) * GK_MAX_CN;
+                mn = 0xffffffffu;
+                for (int t = 0; t < n_set; ++t) {
+                    const uint32_t v =
+                        __ldg(reinterpret_cast<const uint32_t*>(LT + (int64_t)set[t] * M.r_pad) + lane);
+                    mn = __vminu4(mn, v);
+                }
+            }
+            *reinterpret_cast<uint32_t*>(tile + kl * kPitch + lane * 4) = mn;
+        }
+        __syncthreads();
+        // phase 2: half a warp per read row, four consecutive sets per lane -> 256-byte row stores
+        float* P = P_pool + X.P_off + ((int64_t)item.k_blk * M.r_pad + r0) * GK_KB;
+        for (int rl = warp * 2 + half; rl < 128; rl += kWarps * 2) {
+            float4 out;
+            out.x = (float)tile[(kq + 0) * kPitch + rl];
+            out.y = (float)tile[(kq + 1) * kPitch + rl];
+            out.z = (float)tile[(kq + 2) * kPitch + rl];
+            out.w = (float)tile[(kq + 3) * kPitch + rl];
+            *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = out;
+        }
+        __syncthreads();
     }
 }
 

@@ -5,9 +5,17 @@
 // the K x R x A temporary.  In mismatch-count form (max of log-probs == min of
 // mismatch counts) one work item computes, for a tile of kept sets x candidate
 // alleles and a chunk of reads,
-//     S[k, a] += sum_r min(L[r, a], P[r, k])
+//     D[k, a] += sum_r |L[r, a] - P[r, k]|        (sum of absolute differences)
+// from which the consumers recover the min-sum exactly:
+//     sum_r min(L, P) = (colsum_L[a] + colsum_P[k] - D[k, a]) / 2
+// with colsum_L the CN=1 column sums and colsum_P[k] the previous step's score of set k
+// (both already known), so the inner loop is FADD (p - l) + FADD (acc += |d|, the
+// absolute value is a free source modifier).  The direct form FMNMX + FADD computes the
+// same thing but FMNMX issues on the half-rate ALU pipe, which ncu showed to be the
+// limiter (profiles/r01_score_v0_ncu_summary.txt: ALU 78 %, FMA 39 %); both forms are
+// 2 FP32 non-tensor instructions per cell.
 // Reads are the reduction dimension.  Operands are float32 holding small
-// integers, so FMNMX + FADD are exact while a partial sum stays below 2^24
+// integers, so the two FADDs are exact while a partial sum stays below 2^24
 // (the host bounds a chunk to 8192 reads x 255); the partial is converted to
 // an integer and merged with a 32-bit integer atomic, which makes the split-R
 // reduction order-independent and bit-reproducible.
@@ -22,8 +30,8 @@
 // half-warp's 128-bit shared loads hit consecutive banks.  No tensor cores:
 // max-then-sum is not a multiply-accumulate.
 //
-// Bound: FP32 non-tensor issue.  One cell = 1 FMNMX (ALU pipe, 64 lanes/clk/SM) +
-// 1 FADD (FMA pipe) = 2 issue slots; peak = 148 SM x 64 cells/clk x f_clk.
+// Bound: FP32 non-tensor issue.  One cell = 2 FADD = 2 issue slots of the 4 x 32-lane
+// schedulers; peak = 148 SM x 64 cells/clk x f_clk.
 #include "gk_common.cuh"
 
 namespace {
@@ -141,7 +149,7 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 #pragma unroll
             for (int i = 0; i < TK; ++i)
 #pragma unroll
-                for (int j = 0; j < TA; ++j) acc[i][j] += fminf(pv[i], lv[j]);
+                for (int j = 0; j < TA; ++j) acc[i][j] += fabsf(pv[i] - lv[j]);
         }
         __syncwarp();
         if (lane == 0) gk_mbar_arrive(&empty[s]);

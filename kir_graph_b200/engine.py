@@ -30,6 +30,7 @@ from .packing import GenePack
 
 SCORE_READ_CHUNK = 8192     # reads per scoring work item: 8192 * 255 < 2^24 keeps float32 sums exact
 COUNT_READ_CHUNK = 16384    # reads per rescoring work item
+P_READ_CHUNK = 2048         # reads per P-writing work item (multiple of 128)
 MAX_TOP_N = 2048
 MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
 
@@ -366,7 +367,7 @@ class SearchGroup:
         self.d_keys = be.empty(3 * int(alive_cap.sum()), np.uint64)
         out_rows = ns * self.top_n
         self.d_ids = [be.zeros(out_rows * GK_MAX_CN, np.int32), be.zeros(out_rows * GK_MAX_CN, np.int32)]
-        self.d_score = be.zeros(out_rows, np.uint32)
+        self.d_score = [be.zeros(out_rows, np.uint32), be.zeros(out_rows, np.uint32)]
         self.d_cnt_out = be.zeros(out_rows * GK_MAX_CN * GK_MAX_CN, np.uint32)
         self.d_flat = be.zeros(out_rows, np.int32)
         self.d_info = be.zeros(ns * (STEP_INFO_DTYPE.itemsize // 4), np.int32)
@@ -519,12 +520,13 @@ class SearchGroup:
         if not len(idx):
             return np.zeros(0, dtype=P_ITEM_DTYPE)
         n_k64 = -(-kept[idx] // GK_KB)
-        n_rt = self.r_pad[idx] // 128
+        n_rt = -(-self.r_pad[idx] // P_READ_CHUNK)
         search, (ik, ir) = self._product_items([n_k64, n_rt])
         items = np.zeros(len(search), dtype=P_ITEM_DTYPE)
         items["search"] = idx[search]
         items["k_blk"] = ik
-        items["r0"] = ir * 128
+        items["r0"] = ir * P_READ_CHUNK
+        items["r1"] = np.minimum((ir + 1) * P_READ_CHUNK, self.r_pad[idx][search])
         return items
 
     def _count_items(self, active_idx: np.ndarray, n_alive: np.ndarray) -> np.ndarray:
@@ -551,14 +553,14 @@ class SearchGroup:
         d_items = self.be.upload(items)
         self.be.launch("gk_write_p", self.batch.d_table, self.d_tab, d_items, len(items), self.top_n, n_set,
                        self.d_kept, self.d_ids[self.cur], self.batch.d_LT, self.d_P,
-                       work=float(len(items)) * 128 * GK_KB)
+                       work=float((items["r1"] - items["r0"]).sum()) * GK_KB)
 
     def _collect(self, rows: np.ndarray, n: int, info: np.ndarray) -> StepBatch:
         be, tn = self.be, self.top_n
         ids = be.gather_rows(self.d_ids[self.cur], tn * GK_MAX_CN, rows).reshape(len(rows), tn, GK_MAX_CN)
-        score = be.gather_rows(self.d_score, tn, rows).view(np.uint32)
-        cnt = be.gather_rows(self.d_cnt_out, tn * GK_MAX_CN * GK_MAX_CN, rows) \
-            .view(np.uint32).reshape(len(rows), tn, GK_MAX_CN * GK_MAX_CN)[:, :, :n * n]
+        score = be.gather_rows(self.d_score[self.cur], tn, rows).view(np.uint32)
+        cnt = be.gather_rows(self.d_cnt_out[: self.n_search * tn * n * n], tn * n * n, rows) \
+            .view(np.uint32).reshape(len(rows), tn, n * n)
         flat = be.gather_rows(self.d_flat, tn, rows)
         return StepBatch(n, rows, info, ids, score, cnt, flat)
 
@@ -586,7 +588,7 @@ class SearchGroup:
 
         if n == 1:
             be.launch("gk_first_step", bt.d_table, self.d_tab, ns, self.top_n, bt.d_col, self.d_cand,
-                      self.d_ids[new], self.d_score, self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
+                      self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
         else:
             items = self._score_items(active_idx)
             be.zero_(self.d_S)
@@ -595,8 +597,8 @@ class SearchGroup:
                       work=float(self._step_cells))
             self.score_cells += self._step_cells
             be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
-                      self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, self.d_flag, self.d_alive,
-                      self.d_info)
+                      self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, bt.d_col, self.d_score[self.cur],
+                      self.d_flag, self.d_alive, self.d_info)
             info = be.download(self.d_info, None).view(STEP_INFO_DTYPE)     # sync 1: alive counts
             n_alive = np.minimum(info["n_alive"], self.tab["alive_cap"]).astype(np.int64)
             n_alive[~active] = 0
@@ -609,8 +611,8 @@ class SearchGroup:
                       self.d_info, self.d_ids[self.cur], self.d_cand, self.d_alive, bt.d_LT, d_cnt,
                       work=float((n_alive * self.R).sum()) * n)
             be.launch("gk_rank", bt.d_table, self.d_tab, ns, self.top_n, n, self.d_ids[self.cur], self.d_cand,
-                      self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_keys, self.d_ids[new], self.d_score,
-                      self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
+                      self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_score[self.cur], self.d_keys,
+                      self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
         self.cur = new
         info = be.download(self.d_info, None).view(STEP_INFO_DTYPE).copy()   # sync 2: kept counts
         self.kept[active_idx] = info["n_kept"][active_idx]
@@ -620,11 +622,15 @@ class SearchGroup:
             self._write_p(nxt, n)
         return self._collect(np.flatnonzero(collect), n, info)
 
-    def restore(self, s: int, ids: np.ndarray) -> None:
-        """Re-seed search ``s`` with kept sets ``ids`` [K, n] (device state is a pure function
-        of the kept ids: P is rebuilt by gk_write_p)."""
+    def restore(self, s: int, ids: np.ndarray, p_colsum: np.ndarray) -> None:
+        """Re-seed search ``s`` with kept sets ``ids`` [K, n] and their sum_r P[r, k]
+        (``p_colsum``, the score of each set); P itself is rebuilt by gk_write_p."""
         ids = np.asarray(ids, dtype=np.int32)
         k, n = ids.shape
+        sc = self.be.download(self.d_score[self.cur], np.uint32).reshape(self.n_search, self.top_n).copy()
+        sc[s] = 0
+        sc[s, :k] = np.asarray(p_colsum, dtype=np.uint32)
+        self.d_score[self.cur] = self.be.upload(sc)
         if k > self.top_n or n > GK_MAX_CN:
             raise ValueError("kept sets do not fit this search")
         host = self.be.download(self.d_ids[self.cur], np.int32).reshape(self.n_search, self.top_n, GK_MAX_CN).copy()
@@ -656,10 +662,11 @@ class SearchGroup:
         d_ids = be.upload(buf)
         d_tab = be.upload(tab)
         d_kept = be.upload(np.array([k], dtype=np.int32))
-        kb, rr = np.meshgrid(np.arange(n_kblk), np.arange(0, r_pad, 128), indexing="ij")
+        kb, rr = np.meshgrid(np.arange(n_kblk), np.arange(0, r_pad, P_READ_CHUNK), indexing="ij")
         items = np.zeros(kb.size, dtype=P_ITEM_DTYPE)
         items["k_blk"] = kb.reshape(-1)
         items["r0"] = rr.reshape(-1)
+        items["r1"] = np.minimum(rr.reshape(-1) + P_READ_CHUNK, r_pad)
         d_items = be.upload(items)
         d_P = be.empty(n_kblk * r_pad * GK_KB, np.float32)
         be.launch("gk_write_p", bt.d_table, d_tab, d_items, len(items), self.top_n, n, d_kept, d_ids,

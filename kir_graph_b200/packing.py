@@ -50,6 +50,11 @@ class GenePack:
     k_obs: np.ndarray                # int32 [R]   observations per read (K_r)
     kept_reads: np.ndarray           # int64 [R]   index of each packed read in the caller's list
     csr: ReadCSR | None = None       # post-correction lists (for homozygosity / EM / oracle)
+    var_pos: np.ndarray | None = None      # int64 [V]  variant position
+    var_val: list | None = None            # [V] str(variant.val)
+    var_is_del: np.ndarray | None = None   # bool [V]  variant.typ == "deletion"
+    obs_pos: np.ndarray | None = None      # int64 [V]  positive observations after correction
+    obs_neg: np.ndarray | None = None      # int64 [V]  negative observations after correction
 
     @property
     def n_alleles(self) -> int:
@@ -213,6 +218,11 @@ def _finish(gene: str, allele_names: list[str], variant_ids: list[str], member: 
             f"mismatch matrix is one byte per cell (limit {MAX_OBS_PER_READ})")
     pack = GenePack(gene, allele_names, variant_ids, pack_membership(member),
                     ent_off, ent_word, ent_pos, ent_neg, k_obs, kept, csr)
+    n_var = len(variant_ids)
+    pack.obs_pos = (np.bincount(csr.indices["lpv"], minlength=n_var)
+                    + np.bincount(csr.indices["rpv"], minlength=n_var)).astype(np.int64)
+    pack.obs_neg = (np.bincount(csr.indices["lnv"], minlength=n_var)
+                    + np.bincount(csr.indices["rnv"], minlength=n_var)).astype(np.int64)
     return pack, drop
 
 
@@ -240,6 +250,9 @@ def pack_gene(reads: Sequence, variants: Iterable, variant_correction: bool = Tr
     csr = csr_from_reads(reads, vid_to_idx)
     pack, (drop_pos, drop_neg) = _finish(gene, allele_names, variant_ids, member, csr,
                                          variant_correction, no_empty)
+    pack.var_pos = np.array([by_id[v].pos for v in variant_ids], dtype=np.int64)
+    pack.var_val = [str(by_id[v].val) for v in variant_ids]
+    pack.var_is_del = np.array([by_id[v].typ == "deletion" for v in variant_ids], dtype=bool)
     if variant_correction and mutate_reads:
         bad_pos = {variant_ids[i] for i in np.flatnonzero(drop_pos)}
         bad_neg = {variant_ids[i] for i in np.flatnonzero(drop_neg)}
@@ -261,4 +274,25 @@ def pack_synthetic(gene: SyntheticGene, variant_correction: bool = True,
     member = gene.member[:, cols]
     pack, _ = _finish(gene.gene, names, list(gene.variant_ids), member, gene.reads,
                       variant_correction, no_empty)
+    n_var = gene.n_variants
+    pack.var_pos = 25 * np.arange(n_var, dtype=np.int64)
+    pack.var_val = ["ACGT"[v % 4] for v in range(n_var)]
+    pack.var_is_del = np.zeros(n_var, dtype=bool)
     return pack
+
+
+def site_tallies(pack: GenePack) -> list[dict[str, int]]:
+    """Per position: observation counts keyed by allele value (positives) or '*'+value
+    (negatives), deletions skipped -- the tally of isHomozygous
+    (reference: typing_mulit_allele.py:820-832) computed from the packed lists."""
+    pos_cnt, neg_cnt = pack.obs_pos, pack.obs_neg
+    sites: dict[int, dict[str, int]] = {}
+    for v in np.flatnonzero(((pos_cnt + neg_cnt) > 0) & ~pack.var_is_del):
+        site = sites.setdefault(int(pack.var_pos[v]), {})
+        if pos_cnt[v]:
+            key = pack.var_val[v]
+            site[key] = site.get(key, 0) + int(pos_cnt[v])
+        if neg_cnt[v]:
+            key = "*" + pack.var_val[v]
+            site[key] = site.get(key, 0) + int(neg_cnt[v])
+    return list(sites.values())

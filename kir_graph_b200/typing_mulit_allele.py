@@ -104,6 +104,7 @@ class TypingResult:
     frac_num: np.ndarray | None = None
     tie_flags: int = 0
     n_unique: int = 0
+    p_colsum: np.ndarray | None = None   # sum over reads of allele_prob in mismatch counts (search state)
 
     def isFail(self) -> bool:
         return not len(self.value)
@@ -173,7 +174,7 @@ class TypingResult:
             allele_id=self.allele_id[order], allele_name=[self.allele_name[i] for i in order],
             allele_prob=prob, fraction=self.fraction[order], fraction_uniq=self.fraction_uniq[order],
             score=take(self.score), member_colsum=take(self.member_colsum), frac_num=take(self.frac_num),
-            tie_flags=self.tie_flags, n_unique=self.n_unique)
+            tie_flags=self.tie_flags, n_unique=self.n_unique, p_colsum=take(self.p_colsum))
 
     def topRank(self, threshold: float = 0.9) -> Iterable[int]:
         """Rank 0 and every rank with value * threshold >= best value (:173-184)."""
@@ -320,7 +321,8 @@ class AlleleTyping:
             allele_prob=cn1_result.allele_prob, fraction=np.ones((k, cn)) / cn,
             fraction_uniq=np.ones((k, cn)) / cn,
             score=None if cn1_result.score is None else cn1_result.score * cn,
-            member_colsum=rep(cn1_result.member_colsum), tie_flags=cn1_result.tie_flags)
+            member_colsum=rep(cn1_result.member_colsum), tie_flags=cn1_result.tie_flags,
+            p_colsum=cn1_result.p_colsum)
 
     def _ensure_search(self) -> engine.SearchGroup:
         """Device search state is a cache of ``self.result``; rebuild it after deepcopy / reset."""
@@ -328,7 +330,7 @@ class AlleleTyping:
             self._search = engine.SearchGroup(self._batch, [0], self.top_n)
             if self.result:
                 last = self.result[-1]
-                self._search.restore(0, np.asarray(last.allele_id, dtype=np.int32))
+                self._search.restore(0, np.asarray(last.allele_id, dtype=np.int32), last.p_colsum)
         return self._search
 
     def _to_result(self, out: engine.StepOutput, search: engine.SearchGroup, s: int = 0) -> TypingResult:
@@ -391,7 +393,7 @@ def step_to_result(out: engine.StepOutput, colsum: np.ndarray, k_total: int, k_e
         fraction=fraction,
         fraction_uniq=np.ones(fraction.shape),                                      # "fake" in the reference (:584)
         score=out.score, member_colsum=member_colsum, frac_num=frac_num,
-        tie_flags=out.tie_flags, n_unique=out.n_unique)
+        tie_flags=out.tie_flags, n_unique=out.n_unique, p_colsum=out.score.copy())
 
 
 class AlleleTypingExonFirst(AlleleTyping):

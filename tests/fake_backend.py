@@ -125,7 +125,7 @@ class FakeBackend:
         info = info.view(STEP_INFO_DTYPE)
         ids_out = ids_out.reshape(n_search, top_n, GK_MAX_CN)
         score_out = score_out.reshape(n_search, top_n)
-        cnt_out = cnt_out.reshape(n_search, top_n, GK_MAX_CN * GK_MAX_CN)
+        cnt_out = cnt_out[: n_search * top_n].reshape(n_search, top_n, 1)
         flat_out = flat_out.reshape(n_search, top_n)
         for s in range(n_search):
             X = stab[s]
@@ -170,21 +170,28 @@ class FakeBackend:
                 Pt = P[po: po + (r1 - r0) * GK_KB].reshape(r1 - r0, GK_KB)
                 for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw):
                     Lt = self._L_view(M, L)[ab, r0:r1, :]
-                    part = np.minimum(Lt[:, None, :], Pt[:, :, None]).sum(axis=0)   # [GK_KB, tile]
+                    part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)    # [GK_KB, tile]
                     assert part.max(initial=0) < 2 ** 24
                     for kl in range(GK_KB):
                         o = int(X["S_off"]) + (kb * GK_KB + kl) * stride + ab * tile
                         S[o: o + tile] += part[kl].astype(np.uint32)
 
     # --- kernel (c), part 1 ----------------------------------------------------------------
+    @staticmethod
+    def _min_sum(S, col, sprev, X, M, k, a):
+        d = int(S[int(X["S_off"]) + k * int(X["s_stride"]) + a])
+        return (int(sprev[k]) + int(col[int(M["col_off"]) + a]) - d) // 2
+
     def gk_select(self, table, stab, n_search, top_n, n_prev, max_alleles, kept, ids_prev, cand_pool, S,
-                  flag, alive, info):
+                  col, score_prev, flag, alive, info):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         info = info.view(STEP_INFO_DTYPE)
         ids_prev = ids_prev.reshape(n_search, top_n, GK_MAX_CN)
         for s in range(n_search):
             X = stab[s]
+            M = table[X["matrix"]]
+            sprev = score_prev[s * top_n: (s + 1) * top_n]
             K, C = int(kept[s]), int(X["n_cand"])
             N = K * C
             cand = cand_pool[X["cand_off"]: X["cand_off"] + C]
@@ -198,7 +205,7 @@ class FakeBackend:
                 if key not in seen:
                     seen[key] = i
                     uniq[i] = True
-                score[i] = S[int(X["S_off"]) + k * stride + cand[j]]
+                score[i] = self._min_sum(S, col, sprev, X, M, k, cand[j])
             flag[X["flag_off"]: X["flag_off"] + N] = uniq
             n_unique = int(uniq.sum())
             cut = max(top_n, n_unique // 5)
@@ -259,15 +266,15 @@ class FakeBackend:
                         cnt[int(X["cnt_off"]) + (f * n + t) * n + qq - 1] += np.uint32((eq[t] & (q == qq)).sum())
 
     # --- kernel (c), part 2 -----------------------------------------------------------------
-    def gk_rank(self, table, stab, n_search, top_n, n_set, ids_prev, cand_pool, alive, S, cnt, col, keys,
-                ids_out, score_out, cnt_out, flat_out, info, kept_out):
+    def gk_rank(self, table, stab, n_search, top_n, n_set, ids_prev, cand_pool, alive, S, cnt, col, score_prev,
+                keys, ids_out, score_out, cnt_out, flat_out, info, kept_out):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         info = info.view(STEP_INFO_DTYPE)
         ids_prev = ids_prev.reshape(n_search, top_n, GK_MAX_CN)
         ids_out = ids_out.reshape(n_search, top_n, GK_MAX_CN)
         score_out = score_out.reshape(n_search, top_n)
-        cnt_out = cnt_out.reshape(n_search, top_n, GK_MAX_CN * GK_MAX_CN)
+        cnt_out = cnt_out[: n_search * top_n * n_set * n_set].reshape(n_search, top_n, n_set * n_set)
         flat_out = flat_out.reshape(n_search, top_n)
         n = n_set
         for s in range(n_search):
@@ -283,7 +290,8 @@ class FakeBackend:
             num = (cn * w[None, None, :]).sum(axis=2)
             even = int(M["n_reads"]) * LCM[n] // n
             uneven = np.abs(num - even).sum(axis=1)
-            sc = np.array([S[int(X["S_off"]) + (i // C) * stride + ids[f, -1]] for f, i in enumerate(flat)],
+            sprev = score_prev[s * top_n: (s + 1) * top_n]
+            sc = np.array([self._min_sum(S, col, sprev, X, M, i // C, ids[f, -1]) for f, i in enumerate(flat)],
                           dtype=np.int64)
             cs = colv[ids].sum(axis=1) if F else np.zeros(0, np.int64)
             order = np.lexsort((np.arange(F), uneven, cs, sc))
@@ -292,7 +300,7 @@ class FakeBackend:
                 f = order[rank]
                 ids_out[s, rank, :n] = ids[f]
                 score_out[s, rank] = sc[f]
-                cnt_out[s, rank, : n * n] = cn[f].reshape(-1)
+                cnt_out[s, rank, :] = cn[f].reshape(-1)
                 flat_out[s, rank] = flat[f]
             flags = int(info[s]["tie_flags"])
             if F > top_n and sc[order[top_n - 1]] == sc[order[top_n]]:
@@ -315,12 +323,12 @@ class FakeBackend:
             rp = int(M["r_pad"])
             K = int(kept[s])
             m = self._LT_view(M, LT)
-            r0 = int(it["r0"])
-            assert r0 % 128 == 0 and r0 + 128 <= rp
-            tile = np.zeros((128, GK_KB), dtype=np.float32)
-            for kl in range(GK_KB):
-                k = int(it["k_blk"]) * GK_KB + kl
-                if k < K:
-                    tile[:, kl] = m[ids[s, k, :n_set], r0:r0 + 128].min(axis=0)
-            o = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
-            P[o: o + 128 * GK_KB] = tile.reshape(-1)
+            assert int(it["r0"]) % 128 == 0 and int(it["r1"]) % 128 == 0 and int(it["r1"]) <= rp
+            for r0 in range(int(it["r0"]), int(it["r1"]), 128):
+                tile = np.zeros((128, GK_KB), dtype=np.float32)
+                for kl in range(GK_KB):
+                    k = int(it["k_blk"]) * GK_KB + kl
+                    if k < K:
+                        tile[:, kl] = m[ids[s, k, :n_set], r0:r0 + 128].min(axis=0)
+                o = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
+                P[o: o + 128 * GK_KB] = tile.reshape(-1)
