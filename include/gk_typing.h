@@ -83,7 +83,9 @@ typedef struct GkStepInfo {
     uint32_t bar;        /* score of the top_n-th unique candidate                                       */
     int32_t tie_flags;   /* bit0: tie group straddles the M cut, bit1: straddles the final top_n cut,
                             bit2: rank 0 and rank 1 share score / column sums / evenness                 */
-    int32_t pad0, pad1;
+    int32_t best_rank;   /* first rank whose every member fraction >= 1/(2n), else 0
+                            (TypingResult.selectBest, typing_mulit_allele.py:63-103), exact integers    */
+    int32_t pad1;
 } GkStepInfo;
 
 const char* gk_last_error(void);

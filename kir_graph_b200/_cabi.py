@@ -38,7 +38,7 @@ SCORE_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("a_blk", "<i4
 COUNT_ITEM_DTYPE = np.dtype([("search", "<i4"), ("f0", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
 P_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
 STEP_INFO_DTYPE = np.dtype([("n_kept", "<i4"), ("n_unique", "<i4"), ("n_alive", "<i4"), ("cut", "<i4"),
-                            ("bar", "<u4"), ("tie_flags", "<i4"), ("pad0", "<i4"), ("pad1", "<i4")])
+                            ("bar", "<u4"), ("tie_flags", "<i4"), ("best_rank", "<i4"), ("pad1", "<i4")])
 
 _STRUCTS = {
     "GkMatrix": MATRIX_DTYPE, "GkSearch": SEARCH_DTYPE, "GkLikItem": LIK_ITEM_DTYPE,

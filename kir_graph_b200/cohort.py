@@ -140,12 +140,17 @@ class BatchTyper:
         self.group: engine.SearchGroup | None = None
         self.score_cells = 0
         self.homo = np.zeros(len(packs), dtype=bool)
+        self._homo_cache: np.ndarray | None = None
 
     def upload(self) -> None:
         """Host pools -> device (the end-to-end path times this; the resident path does it once)."""
         self.batch = engine.MatrixBatch(self.host, backend=self.be, run=False)
         if self.group is not None:
             self.group.batch = self.batch      # same tables and offsets: search buffers are reused
+
+    def upload_and_run(self) -> list[GeneCall]:
+        self.upload()
+        return self.run()
 
     def run(self) -> list[GeneCall]:
         """Likelihood build + greedy search + calls for every problem of the batch."""
@@ -158,7 +163,9 @@ class BatchTyper:
         else:
             self.group.reset()
         group = self.group
-        self.homo = self.homo_index.decide(self.cns) & (self.n_reads > 0)
+        if self._homo_cache is None:           # the copy numbers are fixed for this batch
+            self._homo_cache = self.homo_index.decide(self.cns) & (self.n_reads > 0)
+        self.homo = self._homo_cache
         cn_live = self.cns[self.live]
         homo_live = self.homo[self.live]
         steps = np.where(homo_live, 1, cn_live)
@@ -170,24 +177,17 @@ class BatchTyper:
         flags = np.zeros(n_live, dtype=np.int64)
         called = np.full((n_live, max(int(cn_live.max(initial=1)), 1)), -1, dtype=np.int64)
         for step in range(1, int(steps.max(initial=0)) + 1):
-            out = group.step(active=steps >= step, need_next=steps > step, collect=steps == step)
+            out = group.step(active=steps >= step, need_next=steps > step, collect=steps == step,
+                             best_only=True)
             rows = out.searches
             if not len(rows):
                 continue
-            n, tn = out.n, self.top_n
+            n = out.n
             kept = out.info["n_kept"][rows].astype(np.int64)
-            weights = np.array([_lcm_upto(n) // q for q in range(1, n + 1)], dtype=np.int64)
-            frac_num = (out.cnt.reshape(len(rows), tn, n, n).astype(np.int64) * weights).sum(axis=3)
-            denom = (group.R[rows] * _lcm_upto(n)).astype(np.float64)
-            fraction = frac_num / denom[:, None, None]
-            ok = np.all(fraction >= (1 / n) / 2, axis=2) & (np.arange(tn)[None, :] < kept[:, None])
-            pick = np.where(ok.any(axis=1), ok.argmax(axis=1), 0)            # selectBest (:63-103)
-            pick = np.where(homo_live[rows], 0, pick)
-            ar = np.arange(len(rows))
-            best[rows] = pick
-            score[rows] = out.score[ar, pick].astype(np.int64)
+            best[rows] = np.where(homo_live[rows], 0, out.info["best_rank"][rows])
+            score[rows] = out.score
             flags[rows] = out.info["tie_flags"][rows]
-            ids = out.ids[ar, pick, :n].astype(np.int64)
+            ids = out.ids.astype(np.int64)
             ids[kept == 0] = -1
             if n == 1:                                                       # homozygous shortcut (:423-454)
                 called[rows] = ids[:, :1]
@@ -217,6 +217,78 @@ class BatchTyper:
             names = pack.allele_names
             calls.append(GeneCall(pack.gene, cn, [names[a] for a in ids], len(pack.k_obs), homo_l[i],
                                   best_l[s], value_l[i], flags_l[s], sc_l[i], ids))
+        return calls
+
+
+class CohortTyper:
+    """Splits a batch into ``n_parts`` sub-batches that run concurrently, each on its own CUDA
+    stream and host thread, so the host-side work of one part (work-item lists, result
+    selection) overlaps the kernels of the others.  Results come back in input order."""
+
+    def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
+                 n_parts: int = 2, group_size: int = 1):
+        """``group_size`` consecutive problems (e.g. the 17 genes of a sample) stay in one part."""
+        self.be = backend if backend is not None else engine.CudaBackend()
+        n = len(packs)
+        n_groups = max(1, -(-n // group_size))
+        n_parts = max(1, min(n_parts, n_groups))
+        bounds = [(g * n_groups // n_parts) * group_size for g in range(n_parts)] + [n]
+        self.slices = [slice(bounds[i], min(bounds[i + 1], n)) for i in range(n_parts)]
+        self.parts = [BatchTyper(packs[sl], list(cns)[sl], top_n=top_n, backend=self.be) for sl in self.slices]
+        self.streams = None
+        self.pool = None
+        if n_parts > 1 and hasattr(self.be, "torch"):
+            from concurrent.futures import ThreadPoolExecutor
+            self.streams = [self.be.torch.cuda.Stream(device=self.be.device) for _ in self.parts]
+            self.pool = ThreadPoolExecutor(max_workers=n_parts)
+
+    @property
+    def score_cells(self) -> int:
+        return sum(p.score_cells for p in self.parts)
+
+    @property
+    def host_nbytes(self) -> int:
+        return sum(p.host.nbytes for p in self.parts)
+
+    def pin(self) -> None:
+        for p in self.parts:
+            p.host.pin(self.be)
+
+    def _on_stream(self, i: int, fn_name: str):
+        part = self.parts[i]
+        if self.streams is None:
+            return getattr(part, fn_name)()
+        torch = self.be.torch
+        torch.cuda.set_device(self.be.device)
+        with torch.cuda.stream(self.streams[i]):
+            out = getattr(part, fn_name)()
+            self.streams[i].synchronize()
+        return out
+
+    def _all(self, fn_name: str) -> list:
+        if self.pool is None:
+            return [self._on_stream(i, fn_name) for i in range(len(self.parts))]
+        if self.streams is not None:
+            cur = self.be.torch.cuda.current_stream(self.be.device)
+            for st in self.streams:
+                st.wait_stream(cur)
+        futures = [self.pool.submit(self._on_stream, i, fn_name) for i in range(len(self.parts))]
+        out = [f.result() for f in futures]
+        return out
+
+    def upload(self) -> None:
+        self._all("upload")
+
+    def run(self) -> list[GeneCall]:
+        calls: list[GeneCall] = []
+        for part in self._all("run"):
+            calls.extend(part)
+        return calls
+
+    def upload_and_run(self) -> list[GeneCall]:
+        calls: list[GeneCall] = []
+        for part in self._all("upload_and_run"):
+            calls.extend(part)
         return calls
 
 

@@ -22,6 +22,63 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kTilePitch = GK_LIK_READS + 16;  // bytes; keeps rows 16-byte aligned
 constexpr int kEntCap = 1024;                  // observation entries of the read tile staged in shared memory
 
+// Per-read work for a CTA whose allele span needs NG lane groups of 32 (uniform per CTA).
+template <int NG>
+__device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int a_tile, int a_span, int e_lo,
+                                          const uint32_t* __restrict__ mem, const int32_t* __restrict__ ent_word,
+                                          const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
+                                          const int* s_eoff, const int* s_word, const uint32_t* s_pos,
+                                          const uint32_t* s_neg, float* __restrict__ L, int64_t blk_stride,
+                                          uint8_t* tile, unsigned int (&csum)[4]) {
+    const int lane = gk_lane();
+    const int warp = gk_warp();
+    bool live[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
+    const uint32_t* mem_lane = mem + a0 + lane;
+#pragma unroll 1
+    for (int i = 0; i < GK_LIK_READS / kWarps; ++i) {
+        const int rl = warp + kWarps * i;
+        const int r = r0 + rl;
+        unsigned int cnt[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) cnt[g] = 0u;
+        if (r < M.n_reads) {
+            const int e0 = s_eoff[rl] - e_lo;
+            const int e1 = s_eoff[rl + 1] - e_lo;
+            for (int e = e0; e < e1; ++e) {
+                int w;
+                uint32_t p, n;
+                if (e < kEntCap) {
+                    w = s_word[e];
+                    p = s_pos[e];
+                    n = s_neg[e];
+                } else {
+                    w = __ldg(ent_word + e_lo + e);
+                    p = __ldg(ent_pos + e_lo + e);
+                    n = __ldg(ent_neg + e_lo + e);
+                }
+                const uint32_t* row = mem_lane + (int64_t)w * M.n_alleles;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t mw = live[g] ? __ldg(row + 32 * g) : 0u;
+                    cnt[g] += __popc((p & ~mw) | (n & mw));
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int a = lane + 32 * g;
+            if (a < a_span) {
+                const unsigned int c = live[g] ? cnt[g] : 0u;
+                L[(a / a_tile) * blk_stride + (int64_t)r * a_tile + (a % a_tile)] = (float)c;
+                tile[a * kTilePitch + rl] = (uint8_t)c;
+                csum[g] += c;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __restrict__ items,
                      const uint32_t* __restrict__ mem_pool, const int32_t* __restrict__ entoff_pool,
@@ -48,7 +105,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 
     const uint32_t* mem = mem_pool + M.mem_off;
     const int32_t* eoff = entoff_pool + M.entoff_off;
-    // group g of this lane is column (lane + 32 g) of the span = block (a_blk + g) when a_tile == 32
+    // group g of a lane is column (lane + 32 g) of the span = block (a_blk + g) when a_tile == 32
     float* L = L_pool + M.L_off + (int64_t)item.a_blk * M.r_pad * a_tile;
     const int64_t blk_stride = (int64_t)M.r_pad * a_tile;
 
@@ -67,51 +124,17 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     }
     __syncthreads();
 
-    bool live[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
-
     unsigned int csum[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 1
-    for (int i = 0; i < GK_LIK_READS / kWarps; ++i) {
-        const int rl = warp + kWarps * i;
-        const int r = r0 + rl;
-        unsigned int cnt[4] = {0u, 0u, 0u, 0u};
-        if (r < M.n_reads) {
-            const int e0 = s_eoff[rl] - e_lo;
-            const int e1 = s_eoff[rl + 1] - e_lo;
-            for (int e = e0; e < e1; ++e) {
-                int w;
-                uint32_t p, n;
-                if (e < kEntCap) {
-                    w = s_word[e];
-                    p = s_pos[e];
-                    n = s_neg[e];
-                } else {
-                    w = __ldg(ent_word + e_lo + e);
-                    p = __ldg(ent_pos + e_lo + e);
-                    n = __ldg(ent_neg + e_lo + e);
-                }
-                const uint32_t* row = mem + (int64_t)w * M.n_alleles + a0 + lane;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (live[g]) {
-                        const uint32_t mw = __ldg(row + 32 * g);
-                        cnt[g] += __popc((p & ~mw) | (n & mw));
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int a = lane + 32 * g;
-            if (a < a_span) {
-                L[(a / a_tile) * blk_stride + (int64_t)r * a_tile + (a % a_tile)] = (float)cnt[g];
-                tile[a * kTilePitch + rl] = (uint8_t)cnt[g];
-                csum[g] += cnt[g];
-            }
-        }
+#define GK_LIK_CASE(NG)                                                                                     \
+    lik_reads<NG>(M, r0, a0, a_tile, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_word, s_pos,  \
+                  s_neg, L, blk_stride, tile, csum)
+    switch ((a_span + 31) / 32) {
+        case 1: GK_LIK_CASE(1); break;
+        case 2: GK_LIK_CASE(2); break;
+        case 3: GK_LIK_CASE(3); break;
+        default: GK_LIK_CASE(4); break;
     }
+#undef GK_LIK_CASE
 #pragma unroll
     for (int g = 0; g < 4; ++g) colpart[warp][lane + 32 * g] = csum[g];
     __syncthreads();

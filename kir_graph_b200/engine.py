@@ -316,6 +316,17 @@ class StepBatch:
         return iter(self._row)
 
 
+class BestBatch:
+    """Per collected search only the set chosen by selectBest (computed on the device)."""
+
+    def __init__(self, n: int, searches: np.ndarray, info: np.ndarray, ids: np.ndarray, score: np.ndarray):
+        self.n = n
+        self.searches = searches
+        self.info = info
+        self.ids = ids          # int32 [len(searches), n]
+        self.score = score      # int64 [len(searches)]
+
+
 # greedy cover of the last (n_ablk % 4) allele blocks by CTA tiles of width 2 and 1
 _A_REM = {0: [], 1: [(0, 1)], 2: [(0, 2)], 3: [(0, 2), (2, 1)]}
 
@@ -565,13 +576,20 @@ class SearchGroup:
         return StepBatch(n, rows, info, ids, score, cnt, flat)
 
     # --- one copy-number step ---------------------------------------------------------
-    def step(self, cands=None, active=None, need_next=None, collect=None) -> StepBatch:
+    def _collect_best(self, rows: np.ndarray, n: int, info: np.ndarray) -> BestBatch:
+        flat = rows.astype(np.int64) * self.top_n + info["best_rank"][rows].astype(np.int64)
+        ids = self.be.gather_rows(self.d_ids[self.cur], GK_MAX_CN, flat)[:, :n]
+        score = self.be.gather_rows(self.d_score[self.cur], 1, flat).view(np.uint32).reshape(-1).astype(np.int64)
+        return BestBatch(n, rows, info, ids, score)
+
+    def step(self, cands=None, active=None, need_next=None, collect=None, best_only: bool = False):
         """Advance the active searches by one allele.
 
         cands      per-search candidate allele ids (None = every allele of the gene)
         active     bool per search (default all)
         need_next  bool per search: will be stepped again (P is only written for those)
         collect    bool per search: download the full step output (default: the active ones)
+        best_only  download only the set picked by selectBest (info.best_rank) per collected search
         """
         ns = self.n_search
         active = np.ones(ns, bool) if active is None else np.asarray(active, bool)
@@ -620,6 +638,8 @@ class SearchGroup:
         nxt = np.flatnonzero(need_next)
         if len(nxt):
             self._write_p(nxt, n)
+        if best_only:
+            return self._collect_best(np.flatnonzero(collect), n, info)
         return self._collect(np.flatnonzero(collect), n, info)
 
     def restore(self, s: int, ids: np.ndarray, p_colsum: np.ndarray) -> None:

@@ -307,7 +307,13 @@ class FakeBackend:
                 flags |= 2
             if F > 1 and sc[order[0]] == sc[order[1]]:
                 flags |= 4
+            best = 0
+            for rank in range(k):
+                if np.all(2 * n * num[order[rank]] >= int(M["n_reads"]) * LCM[n]):
+                    best = rank
+                    break
             info[s]["n_kept"] = k
+            info[s]["best_rank"] = best
             info[s]["tie_flags"] = flags
             kept_out[s] = k
 
