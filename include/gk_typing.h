@@ -49,7 +49,7 @@ typedef struct GkMatrix {
     int32_t n_alleles;
     int32_t n_words;
     int32_t r_pad;       /* multiple of 128; rows >= n_reads are zero                                    */
-    int32_t a_tile;      /* allele block width of L: 16 (genes with <= 16 alleles) or 32                 */
+    int32_t a_tile;      /* allele block width of L (32)                                                 */
     int32_t n_ablk;      /* ceil(n_alleles / a_tile)                                                     */
 } GkMatrix;
 
@@ -70,7 +70,7 @@ typedef struct GkSearch {
 /* Work items (built by the host per launch). */
 typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS */
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
-    shape = k-blocks (1|2) | a-blocks (1|2|4) << 8 covered by the CTA tile */
+    shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48 (from k_blk / a_blk) */
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16 */
 typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 

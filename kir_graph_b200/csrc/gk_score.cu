@@ -23,12 +23,13 @@
 // Data movement: L and P are stored blocked ([a_blk][r][a_tile], [k_blk][r][64]),
 // so each block's GK_RT rows of a stage are one contiguous span, moved by the TMA
 // engine with cp.async.bulk and signalled on an mbarrier; 4 stages in flight.
-// A CTA tile is 1-2 k-blocks x 1-4 a-blocks (64/128 sets x 16..128 alleles) so that
-// ragged K (top_n = 300) and ragged A are covered without computing padding.
-// Math: 16x16 threads, each a TK x TA register tile (8x8 for the full tile) whose
-// rows/columns are interleaved in groups of four (k = 4*tk + i, 64 + 4*tk + i) so a
-// half-warp's 128-bit shared loads hit consecutive banks.  No tensor cores:
-// max-then-sum is not a multiply-accumulate.
+// A CTA tile is {128, 64, 48, 32, 16} kept sets x {128, 64, 48, 32, 16} alleles so that
+// ragged K (top_n = 300) and ragged A are covered at a granularity of 16 instead of
+// computing padding.  Math: 16x16 threads, each a TK x TA register tile (8x8 for the
+// full tile).  In the 128/64 modes a thread's rows/columns are groups of four
+// (k = 4*tk + i, 64 + 4*tk + i) so a half-warp's 128-bit shared loads hit consecutive
+// banks; the remainder modes take row t of each 16-group with scalar loads.  No tensor
+// cores: max-then-sum is not a multiply-accumulate.
 //
 // Bound: FP32 non-tensor issue.  One cell = 2 FADD = 2 issue slots of the 4 x 32-lane
 // schedulers; peak = 148 SM x 64 cells/clk x f_clk.
@@ -40,17 +41,27 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 4;
 
-// TK in {8, 4}: 128 or 64 kept sets per CTA.  TA in {8, 4, 2, 1}: 128/64/32 alleles
-// (a_tile 32) or 16 alleles (a_tile 16).
-template <int TK, int TA>
+// Tile modes per dimension.  F8/F4: 128/64 rows (columns), each thread owns groups of four
+// consecutive ones (float4 shared loads).  S1..S3: the ragged remainder, 16/32/48 rows
+// (columns): thread t owns row t of each 16-group (scalar shared loads).
+enum Mode { F8 = 0, F4 = 1, S1 = 2, S2 = 3, S3 = 4 };
+
+template <int M> struct ModeInfo {
+    static constexpr bool kVec = (M == F8 || M == F4);
+    static constexpr int kPerThread = M == F8 ? 8 : M == F4 ? 4 : (M - S1 + 1);   // rows (columns) per thread
+    static constexpr int kSpan = 16 * kPerThread;                                  // rows (columns) per CTA
+};
+
+template <int KM, int AM>
 __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                            const float* __restrict__ L_pool, const float* __restrict__ P_pool,
                                            uint32_t* __restrict__ S_pool, float* smem, uint64_t* full,
                                            uint64_t* empty) {
-    constexpr int KW = TK / 4;                  // k-blocks of 64
-    constexpr int BA = 16 * TA;                 // alleles per CTA tile
-    constexpr int AT = TA == 1 ? 16 : 32;       // layout block width of L
-    constexpr int AW = BA / AT;                 // a-blocks per CTA tile
+    constexpr int TK = ModeInfo<KM>::kPerThread;
+    constexpr int TA = ModeInfo<AM>::kPerThread;
+    constexpr int AT = 32;                                           // layout block width of L
+    constexpr int KW = (ModeInfo<KM>::kSpan + GK_KB - 1) / GK_KB;    // k-blocks staged (1 or 2)
+    constexpr int AW = (ModeInfo<AM>::kSpan + AT - 1) / AT;          // a-blocks staged (1, 2 or 4)
     constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(float);
     constexpr uint32_t kBytesLBlk = GK_RT * AT * sizeof(float);
     constexpr uint32_t kStageBytes = KW * kBytesPBlk + AW * kBytesLBlk;
@@ -91,17 +102,11 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 #pragma unroll
         for (int j = 0; j < TA; ++j) acc[i][j] = 0.f;
 
-    // shared-memory offsets of this thread's operands inside a stage
-    // k = 4*tk + i (block 0) and, for TK == 8, the same offsets in block 1
-    const int p_off = tk * 4;
-    // a: TA == 8 -> cols 4*ta + j and 64 + 4*ta + j ; TA == 4 -> 4*ta + j ; TA == 2 -> 2*ta + j ; TA == 1 -> ta
-    int l_off[2];
-    {
-        const int c0 = (TA >= 4) ? ta * 4 : ta * TA;
-        l_off[0] = (c0 / AT) * (GK_RT * AT) + (c0 % AT);
-        const int c1 = 64 + ta * 4;
-        l_off[1] = (c1 / AT) * (GK_RT * AT) + (c1 % AT);
-    }
+    // Row / column owned by slot i of thread t, relative to the tile origin.
+    auto k_of = [&](int i) { return ModeInfo<KM>::kVec ? (i < 4 ? tk * 4 + i : 64 + tk * 4 + (i - 4)) : i * 16 + tk; };
+    auto a_of = [&](int j) { return ModeInfo<AM>::kVec ? (j < 4 ? ta * 4 + j : 64 + ta * 4 + (j - 4)) : j * 16 + ta; };
+    // shared-memory offset of column c of the staged L blocks ([a_blk][r][AT])
+    auto l_off = [&](int c) { return (c / AT) * (GK_RT * AT) + (c % AT); };
 
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
@@ -119,32 +124,33 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
         __syncwarp();
         gk_mbar_wait(&full[s], (t / kStages) & 1);
 
-        const float* p = smem + s * kStageFloats + p_off;
-        const float* l = smem + s * kStageFloats + KW * GK_RT * GK_KB;
+        const float* p = smem + s * kStageFloats;                       // [k_blk][r][GK_KB]
+        const float* l = smem + s * kStageFloats + KW * GK_RT * GK_KB;  // [a_blk][r][AT]
 #pragma unroll 4
         for (int r = 0; r < GK_RT; ++r) {
             float pv[TK];
             float lv[TA];
-            {
-                const float4 x = *reinterpret_cast<const float4*>(p + r * GK_KB);
+            if constexpr (ModeInfo<KM>::kVec) {
+                const float4 x = *reinterpret_cast<const float4*>(p + r * GK_KB + tk * 4);
                 pv[0] = x.x; pv[1] = x.y; pv[2] = x.z; pv[3] = x.w;
                 if constexpr (TK == 8) {
-                    const float4 y = *reinterpret_cast<const float4*>(p + GK_RT * GK_KB + r * GK_KB);
+                    const float4 y = *reinterpret_cast<const float4*>(p + GK_RT * GK_KB + r * GK_KB + tk * 4);
                     pv[4] = y.x; pv[5] = y.y; pv[6] = y.z; pv[7] = y.w;
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TK; ++i) pv[i] = p[r * GK_KB + i * 16 + tk];
             }
-            if constexpr (TA >= 4) {
-                const float4 x = *reinterpret_cast<const float4*>(l + l_off[0] + r * AT);
+            if constexpr (ModeInfo<AM>::kVec) {
+                const float4 x = *reinterpret_cast<const float4*>(l + l_off(ta * 4) + r * AT);
                 lv[0] = x.x; lv[1] = x.y; lv[2] = x.z; lv[3] = x.w;
                 if constexpr (TA == 8) {
-                    const float4 y = *reinterpret_cast<const float4*>(l + l_off[1] + r * AT);
+                    const float4 y = *reinterpret_cast<const float4*>(l + l_off(64 + ta * 4) + r * AT);
                     lv[4] = y.x; lv[5] = y.y; lv[6] = y.z; lv[7] = y.w;
                 }
-            } else if constexpr (TA == 2) {
-                const float2 x = *reinterpret_cast<const float2*>(l + l_off[0] + r * AT);
-                lv[0] = x.x; lv[1] = x.y;
             } else {
-                lv[0] = l[l_off[0] + r * AT];
+#pragma unroll
+                for (int j = 0; j < TA; ++j) lv[j] = l[l_off(j * 16 + ta) + r * AT];
             }
 #pragma unroll
             for (int i = 0; i < TK; ++i)
@@ -160,15 +166,26 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
     const int a_base = item.a_blk * AT;
 #pragma unroll
     for (int i = 0; i < TK; ++i) {
-        const int k = k_base + (i < 4 ? tk * 4 + i : 64 + tk * 4 + (i - 4));
+        const int k = k_base + k_of(i);
 #pragma unroll
         for (int j = 0; j < TA; ++j) {
-            int a;
-            if constexpr (TA >= 4) a = a_base + (j < 4 ? ta * 4 + j : 64 + ta * 4 + (j - 4));
-            else a = a_base + ta * TA + j;
             const uint32_t v = (uint32_t)acc[i][j];
-            if (v) atomicAdd(S + (int64_t)k * X.s_stride + a, v);
+            if (v) atomicAdd(S + (int64_t)k * X.s_stride + a_base + a_of(j), v);
         }
+    }
+}
+
+template <int KM>
+__device__ __forceinline__ void score_dispatch_a(int am, const GkScoreItem& item, const GkMatrix& M,
+                                                 const GkSearch& X, const float* __restrict__ L_pool,
+                                                 const float* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
+                                                 float* smem, uint64_t* full, uint64_t* empty) {
+    switch (am) {
+        case F8: score_item<KM, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case F4: score_item<KM, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case S1: score_item<KM, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case S2: score_item<KM, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        default: score_item<KM, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
     }
 }
 
@@ -193,19 +210,15 @@ gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restric
     const GkScoreItem item = items[blockIdx.x];
     const GkSearch X = searches[item.search];
     const GkMatrix M = matrices[X.matrix];
-    const int kw = item.shape & 0xff;         // k-blocks of 64: 1 or 2
-    const int aw = (item.shape >> 8) & 0xff;  // a-blocks: 1, 2 or 4 (a_tile 32) / 1 (a_tile 16)
-#define GK_SCORE_CASE(TK, TA) score_item<TK, TA>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty)
-    if (M.a_tile == 16) {
-        if (kw == 2) GK_SCORE_CASE(8, 1); else GK_SCORE_CASE(4, 1);
-    } else if (aw == 4) {
-        if (kw == 2) GK_SCORE_CASE(8, 8); else GK_SCORE_CASE(4, 8);
-    } else if (aw == 2) {
-        if (kw == 2) GK_SCORE_CASE(8, 4); else GK_SCORE_CASE(4, 4);
-    } else {
-        if (kw == 2) GK_SCORE_CASE(8, 2); else GK_SCORE_CASE(4, 2);
+    const int km = item.shape & 0xff;         // Mode of the kept-set dimension
+    const int am = (item.shape >> 8) & 0xff;  // Mode of the allele dimension
+    switch (km) {
+        case F8: score_dispatch_a<F8>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case F4: score_dispatch_a<F4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case S1: score_dispatch_a<S1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case S2: score_dispatch_a<S2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        default: score_dispatch_a<S3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
     }
-#undef GK_SCORE_CASE
 }
 
 constexpr int kSmemBytes = 128 + kStages * GK_RT * (2 * GK_KB + 128) * (int)sizeof(float);

@@ -153,7 +153,7 @@ class HostBatch:
         for i, p in enumerate(packs):
             if p.n_reads and int(p.k_obs.astype(np.int64).sum()) >= 2 ** 32 - 1:
                 raise ValueError("sum of observations per problem must stay below 2^32 (32-bit score atomics)")
-            a_tile = 16 if p.n_alleles <= 16 else 32
+            a_tile = 32
             n_ablk = max(1, -(-p.n_alleles // a_tile))
             r_pad = max(128, _round_up(p.n_reads, 128))
             table[i] = (mem_off, entoff_off, L_off, LT_off, col_off, p.n_reads, p.n_alleles, p.n_words,
@@ -327,8 +327,30 @@ class BestBatch:
         self.score = score      # int64 [len(searches)]
 
 
-# greedy cover of the last (n_ablk % 4) allele blocks by CTA tiles of width 2 and 1
-_A_REM = {0: [], 1: [(0, 1)], 2: [(0, 2)], 3: [(0, 2), (2, 1)]}
+# scoring tile modes (gk_score.cu): 128 / 64 wide with vector loads, 16 / 32 / 48 wide remainders
+MODE_F8, MODE_F4, MODE_S1, MODE_S2, MODE_S3 = 0, 1, 2, 3, 4
+
+
+def _tile_counts(n16: np.ndarray) -> np.ndarray:
+    """Tiles needed to cover n16 groups of 16: 128-wide, then 64, then a 16/32/48 remainder."""
+    rem = n16 % 8
+    return n16 // 8 + (rem >= 4) + ((rem % 4) > 0)
+
+
+def _tile_decode(n16: np.ndarray, it: np.ndarray, blocks_per_128: int):
+    """(first block, mode) of tile ``it`` in the cover of ``n16`` groups; a block is
+    128 / blocks_per_128 wide (64 for kept sets, 32 for alleles)."""
+    full = n16 // 8
+    rem = n16 % 8
+    has64 = rem >= 4
+    tail = rem % 4
+    is_full = it < full
+    is_64 = ~is_full & has64 & (it == full)
+    blk = np.where(is_full, it * blocks_per_128,
+                   np.where(is_64, full * blocks_per_128,
+                            full * blocks_per_128 + np.where(has64, blocks_per_128 // 2, 0)))
+    mode = np.where(is_full, MODE_F8, np.where(is_64, MODE_F4, MODE_S1 + tail - 1))
+    return blk, mode
 
 
 class SearchGroup:
@@ -452,23 +474,20 @@ class SearchGroup:
             local = local // np.maximum(cs, 1)
         return search, list(reversed(parts))
 
-    def _a_tiles(self, s: int) -> list[tuple[int, int]]:
-        """(a_blk, width-in-blocks) CTA tiles covering the candidate columns of search ``s``."""
-        nb = int(self.n_ablk[s])
-        if self.a_tile[s] == 16:
-            return [(0, 1)]
-        if s in self.restricted:
-            blocks = np.unique(self.restricted[s] // 32)
-        else:
-            blocks = np.arange(nb)
+    def _restricted_a_tiles(self, s: int) -> list[tuple[int, int]]:
+        """(a_blk, mode) CTA tiles covering the 32-column blocks that hold candidates of ``s``."""
+        blocks = np.unique(self.restricted[s] // 32)
         tiles, i = [], 0
         while i < len(blocks):
             run = 1
             while i + run < len(blocks) and blocks[i + run] == blocks[i] + run and run < 4:
                 run += 1
-            w = 4 if run == 4 else (2 if run >= 2 else 1)
-            tiles.append((int(blocks[i]), w))
-            i += w
+            if run == 4:
+                tiles.append((int(blocks[i]), MODE_F8)); i += 4
+            elif run >= 2:
+                tiles.append((int(blocks[i]), MODE_F4)); i += 2
+            else:
+                tiles.append((int(blocks[i]), MODE_S2)); i += 1
         return tiles
 
     def _score_items(self, active_idx: np.ndarray) -> np.ndarray:
@@ -477,17 +496,16 @@ class SearchGroup:
         self._step_cells = int((kept[live] * self.n_cand[live] * self.R[live]).sum())
         if not len(live):
             return np.zeros(0, dtype=SCORE_ITEM_DTYPE)
-        n_k64 = -(-kept[live] // GK_KB)
-        n_kt = -(-n_k64 // 2)
+        k16 = -(-kept[live] // 16)
+        a16 = -(-self.A[live] // 16)
+        n_kt = _tile_counts(k16)
+        n_at = _tile_counts(a16)
         r16 = _round_up_arr(self.R[live], _cabi.GK_RT)
-        # a-tiles as CSR
-        is_restricted = np.array([int(s) in self.restricted for s in live])
-        nb = self.n_ablk[live]
-        n_at = np.where(self.a_tile[live] == 16, 1, nb // 4 + np.array([len(_A_REM[int(x) % 4]) for x in nb]))
         custom = {}
-        for j in np.flatnonzero(is_restricted):
-            custom[j] = self._a_tiles(int(live[j]))
-            n_at[j] = len(custom[j])
+        for j, s in enumerate(live):
+            if int(s) in self.restricted:
+                custom[j] = self._restricted_a_tiles(int(s))
+                n_at[j] = len(custom[j])
         # chunk size: large chunks unless that leaves the GPU underfilled
         chunk = SCORE_READ_CHUNK
         for cand_chunk in (8192, 4096, 2048, 1024):
@@ -500,29 +518,21 @@ class SearchGroup:
         search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
         items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
         items["search"] = live[search]
-        full_k = ikt < (n_k64[search] // 2)
-        items["k_blk"] = np.where(full_k, 2 * ikt, n_k64[search] - 1)
-        kw = np.where(full_k, 2, 1)
-        nbs = nb[search]
-        quad = iat < nbs // 4
-        rem_idx = np.maximum(iat - nbs // 4, 0)
-        rem = nbs % 4
-        rem_blk = np.where(rem_idx == 0, 0, 2)                       # second remainder tile starts 2 blocks in
-        rem_w = np.where(rem == 1, 1, np.where(rem == 2, 2, np.where(rem_idx == 0, 2, 1)))
-        a_blk = np.where(quad, 4 * iat, (nbs // 4) * 4 + rem_blk)
-        aw = np.where(quad, 4, rem_w)
-        aw = np.where(self.a_tile[live][search] == 16, 1, aw)
+        k_blk, k_mode = _tile_decode(k16[search], ikt, 2)
+        a_blk, a_mode = _tile_decode(a16[search], iat, 4)
         for j, tiles in custom.items():
             sel = np.flatnonzero(search == j)
             t = np.array(tiles, dtype=np.int64)
             a_blk[sel] = t[iat[sel], 0]
-            aw[sel] = t[iat[sel], 1]
+            a_mode[sel] = t[iat[sel], 1]
+        items["k_blk"] = k_blk
         items["a_blk"] = a_blk
         items["r0"] = ich * chunk
         items["r1"] = np.minimum((ich + 1) * chunk, r16[search])
-        items["shape"] = kw | (aw << 8)
-        order = np.argsort(-((items["r1"] - items["r0"]).astype(np.int64) * kw * aw
-                             * self.a_tile[live][search]), kind="stable")
+        items["shape"] = k_mode | (a_mode << 8)
+        span = np.array([128, 64, 16, 32, 48], dtype=np.int64)
+        order = np.argsort(-((items["r1"] - items["r0"]).astype(np.int64) * span[k_mode] * span[a_mode]),
+                           kind="stable")
         return items[order]
 
     def _p_items(self, idx: np.ndarray) -> np.ndarray:

@@ -151,6 +151,8 @@ class FakeBackend:
             kept[s] = k
 
     # --- kernel (b) ---------------------------------------------------------------------
+    MODE_SPAN = {0: 128, 1: 64, 2: 16, 3: 32, 4: 48}   # F8, F4, S1, S2, S3
+
     def gk_score(self, table, stab, items, n_items, L, P, S):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
@@ -160,21 +162,22 @@ class FakeBackend:
             M = table[X["matrix"]]
             rp, tile = int(M["r_pad"]), int(M["a_tile"])
             r0, r1 = int(it["r0"]), int(it["r1"])
-            kw, aw = int(it["shape"]) & 0xFF, (int(it["shape"]) >> 8) & 0xFF
-            assert r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
-            assert kw in (1, 2) and aw in (1, 2, 4) and (tile == 32 or aw == 1)
+            kspan = self.MODE_SPAN[int(it["shape"]) & 0xFF]
+            aspan = self.MODE_SPAN[(int(it["shape"]) >> 8) & 0xFF]
+            assert tile == 32 and r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
+            kw, aw = -(-kspan // GK_KB), -(-aspan // tile)
             assert int(it["a_blk"]) + aw <= int(M["n_ablk"])
             stride = int(X["s_stride"])
-            for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw):
-                po = int(X["P_off"]) + (kb * rp + r0) * GK_KB
-                Pt = P[po: po + (r1 - r0) * GK_KB].reshape(r1 - r0, GK_KB)
-                for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw):
-                    Lt = self._L_view(M, L)[ab, r0:r1, :]
-                    part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)    # [GK_KB, tile]
-                    assert part.max(initial=0) < 2 ** 24
-                    for kl in range(GK_KB):
-                        o = int(X["S_off"]) + (kb * GK_KB + kl) * stride + ab * tile
-                        S[o: o + tile] += part[kl].astype(np.uint32)
+            Pt = np.concatenate([
+                P[int(X["P_off"]) + (kb * rp + r0) * GK_KB: int(X["P_off"]) + (kb * rp + r1) * GK_KB]
+                .reshape(r1 - r0, GK_KB) for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)], axis=1)[:, :kspan]
+            Lt = np.concatenate([self._L_view(M, L)[ab, r0:r1, :]
+                                 for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw)], axis=1)[:, :aspan]
+            part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)          # [kspan, aspan]
+            assert part.max(initial=0) < 2 ** 24
+            for kl in range(kspan):
+                o = int(X["S_off"]) + (int(it["k_blk"]) * GK_KB + kl) * stride + int(it["a_blk"]) * tile
+                S[o: o + aspan] += part[kl].astype(np.uint32)
 
     # --- kernel (c), part 1 ----------------------------------------------------------------
     @staticmethod
