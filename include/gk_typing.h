@@ -144,6 +144,31 @@ int gk_write_p(const GkMatrix* matrices, const GkSearch* searches, const GkPItem
                int top_n, int n_set, const int32_t* kept_count, const int32_t* ids,
                const uint8_t* LT_pool, float* P_pool, void* stream);
 
+/* ---- EM path (graphkir/typing_em.py) ------------------------------------------------- */
+
+/* One gene of the EM solver; offsets index the pools passed to gk_em_squarem. */
+typedef struct GkEmProblem {
+    int64_t row_off;     /* uint32 pool: rows[u * n_awords + w], distinct compatibility rows (allele bitsets)   */
+    int64_t wgt_off;     /* uint32 pool: number of read pairs with row u                                        */
+    int64_t len_off;     /* double pool: allele length normalisation (ones when seq_len is not given)           */
+    int64_t out_off;     /* double pool: prob[n_alleles] then 4 * n_alleles + n_rows doubles of scratch         */
+    int32_t n_rows, n_alleles, n_awords, pad;
+} GkEmProblem;
+
+/* Replaces getCandidateAllelePerRead + getMostFreqAllele (typing_em.py:68-104): compatible alleles
+ * per read pair as bitsets.  membT[v * n_awords + w] holds the alleles of variant v; off_x/idx_x are
+ * the CSR lists of positive / negative variants of the left / right mate.  compat has room for
+ * 2 * n_reads rows; rows [0, n_reads) are the result. */
+int gk_em_compat(const uint32_t* membT, int n_awords, int n_alleles, const int32_t* off_lp,
+                 const int32_t* idx_lp, const int32_t* off_ln, const int32_t* idx_ln,
+                 const int32_t* off_rp, const int32_t* idx_rp, const int32_t* off_rn,
+                 const int32_t* idx_rn, int n_reads, uint32_t* compat, void* stream);
+
+/* Replaces hisatEMnp (typing_em.py:107-188): SQUAREM EM, one CTA per problem, float64. */
+int gk_em_squarem(const GkEmProblem* problems, int n_problems, const uint32_t* row_pool,
+                  const uint32_t* wgt_pool, const double* len_pool, double* out_pool,
+                  int32_t* iters_out, int iter_max, double diff_threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,16 +40,19 @@ P_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("r0", "<i4"), ("r
 STEP_INFO_DTYPE = np.dtype([("n_kept", "<i4"), ("n_unique", "<i4"), ("n_alive", "<i4"), ("cut", "<i4"),
                             ("bar", "<u4"), ("tie_flags", "<i4"), ("best_rank", "<i4"), ("pad1", "<i4")])
 
+EM_PROBLEM_DTYPE = np.dtype([("row_off", "<i8"), ("wgt_off", "<i8"), ("len_off", "<i8"), ("out_off", "<i8"),
+                             ("n_rows", "<i4"), ("n_alleles", "<i4"), ("n_awords", "<i4"), ("pad", "<i4")])
+
 _STRUCTS = {
     "GkMatrix": MATRIX_DTYPE, "GkSearch": SEARCH_DTYPE, "GkLikItem": LIK_ITEM_DTYPE,
     "GkScoreItem": SCORE_ITEM_DTYPE, "GkCountItem": COUNT_ITEM_DTYPE, "GkPItem": P_ITEM_DTYPE,
-    "GkStepInfo": STEP_INFO_DTYPE,
+    "GkStepInfo": STEP_INFO_DTYPE, "GkEmProblem": EM_PROBLEM_DTYPE,
 }
 
 # every symbol include/gk_typing.h declares
 EXPORTS = (
     "gk_last_error", "gk_abi_version", "gk_sizeof", "gk_likelihood", "gk_first_step", "gk_score",
-    "gk_select", "gk_rescore_count", "gk_rank", "gk_write_p",
+    "gk_select", "gk_rescore_count", "gk_rank", "gk_write_p", "gk_em_compat", "gk_em_squarem",
 )
 
 _lib = None

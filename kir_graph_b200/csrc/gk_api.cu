@@ -25,5 +25,6 @@ extern "C" int gk_sizeof(const char* name) {
     if (!strcmp(name, "GkCountItem")) return (int)sizeof(GkCountItem);
     if (!strcmp(name, "GkPItem")) return (int)sizeof(GkPItem);
     if (!strcmp(name, "GkStepInfo")) return (int)sizeof(GkStepInfo);
+    if (!strcmp(name, "GkEmProblem")) return (int)sizeof(GkEmProblem);
     return -1;
 }

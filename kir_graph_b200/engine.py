@@ -61,7 +61,7 @@ class CudaBackend:
 
     # --- memory ---------------------------------------------------------------
     _NP2T = {"uint8": "uint8", "int32": "int32", "uint32": "int32", "float32": "float32",
-             "int64": "int64", "uint64": "int64"}
+             "int64": "int64", "uint64": "int64", "float64": "float64"}
 
     def _tdtype(self, dtype):
         return getattr(self.torch, self._NP2T[np.dtype(dtype).name])

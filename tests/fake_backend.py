@@ -14,7 +14,8 @@ from __future__ import annotations
 import numpy as np
 
 from kir_graph_b200._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, LIK_ITEM_DTYPE,
-                                  MATRIX_DTYPE, P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE)
+                                  MATRIX_DTYPE, P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE,
+                                  EM_PROBLEM_DTYPE)
 
 LCM = [1, 1, 2, 6, 12, 60, 60, 420, 840]
 
@@ -341,3 +342,62 @@ class FakeBackend:
                         tile[:, kl] = m[ids[s, k, :n_set], r0:r0 + 128].min(axis=0)
                 o = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
                 P[o: o + 128 * GK_KB] = tile.reshape(-1)
+
+    # --- EM path -------------------------------------------------------------------------------
+    def gk_em_compat(self, membT, n_aw, n_alleles, off_lp, idx_lp, off_ln, idx_ln, off_rp, idx_rp, off_rn,
+                     idx_rn, n_reads, compat):
+        membT = membT.reshape(-1, n_aw)
+        out = compat.reshape(-1, n_aw)
+        full = np.full(n_aw, 0xFFFFFFFF, dtype=np.uint32)
+        if n_alleles & 31:
+            full[-1] = np.uint32((1 << (n_alleles & 31)) - 1)
+        for r in range(n_reads):
+            mates = []
+            for (op, ip, on, in_) in ((off_lp, idx_lp, off_ln, idx_ln), (off_rp, idx_rp, off_rn, idx_rn)):
+                acc = np.zeros(n_aw, dtype=np.uint32)
+                if op[r + 1] > op[r]:
+                    acc = full.copy()
+                    for e in range(op[r], op[r + 1]):
+                        acc &= membT[ip[e]]
+                    for e in range(on[r], on[r + 1]):
+                        acc &= ~membT[in_[e]]
+                mates.append(acc)
+            both = mates[0] & mates[1]
+            out[r] = both if both.any() else (mates[0] | mates[1])
+
+    def gk_em_squarem(self, problems, n_problems, row_pool, wgt_pool, len_pool, out_pool, iters_out, iter_max,
+                      diff_threshold):
+        problems = problems.view(EM_PROBLEM_DTYPE)
+        for i in range(n_problems):
+            E = problems[i]
+            U, A, W = int(E["n_rows"]), int(E["n_alleles"]), int(E["n_awords"])
+            rows = row_pool[E["row_off"]: E["row_off"] + U * W].reshape(U, W)
+            wgt = wgt_pool[E["wgt_off"]: E["wgt_off"] + U].astype(np.float64)
+            length = len_pool[E["len_off"]: E["len_off"] + A]
+            bits = np.zeros((U, A))
+            for a in range(A):
+                bits[:, a] = (rows[:, a >> 5] >> np.uint32(a & 31)) & 1
+
+            def step(p):
+                b = (bits * p).sum(axis=1)
+                binv = np.divide(wgt, b, out=np.zeros(U), where=b != 0)
+                acc = (bits * binv[:, None]).sum(axis=0) * p / length
+                return acc / acc.sum()
+
+            p = step(np.ones(A))
+            it = 0
+            while it < iter_max:
+                p1 = step(p)
+                p2 = step(p1)
+                r = p1 - p
+                v = p2 - p1 - r
+                rr, vv = (r * r).sum(), (v * v).sum()
+                if vv > 0.0:
+                    g = -np.sqrt(rr / vv)
+                    p1 = step(np.maximum(p - r * g * 2 + v * (g * g), 0))
+                if np.abs(p - p1).sum() <= diff_threshold:
+                    break
+                p = p1
+                it += 1
+            out_pool[E["out_off"]: E["out_off"] + A] = p
+            iters_out[i] = it

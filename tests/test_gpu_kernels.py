@@ -138,3 +138,82 @@ def test_split_invariance_and_idempotence(cuda, monkeypatch):
     assert np.all(last.cnt.sum(axis=(1, 2)) >= pack.n_reads)          # every read counted for >= 1 member
     w = np.array([orc.lcm_upto(3) // q for q in (1, 2, 3)])
     assert np.all((last.cnt * w).sum(axis=(1, 2)) == pack.n_reads * orc.lcm_upto(3))   # fractions sum to 1
+
+
+def test_em_path_matches_reference_golden(cuda):
+    from kir_graph_b200 import typing_em
+    cases = load_golden("em_cases")["cases"]
+    kat = cases["kat_candidate"]
+    assert sorted(typing_em.getCandidateAllelePerRead(kat["positive"], kat["negative"], _backend=cuda)) == sorted(kat["out"])
+    for key in ("kat_simple", "syn_a16"):
+        prob = typing_em.hisatEMnp(cases[key]["allele_per_read"], _backend=cuda)
+        assert set(prob) == set(cases[key]["prob"])
+        for name, p in cases[key]["prob"].items():
+            assert abs(prob[name] - p) < 1e-9          # float64, different summation order than NumPy
+    reads, variants = objects_from_input(cases["syn_a16"]["input"])
+    gene = typing_em.preprocessHisatReads({"reads": reads, "variants": variants})["KIRI*BACKBONE"]
+    rows_gpu = typing_em.compatible_alleles(gene, cuda)
+    rows_np = typing_em.compatible_alleles(gene, FakeBackend())
+    assert np.array_equal(rows_gpu, rows_np)
+    got = [sorted(x) for x in typing_em._rows_to_names(rows_gpu, gene.allele_names)]
+    assert got == cases["syn_a16"]["allele_per_read"]
+    # run-to-run bit reproducibility of the EM (fixed summation order)
+    a = typing_em.hisatEMnp(cases["syn_a16"]["allele_per_read"], _backend=cuda)
+    b = typing_em.hisatEMnp(cases["syn_a16"]["allele_per_read"], _backend=cuda)
+    assert a == b
+
+
+def test_em_larger_against_oracle(cuda):
+    from kir_graph_b200 import typing_em
+    gene = synthetic.make_gene([55, 0], "KIREM*BACKBONE", 180, 1440, 3, 20000)
+    reads, variants = gene.to_objects()
+    packed = typing_em.preprocessHisatReads({"reads": reads, "variants": variants})["KIREM*BACKBONE"]
+    rows = typing_em.compatible_alleles(packed, cuda)
+    per_read = typing_em._rows_to_names(rows, packed.allele_names)
+    # oracle set algebra on a sample of reads, EM on everything
+    by_id = {v.id: v.allele for v in variants}
+    for r in range(0, len(reads), 97):
+        want = orc.most_frequent(
+            orc.candidate_alleles_per_mate([by_id[v] for v in reads[r].lpv], [by_id[v] for v in reads[r].lnv])
+            + orc.candidate_alleles_per_mate([by_id[v] for v in reads[r].rpv], [by_id[v] for v in reads[r].rnv]))
+        assert sorted(want) == sorted(per_read[r])
+    ref = orc.em_abundance(per_read)
+    got = typing_em.em_from_rows(rows, packed.allele_names, backend=cuda)
+    assert set(ref) == set(got)
+    for name in ref:
+        assert abs(ref[name] - got[name]) < 1e-9
+
+
+@pytest.mark.parametrize("method", ["full", "exonfirst_1", "em"])
+def test_sample_driver_matches_reference(cuda, tmp_path, method):
+    import os
+    from kir_graph_b200 import kir_typing
+    from kir_graph_b200.hisat2 import writeReadsAndVariantsData
+    sample = load_golden("sample_small")
+    reads, variants = objects_from_input(sample["input"])
+    path = os.path.join(tmp_path, "sample.json")
+    writeReadsAndVariantsData({"reads": reads, "variants": variants}, path)
+    kw = {"full": dict(top_n=60, variant_correction=True), "exonfirst_1": dict(top_n=60), "em": {}}[method]
+    t = kir_typing.selectKirTypingModel(method, path, _backend=cuda, **kw)
+    alleles, warn = t.typing(sample["gene_cn"])
+    ref = sample["calls"][method]
+    assert warn == ref["warnings"]
+    if method == "em":
+        assert sorted(alleles) == sorted(ref["alleles"])
+    else:
+        assert alleles == ref["alleles"] or t.tie_report
+
+
+def test_cohort_batch_equals_per_gene_class(cuda):
+    from kir_graph_b200 import cohort
+    from kir_graph_b200.typing_mulit_allele import AlleleTyping
+    genes = synthetic.make_wgs30x_sample(seed=5, total_reads=30000)
+    packs = [packing.pack_synthetic(g) for g in genes]
+    cns = [g.cn for g in genes]
+    calls = cohort.CohortTyper(packs, cns, top_n=300, backend=cuda, n_parts=2, group_size=6).run()
+    for g, c in zip(genes, calls):
+        reads, variants = g.to_objects()
+        t = AlleleTyping(reads, variants, force_homo=None, top_n=300, _backend=cuda)
+        r = t.typing(g.cn)
+        assert r.selectBest() == c.alleles
+        assert abs(c.value - r.value[c.best_rank]) <= 1e-9 * abs(c.value)
