@@ -209,7 +209,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="cohort", choices=["cohort", "wgs30x", "deep"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -261,8 +261,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     from kir_graph_b200 import cohort, engine
     be = engine.CudaBackend(local_rank)
+    col_shard = reduce_scores = None
+    if args.workload == "deep" and world > 1:
+        col_shard = (rank, world)
+
+        def reduce_scores(d_S):                      # one small collective per copy-number step
+            dist.all_reduce(d_S)
     typer = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=args.parts,
-                               group_size=17 if args.workload != "deep" else 1)
+                               group_size=17 if args.workload != "deep" else 1, col_shard=col_shard,
+                               reduce_scores=reduce_scores)
     typer.pin()
 
     def barrier():
@@ -287,6 +294,8 @@ def main():
         return float(t.item())
 
     # ---- resident: inputs already in HBM ---------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     typer.upload()
     calls = None
     for _ in range(args.warmup):
@@ -295,15 +304,20 @@ def main():
     lik_cells = sum(p.batch.n_cells for p in typer.parts)
     lik_bytes = sum(p.batch.bytes_out for p in typer.parts)
     n_parts = len(typer.parts)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    be.timing = {}
     launches0 = be.launches
     ms_total = timed(typer.run, args.steps)
     launches = be.launches - launches0
+    clocks = sampler.stop()
+    # kernel timing pass: same work, sub-batches one after the other on one stream so that the
+    # CUDA events around each launch do not overlap other kernels
+    torch.cuda.synchronize()
+    be.timing = {}
+    roof_steps = max(1, min(3, args.steps))
+    for _ in range(roof_steps):
+        typer.run_serial()
+    torch.cuda.synchronize()
     timing = be.timing
     be.timing = None
-    clocks = sampler.stop()
 
     # ---- end to end: pinned host arrays -> device -> calls on the host ------------------
     def e2e_step():
@@ -364,7 +378,10 @@ def main():
                 "achieved": score_ops, "peak": fp32_peak, "unit": "T FP32 ops/s (1 FMNMX + 1 FADD per cell)",
                 "frac": score_ops / fp32_peak if fp32_peak else None, "traffic": None,
                 "cells_per_s": work_s / (ms_s * 1e-3) if ms_s else 0.0, "launches": n_s,
-                "kernel_ms_per_step": ms_s / args.steps, "share_of_step": ms_s / ms_total if ms_total else None,
+                "kernel_ms_per_step": ms_s / roof_steps,
+                "share_of_step": (ms_s / roof_steps) / (ms_total / args.steps) if ms_total else None,
+                "measured": f"CUDA events around every launch of {roof_steps} extra step(s) run right after the timed "
+                            "region with the sub-batches serialised on one stream",
                 "peak_source": f"148 SM x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
                                "not in MEASURED_PEAKS.json, which only holds HBM and bf16 tensor peaks",
             },
@@ -374,7 +391,7 @@ def main():
                 "cells_per_s": work_l / (ms_l * 1e-3) if ms_l else 0.0, "bytes_per_cell": 5,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
             },
-            "kernel_ms_per_step": {k: kernel_stats(k)[0] / args.steps for k in timing},
+            "kernel_ms_per_step": {k: kernel_stats(k)[0] / roof_steps for k in timing},
             "parity": {"genes_matching_generator_truth": truth_ok, "genes": len(truth)},
             "build_s": t_build,
         }

@@ -126,8 +126,12 @@ class BatchTyper:
     """Types a fixed batch of gene problems; device buffers are reused across ``run`` calls."""
 
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
-                 host_batch: engine.HostBatch | None = None):
+                 host_batch: engine.HostBatch | None = None, col_shard: tuple[int, int] | None = None,
+                 reduce_scores=None):
+        """``col_shard`` / ``reduce_scores``: shard the candidate columns of every problem over
+        several ranks (see :class:`engine.SearchGroup`); used for one very deep sample."""
         self.be = backend if backend is not None else engine.CudaBackend()
+        self.col_shard, self.reduce_scores = col_shard, reduce_scores
         self.packs = packs
         self.cns = np.asarray(cns, dtype=np.int64)
         self.top_n = top_n
@@ -159,7 +163,8 @@ class BatchTyper:
         batch = self.batch
         batch.run_likelihood()
         if self.group is None:
-            self.group = engine.SearchGroup(batch, self.live, self.top_n)
+            self.group = engine.SearchGroup(batch, self.live, self.top_n, col_shard=self.col_shard,
+                                            reduce_scores=self.reduce_scores)
         else:
             self.group.reset()
         group = self.group
@@ -226,15 +231,19 @@ class CohortTyper:
     selection) overlaps the kernels of the others.  Results come back in input order."""
 
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
-                 n_parts: int = 2, group_size: int = 1):
+                 n_parts: int = 2, group_size: int = 1, col_shard: tuple[int, int] | None = None,
+                 reduce_scores=None):
         """``group_size`` consecutive problems (e.g. the 17 genes of a sample) stay in one part."""
         self.be = backend if backend is not None else engine.CudaBackend()
+        if col_shard is not None and col_shard[1] > 1:
+            n_parts = 1                          # one collective stream: keep the parts serial
         n = len(packs)
         n_groups = max(1, -(-n // group_size))
         n_parts = max(1, min(n_parts, n_groups))
         bounds = [(g * n_groups // n_parts) * group_size for g in range(n_parts)] + [n]
         self.slices = [slice(bounds[i], min(bounds[i + 1], n)) for i in range(n_parts)]
-        self.parts = [BatchTyper(packs[sl], list(cns)[sl], top_n=top_n, backend=self.be) for sl in self.slices]
+        self.parts = [BatchTyper(packs[sl], list(cns)[sl], top_n=top_n, backend=self.be, col_shard=col_shard,
+                                 reduce_scores=reduce_scores) for sl in self.slices]
         self.streams = None
         self.pool = None
         if n_parts > 1 and hasattr(self.be, "torch"):
@@ -278,6 +287,13 @@ class CohortTyper:
 
     def upload(self) -> None:
         self._all("upload")
+
+    def run_serial(self) -> list[GeneCall]:
+        """All parts one after the other on the current stream (used to time kernels in isolation)."""
+        calls: list[GeneCall] = []
+        for part in self.parts:
+            calls.extend(part.run())
+        return calls
 
     def run(self) -> list[GeneCall]:
         calls: list[GeneCall] = []

@@ -356,7 +356,15 @@ def _tile_decode(n16: np.ndarray, it: np.ndarray, blocks_per_128: int):
 class SearchGroup:
     """Greedy searches (one per entry of ``matrix_ids``) advancing in lock step."""
 
-    def __init__(self, batch: MatrixBatch, matrix_ids, top_n: int):
+    def __init__(self, batch: MatrixBatch, matrix_ids, top_n: int, col_shard: tuple[int, int] | None = None,
+                 reduce_scores=None):
+        """``col_shard=(rank, world)`` scores only this rank's share of the candidate-column tiles;
+        ``reduce_scores(d_S)`` must then sum the score pool over the ranks in place (one small
+        collective per copy-number step); everything after scoring runs replicated."""
+        self.col_shard = col_shard
+        self.reduce_scores = reduce_scores
+        if col_shard is not None and col_shard[1] > 1 and reduce_scores is None:
+            raise ValueError("column sharding needs a reduce_scores callable")
         if not 1 <= top_n <= MAX_TOP_N:
             raise ValueError(f"top_n must be in 1..{MAX_TOP_N}")
         self.batch = batch
@@ -531,6 +539,17 @@ class SearchGroup:
         items["r1"] = np.minimum((ich + 1) * chunk, r16[search])
         items["shape"] = k_mode | (a_mode << 8)
         span = np.array([128, 64, 16, 32, 48], dtype=np.int64)
+        if self.col_shard is not None and self.col_shard[1] > 1:
+            rank, world = self.col_shard
+            mine = (iat % world) == rank                 # column tiles dealt round-robin to the ranks
+            k0 = k_blk * GK_KB
+            a0 = a_blk * 32
+            rows = np.minimum(span[k_mode], kept[live][search] - k0)
+            cols = np.minimum(span[a_mode], self.A[live][search] - a0)
+            reads = np.minimum(items["r1"], self.R[live][search]) - items["r0"]
+            useful = np.maximum(rows, 0) * np.maximum(cols, 0) * np.maximum(reads, 0)
+            self._step_cells = int(useful[mine].sum())
+            items, k_mode, a_mode = items[mine], k_mode[mine], a_mode[mine]
         order = np.argsort(-((items["r1"] - items["r0"]).astype(np.int64) * span[k_mode] * span[a_mode]),
                            kind="stable")
         return items[order]
@@ -624,6 +643,8 @@ class SearchGroup:
             be.launch("gk_score", bt.d_table, self.d_tab, d_items, len(items), bt.d_L, self.d_P, self.d_S,
                       work=float(self._step_cells))
             self.score_cells += self._step_cells
+            if self.reduce_scores is not None:
+                self.reduce_scores(self.d_S)             # sum of the per-rank column slices
             be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
                       self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, bt.d_col, self.d_score[self.cur],
                       self.d_flag, self.d_alive, self.d_info)

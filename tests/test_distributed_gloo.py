@@ -1,0 +1,95 @@
+"""Multi-rank paths on CPU (gloo, world_size 2): candidate-column sharding with one score
+reduction per step, and cohort sample sharding.  Kernels are the NumPy test double; this
+covers the host-side sharding logic only (the GPU path runs the same code over NCCL)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from kir_graph_b200 import cohort, engine, packing, synthetic
+from oracle import typing_oracle as orc
+from tests.fake_backend import FakeBackend
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # --- one deep problem, candidate columns sharded -------------------------------
+        gene = synthetic.make_gene([21, 0], "KIRSH*BACKBONE", 300, 2400, 3, 400, homo_prob=0.0)
+        pack = packing.pack_synthetic(gene)
+        be = FakeBackend()
+        batch = engine.MatrixBatch([pack], backend=be)
+
+        def reduce_scores(d_S):
+            t = torch.from_numpy(d_S.view(np.int32))
+            dist.all_reduce(t)
+
+        group = engine.SearchGroup(batch, [0], 40, col_shard=(rank, world), reduce_scores=reduce_scores)
+        steps = [group.step(need_next=[i < 2])[0] for i in range(3)]
+        cells = torch.tensor([group.score_cells], dtype=torch.int64)
+        dist.all_reduce(cells)
+        # --- cohort: samples dealt round-robin, results gathered on rank 0 -----------------
+        samples = list(range(4))
+        mine = cohort.shard(samples, rank, world)
+        calls = {}
+        for sidx in mine:
+            genes = synthetic.make_wgs30x_sample(seed=200 + sidx, total_reads=1500)[:5]
+            packs = [packing.pack_synthetic(g) for g in genes]
+            res = cohort.BatchTyper(packs, [g.cn for g in genes], top_n=20, backend=FakeBackend()).run()
+            calls[sidx] = [c.alleles for c in res]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, calls)
+        if rank == 0:
+            merged = {}
+            for part in gathered:
+                merged.update(part)
+            out.put(("ok", [(s.ids.tolist(), s.score.tolist()) for s in steps], int(cells.item()), merged))
+        else:
+            out.put(("ok", [(s.ids.tolist(), s.score.tolist()) for s in steps], -1, None))
+    except Exception as exc:  # pragma: no cover
+        out.put(("error", repr(exc), 0, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_column_sharding_and_cohort_sharding_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[0] == "ok" for r in results), results
+    # every rank ends with identical kept sets, equal to the unsharded oracle
+    gene = synthetic.make_gene([21, 0], "KIRSH*BACKBONE", 300, 2400, 3, 400, homo_prob=0.0)
+    pack = packing.pack_synthetic(gene)
+    m = engine.MatrixBatch([pack], backend=FakeBackend()).mismatch_counts(0)
+    search = orc.IntSearch(m.astype(np.int64), pack.k_obs, top_n=40)
+    ref = [search.add_candidate() for _ in range(3)]
+    for res in results:
+        for (ids, score), want in zip(res[1], ref):
+            assert ids == want.allele_id.tolist() and score == want.score.tolist()
+    total_cells = max(r[2] for r in results)
+    assert total_cells == sum(len(ref[i].score) * pack.n_alleles * pack.n_reads for i in range(2))
+    merged = [r[3] for r in results if r[3] is not None][0]
+    assert sorted(merged) == [0, 1, 2, 3]
+    for sidx, got in merged.items():
+        genes = synthetic.make_wgs30x_sample(seed=200 + sidx, total_reads=1500)[:5]
+        packs = [packing.pack_synthetic(g) for g in genes]
+        want = cohort.BatchTyper(packs, [g.cn for g in genes], top_n=20, backend=FakeBackend()).run()
+        assert got == [c.alleles for c in want]
