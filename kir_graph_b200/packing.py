@@ -177,16 +177,24 @@ def pack_entries(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.n
                 np.zeros(0, np.uint32), np.zeros(0, np.uint32), k_obs)
 
     # occurrence rank of identical (read, polarity, variant) observations
-    order = np.lexsort((vid, pol, row))
+    # (single 64-bit sort keys: row < 2^31, variant index < 2^30)
+    if len(row) and (int(vid.max()) >= 1 << 30 or n >= 1 << 30):
+        raise ValueError("problem too large for the 64-bit packing keys")
+    key = (row << 31) | (pol << 30) | vid
+    order = np.argsort(key)
+    key = key[order]
     row, pol, vid = row[order], pol[order], vid[order]
     new_run = np.ones(len(row), dtype=bool)
-    new_run[1:] = (row[1:] != row[:-1]) | (pol[1:] != pol[:-1]) | (vid[1:] != vid[:-1])
+    new_run[1:] = key[1:] != key[:-1]
     run_start = np.maximum.accumulate(np.where(new_run, np.arange(len(row)), 0))
     rank = np.arange(len(row)) - run_start
+    if len(rank) and int(rank.max()) >= 256:
+        raise ValueError("an observation is repeated more than 255 times in one read pair")
 
     word = vid >> 5
     bit = (np.uint32(1) << (vid & 31).astype(np.uint32)).astype(np.uint32)
-    order = np.lexsort((word, rank, row))
+    key = (row << 33) | (rank << 25) | word
+    order = np.argsort(key)
     row, rank, word, bit, pol = row[order], rank[order], word[order], bit[order], pol[order]
     new_ent = np.ones(len(row), dtype=bool)
     new_ent[1:] = (row[1:] != row[:-1]) | (rank[1:] != rank[:-1]) | (word[1:] != word[:-1])

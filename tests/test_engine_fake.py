@@ -39,6 +39,7 @@ def check_steps(group_out, ref):
     dict(seed=[7, 1], n_allele=5, n_var=64, cn=4, n_reads=150, top_n=300),
     dict(seed=[7, 2], n_allele=70, n_var=560, cn=2, n_reads=300, top_n=40),
     dict(seed=[7, 3], n_allele=150, n_var=600, cn=2, n_reads=140, top_n=130),
+    dict(seed=[7, 4], n_allele=14, n_var=64, cn=7, n_reads=120, top_n=20),
 ])
 def test_search_group_equals_int_oracle(spec):
     top_n = spec.pop("top_n")

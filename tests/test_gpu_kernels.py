@@ -41,6 +41,7 @@ def _compare_outputs(a, b):
 @pytest.mark.parametrize("specs,top_n,cns", [
     ([(12, 2, 130), (40, 3, 700), (6, 1, 90), (150, 2, 400), (3, 4, 260)], 30, [2, 3, 1, 2, 4]),
     ([(70, 3, 1500), (33, 2, 90)], 300, [3, 2]),
+    ([(40, 6, 500), (12, 5, 300), (90, 8, 260)], 30, [6, 5, 8]),
 ])
 def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns):
     packs = _packs(specs, 101)
