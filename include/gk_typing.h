@@ -42,7 +42,8 @@ extern "C" {
 typedef struct GkMatrix {
     int64_t mem_off;     /* uint32 pool: mem[w * n_alleles + a], bit b = allele a carries variant 32w+b */
     int64_t entoff_off;  /* int32 pool : n_reads+1 entry offsets (absolute indices into the entry pools) */
-    int64_t L_off;       /* float pool : L[(a_blk * r_pad + r) * a_tile + a % a_tile] = m[r, a]          */
+    int64_t L_off;       /* 4-byte pool: L[(a_blk * r_pad + r) * a_tile + a % a_tile] = m[r, a] as float32,
+                            or as half2(m, m) in half mode (all mismatch counts <= 128)                  */
     int64_t LT_off;      /* uint8 pool : LT[a * r_pad + r] = m[r, a]                                     */
     int64_t col_off;     /* uint64 pool: colsum[a] = sum_r m[r, a]                                       */
     int32_t n_reads;
@@ -55,7 +56,8 @@ typedef struct GkMatrix {
 
 /* State of one search.  Strides are fixed by (top_n, GK_MAX_CN). */
 typedef struct GkSearch {
-    int64_t P_off;       /* float pool : P[(k_blk * r_pad + r) * GK_KB + k % GK_KB] = min over members   */
+    int64_t P_off;       /* float (half in half mode) pool: P[(k_blk * r_pad + r) * GK_KB + k % GK_KB]
+                            = min over the members of kept set k of m[r, id]                             */
     int64_t S_off;       /* uint32 pool: S[k * s_stride + a]                                             */
     int64_t cand_off;    /* int32 pool : candidate allele ids of the current step                        */
     int64_t flag_off;    /* uint8 pool : first-occurrence flag per flat candidate k * n_cand + j         */
@@ -70,7 +72,8 @@ typedef struct GkSearch {
 /* Work items (built by the host per launch). */
 typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS */
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
-    shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48 (from k_blk / a_blk) */
+    shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48 (from k_blk / a_blk);
+    half mode rows: 5..8 = 32, 64, 96, 128 kept sets */
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16 */
 typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 
@@ -99,7 +102,7 @@ int gk_sizeof(const char* struct_name);     /* sizeof(GkMatrix) etc., for bindin
 int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, int n_items,
                   const uint32_t* mem_pool, const int32_t* entoff_pool,
                   const int32_t* ent_word, const uint32_t* ent_pos, const uint32_t* ent_neg,
-                  float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, void* stream);
+                  float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, int half_mode, void* stream);
 
 /* CN = 1 step: replaces log_probs[:, idx].sum(0) + argsort()[::-1][:top_n]
  *     (typing_mulit_allele.py:512-532).  One CTA per search.  Order: (colsum, position). */
@@ -114,7 +117,8 @@ int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_sear
  *     caller); the min-sum score is (colsum[a] + score_prev[k] - D[k, a]) / 2, formed by
  *     gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]). */
 int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,
-             const float* L_pool, const float* P_pool, uint32_t* S_pool, void* stream);
+             const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode, int flush_stages,
+             void* stream);
 
 /* (c) segmented selection, part 1: canonical-key dedup (uniqueAllele, :456-476, :551-563),
  *     N_uniq, the cut max(top_n, N_uniq // 5) (:567) and the list of candidates that can
@@ -142,7 +146,7 @@ int gk_rank(const GkMatrix* matrices, const GkSearch* searches, int n_search, in
 /*     P for the next step: P[r, k] = min over members of m[r, id]  (allele_prob, :569). */
 int gk_write_p(const GkMatrix* matrices, const GkSearch* searches, const GkPItem* items, int n_items,
                int top_n, int n_set, const int32_t* kept_count, const int32_t* ids,
-               const uint8_t* LT_pool, float* P_pool, void* stream);
+               const uint8_t* LT_pool, void* P_pool, int half_mode, void* stream);
 
 /* ---- EM path (graphkir/typing_em.py) ------------------------------------------------- */
 

@@ -8,11 +8,14 @@
 // The membership row mem[word, :] is word-major, so the 32 lanes of a warp read
 // 128 consecutive bytes (coalesced; a gene's table is <= 1 MB and stays in L1/L2).
 // Outputs, both written with full 128-byte lines:
-//     L  float32, blocked [a_blk][r][a_tile]  -> operand of the scoring kernel (TMA bulk tiles)
+//     L  4 bytes per cell, blocked [a_blk][r][32] -> operand of the scoring kernel (TMA bulk tiles):
+//        float32(m) for the FP32 scoring path, half2(m, m) for the packed-half path
 //     LT uint8,   allele-major [a][r]         -> rescoring / P kernels stream along reads
 // and the per-allele column sums (CN=1 scores) via one 64-bit atomic per allele per CTA.
 //
 // Bound: HBM writes, 5 B per cell (4 B L + 1 B LT); POPC issue is the secondary limit.
+#include <cuda_fp16.h>
+
 #include "gk_common.cuh"
 
 namespace {
@@ -23,8 +26,8 @@ constexpr int kTilePitch = GK_LIK_READS + 16;  // bytes; keeps rows 16-byte alig
 constexpr int kEntCap = 1024;                  // observation entries of the read tile staged in shared memory
 
 // Per-read work for a CTA whose allele span needs NG lane groups of 32 (uniform per CTA).
-template <int NG>
-__device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int a_tile, int a_span, int e_lo,
+template <int NG, bool HALF>
+__device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int a_span, int e_lo,
                                           const uint32_t* __restrict__ mem, const int32_t* __restrict__ ent_word,
                                           const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
                                           const int* s_eoff, const int* s_word, const uint32_t* s_pos,
@@ -71,7 +74,12 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
             const int a = lane + 32 * g;
             if (a < a_span) {
                 const unsigned int c = live[g] ? cnt[g] : 0u;
-                L[(a / a_tile) * blk_stride + (int64_t)r * a_tile + (a % a_tile)] = (float)c;
+                float* slot = L + g * blk_stride + (int64_t)r * 32 + lane;     // a_tile == 32: block g, column lane
+                if constexpr (HALF) {
+                    *reinterpret_cast<__half2*>(slot) = __half2half2(__ushort2half_rn((unsigned short)c));
+                } else {
+                    *slot = (float)c;
+                }
                 tile[a * kTilePitch + rl] = (uint8_t)c;
                 csum[g] += c;
             }
@@ -84,7 +92,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
                      const uint32_t* __restrict__ mem_pool, const int32_t* __restrict__ entoff_pool,
                      const int32_t* __restrict__ ent_word, const uint32_t* __restrict__ ent_pos,
                      const uint32_t* __restrict__ ent_neg, float* __restrict__ L_pool,
-                     uint8_t* __restrict__ LT_pool, unsigned long long* __restrict__ col_pool) {
+                     uint8_t* __restrict__ LT_pool, unsigned long long* __restrict__ col_pool, int half_mode) {
     __shared__ __align__(16) uint8_t tile[128 * kTilePitch];
     __shared__ unsigned int colpart[kWarps][128];
     __shared__ int s_eoff[GK_LIK_READS + 1];
@@ -94,7 +102,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
-    const int a_tile = M.a_tile;           // 16 (single block) or 32
+    const int a_tile = M.a_tile;           // 32
     const int a0 = item.a_blk * a_tile;
     const int r0 = item.r0;
     int n_blk = M.n_ablk - item.a_blk;     // allele blocks covered by this CTA (<= 4)
@@ -125,9 +133,13 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     __syncthreads();
 
     unsigned int csum[4] = {0u, 0u, 0u, 0u};
-#define GK_LIK_CASE(NG)                                                                                     \
-    lik_reads<NG>(M, r0, a0, a_tile, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_word, s_pos,  \
-                  s_neg, L, blk_stride, tile, csum)
+#define GK_LIK_CASE(NG)                                                                                      \
+    if (half_mode)                                                                                           \
+        lik_reads<NG, true>(M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_word, s_pos, \
+                            s_neg, L, blk_stride, tile, csum);                                               \
+    else                                                                                                     \
+        lik_reads<NG, false>(M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_word,       \
+                             s_pos, s_neg, L, blk_stride, tile, csum)
     switch ((a_span + 31) / 32) {
         case 1: GK_LIK_CASE(1); break;
         case 2: GK_LIK_CASE(2); break;
@@ -163,10 +175,11 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 extern "C" int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, int n_items,
                              const uint32_t* mem_pool, const int32_t* entoff_pool,
                              const int32_t* ent_word, const uint32_t* ent_pos, const uint32_t* ent_neg,
-                             float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, void* stream) {
+                             float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, int half_mode,
+                             void* stream) {
     if (n_items <= 0) return 0;
     gk_likelihood_kernel<<<n_items, kThreads, 0, (cudaStream_t)stream>>>(
-        matrices, items, mem_pool, entoff_pool, ent_word, ent_pos, ent_neg, L_pool, LT_pool, col_pool);
+        matrices, items, mem_pool, entoff_pool, ent_word, ent_pos, ent_neg, L_pool, LT_pool, col_pool, half_mode);
     GK_CHECK_LAUNCH("gk_likelihood");
     return 0;
 }

@@ -12,6 +12,8 @@
 //
 // Both are HBM-bound: per (read, set) they read n bytes (16-byte vector loads, coalesced
 // along reads) and write 0 resp. 4 bytes.
+#include <cuda_fp16.h>
+
 #include "gk_common.cuh"
 
 namespace {
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kThreads)
 gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                   const GkPItem* __restrict__ items, int top_n, int n_set, const int32_t* __restrict__ kept_count,
                   const int32_t* __restrict__ ids, const uint8_t* __restrict__ LT_pool,
-                  float* __restrict__ P_pool) {
+                  void* __restrict__ P_pool_raw, int half_mode) {
     __shared__ __align__(16) uint8_t tile[GK_KB * kPitch];
     const GkPItem item = items[blockIdx.x];
     const GkSearch X = searches[item.search];
@@ -131,14 +133,22 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
         }
         __syncthreads();
         // phase 2: half a warp per read row, four consecutive sets per lane -> 256-byte row stores
-        float* P = P_pool + X.P_off + ((int64_t)item.k_blk * M.r_pad + r0) * GK_KB;
+        const int64_t p_base = X.P_off + ((int64_t)item.k_blk * M.r_pad + r0) * GK_KB;
         for (int rl = warp * 2 + half; rl < 128; rl += kWarps * 2) {
-            float4 out;
-            out.x = (float)tile[(kq + 0) * kPitch + rl];
-            out.y = (float)tile[(kq + 1) * kPitch + rl];
-            out.z = (float)tile[(kq + 2) * kPitch + rl];
-            out.w = (float)tile[(kq + 3) * kPitch + rl];
-            *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = out;
+            const unsigned int v0 = tile[(kq + 0) * kPitch + rl], v1 = tile[(kq + 1) * kPitch + rl];
+            const unsigned int v2 = tile[(kq + 2) * kPitch + rl], v3 = tile[(kq + 3) * kPitch + rl];
+            if (half_mode) {
+                __half* P = reinterpret_cast<__half*>(P_pool_raw) + p_base;
+                __half2 lo = __halves2half2(__ushort2half_rn((unsigned short)v0), __ushort2half_rn((unsigned short)v1));
+                __half2 hi = __halves2half2(__ushort2half_rn((unsigned short)v2), __ushort2half_rn((unsigned short)v3));
+                uint2 out;
+                out.x = *reinterpret_cast<unsigned int*>(&lo);
+                out.y = *reinterpret_cast<unsigned int*>(&hi);
+                *reinterpret_cast<uint2*>(P + (int64_t)rl * GK_KB + kq) = out;
+            } else {
+                float* P = reinterpret_cast<float*>(P_pool_raw) + p_base;
+                *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+            }
         }
         __syncthreads();
     }
@@ -176,11 +186,11 @@ extern "C" int gk_rescore_count(const GkMatrix* matrices, const GkSearch* search
 
 extern "C" int gk_write_p(const GkMatrix* matrices, const GkSearch* searches, const GkPItem* items, int n_items,
                           int top_n, int n_set, const int32_t* kept_count, const int32_t* ids,
-                          const uint8_t* LT_pool, float* P_pool, void* stream) {
+                          const uint8_t* LT_pool, void* P_pool, int half_mode, void* stream) {
     if (n_items <= 0) return 0;
     GK_REQUIRE(n_set >= 1 && n_set <= GK_MAX_CN, "gk_write_p: set size %d outside 1..%d", n_set, GK_MAX_CN);
     gk_write_p_kernel<<<n_items, kThreads, 0, (cudaStream_t)stream>>>(matrices, searches, items, top_n, n_set,
-                                                                      kept_count, ids, LT_pool, P_pool);
+                                                                      kept_count, ids, LT_pool, P_pool, half_mode);
     GK_CHECK_LAUNCH("gk_write_p");
     return 0;
 }

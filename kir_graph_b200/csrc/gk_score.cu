@@ -33,6 +33,8 @@
 //
 // Bound: FP32 non-tensor issue.  One cell = 2 FADD = 2 issue slots of the 4 x 32-lane
 // schedulers; peak = 148 SM x 64 cells/clk x f_clk.
+#include <cuda_fp16.h>
+
 #include "gk_common.cuh"
 
 namespace {
@@ -175,6 +177,203 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Packed-half path: two cells per instruction.
+//
+// P is stored as half [k_blk][r][64], L as half2(m, m) [a_blk][r][32].  A thread owns row
+// pairs (2 tk, 2 tk + 1) of every 32-row group g < G of the tile, so one half2 of P holds the
+// two rows and pairs with the duplicated L value:  d2 = p2 - l2 ; acc2 += |d2|  (HADD2/HFMA2
+// with the |.| source modifier) = 2 half2 instructions for 2 cells.  Mismatch counts are
+// integers <= 128 in this mode, so half arithmetic is exact while an accumulator stays
+// <= 2048; every `flush` stages (16 reads each, flush * 16 * max count <= 2048) the half2
+// accumulators are added to float32 ones, which are merged as integers like in the FP32 path.
+// Tile rows: G in {1..4} groups of 32 kept sets; columns: the same five modes as above.
+template <int G, int AM>
+__device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
+                                             const float* __restrict__ L_pool, const __half* __restrict__ P_pool,
+                                             uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
+                                             uint64_t* full, uint64_t* empty, int flush) {
+    constexpr int TA = ModeInfo<AM>::kPerThread;
+    constexpr int AT = 32;
+    constexpr int KW = (32 * G + GK_KB - 1) / GK_KB;                 // k-blocks staged (1 or 2)
+    constexpr int AW = (ModeInfo<AM>::kSpan + AT - 1) / AT;          // a-blocks staged (1, 2 or 4)
+    constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(__half);
+    constexpr uint32_t kBytesLBlk = GK_RT * AT * sizeof(__half2);
+    constexpr uint32_t kStageBytes = KW * kBytesPBlk + AW * kBytesLBlk;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int tk = tid >> 4;
+    const int ta = tid & 15;
+
+    const int64_t blk_stride_p = (int64_t)M.r_pad * GK_KB;
+    const int64_t blk_stride_l = (int64_t)M.r_pad * AT;
+    const __half* gP = P_pool + X.P_off + item.k_blk * blk_stride_p + (int64_t)item.r0 * GK_KB;
+    const __half2* gL = reinterpret_cast<const __half2*>(L_pool) + M.L_off + item.a_blk * blk_stride_l +
+                        (int64_t)item.r0 * AT;
+    const int n_tiles = (item.r1 - item.r0) / GK_RT;
+
+    auto issue = [&](int tile, int s) {
+        unsigned char* dst = smem_bytes + (size_t)s * kStageBytes;
+        gk_mbar_arrive_expect_tx(&full[s], kStageBytes);
+#pragma unroll
+        for (int b = 0; b < KW; ++b)
+            gk_bulk_g2s(dst + b * kBytesPBlk, gP + b * blk_stride_p + (int64_t)tile * GK_RT * GK_KB, kBytesPBlk,
+                        &full[s]);
+        dst += KW * kBytesPBlk;
+#pragma unroll
+        for (int b = 0; b < AW; ++b)
+            gk_bulk_g2s(dst + b * kBytesLBlk, gL + b * blk_stride_l + (int64_t)tile * GK_RT * AT, kBytesLBlk,
+                        &full[s]);
+    };
+
+    if (tid == 0) {
+        const int pre = n_tiles < kStages ? n_tiles : kStages;
+        for (int s = 0; s < pre; ++s) issue(s, s);
+    }
+
+    float acc[2 * G][TA];
+    __half2 acc2[G][TA];
+    const __half2 zero2 = __float2half2_rn(0.f);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < TA; ++j) {
+            acc[2 * g][j] = 0.f;
+            acc[2 * g + 1][j] = 0.f;
+            acc2[g][j] = zero2;
+        }
+
+    auto a_of = [&](int j) { return ModeInfo<AM>::kVec ? (j < 4 ? ta * 4 + j : 64 + ta * 4 + (j - 4)) : j * 16 + ta; };
+    auto l_off = [&](int c) { return (c / AT) * (GK_RT * AT) + (c % AT); };
+    // rows 32 g + 2 tk + {0, 1}: offset (in halves) inside the staged P blocks [k_blk][r][64]
+    auto p_off = [&](int g) { return ((32 * g) / GK_KB) * (GK_RT * GK_KB) + ((32 * g) % GK_KB) + 2 * tk; };
+
+    auto flush_acc = [&]() {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < TA; ++j) {
+                const float2 f = __half22float2(acc2[g][j]);
+                acc[2 * g][j] += f.x;
+                acc[2 * g + 1][j] += f.y;
+                acc2[g][j] = zero2;
+            }
+    };
+
+    int since_flush = 0;
+#pragma unroll 1
+    for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % kStages;
+        if (tid == 0 && t >= 1) {
+            const int tp = t - 1;
+            const int nt = tp + kStages;
+            if (nt < n_tiles) {
+                const int sp = tp % kStages;
+                gk_mbar_wait(&empty[sp], (tp / kStages) & 1);
+                issue(nt, sp);
+            }
+        }
+        __syncwarp();
+        gk_mbar_wait(&full[s], (t / kStages) & 1);
+
+        const __half* p = reinterpret_cast<const __half*>(smem_bytes + (size_t)s * kStageBytes);
+        const __half2* l = reinterpret_cast<const __half2*>(smem_bytes + (size_t)s * kStageBytes + KW * kBytesPBlk);
+#pragma unroll 4
+        for (int r = 0; r < GK_RT; ++r) {
+            __half2 pv[G];
+            __half2 lv[TA];
+#pragma unroll
+            for (int g = 0; g < G; ++g) pv[g] = *reinterpret_cast<const __half2*>(p + p_off(g) + r * GK_KB);
+            if constexpr (ModeInfo<AM>::kVec) {
+                const uint4 x = *reinterpret_cast<const uint4*>(l + l_off(ta * 4) + r * AT);
+                lv[0] = *reinterpret_cast<const __half2*>(&x.x);
+                lv[1] = *reinterpret_cast<const __half2*>(&x.y);
+                lv[2] = *reinterpret_cast<const __half2*>(&x.z);
+                lv[3] = *reinterpret_cast<const __half2*>(&x.w);
+                if constexpr (TA == 8) {
+                    const uint4 y = *reinterpret_cast<const uint4*>(l + l_off(64 + ta * 4) + r * AT);
+                    lv[4] = *reinterpret_cast<const __half2*>(&y.x);
+                    lv[5] = *reinterpret_cast<const __half2*>(&y.y);
+                    lv[6] = *reinterpret_cast<const __half2*>(&y.z);
+                    lv[7] = *reinterpret_cast<const __half2*>(&y.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TA; ++j) lv[j] = l[l_off(j * 16 + ta) + r * AT];
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int j = 0; j < TA; ++j) acc2[g][j] = __hadd2(acc2[g][j], __habs2(__hsub2(pv[g], lv[j])));
+        }
+        if (++since_flush >= flush) {
+            flush_acc();
+            since_flush = 0;
+        }
+        __syncwarp();
+        if (lane == 0) gk_mbar_arrive(&empty[s]);
+    }
+    flush_acc();
+
+    uint32_t* S = S_pool + X.S_off;
+    const int k_base = item.k_blk * GK_KB;
+    const int a_base = item.a_blk * AT;
+#pragma unroll
+    for (int i = 0; i < 2 * G; ++i) {
+        const int k = k_base + 32 * (i / 2) + 2 * tk + (i & 1);
+#pragma unroll
+        for (int j = 0; j < TA; ++j) {
+            const uint32_t v = (uint32_t)acc[i][j];
+            if (v) atomicAdd(S + (int64_t)k * X.s_stride + a_base + a_of(j), v);
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void score_dispatch_h(int am, const GkScoreItem& item, const GkMatrix& M,
+                                                 const GkSearch& X, const float* __restrict__ L_pool,
+                                                 const __half* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
+                                                 unsigned char* smem, uint64_t* full, uint64_t* empty, int flush) {
+    switch (am) {
+        case F8: score_item_h<G, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case F4: score_item_h<G, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case S1: score_item_h<G, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case S2: score_item_h<G, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        default: score_item_h<G, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+gk_score_half_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
+                     const GkScoreItem* __restrict__ items, const float* __restrict__ L_pool,
+                     const __half* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + kStages;
+    unsigned char* smem = smem_raw + 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            gk_mbar_init(&full[s], 1);
+            gk_mbar_init(&empty[s], kWarps);
+        }
+        gk_fence_barrier_init();
+    }
+    __syncthreads();
+
+    const GkScoreItem item = items[blockIdx.x];
+    const GkSearch X = searches[item.search];
+    const GkMatrix M = matrices[X.matrix];
+    const int g = (item.shape & 0xff) - 4;    // row mode 5..8 = 1..4 groups of 32 kept sets
+    const int am = (item.shape >> 8) & 0xff;
+    switch (g) {
+        case 1: score_dispatch_h<1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case 2: score_dispatch_h<2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case 3: score_dispatch_h<3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        default: score_dispatch_h<4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+    }
+}
+
 template <int KM>
 __device__ __forceinline__ void score_dispatch_a(int am, const GkScoreItem& item, const GkMatrix& M,
                                                  const GkSearch& X, const float* __restrict__ L_pool,
@@ -226,15 +425,28 @@ constexpr int kSmemBytes = 128 + kStages * GK_RT * (2 * GK_KB + 128) * (int)size
 }  // namespace
 
 extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items,
-                        int n_items, const float* L_pool, const float* P_pool, uint32_t* S_pool,
-                        void* stream) {
+                        int n_items, const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode,
+                        int flush_stages, void* stream) {
     if (n_items <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (half_mode) {
+        GK_REQUIRE(flush_stages >= 1, "gk_score: flush interval %d must be >= 1 stage", flush_stages);
+        cudaError_t err = cudaFuncSetAttribute(gk_score_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kSmemBytes);
+        GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemBytes,
+                   cudaGetErrorString(err));
+        gk_score_half_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
+                                                                    reinterpret_cast<const __half*>(P_pool), S_pool,
+                                                                    flush_stages);
+        GK_CHECK_LAUNCH("gk_score (half)");
+        return 0;
+    }
     cudaError_t err =
         cudaFuncSetAttribute(gk_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemBytes,
                cudaGetErrorString(err));
-    gk_score_kernel<<<n_items, kThreads, kSmemBytes, (cudaStream_t)stream>>>(matrices, searches, items, L_pool,
-                                                                              P_pool, S_pool);
+    gk_score_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
+                                                           reinterpret_cast<const float*>(P_pool), S_pool);
     GK_CHECK_LAUNCH("gk_score");
     return 0;
 }

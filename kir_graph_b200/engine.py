@@ -32,6 +32,7 @@ SCORE_READ_CHUNK = 8192     # reads per scoring work item: 8192 * 255 < 2^24 kee
 COUNT_READ_CHUNK = 16384    # reads per rescoring work item
 P_READ_CHUNK = 2048         # reads per P-writing work item (multiple of 128)
 MAX_TOP_N = 2048
+HALF_MAX_COUNT = 128      # largest mismatch count the packed-half scoring path handles exactly
 MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
 
 
@@ -61,7 +62,7 @@ class CudaBackend:
 
     # --- memory ---------------------------------------------------------------
     _NP2T = {"uint8": "uint8", "int32": "int32", "uint32": "int32", "float32": "float32",
-             "int64": "int64", "uint64": "int64", "float64": "float64"}
+             "int64": "int64", "uint64": "int64", "float64": "float64", "float16": "float16"}
 
     def _tdtype(self, dtype):
         return getattr(self.torch, self._NP2T[np.dtype(dtype).name])
@@ -174,6 +175,7 @@ class HostBatch:
         self.ent_word = cat([p.ent_word for p in packs], np.int32)
         self.ent_pos = cat([p.ent_pos for p in packs], np.uint32)
         self.ent_neg = cat([p.ent_neg for p in packs], np.uint32)
+        self.k_max = int(max((int(p.k_obs.max()) for p in packs if p.n_reads), default=0))
         self.k_total = np.array([int(np.where(p.k_obs == 0, 1, p.k_obs).astype(np.int64).sum()) for p in packs],
                                 dtype=np.int64)
         self.L_size, self.LT_size, self.col_size = int(L_off), int(LT_off), int(col_off)
@@ -192,10 +194,18 @@ class HostBatch:
 class MatrixBatch:
     """Likelihood data of a batch of gene problems, resident on one GPU."""
 
-    def __init__(self, packs, backend=None, run: bool = True):
+    def __init__(self, packs, backend=None, run: bool = True, half: bool | None = None):
+        """``half``: use the packed-half scoring path (two cells per instruction).  It is exact
+        while every mismatch count is <= 128, i.e. no read pair of the batch has more than 128
+        variant observations; ``None`` selects it automatically, ``False`` forces FP32."""
         self.be = backend if backend is not None else CudaBackend()
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
+        if half and host.k_max > HALF_MAX_COUNT:
+            raise ValueError(f"packed-half scoring needs <= {HALF_MAX_COUNT} observations per read pair")
+        self.half = (host.k_max <= HALF_MAX_COUNT) if half is None else bool(half)
+        # stages of 16 reads a half accumulator may absorb before it is flushed to float32
+        self.flush_stages = max(1, min(16, 2048 // (_cabi.GK_RT * max(host.k_max, 1))))
         self.packs = host.packs
         self.table = host.table
         self.max_alleles = int(host.table["n_alleles"].max()) if len(host.table) else 0
@@ -239,7 +249,7 @@ class MatrixBatch:
         self.be.zero_(self.d_col)
         self.be.launch("gk_likelihood", self.d_table, self.d_lik_items, self.n_lik_items, self.d_mem,
                        self.d_entoff, self.d_ent_word, self.d_ent_pos, self.d_ent_neg, self.d_L, self.d_LT,
-                       self.d_col, work=float(self.n_cells))
+                       self.d_col, int(self.half), work=float(self.n_cells))
         self._colsum_host = None
 
     # --- read-backs ------------------------------------------------------------
@@ -265,6 +275,10 @@ class MatrixBatch:
         o, a, rp, r = int(t["L_off"]), int(t["n_alleles"]), int(t["r_pad"]), int(t["n_reads"])
         tile, nb = int(t["a_tile"]), int(t["n_ablk"])
         flat = self.be.download(self.d_L[o:o + nb * rp * tile], np.float32)
+        if self.half:
+            pair = flat.view(np.float16).reshape(-1, 2)
+            assert np.array_equal(pair[:, 0], pair[:, 1])
+            flat = pair[:, 0].astype(np.float32)
         return flat.reshape(nb, rp, tile).transpose(1, 0, 2).reshape(rp, nb * tile)[:r, :a]
 
 
@@ -504,9 +518,11 @@ class SearchGroup:
         self._step_cells = int((kept[live] * self.n_cand[live] * self.R[live]).sum())
         if not len(live):
             return np.zeros(0, dtype=SCORE_ITEM_DTYPE)
+        half = self.batch.half
         k16 = -(-kept[live] // 16)
+        k32 = -(-kept[live] // 32)
         a16 = -(-self.A[live] // 16)
-        n_kt = _tile_counts(k16)
+        n_kt = -(-k32 // 4) if half else _tile_counts(k16)
         n_at = _tile_counts(a16)
         r16 = _round_up_arr(self.R[live], _cabi.GK_RT)
         custom = {}
@@ -526,7 +542,11 @@ class SearchGroup:
         search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
         items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
         items["search"] = live[search]
-        k_blk, k_mode = _tile_decode(k16[search], ikt, 2)
+        if half:                                   # tiles of 1..4 groups of 32 kept sets
+            k_blk = 2 * ikt
+            k_mode = 4 + np.minimum(4, k32[search] - 4 * ikt)
+        else:
+            k_blk, k_mode = _tile_decode(k16[search], ikt, 2)
         a_blk, a_mode = _tile_decode(a16[search], iat, 4)
         for j, tiles in custom.items():
             sel = np.flatnonzero(search == j)
@@ -538,10 +558,25 @@ class SearchGroup:
         items["r0"] = ich * chunk
         items["r1"] = np.minimum((ich + 1) * chunk, r16[search])
         items["shape"] = k_mode | (a_mode << 8)
-        span = np.array([128, 64, 16, 32, 48], dtype=np.int64)
+        span = np.array([128, 64, 16, 32, 48, 32, 64, 96, 128], dtype=np.int64)
         if self.col_shard is not None and self.col_shard[1] > 1:
             rank, world = self.col_shard
-            mine = (iat % world) == rank                 # column tiles dealt round-robin to the ranks
+            # column tiles go to the least-loaded rank, widest first (deterministic on every rank)
+            owner = np.zeros(len(search), dtype=np.int64)
+            for j in range(len(live)):
+                sel = np.flatnonzero(search == j)
+                if not len(sel):
+                    continue
+                tiles = np.unique(iat[sel])
+                width = {int(t): int(span[a_mode[sel][iat[sel] == t][0]]) for t in tiles}
+                load = [0] * world
+                assign = {}
+                for t in sorted(width, key=lambda t: (-width[t], t)):
+                    r = min(range(world), key=lambda q: (load[q], q))
+                    assign[t] = r
+                    load[r] += width[t]
+                owner[sel] = np.array([assign[int(t)] for t in iat[sel]])
+            mine = owner == rank
             k0 = k_blk * GK_KB
             a0 = a_blk * 32
             rows = np.minimum(span[k_mode], kept[live][search] - k0)
@@ -589,10 +624,10 @@ class SearchGroup:
         if not len(items):
             return
         if self.d_P is None:
-            self.d_P = self.be.empty(self._p_size, np.float32)
+            self.d_P = self.be.empty(self._p_size, np.float16 if self.batch.half else np.float32)
         d_items = self.be.upload(items)
         self.be.launch("gk_write_p", self.batch.d_table, self.d_tab, d_items, len(items), self.top_n, n_set,
-                       self.d_kept, self.d_ids[self.cur], self.batch.d_LT, self.d_P,
+                       self.d_kept, self.d_ids[self.cur], self.batch.d_LT, self.d_P, int(self.batch.half),
                        work=float((items["r1"] - items["r0"]).sum()) * GK_KB)
 
     def _collect(self, rows: np.ndarray, n: int, info: np.ndarray) -> StepBatch:
@@ -641,7 +676,7 @@ class SearchGroup:
             be.zero_(self.d_S)
             d_items = be.upload(items)
             be.launch("gk_score", bt.d_table, self.d_tab, d_items, len(items), bt.d_L, self.d_P, self.d_S,
-                      work=float(self._step_cells))
+                      int(bt.half), int(bt.flush_stages), work=float(self._step_cells))
             self.score_cells += self._step_cells
             if self.reduce_scores is not None:
                 self.reduce_scores(self.d_S)             # sum of the per-rank column slices
@@ -719,10 +754,11 @@ class SearchGroup:
         items["r0"] = rr.reshape(-1)
         items["r1"] = np.minimum(rr.reshape(-1) + P_READ_CHUNK, r_pad)
         d_items = be.upload(items)
-        d_P = be.empty(n_kblk * r_pad * GK_KB, np.float32)
+        p_dtype = np.float16 if bt.half else np.float32
+        d_P = be.empty(n_kblk * r_pad * GK_KB, p_dtype)
         be.launch("gk_write_p", bt.d_table, d_tab, d_items, len(items), self.top_n, n, d_kept, d_ids,
-                  bt.d_LT, d_P)
-        p = be.download(d_P, np.float32).reshape(n_kblk, r_pad, GK_KB)
+                  bt.d_LT, d_P, int(bt.half))
+        p = be.download(d_P, p_dtype).reshape(n_kblk, r_pad, GK_KB)
         return p.transpose(1, 0, 2).reshape(r_pad, n_kblk * GK_KB)[:r, :k].astype(np.int64)
 
 

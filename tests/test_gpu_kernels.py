@@ -43,10 +43,11 @@ def _compare_outputs(a, b):
     ([(70, 3, 1500), (33, 2, 90)], 300, [3, 2]),
     ([(40, 6, 500), (12, 5, 300), (90, 8, 260)], 30, [6, 5, 8]),
 ])
-def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns):
+@pytest.mark.parametrize("half", [False, True])
+def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
     packs = _packs(specs, 101)
     fake = FakeBackend()
-    bg, bf = engine.MatrixBatch(packs, backend=cuda), engine.MatrixBatch(packs, backend=fake)
+    bg, bf = engine.MatrixBatch(packs, backend=cuda, half=half), engine.MatrixBatch(packs, backend=fake, half=half)
     assert np.array_equal(cuda.download(bg.d_LT, np.uint8), bf.d_LT), "LT"
     assert np.array_equal(cuda.download(bg.d_L, np.float32), bf.d_L), "L"
     assert np.array_equal(cuda.download(bg.d_col, np.uint64), bf.d_col), "colsum"
@@ -64,7 +65,7 @@ def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns):
             assert np.array_equal(cuda.download(gg.d_S, np.uint32), gf.d_S), f"S at step {step + 1}"
         _compare_outputs(og, of)
         if need.any():
-            pg = cuda.download(gg.d_P, np.float32)
+            pg = cuda.download(gg.d_P, np.float16 if half else np.float32)
             for s in np.flatnonzero(need):
                 rp = int(gg.mt["r_pad"][s])
                 n = -(-int(gg.kept[s]) // GK_KB) * rp * GK_KB
@@ -72,11 +73,12 @@ def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns):
                 assert np.array_equal(pg[o:o + n], gf.d_P[o:o + n]), f"P of search {s}"
 
 
+@pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("a,cn,r,top_n", [(120, 3, 6000, 300), (200, 2, 12000, 300), (45, 4, 3000, 64)])
-def test_search_equals_oracle(cuda, a, cn, r, top_n):
+def test_search_equals_oracle(cuda, a, cn, r, top_n, half):
     gene = synthetic.make_gene([77, a], "KIRO*BACKBONE", a, 8 * a, cn, r)
     pack = packing.pack_synthetic(gene)
-    batch = engine.MatrixBatch([pack], backend=cuda)
+    batch = engine.MatrixBatch([pack], backend=cuda, half=half)
     m = batch.mismatch_counts(0)
     # independent m from the CSR lists by set logic
     want = np.zeros_like(m, dtype=np.int64)
@@ -218,3 +220,21 @@ def test_cohort_batch_equals_per_gene_class(cuda):
         r = t.typing(g.cn)
         assert r.selectBest() == c.alleles
         assert abs(c.value - r.value[c.best_rank]) <= 1e-9 * abs(c.value)
+
+
+def test_many_observations_per_read_take_the_fp32_path(cuda):
+    """Reads with more than 128 observations cannot use packed halves; up to 255 stay exact in FP32."""
+    gene = synthetic.make_gene([91, 0], "KIRWIDE*BACKBONE", 30, 400, 2, 1500, w=100)
+    pack = packing.pack_synthetic(gene)
+    assert pack.k_obs.max() > 128
+    batch = engine.MatrixBatch([pack], backend=cuda)
+    assert not batch.half
+    with pytest.raises(ValueError):
+        engine.MatrixBatch([pack], backend=cuda, half=True)
+    m = batch.mismatch_counts(0)
+    search = orc.IntSearch(m.astype(np.int64), pack.k_obs, top_n=40)
+    group = engine.SearchGroup(batch, [0], 40)
+    for step in range(2):
+        out = group.step(need_next=[step < 1])[0]
+        ref = search.add_candidate()
+        assert np.array_equal(out.ids, ref.allele_id) and np.array_equal(out.score, ref.score)
