@@ -194,16 +194,17 @@ class HostBatch:
 class MatrixBatch:
     """Likelihood data of a batch of gene problems, resident on one GPU."""
 
-    def __init__(self, packs, backend=None, run: bool = True, half: bool | None = None):
-        """``half``: use the packed-half scoring path (two cells per instruction).  It is exact
-        while every mismatch count is <= 128, i.e. no read pair of the batch has more than 128
-        variant observations; ``None`` selects it automatically, ``False`` forces FP32."""
+    def __init__(self, packs, backend=None, run: bool = True, half: bool = False):
+        """``half``: use the packed-half scoring path (two cells per instruction, half-size P).
+        It is exact while every mismatch count is <= 128, i.e. no read pair of the batch has more
+        than 128 variant observations.  Off by default: on B200 HADD2/HFMA2 issue at half the FP32
+        rate (profiles/r01_score_half_ncu_summary.txt), so it is not faster than the FP32 path."""
         self.be = backend if backend is not None else CudaBackend()
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
         if half and host.k_max > HALF_MAX_COUNT:
             raise ValueError(f"packed-half scoring needs <= {HALF_MAX_COUNT} observations per read pair")
-        self.half = (host.k_max <= HALF_MAX_COUNT) if half is None else bool(half)
+        self.half = bool(half)
         # stages of 16 reads a half accumulator may absorb before it is flushed to float32
         self.flush_stages = max(1, min(16, 2048 // (_cabi.GK_RT * max(host.k_max, 1))))
         self.packs = host.packs
