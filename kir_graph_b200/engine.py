@@ -31,6 +31,7 @@ from .packing import GenePack
 SCORE_READ_CHUNK = 8192     # reads per scoring work item: 8192 * 255 < 2^24 keeps float32 sums exact
 COUNT_READ_CHUNK = 16384    # reads per rescoring work item
 P_READ_CHUNK = 2048         # reads per P-writing work item (multiple of 128)
+ALIVE_SLACK = 212           # alive sets beyond top_n the rescoring grids are sized for without a read-back
 MAX_TOP_N = 2048
 HALF_MAX_COUNT = 128      # largest mismatch count the packed-half scoring path handles exactly
 MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
@@ -641,6 +642,23 @@ class SearchGroup:
         return StepBatch(n, rows, info, ids, score, cnt, flat)
 
     # --- one copy-number step ---------------------------------------------------------
+    def _rescore_and_rank(self, active_idx: np.ndarray, f_cap: np.ndarray, n: int, new: int) -> None:
+        """gk_rescore_count over the first f_cap[s] alive sets of every search, then gk_rank."""
+        be, bt = self.be, self.batch
+        self.tab["cnt_off"] = _excl_cumsum(f_cap * n * n)
+        tab = self.tab.copy()
+        tab["alive_cap"] = f_cap                 # the kernels clamp the alive count to this capacity
+        self.d_tab = be.upload(tab)
+        d_cnt = be.zeros(int((f_cap * n * n).sum()), np.uint32)
+        c_items = self._count_items(active_idx, f_cap)
+        d_citems = be.upload(c_items)
+        be.launch("gk_rescore_count", bt.d_table, self.d_tab, d_citems, len(c_items), self.top_n, n,
+                  self.d_info, self.d_ids[self.cur], self.d_cand, self.d_alive, bt.d_LT, d_cnt,
+                  work=float((f_cap * self.R).sum()) * n)
+        be.launch("gk_rank", bt.d_table, self.d_tab, self.n_search, self.top_n, n, self.d_ids[self.cur],
+                  self.d_cand, self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_score[self.cur], self.d_keys,
+                  self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
+
     def _collect_best(self, rows: np.ndarray, n: int, info: np.ndarray) -> BestBatch:
         flat = rows.astype(np.int64) * self.top_n + info["best_rank"][rows].astype(np.int64)
         ids = self.be.gather_rows(self.d_ids[self.cur], GK_MAX_CN, flat)[:, :n]
@@ -684,22 +702,20 @@ class SearchGroup:
             be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
                       self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, bt.d_col, self.d_score[self.cur],
                       self.d_flag, self.d_alive, self.d_info)
-            info = be.download(self.d_info, None).view(STEP_INFO_DTYPE)     # sync 1: alive counts
+            # Rescoring grids are sized for top_n + slack alive sets per search, so no read-back
+            # is needed between selection and ranking; a search with more alive sets (a large
+            # exact tie at the cut) makes the step fall back to exactly sized grids below.
+            f_cap = np.where(active, np.minimum(self.tab["alive_cap"], self.top_n + ALIVE_SLACK), 0).astype(np.int64)
+            self._rescore_and_rank(active_idx, f_cap, n, new)
+            info = be.download(self.d_info, None).view(STEP_INFO_DTYPE).copy()   # read-back: counts, calls
             n_alive = np.minimum(info["n_alive"], self.tab["alive_cap"]).astype(np.int64)
             n_alive[~active] = 0
-            self.tab["cnt_off"] = _excl_cumsum(n_alive * n * n)
-            self.d_tab = be.upload(self.tab)
-            d_cnt = be.zeros(int((n_alive * n * n).sum()), np.uint32)
-            c_items = self._count_items(active_idx, n_alive)
-            d_citems = be.upload(c_items)
-            be.launch("gk_rescore_count", bt.d_table, self.d_tab, d_citems, len(c_items), self.top_n, n,
-                      self.d_info, self.d_ids[self.cur], self.d_cand, self.d_alive, bt.d_LT, d_cnt,
-                      work=float((n_alive * self.R).sum()) * n)
-            be.launch("gk_rank", bt.d_table, self.d_tab, ns, self.top_n, n, self.d_ids[self.cur], self.d_cand,
-                      self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_score[self.cur], self.d_keys,
-                      self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
+            if np.any(n_alive > f_cap):
+                self._rescore_and_rank(active_idx, n_alive, n, new)
+                info = None
         self.cur = new
-        info = be.download(self.d_info, None).view(STEP_INFO_DTYPE).copy()   # sync 2: kept counts
+        if n == 1 or info is None:
+            info = be.download(self.d_info, None).view(STEP_INFO_DTYPE).copy()
         self.kept[active_idx] = info["n_kept"][active_idx]
         self.n = n
         nxt = np.flatnonzero(need_next)

@@ -170,3 +170,21 @@ def test_errors_and_empty():
     res = empty.typing(2)
     assert res.isFail() and res.selectBest() == ["fail", "fail"] and empty.getReadsNum() == 0
     assert empty.probs.shape == (0,)
+
+
+def test_alive_overflow_falls_back_to_exact_grids(monkeypatch):
+    """More alive sets than the pre-sized rescoring grid (large exact tie): the step is redone exactly."""
+    monkeypatch.setattr(engine, "ALIVE_SLACK", 0)
+    gene = synthetic.make_gene([7, 9], "KIRTIE*BACKBONE", 30, 240, 3, 40)      # few reads -> many exact ties
+    reads, variants = gene.to_objects()
+    pack = packing.pack_gene(reads, variants, variant_correction=True)
+    m, k, search = oracle_for_pack(pack, reads, variants, 8)
+    be = FakeBackend()
+    group = engine.SearchGroup(engine.MatrixBatch([pack], backend=be), [0], 8)
+    seen_overflow = False
+    for step in range(3):
+        before = be.log.count("gk_rank")
+        out = group.step(need_next=[step < 2])[0]
+        seen_overflow |= be.log.count("gk_rank") - before == 2
+        check_steps(out, search.add_candidate())
+    assert seen_overflow
