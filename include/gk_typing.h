@@ -118,6 +118,7 @@ int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_sear
  *     gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]). */
 int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,
              const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode, int flush_stages,
+             const int32_t* kept_count /* optional: skip tiles whose first row is >= kept_count[search] */,
              void* stream);
 
 /* (c) segmented selection, part 1: canonical-key dedup (uniqueAllele, :456-476, :551-563),

@@ -145,6 +145,7 @@ class BatchTyper:
         self.score_cells = 0
         self.homo = np.zeros(len(packs), dtype=bool)
         self._homo_cache: np.ndarray | None = None
+        self.pipelined = True        # enqueue all steps up front (one read-back); False = read back per step
 
     def upload(self) -> None:
         """Host pools -> device (the end-to-end path times this; the resident path does it once)."""
@@ -181,23 +182,35 @@ class BatchTyper:
         score = np.zeros(n_live, dtype=np.int64)
         flags = np.zeros(n_live, dtype=np.int64)
         called = np.full((n_live, max(int(cn_live.max(initial=1)), 1)), -1, dtype=np.int64)
-        for step in range(1, int(steps.max(initial=0)) + 1):
-            out = group.step(active=steps >= step, need_next=steps > step, collect=steps == step,
-                             best_only=True)
-            rows = out.searches
-            if not len(rows):
-                continue
-            n = out.n
-            kept = out.info["n_kept"][rows].astype(np.int64)
-            best[rows] = np.where(homo_live[rows], 0, out.info["best_rank"][rows])
-            score[rows] = out.score
-            flags[rows] = out.info["tie_flags"][rows]
-            ids = out.ids.astype(np.int64)
+        piped = group.run_pipeline(steps) if (self.pipelined and self.col_shard is None) else None
+        if piped is not None:
+            ids, score, info = piped
+            kept = info["n_kept"].astype(np.int64)
+            best = np.where(homo_live, 0, info["best_rank"]).astype(np.int64)
+            flags = info["tie_flags"].astype(np.int64)
+            ids = ids.copy()
             ids[kept == 0] = -1
-            if n == 1:                                                       # homozygous shortcut (:423-454)
-                called[rows] = ids[:, :1]
-            else:
-                called[rows, :n] = ids
+            called[:, : ids.shape[1]] = ids
+            called[homo_live, 1:] = called[homo_live, :1]                    # homozygous shortcut (:423-454)
+        else:
+            group.reset()
+            for step in range(1, int(steps.max(initial=0)) + 1):
+                out = group.step(active=steps >= step, need_next=steps > step, collect=steps == step,
+                                 best_only=True)
+                rows = out.searches
+                if not len(rows):
+                    continue
+                n = out.n
+                kept = out.info["n_kept"][rows].astype(np.int64)
+                best[rows] = np.where(homo_live[rows], 0, out.info["best_rank"][rows])
+                score[rows] = out.score
+                flags[rows] = out.info["tie_flags"][rows]
+                ids = out.ids.astype(np.int64)
+                ids[kept == 0] = -1
+                if n == 1:                                                   # homozygous shortcut (:423-454)
+                    called[rows] = ids[:, :1]
+                else:
+                    called[rows, :n] = ids
         self.score_cells = group.score_cells
 
         where = np.full(len(self.packs), -1, dtype=np.int64)

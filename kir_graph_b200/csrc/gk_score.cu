@@ -346,7 +346,9 @@ __device__ __forceinline__ void score_dispatch_h(int am, const GkScoreItem& item
 __global__ void __launch_bounds__(kThreads, 2)
 gk_score_half_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                      const GkScoreItem* __restrict__ items, const float* __restrict__ L_pool,
-                     const __half* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush) {
+                     const __half* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush,
+                     const int32_t* __restrict__ kept_count) {
+    if (kept_count != nullptr && items[blockIdx.x].k_blk * GK_KB >= kept_count[items[blockIdx.x].search]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kStages;
@@ -391,7 +393,10 @@ __device__ __forceinline__ void score_dispatch_a(int am, const GkScoreItem& item
 __global__ void __launch_bounds__(kThreads, 2)
 gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                 const GkScoreItem* __restrict__ items, const float* __restrict__ L_pool,
-                const float* __restrict__ P_pool, uint32_t* __restrict__ S_pool) {
+                const float* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
+                const int32_t* __restrict__ kept_count) {
+    // items may have been sized from an upper bound of the kept-set count (no host round trip)
+    if (kept_count != nullptr && items[blockIdx.x].k_blk * GK_KB >= kept_count[items[blockIdx.x].search]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kStages;
@@ -426,7 +431,7 @@ constexpr int kSmemBytes = 128 + kStages * GK_RT * (2 * GK_KB + 128) * (int)size
 
 extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items,
                         int n_items, const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode,
-                        int flush_stages, void* stream) {
+                        int flush_stages, const int32_t* kept_count, void* stream) {
     if (n_items <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (half_mode) {
@@ -437,7 +442,7 @@ extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, cons
                    cudaGetErrorString(err));
         gk_score_half_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
                                                                     reinterpret_cast<const __half*>(P_pool), S_pool,
-                                                                    flush_stages);
+                                                                    flush_stages, kept_count);
         GK_CHECK_LAUNCH("gk_score (half)");
         return 0;
     }
@@ -446,7 +451,7 @@ extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, cons
     GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemBytes,
                cudaGetErrorString(err));
     gk_score_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
-                                                           reinterpret_cast<const float*>(P_pool), S_pool);
+                                                           reinterpret_cast<const float*>(P_pool), S_pool, kept_count);
     GK_CHECK_LAUNCH("gk_score");
     return 0;
 }

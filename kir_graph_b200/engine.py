@@ -112,6 +112,18 @@ class CudaBackend:
         self.d2h_bytes += out.nbytes
         return out
 
+    def snapshot(self, tensor):
+        """Device-side copy (asynchronous on the current stream)."""
+        return tensor.clone()
+
+    def gather_best_device(self, ids, score, info, rows: np.ndarray, top_n: int):
+        """(ids row, score) of rank ``info.best_rank`` for each search in ``rows``; result stays on
+        the device (no synchronisation)."""
+        idx = self.torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device, non_blocking=True)
+        best = info.view(-1, STEP_INFO_DTYPE.itemsize // 4)[:, 6].index_select(0, idx).to(self.torch.int64)
+        flat = idx * top_n + best
+        return ids.view(-1, GK_MAX_CN).index_select(0, flat), score.index_select(0, flat)
+
     def pin(self, array: np.ndarray) -> np.ndarray:
         """Copy a host array into page-locked memory (for timed host->device copies)."""
         flat = np.ascontiguousarray(array).reshape(-1)
@@ -695,7 +707,7 @@ class SearchGroup:
             be.zero_(self.d_S)
             d_items = be.upload(items)
             be.launch("gk_score", bt.d_table, self.d_tab, d_items, len(items), bt.d_L, self.d_P, self.d_S,
-                      int(bt.half), int(bt.flush_stages), work=float(self._step_cells))
+                      int(bt.half), int(bt.flush_stages), None, work=float(self._step_cells))
             self.score_cells += self._step_cells
             if self.reduce_scores is not None:
                 self.reduce_scores(self.d_S)             # sum of the per-rank column slices
@@ -724,6 +736,91 @@ class SearchGroup:
         if best_only:
             return self._collect_best(np.flatnonzero(collect), n, info)
         return self._collect(np.flatnonzero(collect), n, info)
+
+    def run_pipeline(self, steps: np.ndarray):
+        """All copy-number steps of all searches with no host round trip in between.
+
+        ``steps[s]`` is the number of steps of search ``s`` (all alleles are candidates).  Grids
+        are sized from upper bounds of the kept-set counts (``min(top_n, K * A)``; tiles beyond
+        the real count exit at once) and from ``top_n + ALIVE_SLACK`` alive sets, so the host
+        enqueues every launch up front and reads back once at the end.  Returns
+        ``(ids [S, max_step], score [S], info per finishing step [S])`` of the set picked by
+        selectBest for every search, or ``None`` when a search had more alive sets than the
+        pre-sized grids (exact tie at a cut larger than the slack): the caller then repeats the
+        run step by step."""
+        be, bt, ns = self.be, self.batch, self.n_search
+        steps = np.asarray(steps, dtype=np.int64)
+        self.reset()
+        max_step = int(steps.max(initial=0))
+        if max_step > GK_MAX_CN:
+            raise ValueError(f"copy number above {GK_MAX_CN} is not supported by the search kernels")
+        k_ub = np.zeros(ns, dtype=np.int64)
+        snaps, finals, f_caps, actives = [], [], [], []
+        for n in range(1, max_step + 1):
+            active = steps >= n
+            active_idx = np.flatnonzero(active)
+            self.tab["n_cand"] = np.where(active, self.n_cand, 0)
+            self.d_tab = be.upload(self.tab)
+            new = 1 - self.cur
+            if n == 1:
+                be.launch("gk_first_step", bt.d_table, self.d_tab, ns, self.top_n, bt.d_col, self.d_cand,
+                          self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info,
+                          self.d_kept)
+                k_ub = np.minimum(self.top_n, self.n_cand)
+                f_cap = np.zeros(ns, dtype=np.int64)
+            else:
+                self.kept = np.where(active, k_ub, 0).astype(np.int32)        # upper bounds size the grids
+                items = self._score_items(active_idx)
+                be.zero_(self.d_S)
+                d_items = be.upload(items)
+                be.launch("gk_score", bt.d_table, self.d_tab, d_items, len(items), bt.d_L, self.d_P, self.d_S,
+                          int(bt.half), int(bt.flush_stages), self.d_kept, work=float(self._step_cells))
+                if self.reduce_scores is not None:
+                    self.reduce_scores(self.d_S)
+                be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
+                          self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, bt.d_col,
+                          self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info)
+                f_cap = np.where(active, np.minimum(self.tab["alive_cap"], self.top_n + ALIVE_SLACK), 0).astype(np.int64)
+                self._rescore_and_rank(active_idx, f_cap, n, new)
+                k_ub = np.minimum(self.top_n, k_ub * self.n_cand)
+            self.cur = new
+            self.n = n
+            snaps.append(be.snapshot(self.d_info))
+            f_caps.append(f_cap)
+            actives.append(active)
+            done = np.flatnonzero(steps == n)
+            if len(done):
+                finals.append((n, done) + tuple(be.gather_best_device(self.d_ids[self.cur], self.d_score[self.cur],
+                                                                      self.d_info, done, self.top_n)))
+            nxt = np.flatnonzero(steps > n)
+            if len(nxt):
+                self.kept = np.where(steps > n, k_ub, 0).astype(np.int32)
+                self._write_p(nxt, n)
+        # ---- single read-back -----------------------------------------------------------
+        infos = [be.download(t, None).view(STEP_INFO_DTYPE).copy() for t in snaps]
+        cells = 0
+        for i, info in enumerate(infos):
+            n = i + 1
+            if n >= 2:
+                alive = np.where(actives[i], np.minimum(info["n_alive"], self.tab["alive_cap"]), 0)
+                if np.any(alive > f_caps[i]):
+                    return None
+                prev_kept = infos[i - 1]["n_kept"].astype(np.int64)
+                if self.col_shard is None or self.col_shard[1] == 1:
+                    cells += int((np.where(actives[i], prev_kept, 0) * self.n_cand * self.R).sum())
+                else:
+                    cells += -1                                # sharded: use the per-step item accounting instead
+        self.score_cells = cells
+        out_ids = np.full((ns, max(max_step, 1)), -1, dtype=np.int64)
+        out_score = np.zeros(ns, dtype=np.int64)
+        out_info = np.zeros(ns, dtype=STEP_INFO_DTYPE)
+        for n, done, d_ids, d_score in finals:
+            ids = be.download(d_ids, np.int32).reshape(len(done), GK_MAX_CN)[:, :n]
+            out_ids[done, :n] = ids
+            out_score[done] = be.download(d_score, np.uint32).astype(np.int64)
+            out_info[done] = infos[n - 1][done]
+        self.kept = infos[-1]["n_kept"].astype(np.int32) if infos else self.kept
+        return out_ids, out_score, out_info
 
     def restore(self, s: int, ids: np.ndarray, p_colsum: np.ndarray) -> None:
         """Re-seed search ``s`` with kept sets ``ids`` [K, n] and their sum_r P[r, k]

@@ -71,6 +71,15 @@ class FakeBackend:
     def pin(self, array):
         return np.ascontiguousarray(array).reshape(-1)
 
+    def snapshot(self, tensor):
+        return tensor.copy()
+
+    def gather_best_device(self, ids, score, info, rows, top_n):
+        """(ids row, score) of rank info.best_rank for each search in ``rows``; stays on the 'device'."""
+        best = info.view(STEP_INFO_DTYPE)["best_rank"][rows].astype(np.int64)
+        flat = np.asarray(rows, dtype=np.int64) * top_n + best
+        return ids.reshape(-1, GK_MAX_CN)[flat].copy(), score[flat].copy()
+
     def launch(self, name, *args, work=0.0):
         self.launches += 1
         self.log.append(name)
@@ -161,11 +170,13 @@ class FakeBackend:
     # --- kernel (b) ---------------------------------------------------------------------
     MODE_SPAN = {0: 128, 1: 64, 2: 16, 3: 32, 4: 48, 5: 32, 6: 64, 7: 96, 8: 128}   # F8 F4 S1 S2 S3 | half G1..G4
 
-    def gk_score(self, table, stab, items, n_items, L, P, S, half_mode, flush_stages):
+    def gk_score(self, table, stab, items, n_items, L, P, S, half_mode, flush_stages, kept_count):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         items = items.view(SCORE_ITEM_DTYPE)[:n_items]
         for it in items:
+            if kept_count is not None and int(it["k_blk"]) * GK_KB >= int(kept_count[it["search"]]):
+                continue
             X = stab[it["search"]]
             M = table[X["matrix"]]
             rp, tile = int(M["r_pad"]), int(M["a_tile"])

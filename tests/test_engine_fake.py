@@ -188,3 +188,24 @@ def test_alive_overflow_falls_back_to_exact_grids(monkeypatch):
         seen_overflow |= be.log.count("gk_rank") - before == 2
         check_steps(out, search.add_candidate())
     assert seen_overflow
+
+
+def test_pipelined_batch_equals_stepwise_and_falls_back(monkeypatch):
+    from kir_graph_b200 import cohort
+    genes = synthetic.make_wgs30x_sample(seed=12, total_reads=2500)
+    packs = [packing.pack_synthetic(g) for g in genes]
+    cns = [g.cn for g in genes]
+    ref = cohort.BatchTyper(packs, cns, top_n=25, backend=FakeBackend())
+    ref.pipelined = False
+    want = ref.run()
+    fast = cohort.BatchTyper(packs, cns, top_n=25, backend=FakeBackend())
+    got = fast.run()
+    assert [(c.alleles, c.score, c.best_rank, c.tie_flags) for c in got] == \
+           [(c.alleles, c.score, c.best_rank, c.tie_flags) for c in want]
+    assert fast.score_cells == ref.score_cells
+    # a pre-sized grid that is too small is detected at the single read-back and the run is redone stepwise
+    monkeypatch.setattr(engine, "ALIVE_SLACK", 0)
+    be = FakeBackend()
+    slow = cohort.BatchTyper(packs, cns, top_n=25, backend=be)
+    got = slow.run()
+    assert [(c.alleles, c.score) for c in got] == [(c.alleles, c.score) for c in want]
