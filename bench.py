@@ -219,10 +219,10 @@ def main():
     ap.add_argument("--deep-reads", type=int, default=2_000_000)
     ap.add_argument("--deep-alleles", type=int, default=1000)
     ap.add_argument("--deep-cn", type=int, default=6)
-    ap.add_argument("--cpu-scale", type=float, default=0.25)
+    ap.add_argument("--cpu-scale", type=float, default=0.5)
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parts", type=int, default=2, help="concurrent sub-batches (host/device overlap)")
+    ap.add_argument("--parts", type=int, default=1, help="concurrent sub-batches (host/device overlap)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
