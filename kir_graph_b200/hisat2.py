@@ -60,3 +60,326 @@ def removeMultipleMapped(reads_data: ReadsAndVariantsData) -> ReadsAndVariantsDa
         "variants": reads_data["variants"],
         "reads": [r for r in reads_data["reads"] if r.multiple == 1],
     }
+
+
+# ---------------------------------------------------------------------------
+# SAM record -> per-read variant ids.
+# Host-side text/integer logic; the subprocess wrappers (hisat2, samtools) stay in
+# the reference.  Each function cites the reference code whose behaviour it keeps.
+# ---------------------------------------------------------------------------
+import bisect
+import copy
+import re
+from typing import Iterable
+
+from .utils import logger
+
+_CIGAR_RE = re.compile(r"(\d+)(\w)")
+_MD_RE = re.compile(r"\d+|.")
+
+
+def getNH(sam_info: str) -> int:
+    """NH tag of a record, 1 when absent (reference: hisat2.py:95-100)."""
+    found = re.search(r"NH:i:(\d+)", sam_info)
+    return int(found.group(1)) if found else 1
+
+
+def readZs(cols: list[str]) -> list[tuple[int, str, str]]:
+    """``Zs:Z:43|D|hv862,19|D|hv868`` -> [(43, 'D', 'hv862'), (19, 'D', 'hv868')] (:518-527)."""
+    for col in cols:
+        if col.startswith("Zs"):
+            out = []
+            for item in col[5:].split(","):
+                gap, kind, vid = item.split("|")
+                out.append((int(gap), kind, vid))
+            return out
+    return []
+
+
+def readMd(cols: list[str]) -> list[int | str]:
+    """``MD:Z:43^G19`` -> [43, '^', 'G', 19]: numbers as int, everything else per character (:530-538)."""
+    for col in cols:
+        if col.startswith("MD"):
+            return [int(tok) if tok.isdigit() else tok for tok in _MD_RE.findall(col[5:])]
+    return []
+
+
+def filterRead(line: str, num_editdist: int = 4) -> bool:
+    """Keep properly paired records (flag & 2) whose NM tag exists and is <= num_editdist (:541-578)."""
+    fields = line.strip().split("\t")
+    if int(fields[1]) & 2 == 0:
+        return False
+    nm = None
+    for col in fields[11:]:
+        if col.startswith("NM"):
+            nm = int(col[5:])
+    return nm is not None and nm <= num_editdist
+
+
+class _RecordWalker:
+    """Walks CIGAR x MD x Zs of one record.
+
+    State (same meaning as in the reference walk, hisat2.py:342-355):
+      pos     reference position of the current CIGAR operation
+      read_i  read offset of the current CIGAR operation
+      md_i    next MD token;   md_len  reference bases of the MD match run already read but not
+              yet consumed by CIGAR (it carries across an insertion, whose bases MD does not list)
+      zs_i    next Zs entry;   zs_pos  read offset up to which Zs gaps have been consumed
+    """
+
+    def __init__(self, line: str):
+        cols = line.strip().split("\t")
+        self.backbone = cols[2]
+        self.pos = int(cols[3]) - 1
+        self.cigar = [(op, int(n)) for n, op in _CIGAR_RE.findall(cols[5])]
+        self.seq = cols[9]
+        self.zs = readZs(cols[11:])
+        self.md = readMd(cols[11:])
+        self.read_i = 0
+        self.md_i = 0
+        self.md_len = 0
+        self.zs_i = 0
+        self.zs_pos = 0
+
+    def _known_id(self, kind: str) -> str:
+        """Id of the Zs entry sitting exactly at the current read offset, else 'unknown' (:357-371)."""
+        if self.zs_i < len(self.zs):
+            gap, zs_kind, vid = self.zs[self.zs_i]
+            if zs_kind == kind and self.read_i + self.md_len == self.zs_pos + gap:
+                self.zs_pos += gap + (1 if kind == "S" else 0)
+                self.zs_i += 1
+                return vid
+        return "unknown"
+
+    def _skip_zero(self) -> None:
+        if self.md_i < len(self.md) and self.md[self.md_i] == 0:
+            self.md_i += 1
+
+    def _match(self, length: int) -> list[Variant]:
+        """An M operation: match runs split by mismatches (:373-446)."""
+        out = []
+        done = 0                      # reference bases of this operation already emitted
+        while True:
+            if self.md_len <= done and self.md_i < len(self.md) and type(self.md[self.md_i]) is int:
+                self.md_len += self.md[self.md_i]
+                self.md_i += 1
+            if self.md_len >= length:                       # the run reaches the end of the operation
+                self.md_len -= length
+                out.append(Variant(typ="match", ref=self.backbone, pos=self.pos + done, length=length - done))
+                return out
+            base = self.seq[self.read_i + self.md_len]      # mismatching read base
+            if self.md[self.md_i] == 0:
+                self.md_i += 1
+            assert str(self.md[self.md_i]) in "ACGT"
+            assert str(self.md[self.md_i]) != base
+            self.md_i += 1
+            if self.md_len > done:
+                out.append(Variant(typ="match", ref=self.backbone, pos=self.pos + done,
+                                   length=self.md_len - done))
+            out.append(Variant(typ="single", ref=self.backbone, pos=self.pos + self.md_len, length=1,
+                               val=base, id=self._known_id("S")))
+            self.md_len += 1
+            done = self.md_len
+            if self.md_len == length:
+                self.md_len = 0
+                return out
+
+    def walk(self) -> tuple[list[Variant], list[int]]:
+        segments: list[Variant] = []
+        soft_clip = [0, 0]
+        for i, (op, length) in enumerate(self.cigar):
+            self._skip_zero()
+            if op == "M":
+                segments.extend(self._match(length))
+            elif op == "I":
+                segments.append(Variant(typ="insertion", ref=self.backbone, pos=self.pos,
+                                        val=self.seq[self.read_i:self.read_i + length], length=length,
+                                        id=self._known_id("I")))
+            elif op == "D":
+                assert self.md[self.md_i] == "^"
+                self.md_i += 1
+                while (self.md_i < len(self.md) and type(self.md[self.md_i]) is not int
+                       and str(self.md[self.md_i]) in "ACGT"):
+                    self.md_i += 1
+                segments.append(Variant(typ="deletion", ref=self.backbone, pos=self.pos, val=length,
+                                        length=length, id=self._known_id("D")))
+            elif op == "S":
+                soft_clip[0 if i == 0 else 1] = length
+                self.zs_pos += length
+            elif op == "N":
+                raise NotImplementedError("Cannot typing with splicing")
+            else:
+                raise NotImplementedError
+            if op in "MND":
+                self.pos += length
+            if op in "MIS":
+                self.read_i += length
+        self._skip_zero()
+        assert self.zs_i == len(self.zs)
+        assert self.md_i == len(self.md)
+        assert self.read_i == len(self.seq)
+        return segments, soft_clip
+
+
+def recordToRawVariant(line: str) -> tuple[list[Variant], list[int]]:
+    """One SAM record -> (match / single / insertion / deletion segments with 0-based backbone
+    positions, [head soft clip, tail soft clip])  (reference: hisat2.py:279-515)."""
+    return _RecordWalker(line).walk()
+
+
+def findVariantId(variant: Variant, variants_map: dict[Variant, Variant]) -> Variant:
+    """Known variant with the same (pos, ref, typ, val), else a new ``nv<k>`` which is also added
+    to the map; match segments pass through (:581-606)."""
+    if variant in variants_map:
+        return variants_map[variant]
+    if variant.typ in ("single", "insertion", "deletion"):
+        variant.id = f"nv{Variant.novel_id}"
+        Variant.novel_id += 1
+        variants_map[variant] = variant
+        return variant
+    assert variant.typ == "match"
+    return variant
+
+
+def recordToVariants(record: str, variants_map: dict[Variant, Variant], pileup=None,
+                     ignore_softclip: bool = False) -> list[Variant]:
+    """Sorted, id-annotated segments of a record; a soft-clipped record yields nothing (:657-689)."""
+    if pileup:
+        raise NotImplementedError("pileup-based read error correction stays in the reference "
+                                  "(the CLI path passes error_correction=False, main.py:149)")
+    segments, soft_clip = recordToRawVariant(record)
+    if not ignore_softclip and sum(soft_clip) > 0:
+        return []
+    return sorted(findVariantId(v, variants_map) for v in segments)
+
+
+def getVariantsBoundary(read_variants: list[Variant], variants: list[Variant]) -> tuple[int, int]:
+    """Index window [left, right) of the sorted variant table covered by the read (:692-713)."""
+    first, last = read_variants[0], read_variants[-1]
+    lo = Variant(ref=first.ref, pos=first.pos, typ="single", val="A")
+    hi = Variant(ref=first.ref, pos=last.pos + last.length, typ="single", val="T")
+    return bisect.bisect_left(variants, lo), bisect.bisect_left(variants, hi)
+
+
+def getPNFromVariantList(read_variants: list[Variant], variants: list[Variant], exon_only: bool = False,
+                         discard_novel_index: bool = True) -> tuple[list[Variant], list[Variant]]:
+    """Positive variants = the non-match segments of the read; negative variants = every table
+    variant inside the read's window that the read does not carry (:716-800)."""
+    if not read_variants:
+        return [], []
+    left, right = getVariantsBoundary(read_variants, variants)
+    read_end = read_variants[-1].pos + read_variants[-1].length
+    assert left <= right
+    if discard_novel_index:
+        for kind in ("insertion", "deletion"):       # a novel indel is taken as a mapping error
+            if any(v.typ == kind and v.id.startswith("nv") for v in read_variants):
+                return [], []
+    excluded = set()
+    for v in read_variants:
+        if v.val == "N":                              # base masked by error correction
+            for base in "ATCG":
+                alt = copy.deepcopy(v)
+                alt.val = base
+                excluded.add(alt)
+    carried = [v for v in read_variants if v.typ != "match"]
+    positives = [v for v in carried if v.in_exon] if exon_only else carried
+    excluded.update(positives)
+    negatives = []
+    for v in variants[left:right]:
+        if v in excluded or (exon_only and not v.in_exon):
+            continue
+        if v.typ == "deletion" and v.pos + v.val + 10 >= read_end:    # ambiguous near the read end
+            continue
+        negatives.append(v)
+    return positives, negatives
+
+
+def extractVariant(pair_reads: Iterable[tuple[str, str]], variants: list[Variant], pileup=None
+                   ) -> ReadsAndVariantsData:
+    """(left record, right record) pairs -> PairRead list + variant list incl. novel ones (:803-844)."""
+    variants_map = {v: v for v in variants}
+    reads = []
+    for left_record, right_record in pair_reads:
+        lv = recordToVariants(left_record, variants_map, pileup)
+        rv = recordToVariants(right_record, variants_map, pileup)
+        lp, ln = getPNFromVariantList(lv, variants)
+        rp, rn = getPNFromVariantList(rv, variants)
+        reads.append(PairRead(
+            lpv=[v.id for v in lp if v.id is not None], lnv=[v.id for v in ln if v.id is not None],
+            rpv=[v.id for v in rp if v.id is not None], rnv=[v.id for v in rn if v.id is not None],
+            l_sam=left_record, r_sam=right_record, multiple=getNH(left_record),
+            backbone=left_record.split("\t")[2]))
+    logger.info(f"[Graph] Filterd pairs: {len(reads)}")
+    return {"variants": list(variants_map.values()), "reads": reads}
+
+
+def pairRecords(lines: Iterable[str]) -> Iterable[tuple[str, str]]:
+    """Pair up name-sorted SAM records (the body of the reference's readPair, :228-276; the
+    ``samtools sort -n`` subprocess that feeds it stays in the reference)."""
+    pending: dict[tuple[str, str, str, int], str] = {}
+    for line in lines:
+        if not line or line.startswith("@") or line.startswith("[bam_sort_core]"):
+            continue
+        name, flag_str, ref, pos, _, _, next_ref, next_pos = line.split("\t")[:8]
+        if next_ref != "=":
+            continue
+        flag = int(flag_str)
+        mate_key = (name, ref, next_pos, flag & 256)
+        if mate_key in pending:
+            mate = pending[mate_key]
+            if ((int(mate.split("\t")[1]) | flag) & 192) != 192:
+                logger.warning(f"[Graph] Read Pair strange case: {line} {mate}")
+                continue
+            del pending[mate_key]
+            yield line, mate
+        else:
+            pending[(name, ref, pos, flag & 256)] = line
+
+
+# --- index files (.snp / .link / .locus), reference: hisat2.py:121-225 -----------------------
+def readLink(index: str) -> dict[str, list[str]]:
+    out = {}
+    with open(index + ".link") as handle:
+        for line in handle:
+            vid, alleles = line.strip().split("\t")
+            out[vid] = alleles.split()
+    return out
+
+
+def readExons(index: str) -> dict[str, list[tuple[int, int]]]:
+    out = {}
+    with open(index + ".locus") as handle:
+        for line in handle:
+            gene, _, _, _, _, exons, _ = line.split("\t")
+            out[gene] = [(int(e.split("-")[0]) - 1, int(e.split("-")[1]) - 1) for e in exons.split(" ")]
+    return out
+
+
+def readVariants(index: str) -> list[Variant]:
+    out = []
+    with open(index + ".snp") as handle:
+        for line in handle:
+            vid, typ, ref, pos, val = line.strip().split("\t")
+            out.append(Variant(typ=typ, ref=ref, pos=int(pos), id=vid,
+                               val=int(val) if typ == "deletion" else val))
+    return out
+
+
+def isInExon(exons: list[tuple[int, int]], variant: Variant) -> bool:
+    for start, end in exons:
+        if start <= variant.pos < end:
+            return True
+        if variant.typ == "deletion" and variant.pos < start and variant.pos + variant.val >= start:
+            return True
+    return False
+
+
+def getVariants(index: str) -> list[Variant]:
+    """Sorted variant table of a HISAT2 index with allele lists and exon flags (:183-203)."""
+    variants = readVariants(index)
+    links = readLink(index)
+    exons = readExons(index)
+    for v in variants:
+        v.allele = links.get(v.id, [])
+        v.in_exon = isInExon(exons[v.ref], v)
+    return sorted(variants)

@@ -212,6 +212,70 @@ def main() -> None:
         "log10": {"hit": float(np.log10(0.999)), "miss": float(np.log10(0.001))},
     })
 
+    # -- SAM record walk and read-variant extraction (hisat2.py:279-844) --------------------------
+    from tests import sam_sim
+    sam_cases = []
+    for seed in (1, 2):
+        _, table, pairs = sam_sim.simulate_pairs(seed, 45)
+        rtable = [m2h.Variant(**asdict(v)) for v in table]
+        records = []
+        for l, r in pairs:
+            for rec in (l, r):
+                raw, clip = h2.recordToRawVariant(rec)
+                records.append({"raw": [[v.typ, v.pos, v.length, v.val, v.id] for v in raw], "clip": clip,
+                                "filter": bool(h2.filterRead(rec))})
+        m2h.Variant.novel_id = 0
+        data = h2.extractVariant(pairs, rtable)
+        sam_cases.append({
+            "variants": [asdict(v) for v in table], "pairs": pairs, "records": records,
+            "reads": [{"lpv": r.lpv, "lnv": r.lnv, "rpv": r.rpv, "rnv": r.rnv, "multiple": r.multiple,
+                       "backbone": r.backbone} for r in data["reads"]],
+            "variant_ids_after": [v.id for v in data["variants"]],
+        })
+    # Appendix C of SURVEY.md: hand-built records
+    g = "KIRX*BACKBONE"
+    ctab = [m2h.Variant(pos=10, typ="single", ref=g, val="T", id="hv0", allele=["a1", "a2"]),
+            m2h.Variant(pos=20, typ="single", ref=g, val="C", id="hv2", allele=["a3"]),
+            m2h.Variant(pos=20, typ="single", ref=g, val="G", id="hv1", allele=["a2"]),
+            m2h.Variant(pos=30, typ="deletion", ref=g, val=2, id="hv3", allele=["a1"]),
+            m2h.Variant(pos=45, typ="insertion", ref=g, val="AC", id="hv4", allele=["a3"]),
+            m2h.Variant(pos=120, typ="deletion", ref=g, val=3, id="hv5", allele=["a3"]),
+            m2h.Variant(pos=140, typ="single", ref=g, val="A", id="hv6", allele=["a1"])]
+    ctab = sorted(ctab)
+
+    def rec(pos, cigar, md, zs, seq, flag=99, nm=1):
+        f = ["r", str(flag), g, str(pos), "60", cigar, "=", "300", "350", seq, "I" * len(seq), f"NM:i:{nm}", f"MD:Z:{md}"]
+        if zs:
+            f.append(f"Zs:Z:{zs}")
+        f.append("NH:i:1")
+        return "\t".join(f)
+
+    kats = {
+        "k0": rec(1, "30M2D18M", "10C9C9^CC18", "10|S|hv0,9|S|hv1,9|D|hv3", "A" * 10 + "T" + "A" * 9 + "G" + "A" * 27),
+        "k1": rec(1, "60M", "60", "", "A" * 60),
+        "k3": rec(1, "40M", "15G24", "", "A" * 15 + "C" + "A" * 24),
+        "k4": rec(1, "5S35M", "35", "", "A" * 40),
+        "k5": rec(1, "40M", "10G0G28", "10|S|hv0", "A" * 10 + "TC" + "A" * 28),
+        "k6": rec(1, "12M3D28M", "12^GGG28", "", "A" * 40),
+        "k2p": rec(1, "5M2I20M", "25", "", "A" * 5 + "AC" + "A" * 20),
+        "k7": rec(101, "36M", "36", "", "A" * 36),
+        "k8": rec(101, "29M", "29", "", "A" * 29),
+        "k9": rec(22, "9M2D11M", "9^CC0G10", "9|D|hv3", "A" * 9 + "T" + "A" * 10),
+    }
+    kat_out = {}
+    for key, line in kats.items():
+        m2h.Variant.novel_id = 0
+        vmap = {v: v for v in copy.deepcopy(ctab)}
+        rv = h2.recordToVariants(line, vmap)
+        pos_v, neg_v = h2.getPNFromVariantList(rv, ctab)
+        kat_out[key] = {"line": line, "positive": [v.id for v in pos_v], "negative": [v.id for v in neg_v]}
+    flt = {"99_4": h2.filterRead(rec(1, "60M", "60", "", "A" * 60, 99, 4)),
+           "99_5": h2.filterRead(rec(1, "60M", "60", "", "A" * 60, 99, 5)),
+           "97_1": h2.filterRead(rec(1, "60M", "60", "", "A" * 60, 97, 1)),
+           "355_1": h2.filterRead(rec(1, "60M", "60", "", "A" * 60, 355, 1))}
+    dump("sam_walk", {"kind": "sam", "cases": sam_cases, "kat_table": [asdict(v) for v in ctab],
+                      "kats": kat_out, "filter": {k: bool(v) for k, v in flt.items()}})
+
     # -- whole-sample: selectKirTypingModel over a small multi-gene JSON --------
     genes = [syn.make_gene(seed=[41, i], gene=f"KIRZ{i}*BACKBONE", n_allele=a, n_var=max(64, 8 * a),
                            cn=c, n_reads=r, hierarchical=True, variant_id_base=1000 * i)

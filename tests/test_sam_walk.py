@@ -1,0 +1,66 @@
+"""SAM record -> per-read variant ids (kir_graph_b200/hisat2.py) against outputs of the reference
+(tests/golden/sam_walk.json.gz: simulated CIGAR/MD/Zs records and SURVEY.md Appendix C cases)."""
+import copy
+
+import pytest
+
+from kir_graph_b200 import hisat2
+from kir_graph_b200.msa2hisat import Variant
+from tests.helpers import load_golden
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_simulated_records_match_reference(case):
+    data = load_golden("sam_walk")["cases"][case]
+    table = [Variant(**v) for v in data["variants"]]
+    pairs = [tuple(p) for p in data["pairs"]]
+    records = [rec for pair in pairs for rec in pair]
+    for rec, want in zip(records, data["records"]):
+        raw, clip = hisat2.recordToRawVariant(rec)
+        assert [[v.typ, v.pos, v.length, v.val, v.id] for v in raw] == want["raw"]
+        assert clip == want["clip"]
+        assert hisat2.filterRead(rec) == want["filter"]
+    Variant.novel_id = 0
+    out = hisat2.extractVariant(pairs, table)
+    got = [{"lpv": r.lpv, "lnv": r.lnv, "rpv": r.rpv, "rnv": r.rnv, "multiple": r.multiple,
+            "backbone": r.backbone} for r in out["reads"]]
+    assert got == data["reads"]
+    assert [v.id for v in out["variants"]] == data["variant_ids_after"]
+    # pairing of name-sorted records
+    lines = ["@HD\tVN:1.0"]
+    for left, right in pairs:
+        lf, rf = left.split("\t"), right.split("\t")
+        lf[7], rf[7] = rf[3], lf[3]                      # PNEXT = mate position
+        lines += ["\t".join(lf), "\t".join(rf)]
+    paired = list(hisat2.pairRecords(lines))
+    assert len(paired) == len(pairs)
+    assert all(a.split("\t")[0] == b.split("\t")[0] for a, b in paired)
+
+
+def test_appendix_c_known_answers():
+    data = load_golden("sam_walk")
+    table = sorted(Variant(**v) for v in data["kat_table"])
+    for key, want in data["kats"].items():
+        Variant.novel_id = 0
+        vmap = {v: v for v in copy.deepcopy(table)}
+        rv = hisat2.recordToVariants(want["line"], vmap)
+        pos, neg = hisat2.getPNFromVariantList(rv, table)
+        assert [v.id for v in pos] == want["positive"], key
+        assert [v.id for v in neg] == want["negative"], key
+    line = data["kats"]["k1"]["line"]
+    def with_flag_nm(flag, nm):
+        f = line.split("\t"); f[1] = str(flag); f[11] = f"NM:i:{nm}"; return "\t".join(f)
+    assert hisat2.filterRead(with_flag_nm(99, 4)) is data["filter"]["99_4"] is True
+    assert hisat2.filterRead(with_flag_nm(99, 5)) is data["filter"]["99_5"] is False
+    assert hisat2.filterRead(with_flag_nm(97, 1)) is data["filter"]["97_1"] is False
+    assert hisat2.filterRead(with_flag_nm(355, 1)) is data["filter"]["355_1"] is True
+    assert hisat2.filterRead("\t".join(line.split("\t")[:11])) is False       # no NM tag
+    assert hisat2.getNH(line) == 1 and hisat2.getNH(line.replace("NH:i:1", "NH:i:3")) == 3
+
+
+def test_splicing_and_pileup_are_refused():
+    line = load_golden("sam_walk")["kats"]["k1"]["line"].replace("60M", "30M5N30M")
+    with pytest.raises(NotImplementedError):
+        hisat2.recordToRawVariant(line)
+    with pytest.raises(NotImplementedError):
+        hisat2.recordToVariants(load_golden("sam_walk")["kats"]["k1"]["line"], {}, pileup={"x": 1})
