@@ -352,7 +352,15 @@ def main():
         fp32_peak = SM_COUNT * FP32_LANES_PER_SM * sm_max * 1e6 / 1e12          # T lane-ops/s
         ms_s, work_s, n_s = kernel_stats("gk_score")
         ms_l, work_l, n_l = kernel_stats("gk_likelihood")
-        score_ops = 2.0 * work_s / (ms_s * 1e-3) / 1e12 if ms_s else 0.0        # FMNMX + FADD per cell
+        score_ops = 2.0 * work_s / (ms_s * 1e-3) / 1e12 if ms_s else 0.0        # 2 FP32 instructions per cell
+        traffic = None
+        try:                                     # DRAM bytes per launch of the same kernel from an ncu capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            entry = prof.get(args.workload, {}).get("gk_score_kernel")
+            if entry and world == 1:
+                traffic = entry["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         hbm_peak = float(peaks.get("hbm_gbs") or 6650.0)
         lik_gbs = (lik_bytes * n_l / n_parts) / (ms_l * 1e-3) / 1e9 if ms_l else 0.0
         step_ms = ms_total / args.steps
@@ -375,8 +383,8 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "kernel": "gk_score_kernel", "bound": "fp32_nontensor",
-                "achieved": score_ops, "peak": fp32_peak, "unit": "T FP32 ops/s (1 FMNMX + 1 FADD per cell)",
-                "frac": score_ops / fp32_peak if fp32_peak else None, "traffic": None,
+                "achieved": score_ops, "peak": fp32_peak, "unit": "T FP32 ops/s (2 FADD per cell: d = p - l, acc += |d|)",
+                "frac": score_ops / fp32_peak if fp32_peak else None, "traffic": traffic,
                 "cells_per_s": work_s / (ms_s * 1e-3) if ms_s else 0.0, "launches": n_s,
                 "kernel_ms_per_step": ms_s / roof_steps,
                 "share_of_step": (ms_s / roof_steps) / (ms_total / args.steps) if ms_total else None,
