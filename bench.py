@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--cpu-scale", type=float, default=0.5)
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-deep", action="store_true",
+                    help="skip the nested cfg4 deep-sample measurement of the default 1-GPU cohort run")
     ap.add_argument("--parts", type=int, default=1, help="concurrent sub-batches (host/device overlap)")
     args = ap.parse_args()
 
@@ -403,6 +405,34 @@ def main():
             "parity": {"genes_matching_generator_truth": truth_ok, "genes": len(truth)},
             "build_s": t_build,
         }
+        if world == 1 and args.workload == "cohort" and not args.no_deep:
+            # second shape of the same path: one very deep sample (cfg4), scoring kernel dominated
+            del typer
+            torch.cuda.empty_cache()
+            d_packs, d_cns, d_truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
+            deep = cohort.CohortTyper(d_packs, d_cns, top_n=args.top_n, backend=be, n_parts=1)
+            deep.upload()
+            for _ in range(2):
+                d_calls = deep.run()
+            d_steps = 3
+            d_ms = timed(deep.run, d_steps) / d_steps
+            be.timing = {}
+            deep.run_serial()
+            torch.cuda.synchronize()
+            evs = be.timing.get("gk_score", [])
+            be.timing = None
+            d_ms_s = sum(a.elapsed_time(b) for a, b, _ in evs)
+            d_work = sum(w for _, _, w in evs)
+            d_ops = 2.0 * d_work / (d_ms_s * 1e-3) / 1e12 if d_ms_s else 0.0
+            line["deep"] = {
+                "workload": f"cfg4 deep: {args.deep_reads} read pairs x {args.deep_alleles} alleles, CN {args.deep_cn}, "
+                            f"top_n={args.top_n}",
+                "value": deep.score_cells / (d_ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": d_ms,
+                "steps": d_steps, "calls_match_truth": sorted(d_calls[0].alleles) == d_truth[0],
+                "roofline": {"kernel": "gk_score_kernel", "bound": "fp32_nontensor", "achieved": d_ops,
+                             "peak": fp32_peak, "frac": d_ops / fp32_peak if fp32_peak else None,
+                             "cells_per_s": d_work / (d_ms_s * 1e-3) if d_ms_s else 0.0, "launches": len(evs)},
+            }
         if world == 1 and not args.no_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
             c_cells, c_wall, c_n = cpu_reference_step(cores, args.cpu_scale, args.top_n)

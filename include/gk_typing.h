@@ -60,7 +60,8 @@ typedef struct GkSearch {
                             = min over the members of kept set k of m[r, id]                             */
     int64_t S_off;       /* uint32 pool: S[k * s_stride + a]                                             */
     int64_t cand_off;    /* int32 pool : candidate allele ids of the current step                        */
-    int64_t flag_off;    /* uint8 pool : first-occurrence flag per flat candidate k * n_cand + j         */
+    int64_t flag_off;    /* uint32 pool: per flat candidate k * n_cand + j its min-sum score, or 0xffffffff
+                            when an earlier candidate yields the same allele set                          */
     int64_t alive_off;   /* int32 pool : flat candidates that can still reach the final top_n            */
     int64_t cnt_off;     /* uint32 pool: cnt[(f * n + t) * n + (q-1)] tie-split counts per alive set     */
     int32_t matrix;      /* index into the GkMatrix table                                                */
@@ -123,11 +124,13 @@ int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreIt
 
 /* (c) segmented selection, part 1: canonical-key dedup (uniqueAllele, :456-476, :551-563),
  *     N_uniq, the cut max(top_n, N_uniq // 5) (:567) and the list of candidates that can
- *     still reach the final top_n.  One CTA per search. */
+ *     still reach the final top_n.  Dedup runs in slices of 8192 candidates (many CTAs per search),
+ *     the cut and the compaction in one CTA per search. */
 int gk_select(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n, int n_prev,
-              int max_alleles, const int32_t* kept_count, const int32_t* ids_prev, const int32_t* cand_pool,
-              const uint32_t* S_pool, const unsigned long long* col_pool, const uint32_t* score_prev,
-              uint8_t* flag_pool, int32_t* alive_pool, GkStepInfo* info, void* stream);
+              int max_alleles, int max_cand, const int32_t* kept_count, const int32_t* ids_prev,
+              const int32_t* cand_pool, const uint32_t* S_pool, const unsigned long long* col_pool,
+              const uint32_t* score_prev, uint32_t* val_pool, int32_t* alive_pool, GkStepInfo* info,
+              void* stream);
 
 /*     rescoring of the alive sets: replaces log_probs[:, ids].max(2) / np.equal / belong_norm
  *     (:569-580) with integer tie-split counts (cnt zeroed by the caller). */

@@ -415,7 +415,7 @@ class SearchGroup:
         p_size = self.n_kblk_max * self.r_pad * GK_KB
         s_stride = self.n_ablk * self.a_tile
         s_size = self.n_kblk_max * GK_KB * s_stride
-        flag_size = _round_up_arr(self.top_n * cand_cap, 16)
+        flag_size = _round_up_arr(self.top_n * cand_cap, 16)       # uint32 per flat candidate
         alive_cap = np.maximum(self.top_n, (self.top_n * cand_cap) // 5)
         tab["P_off"] = _excl_cumsum(p_size)
         tab["S_off"] = _excl_cumsum(s_size)
@@ -431,7 +431,7 @@ class SearchGroup:
         self.d_P = None
         self._p_size = int(p_size.sum())
         self.d_S = be.zeros(int(s_size.sum()), np.uint32)
-        self.d_flag = be.empty(int(flag_size.sum()), np.uint8)
+        self.d_flag = be.empty(int(flag_size.sum()), np.uint32)
         self.d_alive = be.empty(int(alive_cap.sum()), np.int32)
         self.d_keys = be.empty(3 * int(alive_cap.sum()), np.uint64)
         out_rows = ns * self.top_n
@@ -712,8 +712,8 @@ class SearchGroup:
             if self.reduce_scores is not None:
                 self.reduce_scores(self.d_S)             # sum of the per-rank column slices
             be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
-                      self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, bt.d_col, self.d_score[self.cur],
-                      self.d_flag, self.d_alive, self.d_info)
+                      int(self.cand_cap.max()), self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S,
+                      bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info)
             # Rescoring grids are sized for top_n + slack alive sets per search, so no read-back
             # is needed between selection and ranking; a search with more alive sets (a large
             # exact tie at the cut) makes the step fall back to exactly sized grids below.
@@ -778,8 +778,8 @@ class SearchGroup:
                 if self.reduce_scores is not None:
                     self.reduce_scores(self.d_S)
                 be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
-                          self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S, bt.d_col,
-                          self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info)
+                          int(self.cand_cap.max()), self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S,
+                          bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info)
                 f_cap = np.where(active, np.minimum(self.tab["alive_cap"], self.top_n + ALIVE_SLACK), 0).astype(np.int64)
                 self._rescore_and_rank(active_idx, f_cap, n, new)
                 k_ub = np.minimum(self.top_n, k_ub * self.n_cand)

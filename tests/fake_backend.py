@@ -209,8 +209,8 @@ class FakeBackend:
         d = int(S[int(X["S_off"]) + k * int(X["s_stride"]) + a])
         return (int(sprev[k]) + int(col[int(M["col_off"]) + a]) - d) // 2
 
-    def gk_select(self, table, stab, n_search, top_n, n_prev, max_alleles, kept, ids_prev, cand_pool, S,
-                  col, score_prev, flag, alive, info):
+    def gk_select(self, table, stab, n_search, top_n, n_prev, max_alleles, max_cand, kept, ids_prev, cand_pool,
+                  S, col, score_prev, flag, alive, info):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         info = info.view(STEP_INFO_DTYPE)
@@ -233,7 +233,8 @@ class FakeBackend:
                     seen[key] = i
                     uniq[i] = True
                 score[i] = self._min_sum(S, col, sprev, X, M, k, cand[j])
-            flag[X["flag_off"]: X["flag_off"] + N] = uniq
+            assert C <= max_cand and flag.dtype == np.uint32
+            flag[X["flag_off"]: X["flag_off"] + N] = np.where(uniq, score, np.uint32(0xFFFFFFFF))
             n_unique = int(uniq.sum())
             cut = max(top_n, n_unique // 5)
             us = np.flatnonzero(uniq)
