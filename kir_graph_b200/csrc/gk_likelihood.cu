@@ -26,13 +26,14 @@ constexpr int kTilePitch = GK_LIK_READS + 16;  // bytes; keeps rows 16-byte alig
 constexpr int kEntCap = 1024;                  // observation entries of the read tile staged in shared memory
 
 // Per-read work for a CTA whose allele span needs NG lane groups of 32 (uniform per CTA).
-template <int NG, bool HALF>
+// STAGED: every entry of the read tile sits in shared memory (one 128-bit load per entry); the
+// rare tile with more than kEntCap entries takes the variant that reads them from global memory.
+template <int NG, bool HALF, bool STAGED>
 __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int a_span, int e_lo,
                                           const uint32_t* __restrict__ mem, const int32_t* __restrict__ ent_word,
                                           const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
-                                          const int* s_eoff, const int* s_word, const uint32_t* s_pos,
-                                          const uint32_t* s_neg, float* __restrict__ L, int64_t blk_stride,
-                                          uint8_t* tile, unsigned int (&csum)[4]) {
+                                          const int* s_eoff, const int4* s_ent, float* __restrict__ L,
+                                          int64_t blk_stride, uint8_t* tile, unsigned int (&csum)[4]) {
     const int lane = gk_lane();
     const int warp = gk_warp();
     bool live[NG];
@@ -52,10 +53,11 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
             for (int e = e0; e < e1; ++e) {
                 int w;
                 uint32_t p, n;
-                if (e < kEntCap) {
-                    w = s_word[e];
-                    p = s_pos[e];
-                    n = s_neg[e];
+                if constexpr (STAGED) {
+                    const int4 ent = s_ent[e];
+                    w = ent.x;
+                    p = (uint32_t)ent.y;
+                    n = (uint32_t)ent.z;
                 } else {
                     w = __ldg(ent_word + e_lo + e);
                     p = __ldg(ent_pos + e_lo + e);
@@ -96,9 +98,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     __shared__ __align__(16) uint8_t tile[128 * kTilePitch];
     __shared__ unsigned int colpart[kWarps][128];
     __shared__ int s_eoff[GK_LIK_READS + 1];
-    __shared__ int s_word[kEntCap];
-    __shared__ uint32_t s_pos[kEntCap];
-    __shared__ uint32_t s_neg[kEntCap];
+    __shared__ __align__(16) int4 s_ent[kEntCap];
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
@@ -125,21 +125,25 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     __syncthreads();
     const int e_lo = s_eoff[0];
     const int e_n = s_eoff[GK_LIK_READS] - e_lo;
-    for (int i = threadIdx.x; i < e_n && i < kEntCap; i += kThreads) {
-        s_word[i] = __ldg(ent_word + e_lo + i);
-        s_pos[i] = __ldg(ent_pos + e_lo + i);
-        s_neg[i] = __ldg(ent_neg + e_lo + i);
+    const bool staged = e_n <= kEntCap;
+    if (staged) {
+        for (int i = threadIdx.x; i < e_n; i += kThreads)
+            s_ent[i] = make_int4(__ldg(ent_word + e_lo + i), (int)__ldg(ent_pos + e_lo + i),
+                                 (int)__ldg(ent_neg + e_lo + i), 0);
     }
     __syncthreads();
 
     unsigned int csum[4] = {0u, 0u, 0u, 0u};
-#define GK_LIK_CASE(NG)                                                                                      \
-    if (half_mode)                                                                                           \
-        lik_reads<NG, true>(M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_word, s_pos, \
-                            s_neg, L, blk_stride, tile, csum);                                               \
-    else                                                                                                     \
-        lik_reads<NG, false>(M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_word,       \
-                             s_pos, s_neg, L, blk_stride, tile, csum)
+#define GK_LIK_ARGS M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_ent, L, blk_stride, tile, csum
+#define GK_LIK_CASE(NG)                                              \
+    if (!staged) {                                                   \
+        if (half_mode) lik_reads<NG, true, false>(GK_LIK_ARGS);      \
+        else lik_reads<NG, false, false>(GK_LIK_ARGS);               \
+    } else if (half_mode) {                                          \
+        lik_reads<NG, true, true>(GK_LIK_ARGS);                      \
+    } else {                                                         \
+        lik_reads<NG, false, true>(GK_LIK_ARGS);                     \
+    }
     switch ((a_span + 31) / 32) {
         case 1: GK_LIK_CASE(1); break;
         case 2: GK_LIK_CASE(2); break;
@@ -147,6 +151,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
         default: GK_LIK_CASE(4); break;
     }
 #undef GK_LIK_CASE
+#undef GK_LIK_ARGS
 #pragma unroll
     for (int g = 0; g < 4; ++g) colpart[warp][lane + 32 * g] = csum[g];
     __syncthreads();

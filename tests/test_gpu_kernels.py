@@ -238,3 +238,29 @@ def test_many_observations_per_read_take_the_fp32_path(cuda):
         out = group.step(need_next=[step < 1])[0]
         ref = search.add_candidate()
         assert np.array_equal(out.ids, ref.allele_id) and np.array_equal(out.score, ref.score)
+
+
+def test_scattered_observations_overflow_the_staged_entries(cuda):
+    """Reads whose observations are scattered over the variant table produce more than 1024 entries per
+    64-read tile, which takes the likelihood kernel's unstaged path."""
+    from kir_graph_b200.hisat2 import PairRead
+    from kir_graph_b200.msa2hisat import Variant
+    rng = np.random.default_rng(3)
+    g = "KIRSCAT*BACKBONE"
+    n_var, n_allele = 3000, 45
+    variants = [Variant(pos=7 * i, typ="single", ref=g, val="ACGT"[i % 4], id=f"hv{i}",
+                        allele=[f"KIRSCAT*{a:03d}" for a in np.flatnonzero(rng.random(n_allele) < 0.3)])
+                for i in range(n_var)]
+    reads = []
+    for _ in range(300):
+        ids = [f"hv{i}" for i in rng.choice(n_var, size=48, replace=False)]
+        reads.append(PairRead(backbone=g, lpv=ids[:12], lnv=ids[12:24], rpv=ids[24:36], rnv=ids[36:]))
+    pack = packing.pack_gene(reads, variants, variant_correction=False)
+    assert pack.n_entries / pack.n_reads > 16
+    batch = engine.MatrixBatch([pack], backend=cuda)
+    by_id = {v.id: v for v in variants}
+    col = {n: i for i, n in enumerate(pack.allele_names)}
+    m, k = orc.mismatch_counts(reads, by_id, col)
+    assert np.array_equal(batch.mismatch_counts(0), m)
+    assert np.array_equal(batch.blocked_counts(0), m)
+    assert np.array_equal(batch.colsum(0), m.sum(axis=0))
