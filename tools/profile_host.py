@@ -19,12 +19,14 @@ class NullBackend(FakeBackend):
             k = np.minimum(stab["n_cand"], top_n); info["n_kept"] = k; kept[:] = k
         elif name == "gk_select":
             stab, top_n = args[1].view(SEARCH_DTYPE), args[3]
-            kept = args[6]; info = args[12].view(STEP_INFO_DTYPE)
+            kept = args[7]; info = args[15].view(STEP_INFO_DTYPE)
             info["n_alive"] = np.minimum(kept * stab["n_cand"], top_n + 20)
         elif name == "gk_rank":
-            info = args[16].view(STEP_INFO_DTYPE); kept = args[17]; top_n = args[3]
+            info = args[17].view(STEP_INFO_DTYPE); kept = args[18]; top_n = args[3]
             k = np.minimum(info["n_alive"], top_n); info["n_kept"] = k; kept[:] = k
 
+if __name__ != "__main__":
+    raise SystemExit
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 t0 = time.time()
 packs, cns, truth = bench.build_cohort(list(range(100, 100 + n)), 1.0, 8)
