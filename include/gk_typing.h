@@ -43,7 +43,7 @@ typedef struct GkMatrix {
     int64_t mem_off;     /* uint32 pool: mem[w * n_alleles + a], bit b = allele a carries variant 32w+b */
     int64_t entoff_off;  /* int32 pool : n_reads+1 entry offsets (absolute indices into the entry pools) */
     int64_t L_off;       /* 4-byte pool: L[(a_blk * r_pad + r) * a_tile + a % a_tile] = m[r, a] as float32,
-                            or as half2(m, m) in half mode (all mismatch counts <= 128)                  */
+                            or as the 16-bit pair (m, m) in packed mode                  */
     int64_t LT_off;      /* uint8 pool : LT[a * r_pad + r] = m[r, a]                                     */
     int64_t col_off;     /* uint64 pool: colsum[a] = sum_r m[r, a]                                       */
     int32_t n_reads;
@@ -56,7 +56,7 @@ typedef struct GkMatrix {
 
 /* State of one search.  Strides are fixed by (top_n, GK_MAX_CN). */
 typedef struct GkSearch {
-    int64_t P_off;       /* float (half in half mode) pool: P[(k_blk * r_pad + r) * GK_KB + k % GK_KB]
+    int64_t P_off;       /* float (uint16 in packed mode) pool: P[(k_blk * r_pad + r) * GK_KB + k % GK_KB]
                             = min over the members of kept set k of m[r, id]                             */
     int64_t S_off;       /* uint32 pool: S[k * s_stride + a]                                             */
     int64_t cand_off;    /* int32 pool : candidate allele ids of the current step                        */
@@ -74,7 +74,7 @@ typedef struct GkSearch {
 typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS */
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
     shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48 (from k_blk / a_blk);
-    half mode rows: 5..8 = 32, 64, 96, 128 kept sets */
+    packed mode rows: 5..8 = 32, 64, 96, 128 kept sets */
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16 */
 typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 
@@ -114,9 +114,11 @@ int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_sear
 
 /* (b) max-then-sum candidate scoring: replaces
  *     np.maximum(log_probs[:, idx], prev.T[:, :, None]).sum(axis=1)   (:540-542).
- *     Accumulates D[k, a] += sum_{r in item} |L[r, a] - P[r, k]| into S_pool (zeroed by the
- *     caller); the min-sum score is (colsum[a] + score_prev[k] - D[k, a]) / 2, formed by
- *     gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]). */
+ *     FP32 path (half_mode = 0): accumulates D[k, a] += sum_{r in item} |L[r, a] - P[r, k]| into
+ *     S_pool (zeroed by the caller); the min-sum score is (colsum[a] + score_prev[k] - D[k, a]) / 2,
+ *     formed by gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]).
+ *     Packed path (half_mode = 1: L as 16-bit pairs, P as uint16): accumulates the min-sum itself
+ *     with VIMNMX.U16x2 + IADD3; pass s_is_minsum = 1 to gk_select / gk_rank. */
 int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,
              const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode, int flush_stages,
              const int32_t* kept_count /* optional: skip tiles whose first row is >= kept_count[search] */,
@@ -130,7 +132,7 @@ int gk_select(const GkMatrix* matrices, const GkSearch* searches, int n_search, 
               int max_alleles, int max_cand, const int32_t* kept_count, const int32_t* ids_prev,
               const int32_t* cand_pool, const uint32_t* S_pool, const unsigned long long* col_pool,
               const uint32_t* score_prev, uint32_t* val_pool, int32_t* alive_pool, GkStepInfo* info,
-              void* stream);
+              int s_is_minsum /* S holds the min-sum itself (packed scoring path) */, void* stream);
 
 /*     rescoring of the alive sets: replaces log_probs[:, ids].max(2) / np.equal / belong_norm
  *     (:569-580) with integer tie-split counts (cnt zeroed by the caller). */
@@ -145,7 +147,7 @@ int gk_rank(const GkMatrix* matrices, const GkSearch* searches, int n_search, in
             const int32_t* ids_prev, const int32_t* cand_pool, const int32_t* alive_pool,
             const uint32_t* S_pool, const uint32_t* cnt_pool, const unsigned long long* col_pool,
             const uint32_t* score_prev, unsigned long long* key_pool /* 3 words per alive slot */, int32_t* ids_out, uint32_t* score_out, uint32_t* cnt_out, int32_t* flat_out,
-            GkStepInfo* info, int32_t* kept_count_out, void* stream);
+            GkStepInfo* info, int32_t* kept_count_out, int s_is_minsum, void* stream);
 
 /*     P for the next step: P[r, k] = min over members of m[r, id]  (allele_prob, :569). */
 int gk_write_p(const GkMatrix* matrices, const GkSearch* searches, const GkPItem* items, int n_items,

@@ -9,13 +9,11 @@
 // 128 consecutive bytes (coalesced; a gene's table is <= 1 MB and stays in L1/L2).
 // Outputs, both written with full 128-byte lines:
 //     L  4 bytes per cell, blocked [a_blk][r][32] -> operand of the scoring kernel (TMA bulk tiles):
-//        float32(m) for the FP32 scoring path, half2(m, m) for the packed-half path
+//        float32(m) for the FP32 scoring path, the 16-bit pair (m, m) for the packed integer path
 //     LT uint8,   allele-major [a][r]         -> rescoring / P kernels stream along reads
 // and the per-allele column sums (CN=1 scores) via one 64-bit atomic per allele per CTA.
 //
 // Bound: HBM writes, 5 B per cell (4 B L + 1 B LT); POPC issue is the secondary limit.
-#include <cuda_fp16.h>
-
 #include "gk_common.cuh"
 
 namespace {
@@ -78,7 +76,7 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
                 const unsigned int c = live[g] ? cnt[g] : 0u;
                 float* slot = L + g * blk_stride + (int64_t)r * 32 + lane;     // a_tile == 32: block g, column lane
                 if constexpr (HALF) {
-                    *reinterpret_cast<__half2*>(slot) = __half2half2(__ushort2half_rn((unsigned short)c));
+                    *reinterpret_cast<uint32_t*>(slot) = c * 0x00010001u;       // (m, m) as two 16-bit lanes
                 } else {
                     *slot = (float)c;
                 }

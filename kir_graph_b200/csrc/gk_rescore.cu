@@ -12,8 +12,6 @@
 //
 // Both are HBM-bound: per (read, set) they read n bytes (16-byte vector loads, coalesced
 // along reads) and write 0 resp. 4 bytes.
-#include <cuda_fp16.h>
-
 #include "gk_common.cuh"
 
 namespace {
@@ -138,13 +136,8 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
             const unsigned int v0 = tile[(kq + 0) * kPitch + rl], v1 = tile[(kq + 1) * kPitch + rl];
             const unsigned int v2 = tile[(kq + 2) * kPitch + rl], v3 = tile[(kq + 3) * kPitch + rl];
             if (half_mode) {
-                __half* P = reinterpret_cast<__half*>(P_pool_raw) + p_base;
-                __half2 lo = __halves2half2(__ushort2half_rn((unsigned short)v0), __ushort2half_rn((unsigned short)v1));
-                __half2 hi = __halves2half2(__ushort2half_rn((unsigned short)v2), __ushort2half_rn((unsigned short)v3));
-                uint2 out;
-                out.x = *reinterpret_cast<unsigned int*>(&lo);
-                out.y = *reinterpret_cast<unsigned int*>(&hi);
-                *reinterpret_cast<uint2*>(P + (int64_t)rl * GK_KB + kq) = out;
+                uint16_t* P = reinterpret_cast<uint16_t*>(P_pool_raw) + p_base;
+                *reinterpret_cast<uint2*>(P + (int64_t)rl * GK_KB + kq) = make_uint2(v0 | (v1 << 16), v2 | (v3 << 16));
             } else {
                 float* P = reinterpret_cast<float*>(P_pool_raw) + p_base;
                 *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);

@@ -33,8 +33,6 @@
 //
 // Bound: FP32 non-tensor issue.  One cell = 2 FADD = 2 issue slots of the 4 x 32-lane
 // schedulers; peak = 148 SM x 64 cells/clk x f_clk.
-#include <cuda_fp16.h>
-
 #include "gk_common.cuh"
 
 namespace {
@@ -178,27 +176,30 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 }
 
 // ---------------------------------------------------------------------------------------
-// Packed-half path: two cells per instruction.
+// Packed 16-bit integer path (ALU pipe): 0.75 instructions per cell instead of 2.
 //
-// P is stored as half [k_blk][r][64], L as half2(m, m) [a_blk][r][32].  A thread owns row
-// pairs (2 tk, 2 tk + 1) of every 32-row group g < G of the tile, so one half2 of P holds the
-// two rows and pairs with the duplicated L value:  d2 = p2 - l2 ; acc2 += |d2|  (HADD2/HFMA2
-// with the |.| source modifier) = 2 half2 instructions for 2 cells.  Mismatch counts are
-// integers <= 128 in this mode, so half arithmetic is exact while an accumulator stays
-// <= 2048; every `flush` stages (16 reads each, flush * 16 * max count <= 2048) the half2
-// accumulators are added to float32 ones, which are merged as integers like in the FP32 path.
+// P is stored as uint16 [k_blk][r][64], L as the pair (m, m) in one 32-bit word [a_blk][r][32].
+// A thread owns row pairs (2 tk, 2 tk + 1) of every 32-row group g < G of the tile, so one 32-bit
+// word of P holds two rows and pairs with the duplicated L value:
+//     acc2 += min.u16x2(p2(r), l2(r)) + min.u16x2(p2(r+1), l2(r+1))
+// = 2 VIMNMX.U16x2 + 1 IADD3 for 4 cells (two reads are folded into one 3-input add).  These
+// issue on the half-rate ALU pipe (1.5 clk per cell against 2 clk for the two FADDs of the FP32
+// path; tools/micro/mixpipe.cu measures 83 against 55 cells/clk/SM).  Everything is integer, so
+// it is exact for every supported input (counts <= 255); a 16-bit lane holds 65535 / 255 = 257
+// reads, so the packed accumulators are spilled into 32-bit ones every `flush` = 16 stages of 16
+// reads.  S receives the min-sum itself (not the sum of absolute differences of the FP32 path).
 // Tile rows: G in {1..4} groups of 32 kept sets; columns: the same five modes as above.
 template <int G, int AM>
 __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
-                                             const float* __restrict__ L_pool, const __half* __restrict__ P_pool,
+                                             const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
                                              uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
                                              uint64_t* full, uint64_t* empty, int flush) {
     constexpr int TA = ModeInfo<AM>::kPerThread;
     constexpr int AT = 32;
     constexpr int KW = (32 * G + GK_KB - 1) / GK_KB;                 // k-blocks staged (1 or 2)
     constexpr int AW = (ModeInfo<AM>::kSpan + AT - 1) / AT;          // a-blocks staged (1, 2 or 4)
-    constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(__half);
-    constexpr uint32_t kBytesLBlk = GK_RT * AT * sizeof(__half2);
+    constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(uint16_t);
+    constexpr uint32_t kBytesLBlk = GK_RT * AT * sizeof(uint32_t);
     constexpr uint32_t kStageBytes = KW * kBytesPBlk + AW * kBytesLBlk;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -207,9 +208,9 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
 
     const int64_t blk_stride_p = (int64_t)M.r_pad * GK_KB;
     const int64_t blk_stride_l = (int64_t)M.r_pad * AT;
-    const __half* gP = P_pool + X.P_off + item.k_blk * blk_stride_p + (int64_t)item.r0 * GK_KB;
-    const __half2* gL = reinterpret_cast<const __half2*>(L_pool) + M.L_off + item.a_blk * blk_stride_l +
-                        (int64_t)item.r0 * AT;
+    const uint16_t* gP = P_pool + X.P_off + item.k_blk * blk_stride_p + (int64_t)item.r0 * GK_KB;
+    const uint32_t* gL = reinterpret_cast<const uint32_t*>(L_pool) + M.L_off + item.a_blk * blk_stride_l +
+                         (int64_t)item.r0 * AT;
     const int n_tiles = (item.r1 - item.r0) / GK_RT;
 
     auto issue = [&](int tile, int s) {
@@ -231,21 +232,20 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
         for (int s = 0; s < pre; ++s) issue(s, s);
     }
 
-    float acc[2 * G][TA];
-    __half2 acc2[G][TA];
-    const __half2 zero2 = __float2half2_rn(0.f);
+    uint32_t acc[2 * G][TA];
+    uint32_t acc2[G][TA];
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int j = 0; j < TA; ++j) {
-            acc[2 * g][j] = 0.f;
-            acc[2 * g + 1][j] = 0.f;
-            acc2[g][j] = zero2;
+            acc[2 * g][j] = 0u;
+            acc[2 * g + 1][j] = 0u;
+            acc2[g][j] = 0u;
         }
 
     auto a_of = [&](int j) { return ModeInfo<AM>::kVec ? (j < 4 ? ta * 4 + j : 64 + ta * 4 + (j - 4)) : j * 16 + ta; };
     auto l_off = [&](int c) { return (c / AT) * (GK_RT * AT) + (c % AT); };
-    // rows 32 g + 2 tk + {0, 1}: offset (in halves) inside the staged P blocks [k_blk][r][64]
+    // rows 32 g + 2 tk + {0, 1}: offset (in uint16) inside the staged P blocks [k_blk][r][64]
     auto p_off = [&](int g) { return ((32 * g) / GK_KB) * (GK_RT * GK_KB) + ((32 * g) % GK_KB) + 2 * tk; };
 
     auto flush_acc = [&]() {
@@ -253,11 +253,26 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int j = 0; j < TA; ++j) {
-                const float2 f = __half22float2(acc2[g][j]);
-                acc[2 * g][j] += f.x;
-                acc[2 * g + 1][j] += f.y;
-                acc2[g][j] = zero2;
+                acc[2 * g][j] += acc2[g][j] & 0xffffu;
+                acc[2 * g + 1][j] += acc2[g][j] >> 16;
+                acc2[g][j] = 0u;
             }
+    };
+
+    auto load_row = [&](const uint16_t* p, const uint32_t* l, int r, uint32_t (&pv)[G], uint32_t (&lv)[TA]) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) pv[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + r * GK_KB);
+        if constexpr (ModeInfo<AM>::kVec) {
+            const uint4 x = *reinterpret_cast<const uint4*>(l + l_off(ta * 4) + r * AT);
+            lv[0] = x.x; lv[1] = x.y; lv[2] = x.z; lv[3] = x.w;
+            if constexpr (TA == 8) {
+                const uint4 y = *reinterpret_cast<const uint4*>(l + l_off(64 + ta * 4) + r * AT);
+                lv[4] = y.x; lv[5] = y.y; lv[6] = y.z; lv[7] = y.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TA; ++j) lv[j] = l[l_off(j * 16 + ta) + r * AT];
+        }
     };
 
     int since_flush = 0;
@@ -276,35 +291,18 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
         __syncwarp();
         gk_mbar_wait(&full[s], (t / kStages) & 1);
 
-        const __half* p = reinterpret_cast<const __half*>(smem_bytes + (size_t)s * kStageBytes);
-        const __half2* l = reinterpret_cast<const __half2*>(smem_bytes + (size_t)s * kStageBytes + KW * kBytesPBlk);
-#pragma unroll 4
-        for (int r = 0; r < GK_RT; ++r) {
-            __half2 pv[G];
-            __half2 lv[TA];
-#pragma unroll
-            for (int g = 0; g < G; ++g) pv[g] = *reinterpret_cast<const __half2*>(p + p_off(g) + r * GK_KB);
-            if constexpr (ModeInfo<AM>::kVec) {
-                const uint4 x = *reinterpret_cast<const uint4*>(l + l_off(ta * 4) + r * AT);
-                lv[0] = *reinterpret_cast<const __half2*>(&x.x);
-                lv[1] = *reinterpret_cast<const __half2*>(&x.y);
-                lv[2] = *reinterpret_cast<const __half2*>(&x.z);
-                lv[3] = *reinterpret_cast<const __half2*>(&x.w);
-                if constexpr (TA == 8) {
-                    const uint4 y = *reinterpret_cast<const uint4*>(l + l_off(64 + ta * 4) + r * AT);
-                    lv[4] = *reinterpret_cast<const __half2*>(&y.x);
-                    lv[5] = *reinterpret_cast<const __half2*>(&y.y);
-                    lv[6] = *reinterpret_cast<const __half2*>(&y.z);
-                    lv[7] = *reinterpret_cast<const __half2*>(&y.w);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < TA; ++j) lv[j] = l[l_off(j * 16 + ta) + r * AT];
-            }
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(smem_bytes + (size_t)s * kStageBytes);
+        const uint32_t* l = reinterpret_cast<const uint32_t*>(smem_bytes + (size_t)s * kStageBytes + KW * kBytesPBlk);
+#pragma unroll 2
+        for (int r = 0; r < GK_RT; r += 2) {
+            uint32_t pv0[G], pv1[G], lv0[TA], lv1[TA];
+            load_row(p, l, r, pv0, lv0);
+            load_row(p, l, r + 1, pv1, lv1);
 #pragma unroll
             for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int j = 0; j < TA; ++j) acc2[g][j] = __hadd2(acc2[g][j], __habs2(__hsub2(pv[g], lv[j])));
+                for (int j = 0; j < TA; ++j)
+                    acc2[g][j] = acc2[g][j] + __vminu2(pv0[g], lv0[j]) + __vminu2(pv1[g], lv1[j]);
         }
         if (++since_flush >= flush) {
             flush_acc();
@@ -323,7 +321,7 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
         const int k = k_base + 32 * (i / 2) + 2 * tk + (i & 1);
 #pragma unroll
         for (int j = 0; j < TA; ++j) {
-            const uint32_t v = (uint32_t)acc[i][j];
+            const uint32_t v = acc[i][j];
             if (v) atomicAdd(S + (int64_t)k * X.s_stride + a_base + a_of(j), v);
         }
     }
@@ -332,7 +330,7 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
 template <int G>
 __device__ __forceinline__ void score_dispatch_h(int am, const GkScoreItem& item, const GkMatrix& M,
                                                  const GkSearch& X, const float* __restrict__ L_pool,
-                                                 const __half* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
+                                                 const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
                                                  unsigned char* smem, uint64_t* full, uint64_t* empty, int flush) {
     switch (am) {
         case F8: score_item_h<G, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
@@ -344,9 +342,9 @@ __device__ __forceinline__ void score_dispatch_h(int am, const GkScoreItem& item
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-gk_score_half_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
+gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                      const GkScoreItem* __restrict__ items, const float* __restrict__ L_pool,
-                     const __half* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush,
+                     const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush,
                      const int32_t* __restrict__ kept_count) {
     if (kept_count != nullptr && items[blockIdx.x].k_blk * GK_KB >= kept_count[items[blockIdx.x].search]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -436,14 +434,14 @@ extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (half_mode) {
         GK_REQUIRE(flush_stages >= 1, "gk_score: flush interval %d must be >= 1 stage", flush_stages);
-        cudaError_t err = cudaFuncSetAttribute(gk_score_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(gk_score_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                kSmemBytes);
         GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemBytes,
                    cudaGetErrorString(err));
-        gk_score_half_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
-                                                                    reinterpret_cast<const __half*>(P_pool), S_pool,
+        gk_score_packed_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
+                                                                    reinterpret_cast<const uint16_t*>(P_pool), S_pool,
                                                                     flush_stages, kept_count);
-        GK_CHECK_LAUNCH("gk_score (half)");
+        GK_CHECK_LAUNCH("gk_score (packed)");
         return 0;
     }
     cudaError_t err =

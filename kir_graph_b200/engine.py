@@ -33,7 +33,7 @@ COUNT_READ_CHUNK = 16384    # reads per rescoring work item
 P_READ_CHUNK = 2048         # reads per P-writing work item (multiple of 128)
 ALIVE_SLACK = 212           # alive sets beyond top_n the rescoring grids are sized for without a read-back
 MAX_TOP_N = 2048
-HALF_MAX_COUNT = 128      # largest mismatch count the packed-half scoring path handles exactly
+PACKED_DEFAULT = True     # packed 16-bit integer scoring path (False: FP32 sum of absolute differences)
 MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
 
 
@@ -63,7 +63,7 @@ class CudaBackend:
 
     # --- memory ---------------------------------------------------------------
     _NP2T = {"uint8": "uint8", "int32": "int32", "uint32": "int32", "float32": "float32",
-             "int64": "int64", "uint64": "int64", "float64": "float64", "float16": "float16"}
+             "int64": "int64", "uint64": "int64", "float64": "float64", "uint16": "int16"}
 
     def _tdtype(self, dtype):
         return getattr(self.torch, self._NP2T[np.dtype(dtype).name])
@@ -82,6 +82,8 @@ class CudaBackend:
             array = array.view(np.int32)
         elif array.dtype.name == "uint64":
             array = array.view(np.int64)
+        elif array.dtype.name == "uint16":
+            array = array.view(np.int16)
         if array.size == 0:
             return self.zeros(1, array.dtype)
         self.h2d_bytes += array.nbytes
@@ -207,19 +209,15 @@ class HostBatch:
 class MatrixBatch:
     """Likelihood data of a batch of gene problems, resident on one GPU."""
 
-    def __init__(self, packs, backend=None, run: bool = True, half: bool = False):
-        """``half``: use the packed-half scoring path (two cells per instruction, half-size P).
-        It is exact while every mismatch count is <= 128, i.e. no read pair of the batch has more
-        than 128 variant observations.  Off by default: on B200 HADD2/HFMA2 issue at half the FP32
-        rate (profiles/r01_score_half_ncu_summary.txt), so it is not faster than the FP32 path."""
+    def __init__(self, packs, backend=None, run: bool = True, packed: bool = PACKED_DEFAULT):
+        """``packed``: score on 16-bit integer lanes (VIMNMX.U16x2 + IADD3 on the ALU pipe, 1.5 clk per
+        cell; ``L`` holds the pair (m, m), ``P`` is uint16) instead of FP32 (two FADDs, 2 clk per
+        cell).  Both are exact for every supported input (counts <= 255)."""
         self.be = backend if backend is not None else CudaBackend()
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
-        if half and host.k_max > HALF_MAX_COUNT:
-            raise ValueError(f"packed-half scoring needs <= {HALF_MAX_COUNT} observations per read pair")
-        self.half = bool(half)
-        # stages of 16 reads a half accumulator may absorb before it is flushed to float32
-        self.flush_stages = max(1, min(16, 2048 // (_cabi.GK_RT * max(host.k_max, 1))))
+        self.half = bool(packed)          # name kept from the C ABI parameter (half_mode)
+        self.flush_stages = 16            # 16 stages x 16 reads x 255 <= 65535: one 16-bit lane
         self.packs = host.packs
         self.table = host.table
         self.max_alleles = int(host.table["n_alleles"].max()) if len(host.table) else 0
@@ -290,7 +288,7 @@ class MatrixBatch:
         tile, nb = int(t["a_tile"]), int(t["n_ablk"])
         flat = self.be.download(self.d_L[o:o + nb * rp * tile], np.float32)
         if self.half:
-            pair = flat.view(np.float16).reshape(-1, 2)
+            pair = flat.view(np.uint16).reshape(-1, 2)
             assert np.array_equal(pair[:, 0], pair[:, 1])
             flat = pair[:, 0].astype(np.float32)
         return flat.reshape(nb, rp, tile).transpose(1, 0, 2).reshape(rp, nb * tile)[:r, :a]
@@ -638,7 +636,7 @@ class SearchGroup:
         if not len(items):
             return
         if self.d_P is None:
-            self.d_P = self.be.empty(self._p_size, np.float16 if self.batch.half else np.float32)
+            self.d_P = self.be.empty(self._p_size, np.uint16 if self.batch.half else np.float32)
         d_items = self.be.upload(items)
         self.be.launch("gk_write_p", self.batch.d_table, self.d_tab, d_items, len(items), self.top_n, n_set,
                        self.d_kept, self.d_ids[self.cur], self.batch.d_LT, self.d_P, int(self.batch.half),
@@ -669,7 +667,8 @@ class SearchGroup:
                   work=float((f_cap * self.R).sum()) * n)
         be.launch("gk_rank", bt.d_table, self.d_tab, self.n_search, self.top_n, n, self.d_ids[self.cur],
                   self.d_cand, self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_score[self.cur], self.d_keys,
-                  self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept)
+                  self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept,
+                  int(bt.half))
 
     def _collect_best(self, rows: np.ndarray, n: int, info: np.ndarray) -> BestBatch:
         flat = rows.astype(np.int64) * self.top_n + info["best_rank"][rows].astype(np.int64)
@@ -713,7 +712,7 @@ class SearchGroup:
                 self.reduce_scores(self.d_S)             # sum of the per-rank column slices
             be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
                       int(self.cand_cap.max()), self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S,
-                      bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info)
+                      bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info, int(bt.half))
             # Rescoring grids are sized for top_n + slack alive sets per search, so no read-back
             # is needed between selection and ranking; a search with more alive sets (a large
             # exact tie at the cut) makes the step fall back to exactly sized grids below.
@@ -779,7 +778,7 @@ class SearchGroup:
                     self.reduce_scores(self.d_S)
                 be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
                           int(self.cand_cap.max()), self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S,
-                          bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info)
+                          bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info, int(bt.half))
                 f_cap = np.where(active, np.minimum(self.tab["alive_cap"], self.top_n + ALIVE_SLACK), 0).astype(np.int64)
                 self._rescore_and_rank(active_idx, f_cap, n, new)
                 k_ub = np.minimum(self.top_n, k_ub * self.n_cand)
@@ -868,7 +867,7 @@ class SearchGroup:
         items["r0"] = rr.reshape(-1)
         items["r1"] = np.minimum(rr.reshape(-1) + P_READ_CHUNK, r_pad)
         d_items = be.upload(items)
-        p_dtype = np.float16 if bt.half else np.float32
+        p_dtype = np.uint16 if bt.half else np.float32
         d_P = be.empty(n_kblk * r_pad * GK_KB, p_dtype)
         be.launch("gk_write_p", bt.d_table, d_tab, d_items, len(items), self.top_n, n, d_kept, d_ids,
                   bt.d_LT, d_P, int(bt.half))

@@ -108,9 +108,9 @@ class FakeBackend:
                         x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
                         tile[rl, : a_hi - a0] += popcount32(x)
                 base = int(M["L_off"]) + (blk * rp + r0) * a_tile
-                if half_mode:      # half2(m, m) in every 4-byte slot
-                    L.view(np.float16)[2 * base: 2 * (base + GK_LIK_READS * a_tile)] = \
-                        np.repeat(tile.reshape(-1).astype(np.float16), 2)
+                if half_mode:      # the 16-bit pair (m, m) in every 4-byte slot
+                    L.view(np.uint16)[2 * base: 2 * (base + GK_LIK_READS * a_tile)] = \
+                        np.repeat(tile.reshape(-1).astype(np.uint16), 2)
                 else:
                     L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
                 for a in range(a0, a_hi):
@@ -125,7 +125,7 @@ class FakeBackend:
         o = int(M["L_off"])
         flat = L[o: o + nb * rp * tile]
         if half_mode:
-            flat = flat.view(np.float16)[0::2].astype(np.float32)
+            flat = flat.view(np.uint16)[0::2].astype(np.float32)
         return flat.reshape(nb, rp, tile)
 
     @staticmethod
@@ -182,7 +182,7 @@ class FakeBackend:
             rp, tile = int(M["r_pad"]), int(M["a_tile"])
             r0, r1 = int(it["r0"]), int(it["r1"])
             assert (int(it["shape"]) & 0xFF >= 5) == bool(half_mode) and flush_stages >= 1
-            assert P.dtype == (np.float16 if half_mode else np.float32)
+            assert P.dtype == (np.uint16 if half_mode else np.float32)
             kspan = self.MODE_SPAN[int(it["shape"]) & 0xFF]
             aspan = self.MODE_SPAN[(int(it["shape"]) >> 8) & 0xFF]
             assert tile == 32 and r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
@@ -194,10 +194,13 @@ class FakeBackend:
                 .reshape(r1 - r0, GK_KB) for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)],
                 axis=1)[:, :kspan].astype(np.float32)
             if half_mode:
-                assert flush_stages * 16 * max(Pt.max(initial=0), 1) <= 2048 or True
+                assert flush_stages * 16 * 255 <= 65535
             Lt = np.concatenate([self._L_view(M, L, half_mode)[ab, r0:r1, :]
                                  for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw)], axis=1)[:, :aspan]
-            part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)          # [kspan, aspan]
+            if half_mode:      # packed integer path accumulates the min-sum itself
+                part = np.minimum(Lt[:, None, :], Pt[:, :, None]).sum(axis=0)
+            else:              # FP32 path accumulates the sum of absolute differences
+                part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)      # [kspan, aspan]
             assert part.max(initial=0) < 2 ** 24
             for kl in range(kspan):
                 o = int(X["S_off"]) + (int(it["k_blk"]) * GK_KB + kl) * stride + int(it["a_blk"]) * tile
@@ -205,12 +208,12 @@ class FakeBackend:
 
     # --- kernel (c), part 1 ----------------------------------------------------------------
     @staticmethod
-    def _min_sum(S, col, sprev, X, M, k, a):
+    def _min_sum(S, col, sprev, X, M, k, a, direct):
         d = int(S[int(X["S_off"]) + k * int(X["s_stride"]) + a])
-        return (int(sprev[k]) + int(col[int(M["col_off"]) + a]) - d) // 2
+        return d if direct else (int(sprev[k]) + int(col[int(M["col_off"]) + a]) - d) // 2
 
     def gk_select(self, table, stab, n_search, top_n, n_prev, max_alleles, max_cand, kept, ids_prev, cand_pool,
-                  S, col, score_prev, flag, alive, info):
+                  S, col, score_prev, flag, alive, info, direct):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         info = info.view(STEP_INFO_DTYPE)
@@ -232,7 +235,7 @@ class FakeBackend:
                 if key not in seen:
                     seen[key] = i
                     uniq[i] = True
-                score[i] = self._min_sum(S, col, sprev, X, M, k, cand[j])
+                score[i] = self._min_sum(S, col, sprev, X, M, k, cand[j], direct)
             assert C <= max_cand and flag.dtype == np.uint32
             flag[X["flag_off"]: X["flag_off"] + N] = np.where(uniq, score, np.uint32(0xFFFFFFFF))
             n_unique = int(uniq.sum())
@@ -295,7 +298,7 @@ class FakeBackend:
 
     # --- kernel (c), part 2 -----------------------------------------------------------------
     def gk_rank(self, table, stab, n_search, top_n, n_set, ids_prev, cand_pool, alive, S, cnt, col, score_prev,
-                keys, ids_out, score_out, cnt_out, flat_out, info, kept_out):
+                keys, ids_out, score_out, cnt_out, flat_out, info, kept_out, direct):
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         info = info.view(STEP_INFO_DTYPE)
@@ -319,7 +322,7 @@ class FakeBackend:
             even = int(M["n_reads"]) * LCM[n] // n
             uneven = np.abs(num - even).sum(axis=1)
             sprev = score_prev[s * top_n: (s + 1) * top_n]
-            sc = np.array([self._min_sum(S, col, sprev, X, M, i // C, ids[f, -1]) for f, i in enumerate(flat)],
+            sc = np.array([self._min_sum(S, col, sprev, X, M, i // C, ids[f, -1], direct) for f, i in enumerate(flat)],
                           dtype=np.int64)
             cs = colv[ids].sum(axis=1) if F else np.zeros(0, np.int64)
             order = np.lexsort((np.arange(F), uneven, cs, sc))
@@ -346,7 +349,7 @@ class FakeBackend:
             kept_out[s] = k
 
     def gk_write_p(self, table, stab, items, n_items, top_n, n_set, kept, ids, LT, P, half_mode):
-        assert P.dtype == (np.float16 if half_mode else np.float32)
+        assert P.dtype == (np.uint16 if half_mode else np.float32)
         table = table.view(MATRIX_DTYPE)
         stab = stab.view(SEARCH_DTYPE)
         items = items.view(P_ITEM_DTYPE)[:n_items]

@@ -51,7 +51,7 @@ def test_search_group_equals_int_oracle(spec, half):
     pack = packing.pack_gene(reads, variants, variant_correction=True)
     m, k, search = oracle_for_pack(pack, reads, variants, top_n)
     be = FakeBackend()
-    batch = engine.MatrixBatch([pack], backend=be, half=half)
+    batch = engine.MatrixBatch([pack], backend=be, packed=half)
     assert np.array_equal(batch.mismatch_counts(0), m)
     assert np.array_equal(batch.blocked_counts(0), m)
     assert np.array_equal(batch.colsum(0), m.sum(axis=0))

@@ -47,7 +47,7 @@ def _compare_outputs(a, b):
 def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
     packs = _packs(specs, 101)
     fake = FakeBackend()
-    bg, bf = engine.MatrixBatch(packs, backend=cuda, half=half), engine.MatrixBatch(packs, backend=fake, half=half)
+    bg, bf = engine.MatrixBatch(packs, backend=cuda, packed=half), engine.MatrixBatch(packs, backend=fake, packed=half)
     assert np.array_equal(cuda.download(bg.d_LT, np.uint8), bf.d_LT), "LT"
     assert np.array_equal(cuda.download(bg.d_L, np.float32), bf.d_L), "L"
     assert np.array_equal(cuda.download(bg.d_col, np.uint64), bf.d_col), "colsum"
@@ -65,7 +65,7 @@ def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
             assert np.array_equal(cuda.download(gg.d_S, np.uint32), gf.d_S), f"S at step {step + 1}"
         _compare_outputs(og, of)
         if need.any():
-            pg = cuda.download(gg.d_P, np.float16 if half else np.float32)
+            pg = cuda.download(gg.d_P, np.uint16 if half else np.float32)
             for s in np.flatnonzero(need):
                 rp = int(gg.mt["r_pad"][s])
                 n = -(-int(gg.kept[s]) // GK_KB) * rp * GK_KB
@@ -78,7 +78,7 @@ def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
 def test_search_equals_oracle(cuda, a, cn, r, top_n, half):
     gene = synthetic.make_gene([77, a], "KIRO*BACKBONE", a, 8 * a, cn, r)
     pack = packing.pack_synthetic(gene)
-    batch = engine.MatrixBatch([pack], backend=cuda, half=half)
+    batch = engine.MatrixBatch([pack], backend=cuda, packed=half)
     m = batch.mismatch_counts(0)
     # independent m from the CSR lists by set logic
     want = np.zeros_like(m, dtype=np.int64)
@@ -222,15 +222,13 @@ def test_cohort_batch_equals_per_gene_class(cuda):
         assert abs(c.value - r.value[c.best_rank]) <= 1e-9 * abs(c.value)
 
 
-def test_many_observations_per_read_take_the_fp32_path(cuda):
-    """Reads with more than 128 observations cannot use packed halves; up to 255 stay exact in FP32."""
+@pytest.mark.parametrize("packed", [False, True])
+def test_many_observations_per_read(cuda, packed):
+    """Up to 255 observations per read pair stay exact on both scoring paths."""
     gene = synthetic.make_gene([91, 0], "KIRWIDE*BACKBONE", 30, 400, 2, 1500, w=100)
     pack = packing.pack_synthetic(gene)
     assert pack.k_obs.max() > 128
-    batch = engine.MatrixBatch([pack], backend=cuda)
-    assert not batch.half
-    with pytest.raises(ValueError):
-        engine.MatrixBatch([pack], backend=cuda, half=True)
+    batch = engine.MatrixBatch([pack], backend=cuda, packed=packed)
     m = batch.mismatch_counts(0)
     search = orc.IntSearch(m.astype(np.int64), pack.k_obs, top_n=40)
     group = engine.SearchGroup(batch, [0], 40)
