@@ -35,7 +35,7 @@ extern "C" {
 
 #define GK_MAX_CN 8        /* alleles per set (copy number) supported by the search kernels */
 #define GK_KB 64           /* kept-set block: P is stored [k_block][read][GK_KB]             */
-#define GK_RT 16           /* read rows per shared-memory stage of the scoring kernel        */
+#define GK_RT 32           /* read rows per shared-memory stage of the scoring kernel        */
 #define GK_LIK_READS 64    /* read rows per CTA of the likelihood kernel                     */
 
 /* Likelihood data of one gene problem.  Offsets are in elements of the pool type. */

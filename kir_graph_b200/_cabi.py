@@ -15,7 +15,7 @@ import numpy as np
 
 GK_MAX_CN = 8
 GK_KB = 64
-GK_RT = 16
+GK_RT = 32
 GK_LIK_READS = 64
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgk_typing.so")

@@ -39,7 +39,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStages = 4;
+constexpr int kStagesF = 3;   // FP32 path: 3 stages x 32 KB
+constexpr int kStagesP = 4;   // packed path: 4 stages x 24 KB
+constexpr int kMaxStages = 4;
 
 // Tile modes per dimension.  F8/F4: 128/64 rows (columns), each thread owns groups of four
 // consecutive ones (float4 shared loads).  S1..S3: the ragged remainder, 16/32/48 rows
@@ -92,7 +94,7 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
     };
 
     if (tid == 0) {
-        const int pre = n_tiles < kStages ? n_tiles : kStages;
+        const int pre = n_tiles < kStagesF ? n_tiles : kStagesF;
         for (int s = 0; s < pre; ++s) issue(s, s);
     }
 
@@ -110,19 +112,19 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % kStages;
+        const int s = t % kStagesF;
         // refill the stage that held tile t-1 once every warp has released it
         if (tid == 0 && t >= 1) {
             const int tp = t - 1;
-            const int nt = tp + kStages;
+            const int nt = tp + kStagesF;
             if (nt < n_tiles) {
-                const int sp = tp % kStages;
-                gk_mbar_wait(&empty[sp], (tp / kStages) & 1);
+                const int sp = tp % kStagesF;
+                gk_mbar_wait(&empty[sp], (tp / kStagesF) & 1);
                 issue(nt, sp);
             }
         }
         __syncwarp();
-        gk_mbar_wait(&full[s], (t / kStages) & 1);
+        gk_mbar_wait(&full[s], (t / kStagesF) & 1);
 
         const float* p = smem + s * kStageFloats;                       // [k_blk][r][GK_KB]
         const float* l = smem + s * kStageFloats + KW * GK_RT * GK_KB;  // [a_blk][r][AT]
@@ -228,7 +230,7 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
     };
 
     if (tid == 0) {
-        const int pre = n_tiles < kStages ? n_tiles : kStages;
+        const int pre = n_tiles < kStagesP ? n_tiles : kStagesP;
         for (int s = 0; s < pre; ++s) issue(s, s);
     }
 
@@ -278,18 +280,18 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
     int since_flush = 0;
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % kStages;
+        const int s = t % kStagesP;
         if (tid == 0 && t >= 1) {
             const int tp = t - 1;
-            const int nt = tp + kStages;
+            const int nt = tp + kStagesP;
             if (nt < n_tiles) {
-                const int sp = tp % kStages;
-                gk_mbar_wait(&empty[sp], (tp / kStages) & 1);
+                const int sp = tp % kStagesP;
+                gk_mbar_wait(&empty[sp], (tp / kStagesP) & 1);
                 issue(nt, sp);
             }
         }
         __syncwarp();
-        gk_mbar_wait(&full[s], (t / kStages) & 1);
+        gk_mbar_wait(&full[s], (t / kStagesP) & 1);
 
         const uint16_t* p = reinterpret_cast<const uint16_t*>(smem_bytes + (size_t)s * kStageBytes);
         const uint32_t* l = reinterpret_cast<const uint32_t*>(smem_bytes + (size_t)s * kStageBytes + KW * kBytesPBlk);
@@ -349,11 +351,11 @@ gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __
     if (kept_count != nullptr && items[blockIdx.x].k_blk * GK_KB >= kept_count[items[blockIdx.x].search]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + kStages;
+    uint64_t* empty = full + kMaxStages;
     unsigned char* smem = smem_raw + 128;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kStagesP; ++s) {
             gk_mbar_init(&full[s], 1);
             gk_mbar_init(&empty[s], kWarps);
         }
@@ -397,11 +399,11 @@ gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restric
     if (kept_count != nullptr && items[blockIdx.x].k_blk * GK_KB >= kept_count[items[blockIdx.x].search]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + kStages;
+    uint64_t* empty = full + kMaxStages;
     float* smem = reinterpret_cast<float*>(smem_raw + 128);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kStagesF; ++s) {
             gk_mbar_init(&full[s], 1);
             gk_mbar_init(&empty[s], kWarps);
         }
@@ -423,7 +425,9 @@ gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restric
     }
 }
 
-constexpr int kSmemBytes = 128 + kStages * GK_RT * (2 * GK_KB + 128) * (int)sizeof(float);
+constexpr int kSmemBytesF = kStagesF * GK_RT * (2 * GK_KB + 128) * (int)sizeof(float);
+constexpr int kSmemBytesP = kStagesP * GK_RT * (2 * GK_KB * 2 + 128 * 4);
+constexpr int kSmemBytes = 128 + (kSmemBytesF > kSmemBytesP ? kSmemBytesF : kSmemBytesP);
 
 }  // namespace
 

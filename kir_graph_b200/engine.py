@@ -33,7 +33,10 @@ COUNT_READ_CHUNK = 16384    # reads per rescoring work item
 P_READ_CHUNK = 2048         # reads per P-writing work item (multiple of 128)
 ALIVE_SLACK = 212           # alive sets beyond top_n the rescoring grids are sized for without a read-back
 MAX_TOP_N = 2048
-PACKED_DEFAULT = True     # packed 16-bit integer scoring path (False: FP32 sum of absolute differences)
+import os as _os
+
+# packed 16-bit integer scoring path (False: FP32 sum of absolute differences); GK_PACKED=0/1 overrides
+PACKED_DEFAULT = _os.environ.get("GK_PACKED", "1") != "0"
 MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
 
 
@@ -217,7 +220,7 @@ class MatrixBatch:
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
         self.half = bool(packed)          # name kept from the C ABI parameter (half_mode)
-        self.flush_stages = 16            # 16 stages x 16 reads x 255 <= 65535: one 16-bit lane
+        self.flush_stages = 256 // _cabi.GK_RT     # 256 reads x 255 <= 65535: one 16-bit lane
         self.packs = host.packs
         self.table = host.table
         self.max_alleles = int(host.table["n_alleles"].max()) if len(host.table) else 0

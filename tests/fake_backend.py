@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from kir_graph_b200._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, LIK_ITEM_DTYPE,
+from kir_graph_b200._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK_ITEM_DTYPE,
                                   MATRIX_DTYPE, P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE,
                                   EM_PROBLEM_DTYPE)
 
@@ -185,7 +185,7 @@ class FakeBackend:
             assert P.dtype == (np.uint16 if half_mode else np.float32)
             kspan = self.MODE_SPAN[int(it["shape"]) & 0xFF]
             aspan = self.MODE_SPAN[(int(it["shape"]) >> 8) & 0xFF]
-            assert tile == 32 and r0 % 16 == 0 and r1 % 16 == 0 and r1 <= rp and r1 > r0
+            assert tile == 32 and r0 % GK_RT == 0 and r1 % GK_RT == 0 and r1 <= rp and r1 > r0
             kw, aw = -(-kspan // GK_KB), -(-aspan // tile)
             assert int(it["a_blk"]) + aw <= int(M["n_ablk"])
             stride = int(X["s_stride"])
@@ -194,7 +194,7 @@ class FakeBackend:
                 .reshape(r1 - r0, GK_KB) for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)],
                 axis=1)[:, :kspan].astype(np.float32)
             if half_mode:
-                assert flush_stages * 16 * 255 <= 65535
+                assert flush_stages * GK_RT * 255 <= 65535
             Lt = np.concatenate([self._L_view(M, L, half_mode)[ab, r0:r1, :]
                                  for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw)], axis=1)[:, :aspan]
             if half_mode:      # packed integer path accumulates the min-sum itself
