@@ -34,16 +34,21 @@ extern "C" {
 #endif
 
 #define GK_MAX_CN 8        /* alleles per set (copy number) supported by the search kernels */
-#define GK_KB 64           /* kept-set block: P is stored [k_block][read][GK_KB]             */
-#define GK_RT 32           /* read rows per shared-memory stage of the scoring kernel        */
+#define GK_KB 64           /* kept-set block width of P                                      */
+#define GK_RT 32           /* read rows per row block of L and P = one shared-memory stage of
+                              the scoring kernel                                             */
 #define GK_LIK_READS 64    /* read rows per CTA of the likelihood kernel                     */
 
 /* Likelihood data of one gene problem.  Offsets are in elements of the pool type. */
 typedef struct GkMatrix {
     int64_t mem_off;     /* uint32 pool: mem[w * n_alleles + a], bit b = allele a carries variant 32w+b */
     int64_t entoff_off;  /* int32 pool : n_reads+1 entry offsets (absolute indices into the entry pools) */
-    int64_t L_off;       /* 4-byte pool: L[(a_blk * r_pad + r) * a_tile + a % a_tile] = m[r, a] as float32,
-                            or as the 16-bit pair (m, m) in packed mode                  */
+    int64_t L_off;       /* 4-byte pool, row-blocked: L[r_blk][a_blk][GK_RT][a_tile] with r_blk = r / GK_RT,
+                            a_blk = a / a_tile, i.e. element
+                            ((r_blk * n_ablk + a_blk) * GK_RT + r % GK_RT) * a_tile + a % a_tile
+                            = m[r, a] as float32, or as the 16-bit pair (m, m) in packed mode.  The
+                            GK_RT rows of adjacent allele blocks are contiguous, so a scoring stage is
+                            ONE bulk copy                                                               */
     int64_t LT_off;      /* uint8 pool : LT[a * r_pad + r] = m[r, a]                                     */
     int64_t col_off;     /* uint64 pool: colsum[a] = sum_r m[r, a]                                       */
     int32_t n_reads;
@@ -56,7 +61,9 @@ typedef struct GkMatrix {
 
 /* State of one search.  Strides are fixed by (top_n, GK_MAX_CN). */
 typedef struct GkSearch {
-    int64_t P_off;       /* float (uint16 in packed mode) pool: P[(k_blk * r_pad + r) * GK_KB + k % GK_KB]
+    int64_t P_off;       /* float (uint16 in packed mode) pool, row-blocked like L:
+                            P[r_blk][k_blk][GK_RT][GK_KB], element
+                            ((r_blk * n_kblk + k / GK_KB) * GK_RT + r % GK_RT) * GK_KB + k % GK_KB
                             = min over the members of kept set k of m[r, id]                             */
     int64_t S_off;       /* uint32 pool: S[k * s_stride + a]                                             */
     int64_t cand_off;    /* int32 pool : candidate allele ids of the current step                        */
@@ -68,6 +75,8 @@ typedef struct GkSearch {
     int32_t n_cand;
     int32_t s_stride;    /* n_ablk * a_tile of the matrix                                                */
     int32_t alive_cap;
+    int32_t n_kblk;      /* kept-set blocks allocated in P (ceil(top_n / GK_KB))                         */
+    int32_t pad;
 } GkSearch;
 
 /* Work items (built by the host per launch). */
@@ -118,7 +127,9 @@ int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_sear
  *     S_pool (zeroed by the caller); the min-sum score is (colsum[a] + score_prev[k] - D[k, a]) / 2,
  *     formed by gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]).
  *     Packed path (half_mode = 1: L as 16-bit pairs, P as uint16): accumulates the min-sum itself
- *     with VIMNMX.U16x2 + IADD3; pass s_is_minsum = 1 to gk_select / gk_rank. */
+ *     with VIMNMX.U16x2 + IADD3 on 16-bit lanes that are added to S_pool every flush_stages stages
+ *     of GK_RT reads: flush_stages * GK_RT * (largest m of the batch) must be <= 65535.  Pass
+ *     s_is_minsum = 1 to gk_select / gk_rank. */
 int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,
              const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode, int flush_stages,
              const int32_t* kept_count /* optional: skip tiles whose first row is >= kept_count[search] */,

@@ -18,7 +18,8 @@ GK_KB = 64
 GK_RT = 32
 GK_LIK_READS = 64
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgk_typing.so")
+LIB_PATH = os.environ.get("GK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                   "libgk_typing.so")
 
 MATRIX_DTYPE = np.dtype([
     ("mem_off", "<i8"), ("entoff_off", "<i8"), ("L_off", "<i8"), ("LT_off", "<i8"), ("col_off", "<i8"),
@@ -30,6 +31,7 @@ SEARCH_DTYPE = np.dtype([
     ("P_off", "<i8"), ("S_off", "<i8"), ("cand_off", "<i8"), ("flag_off", "<i8"),
     ("alive_off", "<i8"), ("cnt_off", "<i8"),
     ("matrix", "<i4"), ("n_cand", "<i4"), ("s_stride", "<i4"), ("alive_cap", "<i4"),
+    ("n_kblk", "<i4"), ("pad", "<i4"),
 ], align=True)
 
 LIK_ITEM_DTYPE = np.dtype([("matrix", "<i4"), ("a_blk", "<i4"), ("r0", "<i4"), ("pad", "<i4")])

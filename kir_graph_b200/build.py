@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "--use_fast_math" if False else "-DGK_NO_FAST_MATH",   # exact integer math; no fast-math
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+    *os.environ.get("GK_NVCC_EXTRA", "").split(),      # e.g. -DGK_SCORE_PROBE (tools/probe_pipeline.py)
 ]
 
 

@@ -77,6 +77,21 @@ __device__ __forceinline__ bool gk_mbar_try_wait(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 
+// non-blocking probe of a phase
+__device__ __forceinline__ bool gk_mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(gk_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ void gk_mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!gk_mbar_try_wait(bar, parity)) {
     }
@@ -99,6 +114,12 @@ __device__ __forceinline__ int gk_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ int gk_warp() { return threadIdx.x >> 5; }
 
 __host__ __device__ __forceinline__ int gk_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Element offset of row r in block b of a row-blocked array [r_blk][n_blk][GK_RT][width]
+// (the layout of L and P, include/gk_typing.h).
+__host__ __device__ __forceinline__ int64_t gk_blk_off(int r, int b, int n_blk, int width) {
+    return (((int64_t)(r / GK_RT) * n_blk + b) * GK_RT + (r % GK_RT)) * width;
+}
 
 // bits needed to store ids 0..n_alleles (one spare code so that a packed key is never all ones)
 __host__ __device__ __forceinline__ int gk_id_bits(int n_alleles) {

@@ -31,7 +31,7 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
                                           const uint32_t* __restrict__ mem, const int32_t* __restrict__ ent_word,
                                           const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
                                           const int* s_eoff, const int4* s_ent, float* __restrict__ L,
-                                          int64_t blk_stride, uint8_t* tile, unsigned int (&csum)[4]) {
+                                          uint8_t* tile, unsigned int (&csum)[4]) {
     const int lane = gk_lane();
     const int warp = gk_warp();
     bool live[NG];
@@ -74,7 +74,8 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
             const int a = lane + 32 * g;
             if (a < a_span) {
                 const unsigned int c = live[g] ? cnt[g] : 0u;
-                float* slot = L + g * blk_stride + (int64_t)r * 32 + lane;     // a_tile == 32: block g, column lane
+                // a_tile == 32: allele block a0 / 32 + g, column lane
+                float* slot = L + gk_blk_off(r, (a0 >> 5) + g, M.n_ablk, 32) + lane;
                 if constexpr (HALF) {
                     *reinterpret_cast<uint32_t*>(slot) = c * 0x00010001u;       // (m, m) as two 16-bit lanes
                 } else {
@@ -112,8 +113,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     const uint32_t* mem = mem_pool + M.mem_off;
     const int32_t* eoff = entoff_pool + M.entoff_off;
     // group g of a lane is column (lane + 32 g) of the span = block (a_blk + g) when a_tile == 32
-    float* L = L_pool + M.L_off + (int64_t)item.a_blk * M.r_pad * a_tile;
-    const int64_t blk_stride = (int64_t)M.r_pad * a_tile;
+    float* L = L_pool + M.L_off;
 
     // stage the tile's entry offsets and entries with coalesced loads (they are shared by all lanes)
     for (int i = threadIdx.x; i <= GK_LIK_READS; i += kThreads) {
@@ -132,7 +132,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     __syncthreads();
 
     unsigned int csum[4] = {0u, 0u, 0u, 0u};
-#define GK_LIK_ARGS M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_ent, L, blk_stride, tile, csum
+#define GK_LIK_ARGS M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_ent, L, tile, csum
 #define GK_LIK_CASE(NG)                                              \
     if (!staged) {                                                   \
         if (half_mode) lik_reads<NG, true, false>(GK_LIK_ARGS);      \

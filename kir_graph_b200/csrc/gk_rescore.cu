@@ -131,16 +131,16 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
         }
         __syncthreads();
         // phase 2: half a warp per read row, four consecutive sets per lane -> 256-byte row stores
-        const int64_t p_base = X.P_off + ((int64_t)item.k_blk * M.r_pad + r0) * GK_KB;
         for (int rl = warp * 2 + half; rl < 128; rl += kWarps * 2) {
             const unsigned int v0 = tile[(kq + 0) * kPitch + rl], v1 = tile[(kq + 1) * kPitch + rl];
             const unsigned int v2 = tile[(kq + 2) * kPitch + rl], v3 = tile[(kq + 3) * kPitch + rl];
+            const int64_t o = X.P_off + gk_blk_off(r0 + rl, item.k_blk, X.n_kblk, GK_KB) + kq;
             if (half_mode) {
-                uint16_t* P = reinterpret_cast<uint16_t*>(P_pool_raw) + p_base;
-                *reinterpret_cast<uint2*>(P + (int64_t)rl * GK_KB + kq) = make_uint2(v0 | (v1 << 16), v2 | (v3 << 16));
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(P_pool_raw) + o) =
+                    make_uint2(v0 | (v1 << 16), v2 | (v3 << 16));
             } else {
-                float* P = reinterpret_cast<float*>(P_pool_raw) + p_base;
-                *reinterpret_cast<float4*>(P + (int64_t)rl * GK_KB + kq) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(P_pool_raw) + o) =
+                    make_float4((float)v0, (float)v1, (float)v2, (float)v3);
             }
         }
         __syncthreads();

@@ -39,9 +39,24 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStagesF = 3;   // FP32 path: 3 stages x 32 KB
-constexpr int kStagesP = 4;   // packed path: 4 stages x 24 KB
+#ifndef GK_PACKED_CTAS
+#define GK_PACKED_CTAS 3      // resident CTAs per SM of the packed kernel (80 registers per thread)
+#endif
+constexpr int kStagesF = 3;   // FP32 path
+constexpr int kStagesP = GK_PACKED_CTAS == 3 ? 3 : 4;   // packed path
 constexpr int kMaxStages = 4;
+
+#ifdef GK_SCORE_PROBE
+// Pipeline probe (debug builds only): cycles summed over CTAs of the packed kernel.
+// [0] thread 0 waiting for a free stage, [1] thread 0 issuing the bulk copies, [2] thread 0 and
+// [3] thread 32 waiting for a full stage, [4] thread 32 computing, [5] stages, [6] CTAs.
+__device__ unsigned long long gk_probe[8];
+#define GK_PROBE_T(var) const long long var = clock64()
+#define GK_PROBE_ADD(slot, val) probe[slot] += (unsigned long long)(val)
+#else
+#define GK_PROBE_T(var)
+#define GK_PROBE_ADD(slot, val)
+#endif
 
 // Tile modes per dimension.  F8/F4: 128/64 rows (columns), each thread owns groups of four
 // consecutive ones (float4 shared loads).  S1..S3: the ragged remainder, 16/32/48 rows
@@ -73,24 +88,22 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
     const int tk = tid >> 4;
     const int ta = tid & 15;
 
-    const int64_t blk_stride_p = (int64_t)M.r_pad * GK_KB;
-    const int64_t blk_stride_l = (int64_t)M.r_pad * AT;
-    const float* gP = P_pool + X.P_off + item.k_blk * blk_stride_p + (int64_t)item.r0 * GK_KB;
-    const float* gL = L_pool + M.L_off + item.a_blk * blk_stride_l + (int64_t)item.r0 * AT;
+    // L and P are row-blocked ([r_blk][block][GK_RT][width]): the GK_RT rows of the KW (AW)
+    // adjacent blocks of a tile are contiguous, so a stage is two bulk copies.  Issuing one
+    // costs the issuing thread ~500 cycles whatever its size (tools/micro/bulkcopy.cu), which
+    // is why the layout keeps their number down.
+    const int rb0 = item.r0 / GK_RT;
+    const float* gP = P_pool + X.P_off + ((int64_t)rb0 * X.n_kblk + item.k_blk) * (GK_RT * GK_KB);
+    const float* gL = L_pool + M.L_off + ((int64_t)rb0 * M.n_ablk + item.a_blk) * (GK_RT * AT);
+    const int64_t rb_stride_p = (int64_t)X.n_kblk * (GK_RT * GK_KB);
+    const int64_t rb_stride_l = (int64_t)M.n_ablk * (GK_RT * AT);
     const int n_tiles = (item.r1 - item.r0) / GK_RT;
 
     auto issue = [&](int tile, int s) {
         float* dst = smem + s * kStageFloats;
         gk_mbar_arrive_expect_tx(&full[s], kStageBytes);
-#pragma unroll
-        for (int b = 0; b < KW; ++b)
-            gk_bulk_g2s(dst + b * GK_RT * GK_KB, gP + b * blk_stride_p + (int64_t)tile * GK_RT * GK_KB,
-                        kBytesPBlk, &full[s]);
-        dst += KW * GK_RT * GK_KB;
-#pragma unroll
-        for (int b = 0; b < AW; ++b)
-            gk_bulk_g2s(dst + b * GK_RT * AT, gL + b * blk_stride_l + (int64_t)tile * GK_RT * AT, kBytesLBlk,
-                        &full[s]);
+        gk_bulk_g2s(dst, gP + tile * rb_stride_p, KW * kBytesPBlk, &full[s]);
+        gk_bulk_g2s(dst + KW * GK_RT * GK_KB, gL + tile * rb_stride_l, AW * kBytesLBlk, &full[s]);
     };
 
     if (tid == 0) {
@@ -187,15 +200,17 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 // = 2 VIMNMX.U16x2 + 1 IADD3 for 4 cells (two reads are folded into one 3-input add).  These
 // issue on the half-rate ALU pipe (1.5 clk per cell against 2 clk for the two FADDs of the FP32
 // path; tools/micro/mixpipe.cu measures 83 against 55 cells/clk/SM).  Everything is integer, so
-// it is exact for every supported input (counts <= 255); a 16-bit lane holds 65535 / 255 = 257
-// reads, so the packed accumulators are spilled into 32-bit ones every `flush` = 16 stages of 16
-// reads.  S receives the min-sum itself (not the sum of absolute differences of the FP32 path).
+// it is exact for every supported input (counts <= 255).  A 16-bit lane holds 65535 / m_max reads
+// (m_max = the largest count of the batch, <= 255), so every `flush` stages (the host derives it
+// from m_max) the packed sums are added to S with integer atomics; there are no 32-bit
+// accumulator registers.  S receives the min-sum itself (not the sum of absolute differences of
+// the FP32 path).
 // Tile rows: G in {1..4} groups of 32 kept sets; columns: the same five modes as above.
 template <int G, int AM>
 __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                              const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
                                              uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
-                                             uint64_t* full, uint64_t* empty, int flush) {
+                                             uint64_t* full, uint64_t* empty, int* next, int flush) {
     constexpr int TA = ModeInfo<AM>::kPerThread;
     constexpr int AT = 32;
     constexpr int KW = (32 * G + GK_KB - 1) / GK_KB;                 // k-blocks staged (1 or 2)
@@ -208,55 +223,64 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
     const int tk = tid >> 4;
     const int ta = tid & 15;
 
-    const int64_t blk_stride_p = (int64_t)M.r_pad * GK_KB;
-    const int64_t blk_stride_l = (int64_t)M.r_pad * AT;
-    const uint16_t* gP = P_pool + X.P_off + item.k_blk * blk_stride_p + (int64_t)item.r0 * GK_KB;
-    const uint32_t* gL = reinterpret_cast<const uint32_t*>(L_pool) + M.L_off + item.a_blk * blk_stride_l +
-                         (int64_t)item.r0 * AT;
+    // row-blocked L and P: two bulk copies per stage (see score_item)
+    const int rb0 = item.r0 / GK_RT;
+    const uint16_t* gP = P_pool + X.P_off + ((int64_t)rb0 * X.n_kblk + item.k_blk) * (GK_RT * GK_KB);
+    const uint32_t* gL = reinterpret_cast<const uint32_t*>(L_pool) + M.L_off +
+                         ((int64_t)rb0 * M.n_ablk + item.a_blk) * (GK_RT * AT);
+    const int64_t rb_stride_p = (int64_t)X.n_kblk * (GK_RT * GK_KB);
+    const int64_t rb_stride_l = (int64_t)M.n_ablk * (GK_RT * AT);
     const int n_tiles = (item.r1 - item.r0) / GK_RT;
 
     auto issue = [&](int tile, int s) {
         unsigned char* dst = smem_bytes + (size_t)s * kStageBytes;
         gk_mbar_arrive_expect_tx(&full[s], kStageBytes);
-#pragma unroll
-        for (int b = 0; b < KW; ++b)
-            gk_bulk_g2s(dst + b * kBytesPBlk, gP + b * blk_stride_p + (int64_t)tile * GK_RT * GK_KB, kBytesPBlk,
-                        &full[s]);
-        dst += KW * kBytesPBlk;
-#pragma unroll
-        for (int b = 0; b < AW; ++b)
-            gk_bulk_g2s(dst + b * kBytesLBlk, gL + b * blk_stride_l + (int64_t)tile * GK_RT * AT, kBytesLBlk,
-                        &full[s]);
+        gk_bulk_g2s(dst, gP + tile * rb_stride_p, KW * kBytesPBlk, &full[s]);
+        gk_bulk_g2s(dst + KW * kBytesPBlk, gL + tile * rb_stride_l, AW * kBytesLBlk, &full[s]);
     };
 
+    // Refills are not tied to one thread: `next` is the next tile to fetch, and lane 0 of any warp
+    // that comes by (at the top of a stage, or while it waits for data) claims it once every warp
+    // has released the stage it goes to.  A fixed issuing warp would run ~7 % behind the others,
+    // which then sit at the end of the ring waiting for it while the ALU pipe starves
+    // (tools/probe_pipeline.py).
     if (tid == 0) {
         const int pre = n_tiles < kStagesP ? n_tiles : kStagesP;
         for (int s = 0; s < pre; ++s) issue(s, s);
+        *next = pre;
     }
+    __syncthreads();
+    auto try_refill = [&]() {
+        const int n = *reinterpret_cast<volatile int*>(next);
+        if (n >= n_tiles) return;
+        const int sp = n % kStagesP;
+        if (!gk_mbar_test(&empty[sp], (n / kStagesP - 1) & 1)) return;
+        if (atomicCAS(next, n, n + 1) == n) issue(n, sp);
+    };
 
-    uint32_t acc[2 * G][TA];
-    uint32_t acc2[G][TA];
+    uint32_t acc2[G][TA];      // two 16-bit sums per word: rows 32 g + 2 tk and 32 g + 2 tk + 1
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int j = 0; j < TA; ++j) {
-            acc[2 * g][j] = 0u;
-            acc[2 * g + 1][j] = 0u;
-            acc2[g][j] = 0u;
-        }
+        for (int j = 0; j < TA; ++j) acc2[g][j] = 0u;
 
     auto a_of = [&](int j) { return ModeInfo<AM>::kVec ? (j < 4 ? ta * 4 + j : 64 + ta * 4 + (j - 4)) : j * 16 + ta; };
     auto l_off = [&](int c) { return (c / AT) * (GK_RT * AT) + (c % AT); };
     // rows 32 g + 2 tk + {0, 1}: offset (in uint16) inside the staged P blocks [k_blk][r][64]
     auto p_off = [&](int g) { return ((32 * g) / GK_KB) * (GK_RT * GK_KB) + ((32 * g) % GK_KB) + 2 * tk; };
 
+    // The packed sums go straight to S (no 32-bit accumulator registers: the 32 words of acc2 are
+    // the only accumulators, which leaves the scheduler room to keep the ALU pipe fed).
+    uint32_t* S = S_pool + X.S_off + (int64_t)(item.k_blk * GK_KB + 2 * tk) * X.s_stride + item.a_blk * AT;
     auto flush_acc = [&]() {
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int j = 0; j < TA; ++j) {
-                acc[2 * g][j] += acc2[g][j] & 0xffffu;
-                acc[2 * g + 1][j] += acc2[g][j] >> 16;
+                const uint32_t v = acc2[g][j];
+                uint32_t* cell = S + (int64_t)(32 * g) * X.s_stride + a_of(j);
+                if (v & 0xffffu) atomicAdd(cell, v & 0xffffu);
+                if (v >> 16) atomicAdd(cell + X.s_stride, v >> 16);
                 acc2[g][j] = 0u;
             }
     };
@@ -278,20 +302,30 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
     };
 
     int since_flush = 0;
+#ifdef GK_SCORE_PROBE
+    unsigned long long probe[6] = {0, 0, 0, 0, 0, 0};
+#endif
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
         const int s = t % kStagesP;
-        if (tid == 0 && t >= 1) {
-            const int tp = t - 1;
-            const int nt = tp + kStagesP;
-            if (nt < n_tiles) {
-                const int sp = tp % kStagesP;
-                gk_mbar_wait(&empty[sp], (tp / kStagesP) & 1);
-                issue(nt, sp);
-            }
-        }
+        // Warp-uniform wait (the exit is voted on): a lane-0-only polling loop leaves lane 0 diverged
+        // from the other 31 lanes through the compute loop, doubling the instructions issued.
+        GK_PROBE_T(c0);
+        if (lane == 0) try_refill();
         __syncwarp();
-        gk_mbar_wait(&full[s], (t / kStagesP) & 1);
+        while (true) {
+            // try_wait suspends the thread for a bounded time: a waiting warp costs no issue slots
+            // and looks for a refill to claim every time it wakes up
+            const bool ok = gk_mbar_try_wait(&full[s], (t / kStagesP) & 1);
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (lane == 0) try_refill();
+            __syncwarp();
+        }
+        GK_PROBE_T(c1);
+        GK_PROBE_ADD(0, c1 - c0);
+        GK_PROBE_T(c3);
+        GK_PROBE_T(c4);
+        GK_PROBE_ADD(tid == 0 ? 2 : 3, c4 - c3);
 
         const uint16_t* p = reinterpret_cast<const uint16_t*>(smem_bytes + (size_t)s * kStageBytes);
         const uint32_t* l = reinterpret_cast<const uint32_t*>(smem_bytes + (size_t)s * kStageBytes + KW * kBytesPBlk);
@@ -312,38 +346,42 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
         }
         __syncwarp();
         if (lane == 0) gk_mbar_arrive(&empty[s]);
+        GK_PROBE_T(c5);
+        GK_PROBE_ADD(4, c5 - c4);
     }
     flush_acc();
-
-    uint32_t* S = S_pool + X.S_off;
-    const int k_base = item.k_blk * GK_KB;
-    const int a_base = item.a_blk * AT;
-#pragma unroll
-    for (int i = 0; i < 2 * G; ++i) {
-        const int k = k_base + 32 * (i / 2) + 2 * tk + (i & 1);
-#pragma unroll
-        for (int j = 0; j < TA; ++j) {
-            const uint32_t v = acc[i][j];
-            if (v) atomicAdd(S + (int64_t)k * X.s_stride + a_base + a_of(j), v);
-        }
+#ifdef GK_SCORE_PROBE
+    if (tid == 0) {
+        atomicAdd(&gk_probe[0], probe[0]);
+        atomicAdd(&gk_probe[1], probe[1]);
+        atomicAdd(&gk_probe[2], probe[2]);
+        atomicAdd(&gk_probe[5], (unsigned long long)n_tiles);
+        atomicAdd(&gk_probe[6], 1ull);
     }
+    if (tid == 32) {
+        atomicAdd(&gk_probe[3], probe[3]);
+        atomicAdd(&gk_probe[4], probe[4]);
+    }
+#endif
+
 }
 
 template <int G>
 __device__ __forceinline__ void score_dispatch_h(int am, const GkScoreItem& item, const GkMatrix& M,
                                                  const GkSearch& X, const float* __restrict__ L_pool,
                                                  const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
-                                                 unsigned char* smem, uint64_t* full, uint64_t* empty, int flush) {
+                                                 unsigned char* smem, uint64_t* full, uint64_t* empty, int* next,
+                                                 int flush) {
     switch (am) {
-        case F8: score_item_h<G, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        case F4: score_item_h<G, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        case S1: score_item_h<G, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        case S2: score_item_h<G, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        default: score_item_h<G, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case F8: score_item_h<G, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case F4: score_item_h<G, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case S1: score_item_h<G, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case S2: score_item_h<G, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        default: score_item_h<G, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, GK_PACKED_CTAS)
 gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                      const GkScoreItem* __restrict__ items, const float* __restrict__ L_pool,
                      const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush,
@@ -352,6 +390,7 @@ gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
+    int* next = reinterpret_cast<int*>(smem_raw + 64);      // next tile to fetch (see score_item_h)
     unsigned char* smem = smem_raw + 128;
 
     if (threadIdx.x == 0) {
@@ -369,10 +408,10 @@ gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __
     const int g = (item.shape & 0xff) - 4;    // row mode 5..8 = 1..4 groups of 32 kept sets
     const int am = (item.shape >> 8) & 0xff;
     switch (g) {
-        case 1: score_dispatch_h<1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        case 2: score_dispatch_h<2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        case 3: score_dispatch_h<3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
-        default: score_dispatch_h<4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, flush); break;
+        case 1: score_dispatch_h<1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case 2: score_dispatch_h<2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case 3: score_dispatch_h<3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        default: score_dispatch_h<4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
     }
 }
 
@@ -427,9 +466,19 @@ gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restric
 
 constexpr int kSmemBytesF = kStagesF * GK_RT * (2 * GK_KB + 128) * (int)sizeof(float);
 constexpr int kSmemBytesP = kStagesP * GK_RT * (2 * GK_KB * 2 + 128 * 4);
-constexpr int kSmemBytes = 128 + (kSmemBytesF > kSmemBytesP ? kSmemBytesF : kSmemBytesP);
+constexpr int kSmemF = 128 + kSmemBytesF;
+constexpr int kSmemP = 128 + kSmemBytesP;
 
 }  // namespace
+
+#ifdef GK_SCORE_PROBE
+// debug builds only: read and clear the pipeline probe
+extern "C" int gk_score_probe(unsigned long long* out8) {
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, gk_probe, sizeof(zero)) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(gk_probe, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items,
                         int n_items, const float* L_pool, const void* P_pool, uint32_t* S_pool, int half_mode,
@@ -439,21 +488,20 @@ extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, cons
     if (half_mode) {
         GK_REQUIRE(flush_stages >= 1, "gk_score: flush interval %d must be >= 1 stage", flush_stages);
         cudaError_t err = cudaFuncSetAttribute(gk_score_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               kSmemBytes);
-        GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemBytes,
+                                               kSmemP);
+        GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemP,
                    cudaGetErrorString(err));
-        gk_score_packed_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
-                                                                    reinterpret_cast<const uint16_t*>(P_pool), S_pool,
-                                                                    flush_stages, kept_count);
+        gk_score_packed_kernel<<<n_items, kThreads, kSmemP, st>>>(matrices, searches, items, L_pool,
+                                                                  reinterpret_cast<const uint16_t*>(P_pool), S_pool,
+                                                                  flush_stages, kept_count);
         GK_CHECK_LAUNCH("gk_score (packed)");
         return 0;
     }
-    cudaError_t err =
-        cudaFuncSetAttribute(gk_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemBytes,
+    cudaError_t err = cudaFuncSetAttribute(gk_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF);
+    GK_REQUIRE(err == cudaSuccess, "gk_score: cannot reserve %d bytes of shared memory: %s", kSmemF,
                cudaGetErrorString(err));
-    gk_score_kernel<<<n_items, kThreads, kSmemBytes, st>>>(matrices, searches, items, L_pool,
-                                                           reinterpret_cast<const float*>(P_pool), S_pool, kept_count);
+    gk_score_kernel<<<n_items, kThreads, kSmemF, st>>>(matrices, searches, items, L_pool,
+                                                       reinterpret_cast<const float*>(P_pool), S_pool, kept_count);
     GK_CHECK_LAUNCH("gk_score");
     return 0;
 }

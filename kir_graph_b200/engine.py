@@ -24,7 +24,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _cabi
-from ._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, LIK_ITEM_DTYPE, MATRIX_DTYPE,
+from ._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK_ITEM_DTYPE, MATRIX_DTYPE,
                     P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE)
 from .packing import GenePack
 
@@ -220,8 +220,12 @@ class MatrixBatch:
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
         self.half = bool(packed)          # name kept from the C ABI parameter (half_mode)
-        self.flush_stages = 256 // _cabi.GK_RT     # 256 reads x 255 <= 65535: one 16-bit lane
         self.packs = host.packs
+        # m[r, a] <= K_r (observations of the read pair) <= 255; a 16-bit lane of the packed scoring
+        # kernel therefore holds 65535 // m_max reads before it must be added to S
+        m_max = max([int(p.k_obs.max(initial=1)) for p in self.packs], default=1)
+        m_max = min(max(m_max, 1), 255)
+        self.flush_stages = max(1, min(65535 // m_max, SCORE_READ_CHUNK) // _cabi.GK_RT)
         self.table = host.table
         self.max_alleles = int(host.table["n_alleles"].max()) if len(host.table) else 0
         be = self.be
@@ -294,7 +298,8 @@ class MatrixBatch:
             pair = flat.view(np.uint16).reshape(-1, 2)
             assert np.array_equal(pair[:, 0], pair[:, 1])
             flat = pair[:, 0].astype(np.float32)
-        return flat.reshape(nb, rp, tile).transpose(1, 0, 2).reshape(rp, nb * tile)[:r, :a]
+        # row-blocked [r_blk][a_blk][GK_RT][a_tile] -> [r, a]
+        return flat.reshape(rp // GK_RT, nb, GK_RT, tile).transpose(0, 2, 1, 3).reshape(rp, nb * tile)[:r, :a]
 
 
 # ---------------------------------------------------------------------------
@@ -426,6 +431,7 @@ class SearchGroup:
         tab["matrix"] = self.matrix_ids
         tab["s_stride"] = s_stride
         tab["alive_cap"] = alive_cap
+        tab["n_kblk"] = self.n_kblk_max
         self.tab = tab
         self.cand_cap = cand_cap
         be = self.be
@@ -859,6 +865,7 @@ class SearchGroup:
         r_pad, r = int(self.r_pad[s]), int(self.R[s])
         tab = self.tab[s:s + 1].copy()
         tab["P_off"] = 0
+        tab["n_kblk"] = n_kblk
         buf = np.zeros((self.top_n, GK_MAX_CN), dtype=np.int32)
         buf[:k, :n] = ids
         d_ids = be.upload(buf)
@@ -874,8 +881,8 @@ class SearchGroup:
         d_P = be.empty(n_kblk * r_pad * GK_KB, p_dtype)
         be.launch("gk_write_p", bt.d_table, d_tab, d_items, len(items), self.top_n, n, d_kept, d_ids,
                   bt.d_LT, d_P, int(bt.half))
-        p = be.download(d_P, p_dtype).reshape(n_kblk, r_pad, GK_KB)
-        return p.transpose(1, 0, 2).reshape(r_pad, n_kblk * GK_KB)[:r, :k].astype(np.int64)
+        p = be.download(d_P, p_dtype).reshape(r_pad // GK_RT, n_kblk, GK_RT, GK_KB)
+        return p.transpose(0, 2, 1, 3).reshape(r_pad, n_kblk * GK_KB)[:r, :k].astype(np.int64)
 
 
 def _excl_cumsum(x: np.ndarray) -> np.ndarray:

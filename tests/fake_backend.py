@@ -107,12 +107,14 @@ class FakeBackend:
                         mw = memv[ent_word[e], a0:a_hi]
                         x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
                         tile[rl, : a_hi - a0] += popcount32(x)
-                base = int(M["L_off"]) + (blk * rp + r0) * a_tile
-                if half_mode:      # the 16-bit pair (m, m) in every 4-byte slot
-                    L.view(np.uint16)[2 * base: 2 * (base + GK_LIK_READS * a_tile)] = \
-                        np.repeat(tile.reshape(-1).astype(np.uint16), 2)
-                else:
-                    L[base: base + GK_LIK_READS * a_tile] = tile.reshape(-1).astype(np.float32)
+                for rb in range(GK_LIK_READS // GK_RT):      # row-blocked: [r_blk][a_blk][GK_RT][a_tile]
+                    base = int(M["L_off"]) + ((r0 // GK_RT + rb) * int(M["n_ablk"]) + blk) * GK_RT * a_tile
+                    part = tile[rb * GK_RT:(rb + 1) * GK_RT].reshape(-1)
+                    if half_mode:      # the 16-bit pair (m, m) in every 4-byte slot
+                        L.view(np.uint16)[2 * base: 2 * (base + GK_RT * a_tile)] = \
+                            np.repeat(part.astype(np.uint16), 2)
+                    else:
+                        L[base: base + GK_RT * a_tile] = part.astype(np.float32)
                 for a in range(a0, a_hi):
                     o = int(M["LT_off"]) + a * rp + r0
                     LT[o: o + GK_LIK_READS] = tile[:, a - a0].astype(np.uint8)
@@ -126,7 +128,14 @@ class FakeBackend:
         flat = L[o: o + nb * rp * tile]
         if half_mode:
             flat = flat.view(np.uint16)[0::2].astype(np.float32)
-        return flat.reshape(nb, rp, tile)
+        return flat.reshape(rp // GK_RT, nb, GK_RT, tile).transpose(1, 0, 2, 3).reshape(nb, rp, tile)
+
+    @staticmethod
+    def _P_view(X, M, P):
+        """P of one search as a writable view [r_blk][k_blk][GK_RT][GK_KB]."""
+        nkb, rp = int(X["n_kblk"]), int(M["r_pad"])
+        o = int(X["P_off"])
+        return P[o: o + nkb * rp * GK_KB].reshape(rp // GK_RT, nkb, GK_RT, GK_KB)
 
     @staticmethod
     def _LT_view(M, LT):
@@ -189,14 +198,15 @@ class FakeBackend:
             kw, aw = -(-kspan // GK_KB), -(-aspan // tile)
             assert int(it["a_blk"]) + aw <= int(M["n_ablk"])
             stride = int(X["s_stride"])
-            Pt = np.concatenate([
-                P[int(X["P_off"]) + (kb * rp + r0) * GK_KB: int(X["P_off"]) + (kb * rp + r1) * GK_KB]
-                .reshape(r1 - r0, GK_KB) for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)],
-                axis=1)[:, :kspan].astype(np.float32)
-            if half_mode:
-                assert flush_stages * GK_RT * 255 <= 65535
+            assert int(it["k_blk"]) + kw <= int(X["n_kblk"])
+            Pv = self._P_view(X, M, P)[r0 // GK_RT: r1 // GK_RT]
+            Pt = np.concatenate([Pv[:, kb].reshape(r1 - r0, GK_KB)
+                                 for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)],
+                                axis=1)[:, :kspan].astype(np.float32)
             Lt = np.concatenate([self._L_view(M, L, half_mode)[ab, r0:r1, :]
                                  for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw)], axis=1)[:, :aspan]
+            if half_mode:      # a 16-bit lane sums `flush_stages` stages of min(L, P) <= max L
+                assert flush_stages * GK_RT * int(Lt.max(initial=0)) <= 65535
             if half_mode:      # packed integer path accumulates the min-sum itself
                 part = np.minimum(Lt[:, None, :], Pt[:, :, None]).sum(axis=0)
             else:              # FP32 path accumulates the sum of absolute differences
@@ -368,8 +378,8 @@ class FakeBackend:
                     k = int(it["k_blk"]) * GK_KB + kl
                     if k < K:
                         tile[:, kl] = m[ids[s, k, :n_set], r0:r0 + 128].min(axis=0)
-                o = int(X["P_off"]) + (int(it["k_blk"]) * rp + r0) * GK_KB
-                P[o: o + 128 * GK_KB] = tile.reshape(-1)
+                self._P_view(X, M, P)[r0 // GK_RT: (r0 + 128) // GK_RT, int(it["k_blk"])] = \
+                    tile.reshape(128 // GK_RT, GK_RT, GK_KB)
 
     # --- EM path -------------------------------------------------------------------------------
     def gk_em_compat(self, membT, n_aw, n_alleles, off_lp, idx_lp, off_ln, idx_ln, off_rp, idx_rp, off_rn,

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from kir_graph_b200 import engine, packing, synthetic
-from kir_graph_b200._cabi import GK_KB, STEP_INFO_DTYPE
+from kir_graph_b200._cabi import GK_KB, GK_RT, STEP_INFO_DTYPE
 from oracle import typing_oracle as orc
 from tests.fake_backend import FakeBackend
 from tests.helpers import (assert_same_modulo_ties, golden_names, int_scores_from_values, load_golden,
@@ -67,10 +67,12 @@ def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
         if need.any():
             pg = cuda.download(gg.d_P, np.uint16 if half else np.float32)
             for s in np.flatnonzero(need):
-                rp = int(gg.mt["r_pad"][s])
-                n = -(-int(gg.kept[s]) // GK_KB) * rp * GK_KB
+                rp, nkb = int(gg.mt["r_pad"][s]), int(gg.tab["n_kblk"][s])
+                kb = -(-int(gg.kept[s]) // GK_KB)      # written kept-set blocks
                 o = int(gg.tab["P_off"][s])
-                assert np.array_equal(pg[o:o + n], gf.d_P[o:o + n]), f"P of search {s}"
+                shape = (rp // GK_RT, nkb, GK_RT, GK_KB)
+                assert np.array_equal(pg[o:o + nkb * rp * GK_KB].reshape(shape)[:, :kb],
+                                      gf.d_P[o:o + nkb * rp * GK_KB].reshape(shape)[:, :kb]), f"P of search {s}"
 
 
 @pytest.mark.parametrize("half", [False, True])
