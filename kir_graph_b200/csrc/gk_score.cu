@@ -73,7 +73,7 @@ template <int KM, int AM>
 __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                            const float* __restrict__ L_pool, const float* __restrict__ P_pool,
                                            uint32_t* __restrict__ S_pool, float* smem, uint64_t* full,
-                                           uint64_t* empty) {
+                                           uint64_t* empty, int* next) {
     constexpr int TK = ModeInfo<KM>::kPerThread;
     constexpr int TA = ModeInfo<AM>::kPerThread;
     constexpr int AT = 32;                                           // layout block width of L
@@ -106,10 +106,22 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
         gk_bulk_g2s(dst + KW * GK_RT * GK_KB, gL + tile * rb_stride_l, AW * kBytesLBlk, &full[s]);
     };
 
+    // Refills are not tied to one thread: `next` is the next tile to fetch, and lane 0 of any warp
+    // that comes by (at the top of a stage, or each time it wakes up while waiting for data) claims
+    // it once every warp has released the stage it goes to.
     if (tid == 0) {
         const int pre = n_tiles < kStagesF ? n_tiles : kStagesF;
         for (int s = 0; s < pre; ++s) issue(s, s);
+        *next = pre;
     }
+    __syncthreads();
+    auto try_refill = [&]() {
+        const int n = *reinterpret_cast<volatile int*>(next);
+        if (n >= n_tiles) return;
+        const int sp = n % kStagesF;
+        if (!gk_mbar_test(&empty[sp], (n / kStagesF - 1) & 1)) return;
+        if (atomicCAS(next, n, n + 1) == n) issue(n, sp);
+    };
 
     float acc[TK][TA];
 #pragma unroll
@@ -126,18 +138,18 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
         const int s = t % kStagesF;
-        // refill the stage that held tile t-1 once every warp has released it
-        if (tid == 0 && t >= 1) {
-            const int tp = t - 1;
-            const int nt = tp + kStagesF;
-            if (nt < n_tiles) {
-                const int sp = tp % kStagesF;
-                gk_mbar_wait(&empty[sp], (tp / kStagesF) & 1);
-                issue(nt, sp);
-            }
-        }
+        // Warp-uniform wait (the exit is voted on).  A polling loop run by one lane only leaves that
+        // lane diverged from the other 31 through the compute loop, which doubles the instructions
+        // the warp issues.  try_wait suspends the thread for a bounded time, so a waiting warp costs
+        // no issue slots and looks for a refill to claim every time it wakes up.
+        if (lane == 0) try_refill();
         __syncwarp();
-        gk_mbar_wait(&full[s], (t / kStagesF) & 1);
+        while (true) {
+            const bool ok = gk_mbar_try_wait(&full[s], (t / kStagesF) & 1);
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (lane == 0) try_refill();
+            __syncwarp();
+        }
 
         const float* p = smem + s * kStageFloats;                       // [k_blk][r][GK_KB]
         const float* l = smem + s * kStageFloats + KW * GK_RT * GK_KB;  // [a_blk][r][AT]
@@ -239,11 +251,7 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
         gk_bulk_g2s(dst + KW * kBytesPBlk, gL + tile * rb_stride_l, AW * kBytesLBlk, &full[s]);
     };
 
-    // Refills are not tied to one thread: `next` is the next tile to fetch, and lane 0 of any warp
-    // that comes by (at the top of a stage, or while it waits for data) claims it once every warp
-    // has released the stage it goes to.  A fixed issuing warp would run ~7 % behind the others,
-    // which then sit at the end of the ring waiting for it while the ALU pipe starves
-    // (tools/probe_pipeline.py).
+    // opportunistic refill, as in score_item
     if (tid == 0) {
         const int pre = n_tiles < kStagesP ? n_tiles : kStagesP;
         for (int s = 0; s < pre; ++s) issue(s, s);
@@ -419,13 +427,13 @@ template <int KM>
 __device__ __forceinline__ void score_dispatch_a(int am, const GkScoreItem& item, const GkMatrix& M,
                                                  const GkSearch& X, const float* __restrict__ L_pool,
                                                  const float* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
-                                                 float* smem, uint64_t* full, uint64_t* empty) {
+                                                 float* smem, uint64_t* full, uint64_t* empty, int* next) {
     switch (am) {
-        case F8: score_item<KM, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        case F4: score_item<KM, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        case S1: score_item<KM, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        case S2: score_item<KM, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        default: score_item<KM, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case F8: score_item<KM, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        case F4: score_item<KM, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        case S1: score_item<KM, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        case S2: score_item<KM, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        default: score_item<KM, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
     }
 }
 
@@ -439,6 +447,7 @@ gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restric
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
+    int* next = reinterpret_cast<int*>(smem_raw + 64);      // next tile to fetch (see score_item)
     float* smem = reinterpret_cast<float*>(smem_raw + 128);
 
     if (threadIdx.x == 0) {
@@ -456,11 +465,11 @@ gk_score_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restric
     const int km = item.shape & 0xff;         // Mode of the kept-set dimension
     const int am = (item.shape >> 8) & 0xff;  // Mode of the allele dimension
     switch (km) {
-        case F8: score_dispatch_a<F8>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        case F4: score_dispatch_a<F4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        case S1: score_dispatch_a<S1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        case S2: score_dispatch_a<S2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
-        default: score_dispatch_a<S3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty); break;
+        case F8: score_dispatch_a<F8>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        case F4: score_dispatch_a<F4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        case S1: score_dispatch_a<S1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        case S2: score_dispatch_a<S2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
+        default: score_dispatch_a<S3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next); break;
     }
 }
 
