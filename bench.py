@@ -206,6 +206,28 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def score_roofline(cells, ms, packed, sm_max_mhz):
+    """Roofline entry of the scoring kernel.  Its bound is non-tensor instruction issue, not HBM or
+    the tensor cores: the packed path issues 3 ALU-pipe instructions (2 VIMNMX.U16x2 + 1 IADD3)
+    per 4 cells on the half-rate (64 lanes/clk/SM) ALU pipe, the FP32 path 2 FADD per cell on the
+    128 lanes/clk/SM FMA pipe.  The FP32-equivalent fraction (2 ops per cell against the FP32
+    non-tensor peak) is what BASELINE.json's target is stated in."""
+    cps = cells / (ms * 1e-3) if ms else 0.0
+    fp32_peak = SM_COUNT * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12          # T lane-ops/s
+    src = (f"148 SM x {{lanes}} lanes/clk x {sm_max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); not in "
+           "MEASURED_PEAKS.json, which only holds HBM and bf16 tensor peaks")
+    fp32 = {"achieved": 2.0 * cps / 1e12, "peak": fp32_peak, "frac": 2.0 * cps / 1e12 / fp32_peak}
+    if packed:
+        peak = fp32_peak / 2.0                                                   # ALU pipe: 64 lanes/clk/SM
+        ach = 0.75 * cps / 1e12
+        return {"kernel": "gk_score_packed_kernel", "bound": "alu_nontensor", "achieved": ach, "peak": peak,
+                "unit": "T ALU lane-ops/s (2 VIMNMX.U16x2 + 1 IADD3 per 4 cells)", "frac": ach / peak,
+                "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=64)}
+    return {"kernel": "gk_score_kernel", "bound": "fp32_nontensor", "achieved": fp32["achieved"], "peak": fp32_peak,
+            "unit": "T FP32 ops/s (2 FADD per cell: d = p - l, acc += |d|)", "frac": fp32["frac"],
+            "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=128)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,14 +373,13 @@ def main():
         except (OSError, ValueError):
             pass
         sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-        fp32_peak = SM_COUNT * FP32_LANES_PER_SM * sm_max * 1e6 / 1e12          # T lane-ops/s
         ms_s, work_s, n_s = kernel_stats("gk_score")
         ms_l, work_l, n_l = kernel_stats("gk_likelihood")
-        score_ops = 2.0 * work_s / (ms_s * 1e-3) / 1e12 if ms_s else 0.0        # 2 FP32 instructions per cell
+        packed = bool(engine.PACKED_DEFAULT)
         traffic = None
         try:                                     # DRAM bytes per launch of the same kernel from an ncu capture
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            entry = prof.get(args.workload, {}).get("gk_score_kernel")
+            entry = prof.get(args.workload, {}).get("gk_score_packed_kernel" if packed else "gk_score_kernel")
             if entry and world == 1:
                 traffic = entry["dram_bytes_per_launch"]
         except (OSError, ValueError, KeyError):
@@ -373,7 +394,7 @@ def main():
             "metric": "allele-typing read x candidate GCells/s", "value": value, "unit": "GCells/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong" if args.workload == "cohort" else "replicas",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u16" if packed else "f32", "data": "synthetic",
             "config": {"workload": desc, "top_n": args.top_n, "l2": "inputs larger than L2 (no flush needed)",
                        "timed_region": "likelihood build + all CN steps + calls, packed inputs resident in HBM",
                        "concurrent_sub_batches": n_parts},
@@ -383,18 +404,12 @@ def main():
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {
-                "kernel": "gk_score_kernel", "bound": "fp32_nontensor",
-                "achieved": score_ops, "peak": fp32_peak, "unit": "T FP32 ops/s (2 FADD per cell: d = p - l, acc += |d|)",
-                "frac": score_ops / fp32_peak if fp32_peak else None, "traffic": traffic,
-                "cells_per_s": work_s / (ms_s * 1e-3) if ms_s else 0.0, "launches": n_s,
-                "kernel_ms_per_step": ms_s / roof_steps,
-                "share_of_step": (ms_s / roof_steps) / (ms_total / args.steps) if ms_total else None,
-                "measured": f"CUDA events around every launch of {roof_steps} extra step(s) run right after the timed "
-                            "region with the sub-batches serialised on one stream",
-                "peak_source": f"148 SM x 128 FP32 lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); "
-                               "not in MEASURED_PEAKS.json, which only holds HBM and bf16 tensor peaks",
-            },
+            "roofline": dict(
+                score_roofline(work_s, ms_s, packed, sm_max), traffic=traffic, launches=n_s,
+                kernel_ms_per_step=ms_s / roof_steps,
+                share_of_step=(ms_s / roof_steps) / (ms_total / args.steps) if ms_total else None,
+                measured=f"CUDA events around every launch of {roof_steps} extra step(s) run right after the timed "
+                         "region with the sub-batches serialised on one stream"),
             "roofline_likelihood": {
                 "kernel": "gk_likelihood_kernel", "bound": "hbm", "achieved": lik_gbs, "peak": hbm_peak,
                 "unit": "GB/s", "frac": lik_gbs / hbm_peak if hbm_peak else None, "traffic": None,
@@ -423,15 +438,12 @@ def main():
             be.timing = None
             d_ms_s = sum(a.elapsed_time(b) for a, b, _ in evs)
             d_work = sum(w for _, _, w in evs)
-            d_ops = 2.0 * d_work / (d_ms_s * 1e-3) / 1e12 if d_ms_s else 0.0
             line["deep"] = {
                 "workload": f"cfg4 deep: {args.deep_reads} read pairs x {args.deep_alleles} alleles, CN {args.deep_cn}, "
                             f"top_n={args.top_n}",
                 "value": deep.score_cells / (d_ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": d_ms,
                 "steps": d_steps, "calls_match_truth": sorted(d_calls[0].alleles) == d_truth[0],
-                "roofline": {"kernel": "gk_score_kernel", "bound": "fp32_nontensor", "achieved": d_ops,
-                             "peak": fp32_peak, "frac": d_ops / fp32_peak if fp32_peak else None,
-                             "cells_per_s": d_work / (d_ms_s * 1e-3) if d_ms_s else 0.0, "launches": len(evs)},
+                "roofline": dict(score_roofline(d_work, d_ms_s, packed, sm_max), launches=len(evs)),
             }
         if world == 1 and not args.no_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
