@@ -81,15 +81,16 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, interval_ms: int = 200):
         self.index = index
+        self.interval_ms = interval_ms          # the profiling recipe's -lms 200
         self.proc = None
         self.lines: list[str] = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", str(self.interval_ms),
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -247,6 +248,8 @@ def main():
     ap.add_argument("--no-deep", action="store_true",
                     help="skip the nested cfg4 deep-sample measurement of the default 1-GPU cohort run")
     ap.add_argument("--parts", type=int, default=1, help="concurrent sub-batches (host/device overlap)")
+    ap.add_argument("--clock-interval-ms", type=int, default=200,
+                    help="nvidia-smi sampling period during the timed region (profiling recipe: 200)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,6 +298,12 @@ def main():
                                group_size=17 if args.workload != "deep" else 1, col_shard=col_shard,
                                reduce_scores=reduce_scores)
     typer.pin()
+    # The packed cohort is a large, long-lived heap (thousands of arrays); keep the cyclic garbage
+    # collector from re-traversing it every time the per-run result objects trigger a collection
+    # (measured: 2.5 ms of a 28 ms pass).
+    import gc
+    gc.collect()
+    gc.freeze()
 
     def barrier():
         if world > 1:
@@ -318,7 +327,7 @@ def main():
         return float(t.item())
 
     # ---- resident: inputs already in HBM ---------------------------------------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_interval_ms)
     sampler.start()
     typer.upload()
     calls = None

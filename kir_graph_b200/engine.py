@@ -63,6 +63,30 @@ class CudaBackend:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.timing: dict[str, list] | None = None   # name -> [(start_event, end_event, work)]
+        self._arenas: dict[int, list] = {}            # stream -> [pinned uint8 tensor, bump position]
+
+    # Small host arrays (work-item tables, index lists) go through a page-locked staging arena so
+    # that their copies are asynchronous: a copy from pageable memory synchronises the stream first,
+    # which drains the GPU ~25 times per typing pass.  One arena per stream; it is rewound only after
+    # that stream has been synchronised.
+    ARENA_BYTES = 16 << 20
+    ARENA_MAX_ITEM = 4 << 20
+
+    def _stage(self, raw: np.ndarray):
+        """Copy a flat uint8 host array into the arena of the current stream; pinned torch view."""
+        stream = self.torch.cuda.current_stream(self.device)
+        arena = self._arenas.get(stream.cuda_stream)
+        if arena is None:
+            arena = [self.torch.empty(self.ARENA_BYTES, dtype=self.torch.uint8).pin_memory(), 0]
+            self._arenas[stream.cuda_stream] = arena
+        pos = (arena[1] + 255) & ~255
+        if pos + raw.size > self.ARENA_BYTES:
+            stream.synchronize()                      # every copy staged so far has executed
+            pos = 0
+        view = arena[0][pos:pos + raw.size]
+        view.numpy()[:] = raw
+        arena[1] = pos + raw.size
+        return view
 
     # --- memory ---------------------------------------------------------------
     _NP2T = {"uint8": "uint8", "int32": "int32", "uint32": "int32", "float32": "float32",
@@ -90,7 +114,11 @@ class CudaBackend:
         if array.size == 0:
             return self.zeros(1, array.dtype)
         self.h2d_bytes += array.nbytes
-        return self.torch.from_numpy(array.reshape(-1)).to(self.device, non_blocking=True)
+        flat = array.reshape(-1)
+        if flat.nbytes <= self.ARENA_MAX_ITEM:
+            staged = self._stage(flat.view(np.uint8)).view(self._tdtype(flat.dtype))
+            return self.torch.empty(flat.size, dtype=staged.dtype, device=self.device).copy_(staged, non_blocking=True)
+        return self.torch.from_numpy(flat).to(self.device, non_blocking=True)
 
     def download(self, tensor, dtype=None, count: int | None = None) -> np.ndarray:
         if count is not None:
@@ -109,7 +137,8 @@ class CudaBackend:
         """Download tensor.view(-1, row_len)[rows, :cols] (device-side gather, one copy)."""
         if len(rows) == 0:
             return np.zeros((0, cols or row_len), dtype=np.dtype(str(tensor.dtype).split(".")[-1]))
-        idx = self.torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device)
+        idx = self.upload(np.asarray(rows, dtype=np.int64))
+        self.h2d_bytes -= idx.numel() * 8              # index lists are not payload
         view = tensor.view(-1, row_len).index_select(0, idx)
         if cols is not None:
             view = view[:, :cols].contiguous()
@@ -124,7 +153,11 @@ class CudaBackend:
     def gather_best_device(self, ids, score, info, rows: np.ndarray, top_n: int):
         """(ids row, score) of rank ``info.best_rank`` for each search in ``rows``; result stays on
         the device (no synchronisation)."""
-        idx = self.torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device, non_blocking=True)
+        if hasattr(rows, "data_ptr"):
+            idx = rows
+        else:
+            idx = self.upload(np.asarray(rows, dtype=np.int64))
+            self.h2d_bytes -= idx.numel() * 8
         best = info.view(-1, STEP_INFO_DTYPE.itemsize // 4)[:, 6].index_select(0, idx).to(self.torch.int64)
         flat = idx * top_n + best
         return ids.view(-1, GK_MAX_CN).index_select(0, flat), score.index_select(0, flat)
@@ -455,6 +488,9 @@ class SearchGroup:
         self._pool = self._default_pool.copy()
         self.d_cand = be.upload(self._pool)
         self._pool_dirty = False
+        self._plan_key = None                 # (step vector, matrix table) of the cached launch plan
+        self._plan: dict = {}
+        self._plan_on = False                 # True inside run_pipeline only
         self.reset()
 
     def reset(self) -> None:
@@ -469,6 +505,17 @@ class SearchGroup:
             self._pool = self._default_pool.copy()
             self.d_cand = self.be.upload(self._pool)
             self._pool_dirty = False
+
+    # --- launch plan of the pipelined run ------------------------------------------------
+    def _planned(self, key, build):
+        """Work-item tables of ``run_pipeline`` depend only on the step vector (their grids are sized
+        from upper bounds), so a batch that is typed again reuses the device copies."""
+        if not self._plan_on:
+            return build()
+        hit = self._plan.get(key)
+        if hit is None:
+            hit = self._plan[key] = build()
+        return hit
 
     # --- candidates ------------------------------------------------------------------
     def _set_candidates(self, cands, active: np.ndarray) -> None:
@@ -641,15 +688,18 @@ class SearchGroup:
         return items
 
     def _write_p(self, idx: np.ndarray, n_set: int) -> None:
-        items = self._p_items(idx)
-        if not len(items):
+        def plan():
+            items = self._p_items(idx)
+            return (self.be.upload(items) if len(items) else None, len(items),
+                    float((items["r1"] - items["r0"]).sum()) * GK_KB)
+        d_items, n_items, work = self._planned(("write_p", n_set), plan)
+        if not n_items:
             return
         if self.d_P is None:
             self.d_P = self.be.empty(self._p_size, np.uint16 if self.batch.half else np.float32)
-        d_items = self.be.upload(items)
-        self.be.launch("gk_write_p", self.batch.d_table, self.d_tab, d_items, len(items), self.top_n, n_set,
+        self.be.launch("gk_write_p", self.batch.d_table, self.d_tab, d_items, n_items, self.top_n, n_set,
                        self.d_kept, self.d_ids[self.cur], self.batch.d_LT, self.d_P, int(self.batch.half),
-                       work=float((items["r1"] - items["r0"]).sum()) * GK_KB)
+                       work=work)
 
     def _collect(self, rows: np.ndarray, n: int, info: np.ndarray) -> StepBatch:
         be, tn = self.be, self.top_n
@@ -664,16 +714,19 @@ class SearchGroup:
     def _rescore_and_rank(self, active_idx: np.ndarray, f_cap: np.ndarray, n: int, new: int) -> None:
         """gk_rescore_count over the first f_cap[s] alive sets of every search, then gk_rank."""
         be, bt = self.be, self.batch
-        self.tab["cnt_off"] = _excl_cumsum(f_cap * n * n)
-        tab = self.tab.copy()
-        tab["alive_cap"] = f_cap                 # the kernels clamp the alive count to this capacity
-        self.d_tab = be.upload(tab)
-        d_cnt = be.zeros(int((f_cap * n * n).sum()), np.uint32)
-        c_items = self._count_items(active_idx, f_cap)
-        d_citems = be.upload(c_items)
-        be.launch("gk_rescore_count", bt.d_table, self.d_tab, d_citems, len(c_items), self.top_n, n,
+
+        def plan():
+            self.tab["cnt_off"] = _excl_cumsum(f_cap * n * n)
+            tab = self.tab.copy()
+            tab["alive_cap"] = f_cap             # the kernels clamp the alive count to this capacity
+            c_items = self._count_items(active_idx, f_cap)
+            return (be.upload(tab), be.upload(c_items), len(c_items),
+                    be.empty(int((f_cap * n * n).sum()), np.uint32), float((f_cap * self.R).sum()) * n)
+        self.d_tab, d_citems, n_citems, d_cnt, work = self._planned(("count", n), plan)
+        be.zero_(d_cnt)
+        be.launch("gk_rescore_count", bt.d_table, self.d_tab, d_citems, n_citems, self.top_n, n,
                   self.d_info, self.d_ids[self.cur], self.d_cand, self.d_alive, bt.d_LT, d_cnt,
-                  work=float((f_cap * self.R).sum()) * n)
+                  work=work)
         be.launch("gk_rank", bt.d_table, self.d_tab, self.n_search, self.top_n, n, self.d_ids[self.cur],
                   self.d_cand, self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_score[self.cur], self.d_keys,
                   self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept,
@@ -762,13 +815,24 @@ class SearchGroup:
         max_step = int(steps.max(initial=0))
         if max_step > GK_MAX_CN:
             raise ValueError(f"copy number above {GK_MAX_CN} is not supported by the search kernels")
+        key = (steps.tobytes(), id(bt.host))
+        if key != self._plan_key:
+            self._plan_key, self._plan, self._plan_host = key, {}, bt.host     # (the reference pins the id)
+        self._plan_on = True
+        try:
+            return self._run_pipeline(steps, max_step)
+        finally:
+            self._plan_on = False
+
+    def _run_pipeline(self, steps: np.ndarray, max_step: int):
+        be, bt, ns = self.be, self.batch, self.n_search
         k_ub = np.zeros(ns, dtype=np.int64)
         snaps, finals, f_caps, actives = [], [], [], []
         for n in range(1, max_step + 1):
             active = steps >= n
             active_idx = np.flatnonzero(active)
             self.tab["n_cand"] = np.where(active, self.n_cand, 0)
-            self.d_tab = be.upload(self.tab)
+            self.d_tab = self._planned(("tab", n), lambda: be.upload(self.tab))
             new = 1 - self.cur
             if n == 1:
                 be.launch("gk_first_step", bt.d_table, self.d_tab, ns, self.top_n, bt.d_col, self.d_cand,
@@ -778,11 +842,14 @@ class SearchGroup:
                 f_cap = np.zeros(ns, dtype=np.int64)
             else:
                 self.kept = np.where(active, k_ub, 0).astype(np.int32)        # upper bounds size the grids
-                items = self._score_items(active_idx)
+
+                def score_plan():
+                    items = self._score_items(active_idx)
+                    return be.upload(items), len(items), float(self._step_cells)
+                d_items, n_items, step_cells = self._planned(("score", n), score_plan)
                 be.zero_(self.d_S)
-                d_items = be.upload(items)
-                be.launch("gk_score", bt.d_table, self.d_tab, d_items, len(items), bt.d_L, self.d_P, self.d_S,
-                          int(bt.half), int(bt.flush_stages), self.d_kept, work=float(self._step_cells))
+                be.launch("gk_score", bt.d_table, self.d_tab, d_items, n_items, bt.d_L, self.d_P, self.d_S,
+                          int(bt.half), int(bt.flush_stages), self.d_kept, work=step_cells)
                 if self.reduce_scores is not None:
                     self.reduce_scores(self.d_S)
                 be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
@@ -798,8 +865,9 @@ class SearchGroup:
             actives.append(active)
             done = np.flatnonzero(steps == n)
             if len(done):
+                d_done = self._planned(("done", n), lambda: be.upload(done.astype(np.int64)))
                 finals.append((n, done) + tuple(be.gather_best_device(self.d_ids[self.cur], self.d_score[self.cur],
-                                                                      self.d_info, done, self.top_n)))
+                                                                      self.d_info, d_done, self.top_n)))
             nxt = np.flatnonzero(steps > n)
             if len(nxt):
                 self.kept = np.where(steps > n, k_ub, 0).astype(np.int32)
