@@ -146,6 +146,7 @@ class BatchTyper:
         self.homo = np.zeros(len(packs), dtype=bool)
         self._homo_cache: np.ndarray | None = None
         self.pipelined = True        # enqueue all steps up front (one read-back); False = read back per step
+        self._pending = None
 
     def upload(self) -> None:
         """Host pools -> device (the end-to-end path times this; the resident path does it once)."""
@@ -157,8 +158,18 @@ class BatchTyper:
         self.upload()
         return self.run()
 
+    def upload_and_start(self) -> None:
+        self.upload()
+        self.start()
+
     def run(self) -> list[GeneCall]:
         """Likelihood build + greedy search + calls for every problem of the batch."""
+        self.start()
+        return self.finish()
+
+    def start(self) -> None:
+        """Enqueue the likelihood build and (pipelined mode) every search launch on the current
+        stream without waiting for the device; ``finish`` reads back and forms the calls."""
         if self.batch is None:
             self.upload()
         batch = self.batch
@@ -168,10 +179,16 @@ class BatchTyper:
                                             reduce_scores=self.reduce_scores)
         else:
             self.group.reset()
-        group = self.group
         if self._homo_cache is None:           # the copy numbers are fixed for this batch
             self._homo_cache = self.homo_index.decide(self.cns) & (self.n_reads > 0)
         self.homo = self._homo_cache
+        steps = np.where(self.homo[self.live], 1, self.cns[self.live])
+        self._pending = None
+        if self.pipelined and self.col_shard is None:
+            self._pending = self.group.run_pipeline_start(steps)
+
+    def finish(self) -> list[GeneCall]:
+        group = self.group
         cn_live = self.cns[self.live]
         homo_live = self.homo[self.live]
         steps = np.where(homo_live, 1, cn_live)
@@ -182,7 +199,8 @@ class BatchTyper:
         score = np.zeros(n_live, dtype=np.int64)
         flags = np.zeros(n_live, dtype=np.int64)
         called = np.full((n_live, max(int(cn_live.max(initial=1)), 1)), -1, dtype=np.int64)
-        piped = group.run_pipeline(steps) if (self.pipelined and self.col_shard is None) else None
+        piped = group.run_pipeline_finish(self._pending) if self._pending is not None else None
+        self._pending = None
         if piped is not None:
             ids, score, info = piped
             kept = info["n_kept"].astype(np.int64)
@@ -239,9 +257,10 @@ class BatchTyper:
 
 
 class CohortTyper:
-    """Splits a batch into ``n_parts`` sub-batches that run concurrently, each on its own CUDA
-    stream and host thread, so the host-side work of one part (work-item lists, result
-    selection) overlaps the kernels of the others.  Results come back in input order."""
+    """Splits a batch into ``n_parts`` sub-batches, each on its own CUDA stream.  One host thread
+    enqueues every part (uploads, likelihood build, all search steps) before it blocks on the
+    first read-back, so the host->device copies and the host-side call phase of one part overlap
+    the kernels of the others.  Results come back in input order."""
 
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
                  n_parts: int = 2, group_size: int = 1, col_shard: tuple[int, int] | None = None,
@@ -258,11 +277,8 @@ class CohortTyper:
         self.parts = [BatchTyper(packs[sl], list(cns)[sl], top_n=top_n, backend=self.be, col_shard=col_shard,
                                  reduce_scores=reduce_scores) for sl in self.slices]
         self.streams = None
-        self.pool = None
         if n_parts > 1 and hasattr(self.be, "torch"):
-            from concurrent.futures import ThreadPoolExecutor
             self.streams = [self.be.torch.cuda.Stream(device=self.be.device) for _ in self.parts]
-            self.pool = ThreadPoolExecutor(max_workers=n_parts)
 
     @property
     def score_cells(self) -> int:
@@ -276,30 +292,28 @@ class CohortTyper:
         for p in self.parts:
             p.host.pin(self.be)
 
-    def _on_stream(self, i: int, fn_name: str):
-        part = self.parts[i]
+    def _each(self, fn_name: str) -> list:
+        """``fn_name`` of every part, each under its own stream (no synchronisation)."""
         if self.streams is None:
-            return getattr(part, fn_name)()
+            return [getattr(part, fn_name)() for part in self.parts]
         torch = self.be.torch
-        torch.cuda.set_device(self.be.device)
-        with torch.cuda.stream(self.streams[i]):
-            out = getattr(part, fn_name)()
-            self.streams[i].synchronize()
+        cur = torch.cuda.current_stream(self.be.device)
+        out = []
+        for part, st in zip(self.parts, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                out.append(getattr(part, fn_name)())
         return out
 
-    def _all(self, fn_name: str) -> list:
-        if self.pool is None:
-            return [self._on_stream(i, fn_name) for i in range(len(self.parts))]
+    def _join(self) -> None:
         if self.streams is not None:
             cur = self.be.torch.cuda.current_stream(self.be.device)
             for st in self.streams:
-                st.wait_stream(cur)
-        futures = [self.pool.submit(self._on_stream, i, fn_name) for i in range(len(self.parts))]
-        out = [f.result() for f in futures]
-        return out
+                cur.wait_stream(st)
 
     def upload(self) -> None:
-        self._all("upload")
+        self._each("upload")
+        self._join()
 
     def run_serial(self) -> list[GeneCall]:
         """All parts one after the other on the current stream (used to time kernels in isolation)."""
@@ -309,15 +323,21 @@ class CohortTyper:
         return calls
 
     def run(self) -> list[GeneCall]:
+        self._each("start")                  # every part enqueued ...
         calls: list[GeneCall] = []
-        for part in self._all("run"):
+        for part in self._each("finish"):    # ... before the first read-back blocks the host
             calls.extend(part)
+        self._join()
         return calls
 
     def upload_and_run(self) -> list[GeneCall]:
+        """End-to-end pass: host pools -> device, typing, calls (copies of one part overlap the
+        kernels of the others)."""
+        self._each("upload_and_start")
         calls: list[GeneCall] = []
-        for part in self._all("upload_and_run"):
+        for part in self._each("finish"):
             calls.extend(part)
+        self._join()
         return calls
 
 

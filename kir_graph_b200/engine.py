@@ -809,7 +809,13 @@ class SearchGroup:
         selectBest for every search, or ``None`` when a search had more alive sets than the
         pre-sized grids (exact tie at a cut larger than the slack): the caller then repeats the
         run step by step."""
-        be, bt, ns = self.be, self.batch, self.n_search
+        return self.run_pipeline_finish(self.run_pipeline_start(steps))
+
+    def run_pipeline_start(self, steps: np.ndarray):
+        """Enqueue every launch of ``run_pipeline`` on the current stream without synchronising;
+        ``run_pipeline_finish`` reads the results back.  Lets a caller enqueue several groups (on
+        several streams) before it blocks on the first."""
+        bt = self.batch
         steps = np.asarray(steps, dtype=np.int64)
         self.reset()
         max_step = int(steps.max(initial=0))
@@ -820,11 +826,11 @@ class SearchGroup:
             self._plan_key, self._plan, self._plan_host = key, {}, bt.host     # (the reference pins the id)
         self._plan_on = True
         try:
-            return self._run_pipeline(steps, max_step)
+            return self._enqueue_pipeline(steps, max_step)
         finally:
             self._plan_on = False
 
-    def _run_pipeline(self, steps: np.ndarray, max_step: int):
+    def _enqueue_pipeline(self, steps: np.ndarray, max_step: int):
         be, bt, ns = self.be, self.batch, self.n_search
         k_ub = np.zeros(ns, dtype=np.int64)
         snaps, finals, f_caps, actives = [], [], [], []
@@ -872,7 +878,12 @@ class SearchGroup:
             if len(nxt):
                 self.kept = np.where(steps > n, k_ub, 0).astype(np.int32)
                 self._write_p(nxt, n)
-        # ---- single read-back -----------------------------------------------------------
+        return steps, max_step, snaps, finals, f_caps, actives
+
+    def run_pipeline_finish(self, pending):
+        """The single read-back of a pipelined run (see ``run_pipeline``)."""
+        be, ns = self.be, self.n_search
+        steps, max_step, snaps, finals, f_caps, actives = pending
         infos = [be.download(t, None).view(STEP_INFO_DTYPE).copy() for t in snaps]
         cells = 0
         for i, info in enumerate(infos):
