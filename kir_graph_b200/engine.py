@@ -127,6 +127,35 @@ class CudaBackend:
         self.d2h_bytes += out.nbytes
         return out.view(dtype) if dtype is not None else out
 
+    def download_async(self, tensors: list):
+        """Start ONE device->host copy of several int32 device arrays (concatenated on the device
+        into a page-locked buffer of the current stream); ``download_wait`` returns the arrays."""
+        torch = self.torch
+        flat = torch.cat([t.reshape(-1) for t in tensors]) if len(tensors) != 1 else tensors[0].reshape(-1)
+        assert flat.dtype == torch.int32
+        stream = torch.cuda.current_stream(self.device)
+        self._d2h = getattr(self, "_d2h", {})
+        buf = self._d2h.get(stream.cuda_stream)
+        if buf is None or buf.numel() < flat.numel():
+            buf = torch.empty(max(flat.numel(), 1 << 18), dtype=torch.int32).pin_memory()
+            self._d2h[stream.cuda_stream] = buf
+        view = buf[: flat.numel()]
+        view.copy_(flat, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(stream)
+        return view, event, [t.numel() for t in tensors]
+
+    def download_wait(self, handle) -> list[np.ndarray]:
+        view, event, sizes = handle
+        event.synchronize()
+        host = view.numpy().copy()
+        self.d2h_bytes += host.nbytes
+        out, pos = [], 0
+        for n in sizes:
+            out.append(host[pos:pos + n])
+            pos += n
+        return out
+
     def zero_(self, tensor) -> None:
         tensor.zero_()
 
@@ -878,13 +907,21 @@ class SearchGroup:
             if len(nxt):
                 self.kept = np.where(steps > n, k_ub, 0).astype(np.int32)
                 self._write_p(nxt, n)
-        return steps, max_step, snaps, finals, f_caps, actives
+        # ---- the single read-back: one device->host copy of everything the host needs --------
+        tensors = list(snaps)
+        for _, _, d_ids, d_score in finals:
+            tensors += [d_ids, d_score]
+        handle = be.download_async(tensors)
+        finals = [(n, done) for n, done, _, _ in finals]
+        return steps, max_step, len(snaps), finals, f_caps, actives, handle
 
     def run_pipeline_finish(self, pending):
-        """The single read-back of a pipelined run (see ``run_pipeline``)."""
+        """Wait for the read-back of a pipelined run (see ``run_pipeline``)."""
         be, ns = self.be, self.n_search
-        steps, max_step, snaps, finals, f_caps, actives = pending
-        infos = [be.download(t, None).view(STEP_INFO_DTYPE).copy() for t in snaps]
+        steps, max_step, n_snaps, finals, f_caps, actives, handle = pending
+        arrays = be.download_wait(handle)
+        infos = [a.view(STEP_INFO_DTYPE).copy() for a in arrays[:n_snaps]]
+        arrays = arrays[n_snaps:]
         cells = 0
         for i, info in enumerate(infos):
             n = i + 1
@@ -901,10 +938,10 @@ class SearchGroup:
         out_ids = np.full((ns, max(max_step, 1)), -1, dtype=np.int64)
         out_score = np.zeros(ns, dtype=np.int64)
         out_info = np.zeros(ns, dtype=STEP_INFO_DTYPE)
-        for n, done, d_ids, d_score in finals:
-            ids = be.download(d_ids, np.int32).reshape(len(done), GK_MAX_CN)[:, :n]
+        for j, (n, done) in enumerate(finals):
+            ids = arrays[2 * j].view(np.int32).reshape(len(done), GK_MAX_CN)[:, :n]
             out_ids[done, :n] = ids
-            out_score[done] = be.download(d_score, np.uint32).astype(np.int64)
+            out_score[done] = arrays[2 * j + 1].view(np.uint32).astype(np.int64)
             out_info[done] = infos[n - 1][done]
         self.kept = infos[-1]["n_kept"].astype(np.int32) if infos else self.kept
         return out_ids, out_score, out_info

@@ -58,6 +58,12 @@ class FakeBackend:
         out = np.array(tensor, copy=True)
         return out.view(dtype) if dtype is not None else out
 
+    def download_async(self, tensors):
+        return [np.array(t, copy=True).reshape(-1).view(np.int32) for t in tensors]
+
+    def download_wait(self, handle):
+        return handle
+
     def zero_(self, tensor):
         tensor.view(np.uint8)[:] = 0
 

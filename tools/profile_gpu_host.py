@@ -44,16 +44,12 @@ for _ in range(20): typer.run()
 torch.cuda.synchronize()
 print("gc disabled, 20 runs: wall ms per run", 1e3 * (time.perf_counter() - t0) / 20)
 gc.enable()
-# where does a run spend its wall time?
-import kir_graph_b200.engine as E
-orig = E.SearchGroup.run_pipeline
-marks = {}
-def wrapped(self, steps):
-    t0 = time.perf_counter(); out = orig(self, steps); marks["pipe"] = marks.get("pipe", 0) + time.perf_counter() - t0
-    return out
-E.SearchGroup.run_pipeline = wrapped
-t0 = time.perf_counter()
-for _ in range(20): typer.run()
-torch.cuda.synchronize()
-tot = time.perf_counter() - t0
-print(f"per run: total {1e3*tot/20:.2f} ms, run_pipeline (enqueue + read-back) {1e3*marks['pipe']/20:.2f} ms, rest (likelihood launch + call phase) {1e3*(tot-marks['pipe'])/20:.2f} ms")
+for np_ in (2, 3):
+    ct = cohort.CohortTyper(packs, cns, top_n=300, backend=be, n_parts=np_, group_size=17)
+    ct.pin(); ct.upload()
+    for _ in range(3): ct.run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20): ct.run()
+    torch.cuda.synchronize()
+    print(f"CohortTyper parts={np_} 20 runs: wall ms per run", 1e3 * (time.perf_counter() - t0) / 20)
