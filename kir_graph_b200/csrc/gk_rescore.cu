@@ -19,52 +19,68 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
+// Byte-SIMD tie counting.  Per 32-bit word (4 reads): mn = vmin4 over the members, eq[t] = 0x01 in
+// the bytes where member t attains it, q = sum_t eq[t] (tie size per read), sel[qq] = 0xff where
+// q == qq + 1.  The N*N counters are byte lanes of 32-bit accumulators,
+//     acc[t][qq] += (eq_a[t] & sel_a[qq]) + (eq_b[t] & sel_b[qq])        (two words per IADD3),
+// i.e. 1.5 N^2 + 4 N instructions per word instead of a popcount per (t, qq).  A lane sees at most
+// 16384 / (32 lanes * 4 reads) = 128 words of a work item, so a byte lane (<= 1 per word) cannot
+// overflow; the four lanes are summed once at the end.  Pad reads (r >= n_reads, all-zero rows:
+// every member ties at 0) are not masked in the loop but subtracted from cnt[t][N-1] afterwards.
 template <int N>
 __device__ __forceinline__ void count_set(const uint8_t* const (&rows)[N], int r0, int r1, int n_reads,
                                           uint32_t* __restrict__ out) {
     const int lane = gk_lane();
-    uint32_t cnt[N][N];
+    uint32_t acc[N][N];
 #pragma unroll
     for (int t = 0; t < N; ++t)
 #pragma unroll
-        for (int q = 0; q < N; ++q) cnt[t][q] = 0u;
+        for (int q = 0; q < N; ++q) acc[t][q] = 0u;
+
+    auto word = [&](const uint32_t (&v)[N], uint32_t (&eq)[N], uint32_t (&sel)[N]) {
+        uint32_t mn = v[0];
+#pragma unroll
+        for (int t = 1; t < N; ++t) mn = __vminu4(mn, v[t]);
+        uint32_t q = 0u;
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            eq[t] = __vcmpeq4(v[t], mn) & 0x01010101u;
+            q += eq[t];
+        }
+#pragma unroll
+        for (int qq = 0; qq < N; ++qq) sel[qq] = __vcmpeq4(q, 0x01010101u * (uint32_t)(qq + 1));
+    };
 
     for (int r = r0 + lane * 16; r < r1; r += 32 * 16) {
         uint4 x[N];
 #pragma unroll
         for (int t = 0; t < N; ++t) x[t] = __ldg(reinterpret_cast<const uint4*>(rows[t] + r));
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            uint32_t v[N];
-#pragma unroll
-            for (int t = 0; t < N; ++t) v[t] = w == 0 ? x[t].x : w == 1 ? x[t].y : w == 2 ? x[t].z : x[t].w;
-            uint32_t mn = v[0];
-#pragma unroll
-            for (int t = 1; t < N; ++t) mn = __vminu4(mn, v[t]);
-            int left = n_reads - (r + 4 * w);
-            left = left < 0 ? 0 : (left > 4 ? 4 : left);
-            const uint32_t valid = left == 4 ? 0xffffffffu : ((1u << (8 * left)) - 1u);
-            uint32_t eq[N];
-            uint32_t q = 0u;
+        for (int w = 0; w < 4; w += 2) {
+            uint32_t va[N], vb[N], ea[N], eb[N], sa[N], sb[N];
 #pragma unroll
             for (int t = 0; t < N; ++t) {
-                eq[t] = __vcmpeq4(v[t], mn) & valid;
-                q += eq[t] & 0x01010101u;
+                va[t] = w == 0 ? x[t].x : x[t].z;
+                vb[t] = w == 0 ? x[t].y : x[t].w;
             }
+            word(va, ea, sa);
+            word(vb, eb, sb);
 #pragma unroll
-            for (int qq = 0; qq < N; ++qq) {
-                const uint32_t sel = __vcmpeq4(q, 0x01010101u * (uint32_t)(qq + 1));
+            for (int t = 0; t < N; ++t)
 #pragma unroll
-                for (int t = 0; t < N; ++t) cnt[t][qq] += __popc(eq[t] & sel) >> 3;
-            }
+                for (int qq = 0; qq < N; ++qq) acc[t][qq] += (ea[t] & sa[qq]) + (eb[t] & sb[qq]);
         }
     }
+    // pad reads of this item seen by the whole warp: [max(r0, n_reads), r1)
+    const int pad_lo = r0 > n_reads ? r0 : n_reads;
+    const uint32_t pad = r1 > pad_lo ? (uint32_t)(r1 - pad_lo) : 0u;
 #pragma unroll
     for (int t = 0; t < N; ++t) {
 #pragma unroll
         for (int q = 0; q < N; ++q) {
-            uint32_t c = cnt[t][q];
+            uint32_t c = __vsadu4(acc[t][q], 0u);           // sum of the four byte lanes
             for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (q == N - 1) c -= pad;
             if (lane == 0 && c) atomicAdd(out + t * N + q, c);
         }
     }
