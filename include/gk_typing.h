@@ -84,7 +84,7 @@ typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;         
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
     shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48 (from k_blk / a_blk);
     packed mode rows: 5..8 = 32, 64, 96, 128 kept sets */
-typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16; r1 - r0 <= 32640 (byte-lane tie counters) */
+typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16; */
 typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 
 /* Per-search step outputs (device arrays indexed [search]). */

@@ -19,56 +19,115 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
-// Byte-SIMD tie counting.  Per 32-bit word (4 reads): mn = vmin4 over the members, eq[t] = 0x01 in
-// the bytes where member t attains it, q = sum_t eq[t] (tie size per read), sel[qq] = 0xff where
-// q == qq + 1.  The N*N counters are byte lanes of 32-bit accumulators,
-//     acc[t][qq] += (eq_a[t] & sel_a[qq]) + (eq_b[t] & sel_b[qq])        (two words per IADD3),
-// i.e. 1.5 N^2 + 4 N instructions per word instead of a popcount per (t, qq).  A lane sees at most
-// 16384 / (32 lanes * 4 reads) = 128 words of a work item, so a byte lane (<= 1 per word) cannot
-// overflow; the four lanes are summed once at the end.  Pad reads (r >= n_reads, all-zero rows:
-// every member ties at 0) are not masked in the loop but subtracted from cnt[t][N-1] afterwards.
+// Byte-SIMD tie counting, four reads per 32-bit word.  sm_100a has no native byte-wise min /
+// compare (nvcc expands __vminu4 / __vcmpeq4 into ~9 ALU instructions each, and the ALU pipe is the
+// bound of this kernel: 97 % busy in ncu), so the per-byte predicates are built from carry-free
+// word arithmetic and the N*N counters are accumulated with DP4A, which issues on the otherwise
+// idle FMA pipe:
+//     ge80(a, b)  0x80 in the bytes where a >= b        (5 ALU instructions)
+//     zero80(x)   0x80 in the bytes of x that are zero  (3)
+//     mn          running byte-wise minimum of the members (select through a 0xff mask)
+//     eq[t]       0x01 where member t attains mn; q = sum_t eq[t] = tie size of the read
+//     sel[qq]     0x01 where q == qq + 1 (bit logic on the binary digits of q)
+//     cnt[t][qq] += dp4a(eq[t], sel[qq])
+// Pad reads (r >= n_reads, all-zero rows: every member ties at 0) are not masked in the loop but
+// subtracted from cnt[t][N-1] afterwards.
+__device__ __forceinline__ uint32_t ge80(uint32_t a, uint32_t b) {
+    const uint32_t t = (a | 0x80808080u) - (b & 0x7f7f7f7fu);       // bit 7: low 7 bits of a >= those of b
+    return ((a & ~b) | (~(a ^ b) & t)) & 0x80808080u;
+}
+
+__device__ __forceinline__ uint32_t zero80(uint32_t x) {
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;             // bit 7: low 7 bits non-zero
+    return ~(t | x) & 0x80808080u;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t c) {
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
+}
+
+// Two members: no minimum needed.  a < b: member 0 alone; a > b: member 1 alone; a == b: both.
+__device__ __forceinline__ void count_pair(const uint8_t* row_a, const uint8_t* row_b, int r0, int r1, int n_reads,
+                                           uint32_t* __restrict__ out) {
+    const int lane = gk_lane();
+    uint32_t n_ge = 0u, n_eq = 0u, n_all = 0u;                       // n_ge, n_eq in units of 1/128 read
+    for (int r = r0 + lane * 16; r < r1; r += 32 * 16) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(row_a + r));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(row_b + r));
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            n_ge = __dp4a(ge80(av[w], bv[w]), 0x01010101u, n_ge);
+            n_eq = __dp4a(zero80(av[w] ^ bv[w]), 0x01010101u, n_eq);
+        }
+        n_all += 16u;
+    }
+    n_ge = warp_sum(n_ge) >> 7;
+    n_eq = warp_sum(n_eq) >> 7;
+    n_all = warp_sum(n_all);
+    if (lane == 0) {
+        const int pad_lo = r0 > n_reads ? r0 : n_reads;
+        const uint32_t pad = r1 > pad_lo ? (uint32_t)(r1 - pad_lo) : 0u;
+        const uint32_t lt = n_all - n_ge, gt = n_ge - n_eq, eq = n_eq - pad;
+        if (lt) atomicAdd(out + 0, lt);          // cnt[0][q=1]
+        if (eq) atomicAdd(out + 1, eq);          // cnt[0][q=2]
+        if (gt) atomicAdd(out + 2, gt);          // cnt[1][q=1]
+        if (eq) atomicAdd(out + 3, eq);          // cnt[1][q=2]
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void count_set(const uint8_t* const (&rows)[N], int r0, int r1, int n_reads,
                                           uint32_t* __restrict__ out) {
+    if constexpr (N == 2) {
+        count_pair(rows[0], rows[1], r0, r1, n_reads, out);
+        return;
+    }
     const int lane = gk_lane();
-    uint32_t acc[N][N];
+    uint32_t cnt[N][N];
 #pragma unroll
     for (int t = 0; t < N; ++t)
 #pragma unroll
-        for (int q = 0; q < N; ++q) acc[t][q] = 0u;
-
-    auto word = [&](const uint32_t (&v)[N], uint32_t (&eq)[N], uint32_t (&sel)[N]) {
-        uint32_t mn = v[0];
-#pragma unroll
-        for (int t = 1; t < N; ++t) mn = __vminu4(mn, v[t]);
-        uint32_t q = 0u;
-#pragma unroll
-        for (int t = 0; t < N; ++t) {
-            eq[t] = __vcmpeq4(v[t], mn) & 0x01010101u;
-            q += eq[t];
-        }
-#pragma unroll
-        for (int qq = 0; qq < N; ++qq) sel[qq] = __vcmpeq4(q, 0x01010101u * (uint32_t)(qq + 1));
-    };
+        for (int q = 0; q < N; ++q) cnt[t][q] = 0u;
 
     for (int r = r0 + lane * 16; r < r1; r += 32 * 16) {
         uint4 x[N];
 #pragma unroll
         for (int t = 0; t < N; ++t) x[t] = __ldg(reinterpret_cast<const uint4*>(rows[t] + r));
 #pragma unroll
-        for (int w = 0; w < 4; w += 2) {
-            uint32_t va[N], vb[N], ea[N], eb[N], sa[N], sb[N];
+        for (int w = 0; w < 4; ++w) {
+            uint32_t v[N];
+#pragma unroll
+            for (int t = 0; t < N; ++t) v[t] = w == 0 ? x[t].x : w == 1 ? x[t].y : w == 2 ? x[t].z : x[t].w;
+            uint32_t mn = v[0];
+#pragma unroll
+            for (int t = 1; t < N; ++t) {
+                const uint32_t keep = (ge80(v[t], mn) >> 7) * 0xffu;        // 0xff where mn stays
+                mn = (mn & keep) | (v[t] & ~keep);
+            }
+            uint32_t eq[N];
+            uint32_t q = 0u;
 #pragma unroll
             for (int t = 0; t < N; ++t) {
-                va[t] = w == 0 ? x[t].x : x[t].z;
-                vb[t] = w == 0 ? x[t].y : x[t].w;
+                eq[t] = zero80(v[t] ^ mn) >> 7;
+                q += eq[t];
             }
-            word(va, ea, sa);
-            word(vb, eb, sb);
+            // binary digits of q (1..N <= 8) per byte
+            const uint32_t b0 = q & 0x01010101u, b1 = (q >> 1) & 0x01010101u, b2 = (q >> 2) & 0x01010101u;
 #pragma unroll
-            for (int t = 0; t < N; ++t)
+            for (int qq = 0; qq < N; ++qq) {
+                const int c = qq + 1;
+                uint32_t sel;
+                if (c == 8) {
+                    sel = (q >> 3) & 0x01010101u;
+                } else {       // q == 8 has the digits 000 and cannot match c in 1..7
+                    sel = ((c & 1) ? b0 : ~b0) & ((c & 2) ? b1 : ~b1) & ((c & 4) ? b2 : ~b2) & 0x01010101u;
+                }
 #pragma unroll
-                for (int qq = 0; qq < N; ++qq) acc[t][qq] += (ea[t] & sa[qq]) + (eb[t] & sb[qq]);
+                for (int t = 0; t < N; ++t) cnt[t][qq] = __dp4a(eq[t], sel, cnt[t][qq]);
+            }
         }
     }
     // pad reads of this item seen by the whole warp: [max(r0, n_reads), r1)
@@ -78,8 +137,7 @@ __device__ __forceinline__ void count_set(const uint8_t* const (&rows)[N], int r
     for (int t = 0; t < N; ++t) {
 #pragma unroll
         for (int q = 0; q < N; ++q) {
-            uint32_t c = __vsadu4(acc[t][q], 0u);           // sum of the four byte lanes
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            uint32_t c = warp_sum(cnt[t][q]);
             if (q == N - 1) c -= pad;
             if (lane == 0 && c) atomicAdd(out + t * N + q, c);
         }
