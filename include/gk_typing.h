@@ -82,8 +82,12 @@ typedef struct GkSearch {
 /* Work items (built by the host per launch). */
 typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS */
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
-    shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48 (from k_blk / a_blk);
-    packed mode rows: 5..8 = 32, 64, 96, 128 kept sets */
+    FP32 path: shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48
+    (from k_blk / a_blk).  Packed path, full-width tile: rows 5..8 = 32, 64, 96, 128 kept sets, column mode 0
+    (128 alleles).  Packed path, warp-split tile (small genes, ragged right edge):
+    shape = G' | log2(WK) << 4 | TA' << 8 | GK_SHAPE_WARP_SPLIT = WK * 8 G' kept sets (G' = 1..4, WK = 1, 2, 4)
+    x 8 TA' alleles (TA' = 1..8) */
+#define GK_SHAPE_WARP_SPLIT (1 << 16)
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16; */
 typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 

@@ -374,19 +374,150 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
 
 }
 
-template <int G>
-__device__ __forceinline__ void score_dispatch_h(int am, const GkScoreItem& item, const GkMatrix& M,
+// ---------------------------------------------------------------------------------------
+// Warp-split tiles of the packed path (item.shape & GK_SHAPE_WARP_SPLIT): small problems.
+//
+// A gene with few alleles (or the ragged right edge of a wide one) would leave most of a
+// 128 x 128 CTA tile empty, and a CTA tile cut down to 32 x 32 leaves every thread 2 x 2 cells,
+// i.e. more shared loads than minima.  Here the tile is 8 TA' columns (TA' = 1..8) by
+// WK x 8 G' rows (G' = 1..4 groups of 8, WK = 1, 2 or 4 warps side by side), a lane still owns
+// 2 G' rows x TA' columns (lane = 4 row pairs x 8 columns), and the 8 / WK warps that share
+// the rows split the 32 reads of every stage between them.  Granularity 8 in both dimensions,
+// same instruction mix as the full tile.  Partial sums meet in S through the atomics anyway.
+template <int GP, int TAP>
+__device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
+                                             const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
+                                             uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
+                                             uint64_t* full, uint64_t* empty, int* next, int flush, int wk_log2) {
+    constexpr int AT = 32;
+    constexpr int AW = (8 * TAP + AT - 1) / AT;                      // a-blocks staged (1 or 2)
+    constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(uint16_t);
+    constexpr uint32_t kBytesLBlk = GK_RT * AT * sizeof(uint32_t);
+    constexpr uint32_t kStageStride = 2 * kBytesPBlk + 2 * kBytesLBlk;
+    const int KW = ((8 * GP) << wk_log2) > GK_KB ? 2 : 1;            // k-blocks staged
+    const uint32_t stage_bytes = KW * kBytesPBlk + AW * kBytesLBlk;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int tk = lane >> 3;                                        // row pair inside a group of 8 rows
+    const int ta = lane & 7;                                         // column inside a group of 8 columns
+    const int row0 = (warp & ((1 << wk_log2) - 1)) * (8 * GP);       // first row of this warp
+    const int reads_per_warp = 4 << wk_log2;                         // 32 reads / (8 >> wk_log2) warps
+    const int rd0 = (warp >> wk_log2) * reads_per_warp;
+
+    const int rb0 = item.r0 / GK_RT;
+    const uint16_t* gP = P_pool + X.P_off + ((int64_t)rb0 * X.n_kblk + item.k_blk) * (GK_RT * GK_KB);
+    const uint32_t* gL = reinterpret_cast<const uint32_t*>(L_pool) + M.L_off +
+                         ((int64_t)rb0 * M.n_ablk + item.a_blk) * (GK_RT * AT);
+    const int64_t rb_stride_p = (int64_t)X.n_kblk * (GK_RT * GK_KB);
+    const int64_t rb_stride_l = (int64_t)M.n_ablk * (GK_RT * AT);
+    const int n_tiles = (item.r1 - item.r0) / GK_RT;
+
+    auto issue = [&](int tile, int s) {
+        unsigned char* dst = smem_bytes + (size_t)s * kStageStride;
+        gk_mbar_arrive_expect_tx(&full[s], stage_bytes);
+        gk_bulk_g2s(dst, gP + tile * rb_stride_p, KW * kBytesPBlk, &full[s]);
+        gk_bulk_g2s(dst + 2 * kBytesPBlk, gL + tile * rb_stride_l, AW * kBytesLBlk, &full[s]);
+    };
+    if (tid == 0) {
+        const int pre = n_tiles < kStagesP ? n_tiles : kStagesP;
+        for (int s = 0; s < pre; ++s) issue(s, s);
+        *next = pre;
+    }
+    __syncthreads();
+    auto try_refill = [&]() {
+        const int n = *reinterpret_cast<volatile int*>(next);
+        if (n >= n_tiles) return;
+        const int sp = n % kStagesP;
+        if (!gk_mbar_test(&empty[sp], (n / kStagesP - 1) & 1)) return;
+        if (atomicCAS(next, n, n + 1) == n) issue(n, sp);
+    };
+
+    uint32_t acc2[GP][TAP];
+#pragma unroll
+    for (int g = 0; g < GP; ++g)
+#pragma unroll
+        for (int j = 0; j < TAP; ++j) acc2[g][j] = 0u;
+
+    // rows row0 + 8 g + 2 tk + {0, 1}: offset (in uint16) inside the staged P blocks [k_blk][r][64]
+    auto p_off = [&](int g) {
+        const int k = row0 + 8 * g + 2 * tk;
+        return (k / GK_KB) * (GK_RT * GK_KB) + (k % GK_KB);
+    };
+    // column 8 j + ta inside the staged L blocks [a_blk][r][32]
+    auto l_off = [&](int j) { return (j / 4) * (GK_RT * AT) + (j % 4) * 8 + ta; };
+
+    uint32_t* S = S_pool + X.S_off + (int64_t)(item.k_blk * GK_KB + row0 + 2 * tk) * X.s_stride + item.a_blk * AT + ta;
+    auto flush_acc = [&]() {
+#pragma unroll
+        for (int g = 0; g < GP; ++g)
+#pragma unroll
+            for (int j = 0; j < TAP; ++j) {
+                const uint32_t v = acc2[g][j];
+                uint32_t* cell = S + (int64_t)(8 * g) * X.s_stride + 8 * j;
+                if (v & 0xffffu) atomicAdd(cell, v & 0xffffu);
+                if (v >> 16) atomicAdd(cell + X.s_stride, v >> 16);
+                acc2[g][j] = 0u;
+            }
+    };
+
+    int since_flush = 0;
+#pragma unroll 1
+    for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % kStagesP;
+        if (lane == 0) try_refill();
+        __syncwarp();
+        while (true) {                       // warp-uniform wait, see score_item
+            const bool ok = gk_mbar_try_wait(&full[s], (t / kStagesP) & 1);
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (lane == 0) try_refill();
+            __syncwarp();
+        }
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(smem_bytes + (size_t)s * kStageStride);
+        const uint32_t* l = reinterpret_cast<const uint32_t*>(smem_bytes + (size_t)s * kStageStride + 2 * kBytesPBlk);
+#pragma unroll 2
+        for (int i = 0; i < reads_per_warp; i += 2) {
+            const int r = rd0 + i;
+            uint32_t pv0[GP], pv1[GP], lv0[TAP], lv1[TAP];
+#pragma unroll
+            for (int g = 0; g < GP; ++g) {
+                pv0[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + r * GK_KB);
+                pv1[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + (r + 1) * GK_KB);
+            }
+#pragma unroll
+            for (int j = 0; j < TAP; ++j) {
+                lv0[j] = l[l_off(j) + r * AT];
+                lv1[j] = l[l_off(j) + (r + 1) * AT];
+            }
+#pragma unroll
+            for (int g = 0; g < GP; ++g)
+#pragma unroll
+                for (int j = 0; j < TAP; ++j)
+                    acc2[g][j] = acc2[g][j] + __vminu2(pv0[g], lv0[j]) + __vminu2(pv1[g], lv1[j]);
+        }
+        if (++since_flush >= flush) {
+            flush_acc();
+            since_flush = 0;
+        }
+        __syncwarp();
+        if (lane == 0) gk_mbar_arrive(&empty[s]);
+    }
+    flush_acc();
+}
+
+template <int GP>
+__device__ __forceinline__ void score_dispatch_w(int tap, const GkScoreItem& item, const GkMatrix& M,
                                                  const GkSearch& X, const float* __restrict__ L_pool,
                                                  const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
                                                  unsigned char* smem, uint64_t* full, uint64_t* empty, int* next,
-                                                 int flush) {
-    switch (am) {
-        case F8: score_item_h<G, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case F4: score_item_h<G, F4>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case S1: score_item_h<G, S1>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case S2: score_item_h<G, S2>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        default: score_item_h<G, S3>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+                                                 int flush, int wk_log2) {
+#define GK_W_CASE(T) \
+    case T: score_item_w<GP, T>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+    switch (tap) {
+        GK_W_CASE(1) GK_W_CASE(2) GK_W_CASE(3) GK_W_CASE(4) GK_W_CASE(5) GK_W_CASE(6) GK_W_CASE(7)
+        default: score_item_w<GP, 8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
     }
+#undef GK_W_CASE
 }
 
 __global__ void __launch_bounds__(kThreads, GK_PACKED_CTAS)
@@ -413,13 +544,23 @@ gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __
     const GkScoreItem item = items[blockIdx.x];
     const GkSearch X = searches[item.search];
     const GkMatrix M = matrices[X.matrix];
-    const int g = (item.shape & 0xff) - 4;    // row mode 5..8 = 1..4 groups of 32 kept sets
-    const int am = (item.shape >> 8) & 0xff;
-    switch (g) {
-        case 1: score_dispatch_h<1>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case 2: score_dispatch_h<2>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case 3: score_dispatch_h<3>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        default: score_dispatch_h<4>(am, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+    if (item.shape & GK_SHAPE_WARP_SPLIT) {      // G' | log2(WK) << 4 | TA' << 8
+        const int tap = (item.shape >> 8) & 0xff;
+        const int wk_log2 = (item.shape >> 4) & 0xf;
+        switch (item.shape & 0xf) {
+            case 1: score_dispatch_w<1>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+            case 2: score_dispatch_w<2>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+            case 3: score_dispatch_w<3>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+            default: score_dispatch_w<4>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+        }
+        return;
+    }
+    // full-width tile: 1..4 groups of 32 kept sets (row mode 5..8) x 128 alleles
+    switch ((item.shape & 0xff) - 4) {
+        case 1: score_item_h<1, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case 2: score_item_h<2, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case 3: score_item_h<3, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        default: score_item_h<4, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
     }
 }
 

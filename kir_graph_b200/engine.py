@@ -425,6 +425,7 @@ class BestBatch:
 
 # scoring tile modes (gk_score.cu): 128 / 64 wide with vector loads, 16 / 32 / 48 wide remainders
 MODE_F8, MODE_F4, MODE_S1, MODE_S2, MODE_S3 = 0, 1, 2, 3, 4
+SHAPE_WARP_SPLIT = 1 << 16      # GkScoreItem.shape flag: warp-split tile of the packed scoring kernel
 
 
 def _tile_counts(n16: np.ndarray) -> np.ndarray:
@@ -619,8 +620,10 @@ class SearchGroup:
         k16 = -(-kept[live] // 16)
         k32 = -(-kept[live] // 32)
         a16 = -(-self.A[live] // 16)
+        a8 = -(-self.A[live] // 8)
         n_kt = -(-k32 // 4) if half else _tile_counts(k16)
-        n_at = _tile_counts(a16)
+        # packed path: 128-column tiles, then one or two warp-split tiles of 8..64 columns
+        n_at = (a8 // 16 + (a8 % 16 > 0) + (a8 % 16 > 8)) if half else _tile_counts(a16)
         r16 = _round_up_arr(self.R[live], _cabi.GK_RT)
         custom = {}
         for j, s in enumerate(live):
@@ -639,23 +642,45 @@ class SearchGroup:
         search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
         items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
         items["search"] = live[search]
-        if half:                                   # tiles of 1..4 groups of 32 kept sets
+        mode_span = np.array([128, 64, 16, 32, 48, 32, 64, 96, 128], dtype=np.int64)
+        if half:
+            # columns: (first 32-column block, warp-split flag, columns / 8)
+            n128 = (a8 // 16)[search]
+            rem8 = (a8 % 16)[search]
+            a_blk = np.where(iat < n128, 4 * iat, 4 * n128 + 2 * (iat - n128))
+            a_w = iat >= n128
+            ta8 = np.where(iat == n128, np.minimum(rem8, 8), rem8 - 8)
+            for j, tiles in custom.items():           # restricted candidates: explicit block runs
+                sel = np.flatnonzero(search == j)
+                t = np.array(tiles, dtype=np.int64)
+                a_blk[sel] = t[iat[sel], 0]
+                a_w[sel] = t[iat[sel], 1] != MODE_F8
+                ta8[sel] = np.where(t[iat[sel], 1] == MODE_F4, 8, 4)
+            # rows: 128 per tile; the last tile of a search may be shorter
             k_blk = 2 * ikt
-            k_mode = 4 + np.minimum(4, k32[search] - 4 * ikt)
+            rows = np.minimum(128, kept[live][search] - 128 * ikt)
+            g32 = -(-rows // 32)                                   # full-width tiles: 1..4 groups of 32 rows
+            rows8 = -(-rows // 8)                                  # warp-split tiles: WK warps x G' groups of 8 rows
+            wk_log2 = np.where(rows8 <= 4, 0, np.where(rows8 <= 8, 1, 2))
+            gp = -(-rows8 // (1 << wk_log2))
+            kspan = np.where(a_w, (8 * gp) << wk_log2, 32 * g32)
+            aspan = np.where(a_w, 8 * ta8, 128)
+            shape = np.where(a_w, gp | (wk_log2 << 4) | (ta8 << 8) | SHAPE_WARP_SPLIT, (4 + g32) | (MODE_F8 << 8))
         else:
             k_blk, k_mode = _tile_decode(k16[search], ikt, 2)
-        a_blk, a_mode = _tile_decode(a16[search], iat, 4)
-        for j, tiles in custom.items():
-            sel = np.flatnonzero(search == j)
-            t = np.array(tiles, dtype=np.int64)
-            a_blk[sel] = t[iat[sel], 0]
-            a_mode[sel] = t[iat[sel], 1]
+            a_blk, a_mode = _tile_decode(a16[search], iat, 4)
+            for j, tiles in custom.items():
+                sel = np.flatnonzero(search == j)
+                t = np.array(tiles, dtype=np.int64)
+                a_blk[sel] = t[iat[sel], 0]
+                a_mode[sel] = t[iat[sel], 1]
+            kspan, aspan = mode_span[k_mode], mode_span[a_mode]
+            shape = k_mode | (a_mode << 8)
         items["k_blk"] = k_blk
         items["a_blk"] = a_blk
         items["r0"] = ich * chunk
         items["r1"] = np.minimum((ich + 1) * chunk, r16[search])
-        items["shape"] = k_mode | (a_mode << 8)
-        span = np.array([128, 64, 16, 32, 48, 32, 64, 96, 128], dtype=np.int64)
+        items["shape"] = shape
         if self.col_shard is not None and self.col_shard[1] > 1:
             rank, world = self.col_shard
             # column tiles go to the least-loaded rank, widest first (deterministic on every rank)
@@ -665,7 +690,7 @@ class SearchGroup:
                 if not len(sel):
                     continue
                 tiles = np.unique(iat[sel])
-                width = {int(t): int(span[a_mode[sel][iat[sel] == t][0]]) for t in tiles}
+                width = {int(t): int(aspan[sel][iat[sel] == t][0]) for t in tiles}
                 load = [0] * world
                 assign = {}
                 for t in sorted(width, key=lambda t: (-width[t], t)):
@@ -676,13 +701,13 @@ class SearchGroup:
             mine = owner == rank
             k0 = k_blk * GK_KB
             a0 = a_blk * 32
-            rows = np.minimum(span[k_mode], kept[live][search] - k0)
-            cols = np.minimum(span[a_mode], self.A[live][search] - a0)
+            rows_u = np.minimum(kspan, kept[live][search] - k0)
+            cols_u = np.minimum(aspan, self.A[live][search] - a0)
             reads = np.minimum(items["r1"], self.R[live][search]) - items["r0"]
-            useful = np.maximum(rows, 0) * np.maximum(cols, 0) * np.maximum(reads, 0)
+            useful = np.maximum(rows_u, 0) * np.maximum(cols_u, 0) * np.maximum(reads, 0)
             self._step_cells = int(useful[mine].sum())
-            items, k_mode, a_mode = items[mine], k_mode[mine], a_mode[mine]
-        order = np.argsort(-((items["r1"] - items["r0"]).astype(np.int64) * span[k_mode] * span[a_mode]),
+            items, kspan, aspan = items[mine], kspan[mine], aspan[mine]
+        order = np.argsort(-((items["r1"] - items["r0"]).astype(np.int64) * kspan * aspan),
                            kind="stable")
         return items[order]
 

@@ -196,10 +196,18 @@ class FakeBackend:
             M = table[X["matrix"]]
             rp, tile = int(M["r_pad"]), int(M["a_tile"])
             r0, r1 = int(it["r0"]), int(it["r1"])
-            assert (int(it["shape"]) & 0xFF >= 5) == bool(half_mode) and flush_stages >= 1
+            shape = int(it["shape"])
+            assert flush_stages >= 1
             assert P.dtype == (np.uint16 if half_mode else np.float32)
-            kspan = self.MODE_SPAN[int(it["shape"]) & 0xFF]
-            aspan = self.MODE_SPAN[(int(it["shape"]) >> 8) & 0xFF]
+            if shape & (1 << 16):      # warp-split tile: WK warps x G' groups of 8 rows, 8 TA' columns
+                assert half_mode
+                gp, wk, ta8 = shape & 0xF, 1 << ((shape >> 4) & 0xF), (shape >> 8) & 0xFF
+                assert 1 <= gp <= 4 and wk in (1, 2, 4) and 1 <= ta8 <= 8
+                kspan, aspan = 8 * gp * wk, 8 * ta8
+            else:
+                assert (shape & 0xFF >= 5) == bool(half_mode)
+                kspan = self.MODE_SPAN[shape & 0xFF]
+                aspan = self.MODE_SPAN[(shape >> 8) & 0xFF]
             assert tile == 32 and r0 % GK_RT == 0 and r1 % GK_RT == 0 and r1 <= rp and r1 > r0
             kw, aw = -(-kspan // GK_KB), -(-aspan // tile)
             assert int(it["a_blk"]) + aw <= int(M["n_ablk"])

@@ -53,3 +53,14 @@ for np_ in (2, 3):
     for _ in range(20): ct.run()
     torch.cuda.synchronize()
     print(f"CohortTyper parts={np_} 20 runs: wall ms per run", 1e3 * (time.perf_counter() - t0) / 20)
+be.timing = {}
+typer.run(); torch.cuda.synchronize()
+for s, e, work in be.timing.get("gk_score", []):
+    ms = s.elapsed_time(e)
+    print(f"gk_score launch: {ms:.3f} ms, {work/1e9:.1f} G cells, {work/ms/1e9:.2f} TCells/s")
+be.timing = None
+g = typer.group
+print("searches", g.n_search, "A mean", g.A.mean(), "A min/max", g.A.min(), g.A.max(), "R mean", g.R.mean())
+import numpy as np
+steps = np.where(typer.homo[typer.live], 1, typer.cns[typer.live])
+print("steps histogram", np.bincount(steps))
