@@ -169,52 +169,72 @@ gk_rescore_count_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* _
     count_set<N>(rows, item.r0, item.r1, M.n_reads, cnt_pool + X.cnt_off + (int64_t)f * N * N);
 }
 
-// P tiles: one k-block (GK_KB = 64 kept sets) x 128 reads at a time, over the item's read range.
-constexpr int kPitch = 132;  // bytes per set row in shared memory (33 words)
+// P tiles: one k-block (GK_KB = 64 kept sets) x 512 reads at a time, over the item's read range.
+//   phase 1  one warp per set row: every lane loads 16 reads (128 bits) of each member row of LT and
+//            keeps the byte-wise minimum; the row goes to shared memory as 32 quads of 4 words, the
+//            quad index XOR-swizzled with (row / 4) so that phase 2 is (almost) conflict free;
+//   phase 2  a thread takes 4 sets x 4 reads (four 32-bit words), transposes them with byte permutes
+//            and stores 4 sets of one read as 8 bytes: 16 lanes write one 128-byte row of the
+//            k-block, and consecutive reads are consecutive rows of the row-blocked P.
+constexpr int kPReads = 512;
+constexpr int kPWords = kPReads / 4;     // words per set row in shared memory
 
 __global__ void __launch_bounds__(kThreads)
 gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                   const GkPItem* __restrict__ items, int top_n, int n_set, const int32_t* __restrict__ kept_count,
                   const int32_t* __restrict__ ids, const uint8_t* __restrict__ LT_pool,
                   void* __restrict__ P_pool_raw, int half_mode) {
-    __shared__ __align__(16) uint8_t tile[GK_KB * kPitch];
+    __shared__ __align__(16) uint32_t tile[GK_KB * kPWords];
+    __shared__ int32_t s_ids[GK_KB * GK_MAX_CN];
     const GkPItem item = items[blockIdx.x];
     const GkSearch X = searches[item.search];
     const GkMatrix M = matrices[X.matrix];
     const int K = kept_count[item.search];
     const int lane = gk_lane();
     const int warp = gk_warp();
-    const int half = lane >> 4;
-    const int kq = (lane & 15) * 4;
-    for (int r0 = item.r0; r0 < item.r1; r0 += 128) {
-        const uint8_t* LT = LT_pool + M.LT_off + r0;
-        // phase 1: one warp per set row, one 4-byte word (4 reads) per lane
+    // member ids of the 64 sets of this k-block
+    for (int i = threadIdx.x; i < GK_KB * GK_MAX_CN; i += kThreads) {
+        const int k = item.k_blk * GK_KB + i / GK_MAX_CN;
+        s_ids[i] = k < K ? ids[((int64_t)item.search * top_n + k) * GK_MAX_CN + (i % GK_MAX_CN)] : 0;
+    }
+    __syncthreads();
+    const int l16 = threadIdx.x & 15;            // phase 2: sets 4 l16 .. 4 l16 + 3
+    const int h16 = threadIdx.x >> 4;            // phase 2: read quads h16, h16 + 16, ...
+    for (int r0 = item.r0; r0 < item.r1; r0 += kPReads) {
+        const int n_reads = item.r1 - r0 < kPReads ? item.r1 - r0 : kPReads;      // multiple of 128
+        const uint8_t* LT = LT_pool + M.LT_off + r0 + lane * 16;
+        const bool in_range = lane * 16 < n_reads;
         for (int kl = warp; kl < GK_KB; kl += kWarps) {
-            const int k = item.k_blk * GK_KB + kl;
-            uint32_t mn = 0u;
-            if (k < K) {
-                const int32_t* set = ids + ((int64_t)item.search * top_n + k) * GK_MAX_CN;
-                mn = 0xffffffffu;
+            uint4 mn = make_uint4(0u, 0u, 0u, 0u);
+            if (in_range && item.k_blk * GK_KB + kl < K) {
+                mn = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
                 for (int t = 0; t < n_set; ++t) {
-                    const uint32_t v =
-                        __ldg(reinterpret_cast<const uint32_t*>(LT + (int64_t)set[t] * M.r_pad) + lane);
-                    mn = __vminu4(mn, v);
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(LT + (int64_t)s_ids[kl * GK_MAX_CN + t] * M.r_pad));
+                    mn.x = __vminu4(mn.x, v.x);
+                    mn.y = __vminu4(mn.y, v.y);
+                    mn.z = __vminu4(mn.z, v.z);
+                    mn.w = __vminu4(mn.w, v.w);
                 }
             }
-            *reinterpret_cast<uint32_t*>(tile + kl * kPitch + lane * 4) = mn;
+            *reinterpret_cast<uint4*>(tile + kl * kPWords + 4 * (lane ^ ((kl >> 2) & 15))) = mn;
         }
         __syncthreads();
-        // phase 2: half a warp per read row, four consecutive sets per lane -> 256-byte row stores
-        for (int rl = warp * 2 + half; rl < 128; rl += kWarps * 2) {
-            const unsigned int v0 = tile[(kq + 0) * kPitch + rl], v1 = tile[(kq + 1) * kPitch + rl];
-            const unsigned int v2 = tile[(kq + 2) * kPitch + rl], v3 = tile[(kq + 3) * kPitch + rl];
-            const int64_t o = X.P_off + gk_blk_off(r0 + rl, item.k_blk, X.n_kblk, GK_KB) + kq;
-            if (half_mode) {
-                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(P_pool_raw) + o) =
-                    make_uint2(v0 | (v1 << 16), v2 | (v3 << 16));
-            } else {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(P_pool_raw) + o) =
-                    make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+        for (int rq = h16; rq < n_reads / 4; rq += kThreads / 16) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = tile[(4 * l16 + i) * kPWords + 4 * ((rq >> 2) ^ l16) + (rq & 3)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t o = X.P_off + gk_blk_off(r0 + 4 * rq + j, item.k_blk, X.n_kblk, GK_KB) + 4 * l16;
+                const uint32_t sel = 0x0400u + 0x0101u * j;      // byte j of both inputs -> bytes 0 and 2
+                if (half_mode) {
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(P_pool_raw) + o) =
+                        make_uint2(__byte_perm(w[0], w[1], sel) & 0x00ff00ffu, __byte_perm(w[2], w[3], sel) & 0x00ff00ffu);
+                } else {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(P_pool_raw) + o) =
+                        make_float4((float)((w[0] >> (8 * j)) & 0xffu), (float)((w[1] >> (8 * j)) & 0xffu),
+                                    (float)((w[2] >> (8 * j)) & 0xffu), (float)((w[3] >> (8 * j)) & 0xffu));
+                }
             }
         }
         __syncthreads();
