@@ -11,6 +11,7 @@ process per GPU; rank r takes samples r, r + world, ...).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -147,10 +148,16 @@ class BatchTyper:
         self._homo_cache: np.ndarray | None = None
         self.pipelined = True        # enqueue all steps up front (one read-back); False = read back per step
         self._pending = None
+        # A batch that is typed repeatedly replays its launches as one CUDA graph from the third
+        # pass on (the work-item tables are cached by then, so nothing is uploaded inside the graph).
+        self.use_graph = hasattr(self.be, "torch") and os.environ.get("GK_GRAPH", "1") != "0"
+        self._graph = None           # (CUDAGraph, pending core, group state, launches)
+        self._graph_runs = 0
 
     def upload(self) -> None:
         """Host pools -> device (the end-to-end path times this; the resident path does it once)."""
         self.batch = engine.MatrixBatch(self.host, backend=self.be, run=False)
+        self._graph, self._graph_runs = None, 0          # a captured graph names the old buffers
         if self.group is not None:
             self.group.batch = self.batch      # same tables and offsets: search buffers are reused
 
@@ -167,11 +174,7 @@ class BatchTyper:
         self.start()
         return self.finish()
 
-    def start(self) -> None:
-        """Enqueue the likelihood build and (pipelined mode) every search launch on the current
-        stream without waiting for the device; ``finish`` reads back and forms the calls."""
-        if self.batch is None:
-            self.upload()
+    def _start_eager(self) -> None:
         batch = self.batch
         batch.run_likelihood()
         if self.group is None:
@@ -186,6 +189,56 @@ class BatchTyper:
         self._pending = None
         if self.pipelined and self.col_shard is None:
             self._pending = self.group.run_pipeline_start(steps)
+
+    def start(self) -> None:
+        """Enqueue the likelihood build and (pipelined mode) every search launch on the current
+        stream without waiting for the device; ``finish`` reads back and forms the calls."""
+        if self.batch is None:
+            self.upload()
+        graphable = (self.use_graph and self.pipelined and self.col_shard is None and self.group is not None
+                     and self.be.timing is None)
+        if not graphable:
+            self._graph_runs += 1
+            self._start_eager()
+            return
+        if self._graph is None and self._graph_runs >= 2:
+            self._capture()
+        if self._graph is None:
+            self._graph_runs += 1
+            self._start_eager()
+            return
+        graph, core, flat, sizes, state, launches = self._graph
+        graph.replay()
+        self.be.launches += launches
+        self.batch._colsum_host = None
+        group = self.group
+        group.reset()
+        group.cur, group.n = state
+        self._pending = core + (self.be.download_async(flat, sizes),)
+
+    def _capture(self) -> None:
+        """Record one pass (likelihood build + every search launch) into a CUDA graph."""
+        torch = self.be.torch
+        steps = np.where(self.homo[self.live], 1, self.cns[self.live])
+        launches0 = self.be.launches
+        try:
+            torch.cuda.current_stream(self.be.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            self.be.capturing = True                  # an upload inside the graph would replay stale bytes
+            with torch.cuda.graph(graph):
+                self.batch.run_likelihood()
+                core = self.group.run_pipeline_enqueue(steps)
+                flat = torch.cat([t.reshape(-1) for t in core[-1]])
+            self._graph = (graph, core[:-1], flat, [t.numel() for t in core[-1]],
+                           (self.group.cur, self.group.n), self.be.launches - launches0)
+        except Exception as exc:                      # capture is an optimisation: fall back to eager launches
+            self.use_graph = False
+            self._graph = None
+            self.graph_error = repr(exc)
+            torch.cuda.synchronize(self.be.device)
+        finally:
+            self.be.capturing = False
+        self.be.launches = launches0
 
     def finish(self) -> list[GeneCall]:
         group = self.group

@@ -64,6 +64,7 @@ class CudaBackend:
         self.d2h_bytes = 0
         self.timing: dict[str, list] | None = None   # name -> [(start_event, end_event, work)]
         self._arenas: dict[int, list] = {}            # stream -> [pinned uint8 tensor, bump position]
+        self.capturing = False                        # True while a CUDA graph is being recorded
 
     # Small host arrays (work-item tables, index lists) go through a page-locked staging arena so
     # that their copies are asynchronous: a copy from pageable memory synchronises the stream first,
@@ -102,6 +103,8 @@ class CudaBackend:
         return self.torch.empty(max(int(n), 1), dtype=self._tdtype(dtype), device=self.device)
 
     def upload(self, array: np.ndarray):
+        if self.capturing:
+            raise _cabi.GkError("host->device copy inside a CUDA-graph capture (launch plan not cached)")
         array = np.ascontiguousarray(array)
         if array.dtype.fields is not None or array.dtype.name not in self._NP2T:
             array = array.view(np.uint8)
@@ -127,11 +130,16 @@ class CudaBackend:
         self.d2h_bytes += out.nbytes
         return out.view(dtype) if dtype is not None else out
 
-    def download_async(self, tensors: list):
+    def download_async(self, tensors, sizes=None):
         """Start ONE device->host copy of several int32 device arrays (concatenated on the device
-        into a page-locked buffer of the current stream); ``download_wait`` returns the arrays."""
+        into a page-locked buffer of the current stream); ``download_wait`` returns the arrays.
+        With ``sizes`` the first argument is the already concatenated array."""
         torch = self.torch
-        flat = torch.cat([t.reshape(-1) for t in tensors]) if len(tensors) != 1 else tensors[0].reshape(-1)
+        if sizes is not None:
+            flat = tensors
+        else:
+            flat = torch.cat([t.reshape(-1) for t in tensors]) if len(tensors) != 1 else tensors[0].reshape(-1)
+            sizes = [t.numel() for t in tensors]
         assert flat.dtype == torch.int32
         stream = torch.cuda.current_stream(self.device)
         self._d2h = getattr(self, "_d2h", {})
@@ -143,7 +151,7 @@ class CudaBackend:
         view.copy_(flat, non_blocking=True)
         event = torch.cuda.Event()
         event.record(stream)
-        return view, event, [t.numel() for t in tensors]
+        return view, event, sizes
 
     def download_wait(self, handle) -> list[np.ndarray]:
         view, event, sizes = handle
@@ -869,6 +877,13 @@ class SearchGroup:
         """Enqueue every launch of ``run_pipeline`` on the current stream without synchronising;
         ``run_pipeline_finish`` reads the results back.  Lets a caller enqueue several groups (on
         several streams) before it blocks on the first."""
+        core = self.run_pipeline_enqueue(steps)
+        return core[:-1] + (self.be.download_async(core[-1]),)
+
+    def run_pipeline_enqueue(self, steps: np.ndarray):
+        """The launches of ``run_pipeline_start`` without the read-back: the last element of the
+        returned tuple is the list of device arrays to read instead of the download handle (the
+        part a CUDA graph can capture)."""
         bt = self.batch
         steps = np.asarray(steps, dtype=np.int64)
         self.reset()
@@ -936,9 +951,8 @@ class SearchGroup:
         tensors = list(snaps)
         for _, _, d_ids, d_score in finals:
             tensors += [d_ids, d_score]
-        handle = be.download_async(tensors)
         finals = [(n, done) for n, done, _, _ in finals]
-        return steps, max_step, len(snaps), finals, f_caps, actives, handle
+        return steps, max_step, len(snaps), finals, f_caps, actives, tensors
 
     def run_pipeline_finish(self, pending):
         """Wait for the read-back of a pipelined run (see ``run_pipeline``)."""

@@ -224,6 +224,29 @@ def test_cohort_batch_equals_per_gene_class(cuda):
         assert abs(c.value - r.value[c.best_rank]) <= 1e-9 * abs(c.value)
 
 
+def test_repeated_passes_replay_a_cuda_graph(cuda):
+    """A batch typed again and again is replayed as one CUDA graph from the third pass on; the calls
+    must not depend on whether a pass was launched eagerly, captured, or replayed, nor on a re-upload."""
+    from kir_graph_b200 import cohort
+    genes = synthetic.make_wgs30x_sample(seed=11, total_reads=24000)
+    packs = [packing.pack_synthetic(g) for g in genes]
+    cns = [g.cn for g in genes]
+    typer = cohort.BatchTyper(packs, cns, top_n=300, backend=cuda)
+    key = lambda calls: [(c.gene, tuple(c.alleles), c.best_rank, c.score, c.tie_flags) for c in calls]
+    first = key(typer.run())
+    for _ in range(4):
+        assert key(typer.run()) == first
+    assert getattr(typer, "graph_error", None) is None and typer._graph is not None
+    assert key(typer.upload_and_run()) == first          # new device buffers: the graph is dropped ...
+    assert typer._graph is None
+    for _ in range(3):
+        assert key(typer.run()) == first
+    assert typer._graph is not None                      # ... and recorded again
+    eager = cohort.BatchTyper(packs, cns, top_n=300, backend=cuda)
+    eager.use_graph = False
+    assert key(eager.run()) == first and key(eager.run()) == first
+
+
 @pytest.mark.parametrize("packed", [False, True])
 def test_many_observations_per_read(cuda, packed):
     """Up to 255 observations per read pair stay exact on both scoring paths."""
