@@ -187,7 +187,7 @@ class BatchTyper:
         self.homo = self._homo_cache
         steps = np.where(self.homo[self.live], 1, self.cns[self.live])
         self._pending = None
-        if self.pipelined and self.col_shard is None:
+        if self.pipelined:
             self._pending = self.group.run_pipeline_start(steps)
 
     def start(self) -> None:

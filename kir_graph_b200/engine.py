@@ -903,6 +903,7 @@ class SearchGroup:
         be, bt, ns = self.be, self.batch, self.n_search
         k_ub = np.zeros(ns, dtype=np.int64)
         snaps, finals, f_caps, actives = [], [], [], []
+        self._pipe_cells = 0.0
         for n in range(1, max_step + 1):
             active = steps >= n
             active_idx = np.flatnonzero(active)
@@ -922,6 +923,7 @@ class SearchGroup:
                     items = self._score_items(active_idx)
                     return be.upload(items), len(items), float(self._step_cells)
                 d_items, n_items, step_cells = self._planned(("score", n), score_plan)
+                self._pipe_cells += step_cells
                 be.zero_(self.d_S)
                 be.launch("gk_score", bt.d_table, self.d_tab, d_items, n_items, bt.d_L, self.d_P, self.d_S,
                           int(bt.half), int(bt.flush_stages), self.d_kept, work=step_cells)
@@ -969,10 +971,11 @@ class SearchGroup:
                 if np.any(alive > f_caps[i]):
                     return None
                 prev_kept = infos[i - 1]["n_kept"].astype(np.int64)
-                if self.col_shard is None or self.col_shard[1] == 1:
-                    cells += int((np.where(actives[i], prev_kept, 0) * self.n_cand * self.R).sum())
-                else:
-                    cells += -1                                # sharded: use the per-step item accounting instead
+                cells += int((np.where(actives[i], prev_kept, 0) * self.n_cand * self.R).sum())
+        if self.col_shard is not None and self.col_shard[1] > 1:
+            # sharded columns: this rank's share, from the work items (sized from the kept-set upper
+            # bounds, which are exact whenever a step keeps top_n sets)
+            cells = int(self._pipe_cells)
         self.score_cells = cells
         out_ids = np.full((ns, max(max_step, 1)), -1, dtype=np.int64)
         out_score = np.zeros(ns, dtype=np.int64)
