@@ -10,10 +10,13 @@ samples/s).
 One step = one pass of the hot path over the whole batch: likelihood build (kernel a), every
 copy-number step of the greedy search (kernels b, c) and the allele calls.
 
-  value   whole-job scoring GCells/s with the packed inputs already resident in HBM
-  e2e     the same pass through the public host API (``BatchTyper.upload() + run()``): packed host
-          arrays in pinned memory -> device, results back to the host, every step
-  roofline        dominant kernel (gk_score), CUDA events around every launch in the timed region
+  value   whole-job scoring GCells/s with the packed inputs already resident in HBM (a batch that is
+          typed repeatedly replays its launches as one CUDA graph from the third pass on)
+  e2e     the same pass through the public host API (``CohortTyper.upload_and_run()``): packed host
+          arrays in pinned memory -> device, results back to the host, every step; sub-batches on
+          their own streams so that the copies of one overlap the kernels of the others
+  roofline        dominant kernel (gk_score), CUDA events around every launch of extra passes run
+                  right after the timed region (eager launches, one stream)
   cpu_baseline    the oracle (kind "port": reference NumPy expressions, read-chunked) on host cores
 
 Workloads: cohort = cfg5 (96 x cfg3, sample-sharded over the ranks, strong
@@ -452,7 +455,7 @@ def main():
             d_packs, d_cns, d_truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
             deep = cohort.CohortTyper(d_packs, d_cns, top_n=args.top_n, backend=be, n_parts=1)
             deep.upload()
-            for _ in range(2):
+            for _ in range(3):                       # the third pass records the CUDA graph
                 d_calls = deep.run()
             d_steps = 3
             d_ms = timed(deep.run, d_steps) / d_steps
