@@ -42,6 +42,11 @@ def _compare_outputs(a, b):
     ([(12, 2, 130), (40, 3, 700), (6, 1, 90), (150, 2, 400), (3, 4, 260)], 30, [2, 3, 1, 2, 4]),
     ([(70, 3, 1500), (33, 2, 90)], 300, [3, 2]),
     ([(40, 6, 500), (12, 5, 300), (90, 8, 260)], 30, [6, 5, 8]),
+    # ragged allele / kept-set counts around every tile boundary of the packed path (full-width tiles of
+    # 128 alleles, warp-split tiles of 8..64 alleles x 8..128 kept sets, two of them after a 128 tile)
+    ([(4, 2, 200), (9, 2, 300), (17, 3, 330), (33, 2, 410), (65, 2, 280), (100, 2, 300), (129, 2, 310),
+      (161, 2, 290), (200, 2, 270)], 300, [2, 2, 3, 2, 2, 2, 2, 2, 2]),
+    ([(57, 3, 900), (136, 3, 520), (250, 2, 300)], 100, [3, 3, 2]),
 ])
 @pytest.mark.parametrize("half", [False, True])
 def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
