@@ -32,15 +32,25 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
                                           const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
                                           const int* s_eoff, const int4* s_ent, float* __restrict__ L,
                                           uint8_t* tile, unsigned int (&csum)[4]) {
+    constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;            // 8 consecutive reads per warp
+    static_assert(GK_RT % kReadsPerWarp == 0 && kReadsPerWarp == 8, "a warp's reads lie in one row block of L");
     const int lane = gk_lane();
     const int warp = gk_warp();
     bool live[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
     const uint32_t* mem_lane = mem + a0 + lane;
+    // The 8 reads of a warp are consecutive rows of one row block of L, and group g of a lane is
+    // allele block a0 / 32 + g, column `lane`: one pointer that advances by a row per read, with
+    // the block as a constant offset.  Their 8 byte counts per group go to the LT tile as two words.
+    const int rl0 = warp * kReadsPerWarp;
+    float* slot = L + gk_blk_off(r0 + rl0, a0 >> 5, M.n_ablk, 32) + lane;
+    uint32_t lo[NG], hi[NG];                                        // counts of reads 0..3 / 4..7 as bytes
+#pragma unroll
+    for (int g = 0; g < NG; ++g) lo[g] = hi[g] = 0u;
 #pragma unroll 1
-    for (int i = 0; i < GK_LIK_READS / kWarps; ++i) {
-        const int rl = warp + kWarps * i;
+    for (int i = 0; i < kReadsPerWarp; ++i, slot += 32) {
+        const int rl = rl0 + i;
         const int r = r0 + rl;
         unsigned int cnt[NG];
 #pragma unroll
@@ -69,23 +79,23 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
                 }
             }
         }
+        const int sh = 8 * (i & 3);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int a = lane + 32 * g;
-            if (a < a_span) {
-                const unsigned int c = live[g] ? cnt[g] : 0u;
-                // a_tile == 32: allele block a0 / 32 + g, column lane
-                float* slot = L + gk_blk_off(r, (a0 >> 5) + g, M.n_ablk, 32) + lane;
-                if constexpr (HALF) {
-                    *reinterpret_cast<uint32_t*>(slot) = c * 0x00010001u;       // (m, m) as two 16-bit lanes
-                } else {
-                    *slot = (float)c;
-                }
-                tile[a * kTilePitch + rl] = (uint8_t)c;
-                csum[g] += c;
+        for (int g = 0; g < NG; ++g) {                              // lane + 32 g < a_span = 32 NG always
+            const unsigned int c = live[g] ? cnt[g] : 0u;
+            if constexpr (HALF) {
+                reinterpret_cast<uint32_t*>(slot)[g * (GK_RT * 32)] = c * 0x00010001u;   // (m, m) as two 16-bit lanes
+            } else {
+                slot[g * (GK_RT * 32)] = (float)c;
             }
+            if (i < 4) lo[g] |= c << sh;
+            else hi[g] |= c << sh;
+            csum[g] += c;
         }
     }
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+        *reinterpret_cast<uint2*>(tile + (lane + 32 * g) * kTilePitch + rl0) = make_uint2(lo[g], hi[g]);
 }
 
 __global__ void __launch_bounds__(kThreads)
