@@ -37,7 +37,7 @@ extern "C" {
 #define GK_KB 64           /* kept-set block width of P                                      */
 #define GK_RT 32           /* read rows per row block of L and P = one shared-memory stage of
                               the scoring kernel                                             */
-#define GK_LIK_READS 64    /* read rows per CTA of the likelihood kernel                     */
+#define GK_LIK_READS 128   /* read rows per CTA of the likelihood kernel                     */
 
 /* Likelihood data of one gene problem.  Offsets are in elements of the pool type. */
 typedef struct GkMatrix {

@@ -16,7 +16,7 @@ import numpy as np
 GK_MAX_CN = 8
 GK_KB = 64
 GK_RT = 32
-GK_LIK_READS = 64
+GK_LIK_READS = 128
 
 LIB_PATH = os.environ.get("GK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                    "libgk_typing.so")

@@ -32,70 +32,71 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
                                           const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
                                           const int* s_eoff, const int4* s_ent, float* __restrict__ L,
                                           uint8_t* tile, unsigned int (&csum)[4]) {
-    constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;            // 8 consecutive reads per warp
-    static_assert(GK_RT % kReadsPerWarp == 0 && kReadsPerWarp == 8, "a warp's reads lie in one row block of L");
+    constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;            // consecutive reads per warp
+    static_assert(GK_RT % kReadsPerWarp == 0 && kReadsPerWarp % 4 == 0, "a warp's reads lie in one row block of L");
     const int lane = gk_lane();
     const int warp = gk_warp();
     bool live[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
     const uint32_t* mem_lane = mem + a0 + lane;
-    // The 8 reads of a warp are consecutive rows of one row block of L, and group g of a lane is
+    // The reads of a warp are consecutive rows of one row block of L, and group g of a lane is
     // allele block a0 / 32 + g, column `lane`: one pointer that advances by a row per read, with
-    // the block as a constant offset.  Their 8 byte counts per group go to the LT tile as two words.
+    // the block as a constant offset.  Four byte counts at a time go to the LT tile as one word.
     const int rl0 = warp * kReadsPerWarp;
     float* slot = L + gk_blk_off(r0 + rl0, a0 >> 5, M.n_ablk, 32) + lane;
-    uint32_t lo[NG], hi[NG];                                        // counts of reads 0..3 / 4..7 as bytes
-#pragma unroll
-    for (int g = 0; g < NG; ++g) lo[g] = hi[g] = 0u;
 #pragma unroll 1
-    for (int i = 0; i < kReadsPerWarp; ++i, slot += 32) {
-        const int rl = rl0 + i;
-        const int r = r0 + rl;
-        unsigned int cnt[NG];
+    for (int q = 0; q < kReadsPerWarp; q += 4) {
+        uint32_t word[NG];                                          // counts of reads q .. q + 3 as bytes
 #pragma unroll
-        for (int g = 0; g < NG; ++g) cnt[g] = 0u;
-        if (r < M.n_reads) {
-            const int e0 = s_eoff[rl] - e_lo;
-            const int e1 = s_eoff[rl + 1] - e_lo;
-            for (int e = e0; e < e1; ++e) {
-                int w;
-                uint32_t p, n;
-                if constexpr (STAGED) {
-                    const int4 ent = s_ent[e];
-                    w = ent.x;
-                    p = (uint32_t)ent.y;
-                    n = (uint32_t)ent.z;
+        for (int g = 0; g < NG; ++g) word[g] = 0u;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j, slot += 32) {
+            const int rl = rl0 + q + j;
+            const int r = r0 + rl;
+            unsigned int cnt[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) cnt[g] = 0u;
+            if (r < M.n_reads) {
+                const int e0 = s_eoff[rl] - e_lo;
+                const int e1 = s_eoff[rl + 1] - e_lo;
+                for (int e = e0; e < e1; ++e) {
+                    int w;
+                    uint32_t p, n;
+                    if constexpr (STAGED) {
+                        const int4 ent = s_ent[e];
+                        w = ent.x;
+                        p = (uint32_t)ent.y;
+                        n = (uint32_t)ent.z;
+                    } else {
+                        w = __ldg(ent_word + e_lo + e);
+                        p = __ldg(ent_pos + e_lo + e);
+                        n = __ldg(ent_neg + e_lo + e);
+                    }
+                    const uint32_t* row = mem_lane + (int64_t)w * M.n_alleles;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const uint32_t mw = live[g] ? __ldg(row + 32 * g) : 0u;
+                        cnt[g] += __popc((p & ~mw) | (n & mw));
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {                          // lane + 32 g < a_span = 32 NG always
+                const unsigned int c = live[g] ? cnt[g] : 0u;
+                if constexpr (HALF) {
+                    reinterpret_cast<uint32_t*>(slot)[g * (GK_RT * 32)] = c * 0x00010001u;   // (m, m) as two 16-bit lanes
                 } else {
-                    w = __ldg(ent_word + e_lo + e);
-                    p = __ldg(ent_pos + e_lo + e);
-                    n = __ldg(ent_neg + e_lo + e);
+                    slot[g * (GK_RT * 32)] = (float)c;
                 }
-                const uint32_t* row = mem_lane + (int64_t)w * M.n_alleles;
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const uint32_t mw = live[g] ? __ldg(row + 32 * g) : 0u;
-                    cnt[g] += __popc((p & ~mw) | (n & mw));
-                }
+                word[g] |= c << (8 * j);
+                csum[g] += c;
             }
         }
-        const int sh = 8 * (i & 3);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {                              // lane + 32 g < a_span = 32 NG always
-            const unsigned int c = live[g] ? cnt[g] : 0u;
-            if constexpr (HALF) {
-                reinterpret_cast<uint32_t*>(slot)[g * (GK_RT * 32)] = c * 0x00010001u;   // (m, m) as two 16-bit lanes
-            } else {
-                slot[g * (GK_RT * 32)] = (float)c;
-            }
-            if (i < 4) lo[g] |= c << sh;
-            else hi[g] |= c << sh;
-            csum[g] += c;
-        }
+        for (int g = 0; g < NG; ++g)
+            *reinterpret_cast<uint32_t*>(tile + (lane + 32 * g) * kTilePitch + rl0 + q) = word[g];
     }
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-        *reinterpret_cast<uint2*>(tile + (lane + 32 * g) * kTilePitch + rl0) = make_uint2(lo[g], hi[g]);
 }
 
 __global__ void __launch_bounds__(kThreads)
