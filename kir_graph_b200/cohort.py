@@ -21,7 +21,7 @@ from .packing import GenePack, site_tallies
 from .typing_mulit_allele import C_HIT, C_MISS, _lcm_upto, _no_hetero_site, isHetrozygous
 
 
-@dataclass
+@dataclass(slots=True)
 class GeneCall:
     """Typing outcome of one gene problem."""
 
@@ -141,6 +141,8 @@ class BatchTyper:
         typable = np.array([p.n_reads > 0 and p.n_alleles > 0 for p in packs], dtype=bool)
         self.live = np.flatnonzero((self.cns > 0) & typable)
         self.n_reads = np.array([p.n_reads for p in packs], dtype=np.int64)
+        # per problem: what the call phase needs without attribute look-ups in its loop
+        self._static = [(p.gene, p.allele_names, p.n_reads, int(c)) for p, c in zip(packs, self.cns)]
         self.batch: engine.MatrixBatch | None = None
         self.group: engine.SearchGroup | None = None
         self.score_cells = 0
@@ -292,20 +294,19 @@ class BatchTyper:
         value = (self.host.k_total * C_HIT + sc_all * (C_MISS - C_HIT)) * mult
         sc_all = sc_all * mult
         calls: list[GeneCall] = []
+        append = calls.append
         called_l, best_l, flags_l = called.tolist(), best.tolist(), flags.tolist()
         value_l, sc_l, homo_l, where_l = value.tolist(), sc_all.tolist(), self.homo.tolist(), where.tolist()
-        for i, pack in enumerate(self.packs):
-            cn = int(self.cns[i])
+        for i, (gene, names, n_reads, cn) in enumerate(self._static):
             if cn == 0:
                 continue
             s = where_l[i]
             if s < 0 or called_l[s][0] < 0:
-                calls.append(GeneCall(pack.gene, cn, ["fail"] * cn, pack.n_reads, False))
+                append(GeneCall(gene, cn, ["fail"] * cn, n_reads, False))
                 continue
             ids = called_l[s][:cn]
-            names = pack.allele_names
-            calls.append(GeneCall(pack.gene, cn, [names[a] for a in ids], len(pack.k_obs), homo_l[i],
-                                  best_l[s], value_l[i], flags_l[s], sc_l[i], ids))
+            append(GeneCall(gene, cn, [names[a] for a in ids], n_reads, homo_l[i],
+                            best_l[s], value_l[i], flags_l[s], sc_l[i], ids))
         return calls
 
 
