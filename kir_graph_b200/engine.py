@@ -123,6 +123,15 @@ class CudaBackend:
             return self.torch.empty(flat.size, dtype=staged.dtype, device=self.device).copy_(staged, non_blocking=True)
         return self.torch.from_numpy(flat).to(self.device, non_blocking=True)
 
+    def copy_into(self, tensor, array: np.ndarray) -> None:
+        """Asynchronous host->device copy into an existing device array of the same byte size."""
+        flat = np.ascontiguousarray(array).reshape(-1)
+        if flat.size == 0:
+            return
+        src = self.torch.from_numpy(flat.view(np.uint8))
+        self.h2d_bytes += flat.nbytes
+        tensor.view(self.torch.uint8)[: flat.nbytes].copy_(src, non_blocking=True)
+
     def download(self, tensor, dtype=None, count: int | None = None) -> np.ndarray:
         if count is not None:
             tensor = tensor[:count]
@@ -235,6 +244,7 @@ class HostBatch:
 
     def __init__(self, packs: list[GenePack]):
         self.packs = packs
+        self._m_max = None
         n = len(packs)
         table = np.zeros(n, dtype=MATRIX_DTYPE)
         mem_off = entoff_off = ent_base = L_off = LT_off = col_off = 0
@@ -268,6 +278,14 @@ class HostBatch:
                                 dtype=np.int64)
         self.L_size, self.LT_size, self.col_size = int(L_off), int(LT_off), int(col_off)
 
+    @property
+    def m_max(self) -> int:
+        """Upper bound of every mismatch count of the batch: m[r, a] <= K_r <= 255."""
+        if self._m_max is None:
+            m = max([int(p.k_obs.max(initial=1)) for p in self.packs], default=1)
+            self._m_max = min(max(m, 1), 255)
+        return self._m_max
+
     def pin(self, backend) -> "HostBatch":
         for name in ("mem", "entoff", "ent_word", "ent_pos", "ent_neg"):
             setattr(self, name, backend.pin(getattr(self, name)))
@@ -293,9 +311,7 @@ class MatrixBatch:
         self.packs = host.packs
         # m[r, a] <= K_r (observations of the read pair) <= 255; a 16-bit lane of the packed scoring
         # kernel therefore holds 65535 // m_max reads before it must be added to S
-        m_max = max([int(p.k_obs.max(initial=1)) for p in self.packs], default=1)
-        m_max = min(max(m_max, 1), 255)
-        self.flush_stages = max(1, min(65535 // m_max, SCORE_READ_CHUNK) // _cabi.GK_RT)
+        self.flush_stages = max(1, min(65535 // host.m_max, SCORE_READ_CHUNK) // _cabi.GK_RT)
         self.table = host.table
         self.max_alleles = int(host.table["n_alleles"].max()) if len(host.table) else 0
         be = self.be
@@ -315,6 +331,16 @@ class MatrixBatch:
         self.d_lik_items = None
         if run:
             self.run_likelihood()
+
+    INPUTS = (("d_table", "table"), ("d_mem", "mem"), ("d_entoff", "entoff"), ("d_ent_word", "ent_word"),
+              ("d_ent_pos", "ent_pos"), ("d_ent_neg", "ent_neg"))
+
+    def reload(self) -> None:
+        """Copy the host pools into the existing device buffers again (same batch layout): device
+        addresses stay put, so a recorded CUDA graph and the cached launch plan remain valid."""
+        for dev, host in self.INPUTS:
+            self.be.copy_into(getattr(self, dev), getattr(self.host, host))
+        self._colsum_host = None
 
     def lik_items(self) -> np.ndarray:
         t = self.table

@@ -52,6 +52,11 @@ class FakeBackend:
             return np.zeros(1, dtype=array.dtype)
         return array.reshape(-1).copy()
 
+    def copy_into(self, tensor, array):
+        flat = np.ascontiguousarray(array).reshape(-1)
+        if flat.size:
+            tensor.view(np.uint8)[: flat.nbytes] = flat.view(np.uint8)
+
     def download(self, tensor, dtype=None, count=None):
         if count is not None:
             tensor = tensor[:count]
