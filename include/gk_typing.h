@@ -194,6 +194,13 @@ int gk_em_squarem(const GkEmProblem* problems, int n_problems, const uint32_t* r
                   const uint32_t* wgt_pool, const double* len_pool, double* out_pool,
                   int32_t* iters_out, int iter_max, double diff_threshold, void* stream);
 
+/* Read grouping by called alleles: replaces
+ *     np.equal(probs[:, ids], probs[:, ids].max(axis=1)[:, None])      (graphkir/novel_discover.py:62-64)
+ * on the device-resident likelihood of matrix `matrix`: pattern[r] bit t = allele ids[t] attains the
+ * smallest mismatch count of read r among the n_ids (1..32) alleles.  pattern has n_reads entries. */
+int gk_group_reads(const GkMatrix* matrices, int matrix, int n_reads, const int32_t* ids, int n_ids,
+                   const uint8_t* LT_pool, uint32_t* pattern, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -384,6 +384,23 @@ class MatrixBatch:
         flat = self.be.download(self.d_LT[o:o + a * rp], np.uint8)
         return np.ascontiguousarray(flat.reshape(a, rp)[:, :r].T)
 
+    def group_pattern(self, i: int, allele_ids) -> np.ndarray:
+        """uint32 [R]: bit t set where allele ``allele_ids[t]`` attains the smallest mismatch count of
+        the read among the given alleles (= the row maximum of ``probs``; novel_discover.py:62-64)."""
+        ids = np.asarray(allele_ids, dtype=np.int32)
+        t = self.table[i]
+        r, a = int(t["n_reads"]), int(t["n_alleles"])
+        if not 1 <= len(ids) <= 32:
+            raise ValueError("between 1 and 32 alleles can be compared")
+        if len(ids) and (ids.min() < 0 or ids.max() >= a):
+            raise ValueError("allele id out of range")
+        if r == 0:
+            return np.zeros(0, dtype=np.uint32)
+        be = self.be
+        d_pat = be.empty(r, np.uint32)
+        be.launch("gk_group_reads", self.d_table, int(i), r, be.upload(ids), len(ids), self.d_LT, d_pat)
+        return be.download(d_pat, np.uint32)
+
     def blocked_counts(self, i: int) -> np.ndarray:
         """m[r, a] decoded from the blocked float32 copy (what the scoring kernel reads)."""
         t = self.table[i]

@@ -265,6 +265,13 @@ class AlleleTyping:
     def getReadsNum(self) -> int:
         return self._pack.n_reads
 
+    def group_pattern(self, allele_ids) -> np.ndarray:
+        """uint32 per read: bit t set where allele ``allele_ids[t]`` attains the row maximum of
+        ``probs[:, allele_ids]`` (novel_discover.py:62-64), from the device-resident likelihood."""
+        if self._batch is None:
+            return np.zeros(0, dtype=np.uint32)
+        return self._batch.group_pattern(0, allele_ids)
+
     # --- reference static helpers ------------------------------------------------------
     @staticmethod
     def removeEmptyReads(reads):

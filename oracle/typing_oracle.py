@@ -522,3 +522,32 @@ def em_call(report: list[tuple[str, float]], cn: int) -> list[str]:
         if cn <= 0:
             break
     return called
+
+
+# ---------------------------------------------------------------------------
+# read grouping of novel discovery (graphkir/novel_discover.py:48-70)
+# ---------------------------------------------------------------------------
+def group_reads_float(probs_called: np.ndarray, names: list[str]) -> dict[tuple[str, ...], list[int]]:
+    """Literal restatement: ``is_max = np.equal(probs[:, ids], probs[:, ids].max(axis=1)[:, None])``
+    (:62-64), then every read goes to the sorted tuple of the alleles at the row maximum (:66-69).
+    Returns read indices per key, keys in order of first occurrence (the reference's dict order)."""
+    probs_called = np.asarray(probs_called, dtype=np.float64)
+    is_max = np.equal(probs_called, probs_called.max(axis=1)[:, None])
+    groups: dict[tuple[str, ...], list[int]] = {}
+    arr = np.array(names)
+    for i, row in enumerate(is_max):
+        groups.setdefault(tuple(sorted(arr[row].tolist())), []).append(i)
+    return groups
+
+
+def group_reads_int(m_called: np.ndarray, names: list[str]) -> dict[tuple[str, ...], list[int]]:
+    """The same grouping decided on the integer mismatch counts: probs is strictly decreasing in m for a
+    fixed read, so the row maximum of probs is the row minimum of m; exact ties stay ties (the float
+    comparison above can split them by the rounding of the ordered product)."""
+    m_called = np.asarray(m_called, dtype=np.int64)
+    is_min = m_called == m_called.min(axis=1)[:, None]
+    groups: dict[tuple[str, ...], list[int]] = {}
+    arr = np.array(names)
+    for i, row in enumerate(is_min):
+        groups.setdefault(tuple(sorted(arr[row].tolist())), []).append(i)
+    return groups

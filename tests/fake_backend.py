@@ -400,6 +400,14 @@ class FakeBackend:
                 self._P_view(X, M, P)[r0 // GK_RT: (r0 + 128) // GK_RT, int(it["k_blk"])] = \
                     tile.reshape(128 // GK_RT, GK_RT, GK_KB)
 
+    # --- read grouping (section 8f rank 3) ---------------------------------------------------------
+    def gk_group_reads(self, table, matrix, n_reads, ids, n_ids, LT, pattern):
+        M = table.view(MATRIX_DTYPE)[matrix]
+        m = self._LT_view(M, LT)[np.asarray(ids[:n_ids], dtype=np.int64), :n_reads].astype(np.int64)
+        is_min = m == m.min(axis=0, keepdims=True)
+        pattern.view(np.uint32)[:n_reads] = (is_min.astype(np.uint64) << np.arange(n_ids, dtype=np.uint64)[:, None]) \
+            .sum(axis=0).astype(np.uint32)
+
     # --- EM path -------------------------------------------------------------------------------
     def gk_em_compat(self, membT, n_aw, n_alleles, off_lp, idx_lp, off_ln, idx_ln, off_rp, idx_rp, off_rn,
                      idx_rn, n_reads, compat):

@@ -304,6 +304,39 @@ def main() -> None:
     os.remove(path)
     dump("sample_small", sample)
 
+    # -- read grouping of novel discovery: reference groupReadByAllele -------------
+    for extra in ("Bio.Seq", "Bio.SeqRecord", "pysam"):
+        sys.modules.setdefault(extra, types.ModuleType(extra))
+    sys.modules["Bio.Seq"].Seq = object
+    sys.modules["Bio.SeqRecord"].SeqRecord = object
+    sys.modules["pysam"].AlignmentFile = object
+    import graphkir.novel_discover as nd
+    cases = []
+    for seed, a, cn, r in ((21, 40, 2, 600), (22, 25, 3, 900), (23, 60, 4, 700), (24, 12, 1, 300)):
+        gene = syn.make_gene([seed, 0], f"KIRG{seed}*BACKBONE", a, 8 * a, cn, r)
+        reads, variants = gene.to_objects()
+        # one read without any observation: kept by no_empty=False, ties over every allele
+        reads.insert(3, PairRead(l_sam="empty\t", r_sam="empty\t", backbone=gene.gene))
+        rr, rv = ref_objects(h2, m2h, reads, variants)
+        typ = tma.AlleleTyping(rr, rv, no_empty=False)
+        predict = [gene.allele_names[t] for t in gene.truth] + ["KIRNOT*00001"]
+        if seed == 23:
+            predict = predict[::-1]
+        groups = nd.groupReadByAllele(typ, predict, rr)
+        index = {id(x): i for i, x in enumerate(rr)}
+        # probs of the called alleles are stored too: the test also checks the grouping on rounded
+        # values (the reference's float comparison can split exact ties by the rounding of the ordered
+        # product)
+        names = [n for n in predict if n in typ.allele_to_id]
+        ids = [typ.allele_to_id[n] for n in names]
+        cases.append({
+            "name": f"group_{seed}", "predict_alleles": predict,
+            "input": {"variants": [asdict(v) for v in variants], "reads": [asdict(x) for x in reads]},
+            "groups": [[list(k), [index[id(x)] for x in v]] for k, v in groups.items()],
+            "probs_called": np.asarray(typ.probs)[:, ids].tolist(),
+        })
+    dump("group_reads", {"kind": "group_reads", "cases": cases})
+
 
 if __name__ == "__main__":
     main()
