@@ -201,6 +201,31 @@ int gk_em_squarem(const GkEmProblem* problems, int n_problems, const uint32_t* r
 int gk_group_reads(const GkMatrix* matrices, int matrix, int n_reads, const int32_t* ids, int n_ids,
                    const uint8_t* LT_pool, uint32_t* pattern, void* stream);
 
+/* Host-side fast path for `{prefix}.variant.json` (reference reader
+ * graphkir/hisat2.py:847-866 + kir_typing.py:92-97).  No CUDA involved.  gk_json_scan walks the JSON
+ * text once and keeps, for every element of "reads", backbone (interned), multiple and the four
+ * variant-id lists as CSR arrays; the raw SAM text is skipped.  It returns an opaque handle (NULL on
+ * error, message in gk_last_error()) and fills
+ *   sizes[0]      reads
+ *   sizes[1..4]   total ids of lpv, lnv, rpv, rnv
+ *   sizes[5], [6] distinct id strings, their bytes     sizes[7], [8] distinct backbone strings, their bytes
+ *   sizes[9], [10] byte span of the "variants" value (for the caller's JSON parser; -1 if absent)
+ * gk_json_fill copies into caller-allocated arrays (off[w] has reads + 1 entries; the string tables
+ * are offsets [n + 1] into a byte blob); gk_json_free releases the handle. */
+void* gk_json_scan(const char* buf, int64_t len, int64_t* sizes);
+int gk_json_fill(void* handle, int32_t* backbone, int32_t* multiple, int64_t* const* off,
+                 int32_t* const* idx, int64_t* id_off, char* id_bytes, int64_t* gene_off, char* gene_bytes);
+void gk_json_free(void* handle);
+
+/* Host: observation entries of the likelihood kernel from the CSR lists of a gene (see GkMatrix:
+ * entoff / ent_word / ent_pos / ent_neg).  off[w] / idx[w], w < 4: CSR lists of variant indices per
+ * read, polarity[w] = 1 for positive lists.  Duplicates of an observation go to separate entries
+ * (occurrence rank) so that multiplicities are exact; entries of a read are ordered by (rank, word).
+ * The entry arrays need room for one entry per observation.  Returns the number of entries or -1. */
+int64_t gk_pack_entries(int64_t n_reads, const int64_t* const* off, const int32_t* const* idx,
+                        const int32_t* polarity, int32_t* ent_off, int32_t* ent_word, uint32_t* ent_pos,
+                        uint32_t* ent_neg, int32_t* k_obs);
+
 #ifdef __cplusplus
 }
 #endif

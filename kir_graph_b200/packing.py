@@ -159,7 +159,37 @@ def pack_membership(member: np.ndarray) -> np.ndarray:
 
 
 def pack_entries(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
-    """CSR lists -> (ent_off, ent_word, ent_pos, ent_neg, k_obs)."""
+    """CSR lists -> (ent_off, ent_word, ent_pos, ent_neg, k_obs) through the host routine of
+    libgk_typing.so (``gk_pack_entries``); ``pack_entries_numpy`` is the array statement of the same
+    thing (tests compare them)."""
+    import ctypes
+    from . import _cabi
+    lib = _cabi.load()
+    n = csr.n_reads
+    offs = [np.ascontiguousarray(csr.offsets[name], dtype=np.int64) for name in LIST_NAMES]
+    idxs = [np.ascontiguousarray(csr.indices[name], dtype=np.int32) for name in LIST_NAMES]
+    total = int(sum(int(o[-1]) for o in offs))
+    if total and (max(int(i.max(initial=0)) for i in idxs) >= 1 << 30 or n >= 1 << 30):
+        raise ValueError("problem too large for the 64-bit packing keys")
+    pol = np.array([1 if name in ("lpv", "rpv") else 0 for name in LIST_NAMES], dtype=np.int32)
+    ent_off = np.zeros(n + 1, dtype=np.int32)
+    ent_word = np.zeros(max(total, 1), dtype=np.int32)
+    ent_pos = np.zeros(max(total, 1), dtype=np.uint32)
+    ent_neg = np.zeros(max(total, 1), dtype=np.uint32)
+    k_obs = np.zeros(n, dtype=np.int32)
+    lib.gk_pack_entries.restype = ctypes.c_int64
+    lib.gk_pack_entries.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 8
+    n_ent = lib.gk_pack_entries(
+        n, (ctypes.c_void_p * 4)(*[o.ctypes.data for o in offs]), (ctypes.c_void_p * 4)(*[i.ctypes.data for i in idxs]),
+        pol.ctypes.data, ent_off.ctypes.data, ent_word.ctypes.data, ent_pos.ctypes.data, ent_neg.ctypes.data,
+        k_obs.ctypes.data)
+    if n_ent < 0:
+        raise ValueError(lib.gk_last_error().decode().split(": ", 1)[-1])
+    return ent_off, ent_word[:n_ent].copy(), ent_pos[:n_ent].copy(), ent_neg[:n_ent].copy(), k_obs
+
+
+def pack_entries_numpy(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """Array statement of ``pack_entries`` (two sorts over all observations of the gene)."""
     n = csr.n_reads
     rows, pols, vids = [], [], []
     for name in LIST_NAMES:
@@ -234,15 +264,8 @@ def _finish(gene: str, allele_names: list[str], variant_ids: list[str], member: 
     return pack, drop
 
 
-def pack_gene(reads: Sequence, variants: Iterable, variant_correction: bool = True,
-              no_empty: bool = True, mutate_reads: bool = True, gene: str = "") -> GenePack:
-    """Object-level entry: the work of ``AlleleTyping.__init__`` up to the likelihood.
-
-    With ``mutate_reads`` the surviving ids are written back into the caller's
-    read objects, reproducing the in-place side effect of the reference's
-    ``errorCorrection`` (typing_mulit_allele.py:333-338).
-    """
-    variants = list(variants)
+def _variant_tables(variants: list):
+    """(by_id, variant_ids, allele_names, member) of a gene's variant list (:253-255, :283-285)."""
     by_id: dict[str, object] = {str(v.id): v for v in variants}      # later duplicates win (:253)
     variant_ids = list(by_id.keys())
     vid_to_idx = {vid: i for i, vid in enumerate(variant_ids)}
@@ -252,15 +275,32 @@ def pack_gene(reads: Sequence, variants: Iterable, variant_correction: bool = Tr
     for vid, i in vid_to_idx.items():
         for name in by_id[vid].allele:
             member[i, col[name]] = True
+    return by_id, variant_ids, vid_to_idx, allele_names, member
+
+
+def _annotate(pack: GenePack, by_id: dict, variant_ids: list[str]) -> None:
+    pack.var_pos = np.array([by_id[v].pos for v in variant_ids], dtype=np.int64)
+    pack.var_val = [str(by_id[v].val) for v in variant_ids]
+    pack.var_is_del = np.array([by_id[v].typ == "deletion" for v in variant_ids], dtype=bool)
+
+
+def pack_gene(reads: Sequence, variants: Iterable, variant_correction: bool = True,
+              no_empty: bool = True, mutate_reads: bool = True, gene: str = "") -> GenePack:
+    """Object-level entry: the work of ``AlleleTyping.__init__`` up to the likelihood.
+
+    With ``mutate_reads`` the surviving ids are written back into the caller's
+    read objects, reproducing the in-place side effect of the reference's
+    ``errorCorrection`` (typing_mulit_allele.py:333-338).
+    """
+    variants = list(variants)
+    by_id, variant_ids, vid_to_idx, allele_names, member = _variant_tables(variants)
     if not gene and variants:
         gene = str(variants[0].ref)
 
     csr = csr_from_reads(reads, vid_to_idx)
     pack, (drop_pos, drop_neg) = _finish(gene, allele_names, variant_ids, member, csr,
                                          variant_correction, no_empty)
-    pack.var_pos = np.array([by_id[v].pos for v in variant_ids], dtype=np.int64)
-    pack.var_val = [str(by_id[v].val) for v in variant_ids]
-    pack.var_is_del = np.array([by_id[v].typ == "deletion" for v in variant_ids], dtype=bool)
+    _annotate(pack, by_id, variant_ids)
     if variant_correction and mutate_reads:
         bad_pos = {variant_ids[i] for i in np.flatnonzero(drop_pos)}
         bad_neg = {variant_ids[i] for i in np.flatnonzero(drop_neg)}
@@ -269,6 +309,20 @@ def pack_gene(reads: Sequence, variants: Iterable, variant_correction: bool = Tr
             read.rpv = [v for v in read.rpv if v not in bad_pos]
             read.lnv = [v for v in read.lnv if v not in bad_neg]
             read.rnv = [v for v in read.rnv if v not in bad_neg]
+    return pack
+
+
+def pack_gene_csr(variants: Iterable, csr: ReadCSR, variant_correction: bool = True, no_empty: bool = True,
+                  gene: str = "") -> GenePack:
+    """Array-level entry: like ``pack_gene`` for reads that are already CSR lists of indices into the
+    gene's variant table in ``dict.fromkeys(str(v.id) for v in variants)`` order (the fast
+    ``.variant.json`` path, :mod:`kir_graph_b200.fastjson`)."""
+    variants = list(variants)
+    by_id, variant_ids, _, allele_names, member = _variant_tables(variants)
+    if not gene and variants:
+        gene = str(variants[0].ref)
+    pack, _ = _finish(gene, allele_names, variant_ids, member, csr, variant_correction, no_empty)
+    _annotate(pack, by_id, variant_ids)
     return pack
 
 

@@ -31,7 +31,7 @@ from typing import Iterable, Optional
 import numpy as np
 
 from . import engine
-from .packing import GenePack, pack_gene
+from .packing import GenePack, pack_gene, site_tallies
 from .utils import logger
 
 C_HIT = float(np.log10(0.999))
@@ -225,6 +225,7 @@ class AlleleTyping:
         self.id_to_allele: dict[int, str] = dict(enumerate(pack.allele_names))      # (:254)
         self.allele_to_id: dict[str, int] = {j: i for i, j in self.id_to_allele.items()}
         self.reads = [reads[i] for i in pack.kept_reads] if reads is not None else []
+        self._reads_given = reads is not None
         self.result: list[TypingResult] = []
         self.tie_report: list[dict] = []
         # K_r as used by the likelihood: an empty read kept by no_empty=False counts one 0.999 (:372-374)
@@ -299,7 +300,12 @@ class AlleleTyping:
         """Top-n allele sets of size ``cn`` (:383-410)."""
         if cn < 1:
             raise ValueError(f"CN should be >= 1, got {cn}")
-        homo = isHomozygous(self.reads, self.variants, cn) if self.force_homo is None else self.force_homo
+        if self.force_homo is not None:
+            homo = self.force_homo
+        elif self._reads_given:
+            homo = isHomozygous(self.reads, self.variants, cn)
+        else:          # built from a pack only (fast .variant.json path): the same tally from the packed lists
+            homo = cn > 1 and _no_hetero_site(site_tallies(self._pack), cn)
         self.result = []
         if homo:
             self.addCandidate()
