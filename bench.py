@@ -361,9 +361,9 @@ def main():
     # ---- end to end: pinned host arrays -> device -> calls on the host ------------------
     e2e_typer = typer
     if args.e2e_parts != len(typer.parts) and col_shard is None:
-        # about 16 samples per sub-batch: smaller ones cost more in fixed per-part work than the
+        # at least 12 samples per sub-batch: smaller ones cost more in fixed per-part work than the
         # copy/compute overlap returns
-        e2e_parts = max(1, min(args.e2e_parts, n_samples_local // 16))
+        e2e_parts = max(1, min(args.e2e_parts, n_samples_local // 12))
         cand = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=e2e_parts,
                                   group_size=17 if args.workload != "deep" else 1)
         if len(cand.parts) != len(typer.parts):
