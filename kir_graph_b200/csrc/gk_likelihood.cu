@@ -1,14 +1,14 @@
 // Kernel (a): likelihood build.
 //
 // Replaces AlleleTyping.reads2AlleleProb + np.log10 (reference:
-// graphkir/typing_mulit_allele.py:340-381, :263).  For a tile of 64 reads x up to four
+// graphkir/typing_mulit_allele.py:340-381, :263).  For a tile of 128 reads x up to four
 // allele blocks (128 alleles), every lane owns up to four alleles (lane, lane+32, ...) and
 // walks the read's packed observation entries:
 //     m[r, a] += popc((pos & ~mem[word, a]) | (neg & mem[word, a]))
 // The membership row mem[word, :] is word-major, so the 32 lanes of a warp read
 // 128 consecutive bytes (coalesced; a gene's table is <= 1 MB and stays in L1/L2).
 // Outputs, both written with full 128-byte lines:
-//     L  4 bytes per cell, blocked [a_blk][r][32] -> operand of the scoring kernel (TMA bulk tiles):
+//     L  4 bytes per cell, row-blocked [r_blk][a_blk][32 reads][32] -> operand of the scoring kernel (TMA bulk tiles):
 //        float32(m) for the FP32 scoring path, the 16-bit pair (m, m) for the packed integer path
 //     LT uint8,   allele-major [a][r]         -> rescoring / P kernels stream along reads
 // and the per-allele column sums (CN=1 scores) via one 64-bit atomic per allele per CTA.

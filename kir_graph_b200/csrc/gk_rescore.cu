@@ -7,11 +7,12 @@
 //                      (reference: typing_mulit_allele.py:569, :575-580) with exact integer
 //                      counts; fraction[t] = sum_q cnt[t][q] / q / R is formed later.
 //   gk_write_p         P[r, k] = min over the members of kept set k of m[r, id]
-//                      (allele_prob for the next step, :569) in the blocked float layout
-//                      the scoring kernel's TMA stages expect; columns k >= n_kept are zero.
+//                      (allele_prob for the next step, :569) in the row-blocked layout (uint16, or
+//                      float for the FP32 path) the scoring kernel's TMA stages expect; columns
+//                      k >= n_kept are zero.
 //
-// Both are HBM-bound: per (read, set) they read n bytes (16-byte vector loads, coalesced
-// along reads) and write 0 resp. 4 bytes.
+// Per (read, set) they read n bytes (16-byte vector loads, coalesced along reads) and write 0 resp.
+// 2 bytes; the tie counting is ALU-pipe-bound, the P writer HBM-bound.
 #include "gk_common.cuh"
 
 namespace {

@@ -1,38 +1,36 @@
 // Kernel (b): max-then-sum candidate scoring, tiled like a GEMM.
 //
 // Replaces   np.maximum(log_probs[:, idx], prev.T[:, :, None]).sum(axis=1)
-// (reference: graphkir/typing_mulit_allele.py:540-542) without materialising
-// the K x R x A temporary.  In mismatch-count form (max of log-probs == min of
-// mismatch counts) one work item computes, for a tile of kept sets x candidate
-// alleles and a chunk of reads,
-//     D[k, a] += sum_r |L[r, a] - P[r, k]|        (sum of absolute differences)
-// from which the consumers recover the min-sum exactly:
-//     sum_r min(L, P) = (colsum_L[a] + colsum_P[k] - D[k, a]) / 2
-// with colsum_L the CN=1 column sums and colsum_P[k] the previous step's score of set k
-// (both already known), so the inner loop is FADD (p - l) + FADD (acc += |d|, the
-// absolute value is a free source modifier).  The direct form FMNMX + FADD computes the
-// same thing but FMNMX issues on the half-rate ALU pipe, which ncu showed to be the
-// limiter (profiles/r01_score_v0_ncu_summary.txt: ALU 78 %, FMA 39 %); both forms are
-// 2 FP32 non-tensor instructions per cell.
-// Reads are the reduction dimension.  Operands are float32 holding small
-// integers, so the two FADDs are exact while a partial sum stays below 2^24
-// (the host bounds a chunk to 8192 reads x 255); the partial is converted to
-// an integer and merged with a 32-bit integer atomic, which makes the split-R
-// reduction order-independent and bit-reproducible.
+// (reference: graphkir/typing_mulit_allele.py:540-542) without materialising the K x R x A
+// temporary.  In mismatch-count form (max of log-probs == min of mismatch counts) one work item
+// accumulates, for a tile of kept sets x candidate alleles and a chunk of reads, sum_r min(L, P).
+// Reads are the reduction dimension.  No tensor cores: max-then-sum is not a multiply-accumulate.
 //
-// Data movement: L and P are stored blocked ([a_blk][r][a_tile], [k_blk][r][64]),
-// so each block's GK_RT rows of a stage are one contiguous span, moved by the TMA
-// engine with cp.async.bulk and signalled on an mbarrier; 4 stages in flight.
-// A CTA tile is {128, 64, 48, 32, 16} kept sets x {128, 64, 48, 32, 16} alleles so that
-// ragged K (top_n = 300) and ragged A are covered at a granularity of 16 instead of
-// computing padding.  Math: 16x16 threads, each a TK x TA register tile (8x8 for the
-// full tile).  In the 128/64 modes a thread's rows/columns are groups of four
-// (k = 4*tk + i, 64 + 4*tk + i) so a half-warp's 128-bit shared loads hit consecutive
-// banks; the remainder modes take row t of each 16-group with scalar loads.  No tensor
-// cores: max-then-sum is not a multiply-accumulate.
+// Two kernels share the tiling and the pipeline:
+//   gk_score_packed_kernel (default)  16-bit integer lanes: 2 VIMNMX.U16x2 + 1 IADD3 per 4 cells on
+//       the ALU pipe, the min-sum itself goes to S (see score_item_h / score_item_w below);
+//   gk_score_kernel                   FP32: D[k, a] += sum_r |L[r, a] - P[r, k]| with two FADDs per
+//       cell; the consumers recover sum_r min(L, P) = (colsum_L[a] + colsum_P[k] - D[k, a]) / 2
+//       (colsum_L = the CN=1 column sums, colsum_P[k] = the previous step's score of set k).  The
+//       direct form FMNMX + FADD computes the same thing but FMNMX issues on the half-rate ALU pipe
+//       (profiles/r01_score_v0_ncu_summary.txt: ALU 78 %, FMA 39 %).  Operands are float32 holding
+//       small integers, exact while a partial sum stays below 2^24 (a chunk is <= 8192 reads x 255).
+// Partial sums of the read chunks are merged with 32-bit integer atomics: order independent and
+// bit-reproducible.
 //
-// Bound: FP32 non-tensor issue.  One cell = 2 FADD = 2 issue slots of the 4 x 32-lane
-// schedulers; peak = 148 SM x 64 cells/clk x f_clk.
+// Data movement: L and P are row-blocked ([r_blk][a_blk][GK_RT][32], [r_blk][k_blk][GK_RT][64]), so the
+// GK_RT = 32 reads of the adjacent blocks of a tile are one contiguous span each: a stage is two
+// cp.async.bulk copies (TMA engine) signalled on an mbarrier, 3 stages in flight, refilled by
+// whichever warp comes by (see score_item).  A full CTA tile is 128 kept sets x 128 alleles, 16 x 16
+// threads with an 8 x 8 register tile each; a thread's rows / columns are groups of four
+// (k = 4 tk + i, 64 + 4 tk + i) so that a half-warp's 128-bit shared loads hit consecutive banks.
+// Ragged K (top_n = 300) and ragged A are covered by smaller tiles instead of computing padding:
+// the remainder modes of the FP32 path (granularity 16), the warp-split tiles of the packed path
+// (granularity 8).
+//
+// Bound: non-tensor instruction issue.  FP32 path: 2 FADD per cell on the 128 lanes/clk/SM FMA pipe
+// = 148 SM x 64 cells/clk x f_clk; packed path: 0.75 instructions per cell on the 64 lanes/clk/SM
+// ALU pipe = 148 SM x 85.3 cells/clk x f_clk.
 #include "gk_common.cuh"
 
 namespace {
