@@ -151,21 +151,27 @@ class CudaBackend:
             sizes = [t.numel() for t in tensors]
         assert flat.dtype == torch.int32
         stream = torch.cuda.current_stream(self.device)
-        self._d2h = getattr(self, "_d2h", {})
-        buf = self._d2h.get(stream.cuda_stream)
-        if buf is None or buf.numel() < flat.numel():
+        # page-locked result buffers are pooled: one is busy from here until download_wait returns,
+        # so several reads may be in flight (even on one stream) without sharing a buffer
+        self._d2h_free = getattr(self, "_d2h_free", [])
+        buf = None
+        for i, cand in enumerate(self._d2h_free):
+            if cand.numel() >= flat.numel():
+                buf = self._d2h_free.pop(i)
+                break
+        if buf is None:
             buf = torch.empty(max(flat.numel(), 1 << 18), dtype=torch.int32).pin_memory()
-            self._d2h[stream.cuda_stream] = buf
         view = buf[: flat.numel()]
         view.copy_(flat, non_blocking=True)
         event = torch.cuda.Event()
         event.record(stream)
-        return view, event, sizes
+        return view, event, sizes, buf
 
     def download_wait(self, handle) -> list[np.ndarray]:
-        view, event, sizes = handle
+        view, event, sizes, buf = handle
         event.synchronize()
         host = view.numpy().copy()
+        self._d2h_free.append(buf)
         self.d2h_bytes += host.nbytes
         out, pos = [], 0
         for n in sizes:

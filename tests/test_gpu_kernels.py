@@ -253,6 +253,23 @@ def test_repeated_passes_replay_a_cuda_graph(cuda):
     assert key(eager.run()) == first and key(eager.run()) == first
 
 
+def test_two_batches_in_flight_on_one_stream(cuda):
+    """start() of two typers before finish() of the first: the read-backs must not share a buffer."""
+    from kir_graph_b200 import cohort
+    key = lambda calls: [(c.gene, tuple(c.alleles), c.best_rank, c.score, c.tie_flags) for c in calls]
+    typers, want = [], []
+    for seed in (12, 13):
+        genes = synthetic.make_wgs30x_sample(seed=seed, total_reads=20000)
+        packs, cns = [packing.pack_synthetic(g) for g in genes], [g.cn for g in genes]
+        typers.append(cohort.BatchTyper(packs, cns, top_n=300, backend=cuda))
+        want.append(key(cohort.BatchTyper(packs, cns, top_n=300, backend=cuda).run()))
+    for _ in range(4):                                   # eager passes, then graph replays
+        typers[0].start()
+        typers[1].start()
+        assert key(typers[0].finish()) == want[0]
+        assert key(typers[1].finish()) == want[1]
+
+
 @pytest.mark.parametrize("packed", [False, True])
 def test_many_observations_per_read(cuda, packed):
     """Up to 255 observations per read pair stay exact on both scoring paths."""
