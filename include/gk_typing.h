@@ -226,6 +226,16 @@ int64_t gk_pack_entries(int64_t n_reads, const int64_t* const* off, const int32_
                         const int32_t* polarity, int32_t* ent_off, int32_t* ent_word, uint32_t* ent_pos,
                         uint32_t* ent_neg, int32_t* k_obs);
 
+/* Host: walk of one SAM record, CIGAR x MD x Zs -> match / single / insertion / deletion segments
+ * (replaces recordToRawVariant + readZs + readMd, graphkir/hisat2.py:279-538).
+ * seg: int32 [max_seg][7] = typ (0 match, 1 single, 2 insertion, 3 deletion), 0-based backbone pos,
+ * length, value span (offset, length in `line`; length -2 = none, -1 = the value is `length`), id
+ * span (length -2 = none, -1 = "unknown").  meta[0], meta[1] = head / tail soft clip, meta[2], meta[3]
+ * = span of the backbone name.  Returns the number of segments, or -3 splicing (N), -4 unsupported
+ * CIGAR operation, -5 inconsistent record (the reference's asserts), -6 index out of range,
+ * -7 malformed number or Zs item, -8 more than max_seg segments. */
+int gk_sam_walk(const char* line, int64_t len, int32_t* seg, int max_seg, int32_t* meta);
+
 #ifdef __cplusplus
 }
 #endif

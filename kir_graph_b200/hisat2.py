@@ -221,10 +221,57 @@ class _RecordWalker:
         return segments, soft_clip
 
 
+def recordToRawVariantPy(line: str) -> tuple[list[Variant], list[int]]:
+    """Python statement of ``recordToRawVariant`` (the tests compare the C++ walk with it)."""
+    return _RecordWalker(line).walk()
+
+
+_WALK_ERRORS = {-3: lambda: NotImplementedError("Cannot typing with splicing"), -4: NotImplementedError,
+                -5: AssertionError, -6: IndexError, -7: ValueError}
+_walk_fn = None
+_walk_seg = None
+_walk_meta = None
+
+
 def recordToRawVariant(line: str) -> tuple[list[Variant], list[int]]:
     """One SAM record -> (match / single / insertion / deletion segments with 0-based backbone
-    positions, [head soft clip, tail soft clip])  (reference: hisat2.py:279-515)."""
-    return _RecordWalker(line).walk()
+    positions, [head soft clip, tail soft clip])  (reference: hisat2.py:279-515), through the host
+    routine ``gk_sam_walk`` of libgk_typing.so.  (Most of the time per record is the construction of
+    the ``Variant`` objects the reference's interface asks for, not the walk.)"""
+    global _walk_fn, _walk_seg, _walk_meta
+    import ctypes
+    if _walk_fn is None:
+        from . import _cabi
+        fn = _cabi.load().gk_sam_walk
+        fn.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+        _walk_fn, _walk_seg, _walk_meta = fn, (ctypes.c_int32 * (7 * 64))(), (ctypes.c_int32 * 4)()
+    buf = line.encode("utf-8")
+    seg_buf, meta, max_seg = _walk_seg, _walk_meta, 64
+    n = _walk_fn(buf, len(buf), seg_buf, max_seg, meta)
+    if n == -8:                                            # more segments than the reusable buffer holds
+        max_seg = len(buf) + 1
+        seg_buf = (ctypes.c_int32 * (7 * max_seg))()
+        n = _walk_fn(buf, len(buf), seg_buf, max_seg, meta)
+    if n < 0:
+        raise _WALK_ERRORS[n]()
+    flat = seg_buf[:7 * n]
+    seg = [flat[i:i + 7] for i in range(0, 7 * n, 7)]
+    backbone = buf[meta[2]:meta[2] + meta[3]].decode("utf-8")
+    out = []
+    for typ, pos, length, v_off, v_len, i_off, i_len in seg:
+        vid = "unknown" if i_len == -1 else buf[i_off:i_off + i_len].decode("utf-8")
+        if typ == 0:
+            out.append(Variant(typ="match", ref=backbone, pos=pos, length=length))
+        elif typ == 1:
+            out.append(Variant(typ="single", ref=backbone, pos=pos, length=1,
+                               val=buf[v_off:v_off + v_len].decode("utf-8"), id=vid))
+        elif typ == 2:
+            out.append(Variant(typ="insertion", ref=backbone, pos=pos, val=buf[v_off:v_off + v_len].decode("utf-8"),
+                               length=length, id=vid))
+        else:
+            out.append(Variant(typ="deletion", ref=backbone, pos=pos, val=length, length=length, id=vid))
+    return out, [int(meta[0]), int(meta[1])]
 
 
 def findVariantId(variant: Variant, variants_map: dict[Variant, Variant]) -> Variant:

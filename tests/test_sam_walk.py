@@ -64,3 +64,45 @@ def test_splicing_and_pileup_are_refused():
         hisat2.recordToRawVariant(line)
     with pytest.raises(NotImplementedError):
         hisat2.recordToVariants(load_golden("sam_walk")["kats"]["k1"]["line"], {}, pileup={"x": 1})
+
+
+def _outcome(fn, rec):
+    try:
+        raw, clip = fn(rec)
+        return [[v.typ, v.pos, v.length, v.val, v.id, v.ref] for v in raw], clip
+    except (NotImplementedError, AssertionError, IndexError, ValueError) as exc:
+        return type(exc).__name__
+
+
+def test_native_walk_equals_python_statement_on_mutated_records():
+    """gk_sam_walk (host C++) against the Python walker: simulated records, then the same records
+    with CIGAR / MD / Zs / sequence damaged at random - same segments or the same exception type."""
+    import numpy as np
+    from tests import sam_sim
+    rng = np.random.default_rng(17)
+    records = []
+    for seed in (3, 4, 5):
+        _, _, pairs = sam_sim.simulate_pairs(seed, n_pairs=40)
+        records += [rec for pair in pairs for rec in pair]
+    assert all(_outcome(hisat2.recordToRawVariant, r) == _outcome(hisat2.recordToRawVariantPy, r) for r in records)
+    alphabet = "0123456789MIDSNHX=^ACGT|,*Zs:"
+    n_err = 0
+    for rec in records:
+        for _ in range(12):
+            cols = rec.split("\t")
+            c = int(rng.choice([3, 5, 9] + list(range(11, len(cols)))))
+            s = cols[c]
+            if not s:
+                continue
+            i = int(rng.integers(len(s)))
+            kind = int(rng.integers(3))
+            ch = alphabet[int(rng.integers(len(alphabet)))]
+            cols[c] = s[:i] + ch + s[i + 1:] if kind == 0 else s[:i] + s[i + 1:] if kind == 1 else s[:i] + ch + s[i:]
+            bad = "\t".join(cols)
+            a, b = _outcome(hisat2.recordToRawVariant, bad), _outcome(hisat2.recordToRawVariantPy, bad)
+            assert a == b, (bad, a, b)
+            n_err += isinstance(a, str)
+    assert n_err > 100                                   # the damage does exercise the error paths
+    for rec in ("r\t99\tG\t5\t60\t*\t=\t1\t0\tACGT\tFFFF", "r\t99\tG\t5\t60\t4M\t=\t1\t0\tACGT\tFFFF\tMD:Z:4",
+                "r\t99\tG\t5\t60\t2S2M\t=\t1\t0\tACGT\tFFFF\tMD:Z:2\tZs:Z:", "r\t99\tG\tx\t60\t4M", ""):
+        assert _outcome(hisat2.recordToRawVariant, rec) == _outcome(hisat2.recordToRawVariantPy, rec), rec
