@@ -28,16 +28,17 @@ from ._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK
                     P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE)
 from .packing import GenePack
 
+import os as _os
+
 SCORE_READ_CHUNK = 8192     # reads per scoring work item: 8192 * 255 < 2^24 keeps float32 sums exact
-COUNT_READ_CHUNK = 16384    # reads per rescoring work item
-P_READ_CHUNK = 2048         # reads per P-writing work item (multiple of 128)
+COUNT_READ_CHUNK = int(_os.environ.get("GK_COUNT_CHUNK", 16384))    # reads per rescoring work item
+P_READ_CHUNK = int(_os.environ.get("GK_P_CHUNK", 2048))             # reads per P-writing work item (multiple of 128)
 ALIVE_SLACK = 212           # alive sets beyond top_n the rescoring grids are sized for without a read-back
 MAX_TOP_N = 2048
-import os as _os
 
 # packed 16-bit integer scoring path (False: FP32 sum of absolute differences); GK_PACKED=0/1 overrides
 PACKED_DEFAULT = _os.environ.get("GK_PACKED", "1") != "0"
-MIN_SCORE_ITEMS = 1184   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
+MIN_SCORE_ITEMS = int(_os.environ.get("GK_MIN_SCORE_ITEMS", 1184))   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
 
 
 def _round_up(x: int, m: int) -> int:
