@@ -8,6 +8,13 @@ of a batch advances through the copy-number steps together, so each step is a
 handful of grouped kernel launches over all problems; samples are independent,
 so a cohort shards across ranks with no communication on the data path (one
 process per GPU; rank r takes samples r, r + world, ...).
+
+``BatchTyper``   one resident batch: ``start()`` enqueues a whole pass (from the third
+                 pass of the same batch on: one CUDA-graph replay), ``finish()`` reads
+                 back once and forms the calls.
+``CohortTyper``  sub-batches on their own streams, all started before the first is
+                 finished, so that host->device copies and the host-side call phase
+                 of one overlap the kernels of the others.
 """
 from __future__ import annotations
 

@@ -5,10 +5,14 @@ Batched typing engine: drives the CUDA kernels of libgk_typing.so.
                   pairs into pooled device buffers and runs the likelihood
                   kernel once (kernel (a)).
 ``SearchGroup``   advances any number of greedy top-N searches over those
-                  matrices in lock step, one copy-number step per call
-                  (kernels (b) and (c)): score -> dedup/select -> rescore ->
-                  rank -> next P.  Work-item lists are built on the host with
-                  NumPy; two small device->host reads per step size the grids.
+                  matrices in lock step (kernels (b) and (c)): score ->
+                  dedup/select -> rescore -> rank -> next P.  ``step()`` does one
+                  copy-number step and reads its result back; ``run_pipeline()``
+                  enqueues every step up front (grids sized from upper bounds,
+                  work-item tables cached per batch) and reads back once.
+``CudaBackend``   device memory, asynchronous staging of small host arrays,
+                  pooled read-back buffers and the kernel launches; everything
+                  it enqueues can be recorded into a CUDA graph.
 
 Batching over genes and samples is what fills a 148-SM GPU: one WGS sample is
 17 problems of a few thousand reads each.
