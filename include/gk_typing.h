@@ -80,7 +80,10 @@ typedef struct GkSearch {
 } GkSearch;
 
 /* Work items (built by the host per launch). */
-typedef struct GkLikItem { int32_t matrix, a_blk, r0, pad; } GkLikItem;              /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS */
+typedef struct GkLikItem { int32_t matrix, a_blk, r0, flags; } GkLikItem;            /* up to 4 a-blocks from a_blk; r0 multiple of GK_LIK_READS;
+    flags bit 0 (GK_LIK_COLSUM_ONLY): accumulate colsum only, write neither L nor LT (a problem that is
+    typed with one step - CN 1 or the homozygous shortcut - never reads them) */
+#define GK_LIK_COLSUM_ONLY 1
 typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkScoreItem; /* [r0, r1) multiple of GK_RT;
     FP32 path: shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48
     (from k_blk / a_blk).  Packed path, full-width tile: rows 5..8 = 32, 64, 96, 128 kept sets, column mode 0

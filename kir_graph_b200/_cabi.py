@@ -34,7 +34,8 @@ SEARCH_DTYPE = np.dtype([
     ("n_kblk", "<i4"), ("pad", "<i4"),
 ], align=True)
 
-LIK_ITEM_DTYPE = np.dtype([("matrix", "<i4"), ("a_blk", "<i4"), ("r0", "<i4"), ("pad", "<i4")])
+LIK_ITEM_DTYPE = np.dtype([("matrix", "<i4"), ("a_blk", "<i4"), ("r0", "<i4"), ("flags", "<i4")])
+GK_LIK_COLSUM_ONLY = 1
 SCORE_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("a_blk", "<i4"),
                              ("r0", "<i4"), ("r1", "<i4"), ("shape", "<i4")])
 COUNT_ITEM_DTYPE = np.dtype([("search", "<i4"), ("f0", "<i4"), ("r0", "<i4"), ("r1", "<i4")])

@@ -186,9 +186,18 @@ class BatchTyper:
         self.start()
         return self.finish()
 
+    def _colsum_only(self) -> np.ndarray:
+        """Problems whose likelihood matrix is never read: not typed at all, or typed with one step
+        (CN 1, homozygous shortcut) - the first step needs the column sums only."""
+        if self._homo_cache is None:           # the copy numbers are fixed for this batch
+            self._homo_cache = self.homo_index.decide(self.cns) & (self.n_reads > 0)
+        only = np.ones(len(self.packs), dtype=bool)
+        only[self.live] = np.where(self._homo_cache[self.live], 1, self.cns[self.live]) <= 1
+        return only
+
     def _start_eager(self) -> None:
         batch = self.batch
-        batch.run_likelihood()
+        batch.run_likelihood(self._colsum_only())
         if self.group is None:
             self.group = engine.SearchGroup(batch, self.live, self.top_n, col_shard=self.col_shard,
                                             reduce_scores=self.reduce_scores)
@@ -238,7 +247,7 @@ class BatchTyper:
             graph = torch.cuda.CUDAGraph()
             self.be.capturing = True                  # an upload inside the graph would replay stale bytes
             with torch.cuda.graph(graph):
-                self.batch.run_likelihood()
+                self.batch.run_likelihood(self._colsum_only())
                 core = self.group.run_pipeline_enqueue(steps)
                 flat = torch.cat([t.reshape(-1) for t in core[-1]])
             self._graph = (graph, core[:-1], flat, [t.numel() for t in core[-1]],

@@ -26,7 +26,7 @@ constexpr int kEntCap = 1024;                  // observation entries of the rea
 // Per-read work for a CTA whose allele span needs NG lane groups of 32 (uniform per CTA).
 // STAGED: every entry of the read tile sits in shared memory (one 128-bit load per entry); the
 // rare tile with more than kEntCap entries takes the variant that reads them from global memory.
-template <int NG, bool HALF, bool STAGED>
+template <int NG, bool HALF, bool STAGED, bool WRITE>
 __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int a_span, int e_lo,
                                           const uint32_t* __restrict__ mem, const int32_t* __restrict__ ent_word,
                                           const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
@@ -84,18 +84,22 @@ __device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int
 #pragma unroll
             for (int g = 0; g < NG; ++g) {                          // lane + 32 g < a_span = 32 NG always
                 const unsigned int c = live[g] ? cnt[g] : 0u;
-                if constexpr (HALF) {
-                    reinterpret_cast<uint32_t*>(slot)[g * (GK_RT * 32)] = c * 0x00010001u;   // (m, m) as two 16-bit lanes
-                } else {
-                    slot[g * (GK_RT * 32)] = (float)c;
+                if constexpr (WRITE) {
+                    if constexpr (HALF) {
+                        reinterpret_cast<uint32_t*>(slot)[g * (GK_RT * 32)] = c * 0x00010001u;   // (m, m) as two 16-bit lanes
+                    } else {
+                        slot[g * (GK_RT * 32)] = (float)c;
+                    }
+                    word[g] |= c << (8 * j);
                 }
-                word[g] |= c << (8 * j);
                 csum[g] += c;
             }
         }
+        if constexpr (WRITE) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
-            *reinterpret_cast<uint32_t*>(tile + (lane + 32 * g) * kTilePitch + rl0 + q) = word[g];
+            for (int g = 0; g < NG; ++g)
+                *reinterpret_cast<uint32_t*>(tile + (lane + 32 * g) * kTilePitch + rl0 + q) = word[g];
+        }
     }
 }
 
@@ -112,6 +116,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
+    const bool colsum_only = (item.flags & GK_LIK_COLSUM_ONLY) != 0;
     const int a_tile = M.a_tile;           // 32
     const int a0 = item.a_blk * a_tile;
     const int r0 = item.r0;
@@ -144,14 +149,17 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
 
     unsigned int csum[4] = {0u, 0u, 0u, 0u};
 #define GK_LIK_ARGS M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_ent, L, tile, csum
-#define GK_LIK_CASE(NG)                                              \
-    if (!staged) {                                                   \
-        if (half_mode) lik_reads<NG, true, false>(GK_LIK_ARGS);      \
-        else lik_reads<NG, false, false>(GK_LIK_ARGS);               \
-    } else if (half_mode) {                                          \
-        lik_reads<NG, true, true>(GK_LIK_ARGS);                      \
-    } else {                                                         \
-        lik_reads<NG, false, true>(GK_LIK_ARGS);                     \
+#define GK_LIK_CASE(NG)                                                    \
+    if (colsum_only) {             /* no L / LT: the layout flag is moot */   \
+        if (staged) lik_reads<NG, false, true, false>(GK_LIK_ARGS);        \
+        else lik_reads<NG, false, false, false>(GK_LIK_ARGS);              \
+    } else if (!staged) {                                                  \
+        if (half_mode) lik_reads<NG, true, false, true>(GK_LIK_ARGS);      \
+        else lik_reads<NG, false, false, true>(GK_LIK_ARGS);               \
+    } else if (half_mode) {                                                \
+        lik_reads<NG, true, true, true>(GK_LIK_ARGS);                      \
+    } else {                                                               \
+        lik_reads<NG, false, true, true>(GK_LIK_ARGS);                     \
     }
     switch ((a_span + 31) / 32) {
         case 1: GK_LIK_CASE(1); break;
@@ -173,6 +181,7 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
         if (a0 + a < M.n_alleles && s) atomicAdd(col + a0 + a, (unsigned long long)s);
     }
 
+    if (colsum_only) return;
     uint8_t* LT = LT_pool + M.LT_off;
     for (int idx = threadIdx.x; idx < a_span * (GK_LIK_READS / 16); idx += kThreads) {
         const int a = idx / (GK_LIK_READS / 16);

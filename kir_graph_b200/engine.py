@@ -340,6 +340,7 @@ class MatrixBatch:
         self.bytes_out = host.L_size * 4 + host.LT_size
         self._colsum_host: np.ndarray | None = None
         self.d_lik_items = None
+        self._lik_key = None
         if run:
             self.run_likelihood()
 
@@ -367,11 +368,21 @@ class MatrixBatch:
         items["r0"] = (local % tiles[mat]) * GK_LIK_READS
         return items
 
-    def run_likelihood(self) -> None:
-        if self.d_lik_items is None:
+    def run_likelihood(self, colsum_only: np.ndarray | None = None) -> None:
+        """Kernel (a) over every problem of the batch.  ``colsum_only`` (bool per problem): only the
+        column sums are needed for those (they will be typed with one step), so ``L`` and ``LT`` are
+        not written for them - they must not be read back or searched beyond the first step."""
+        key = None if colsum_only is None or not np.any(colsum_only) else np.asarray(colsum_only, bool).tobytes()
+        if self.d_lik_items is None or key != self._lik_key:
             items = self.lik_items()
+            if key is not None:
+                items["flags"] = np.where(np.asarray(colsum_only, bool)[items["matrix"]], _cabi.GK_LIK_COLSUM_ONLY, 0)
             self.n_lik_items = len(items)
             self.d_lik_items = self.be.upload(items)
+            self._lik_key = key
+            t = self.table                    # bytes the kernel writes: L (4 B) + LT (1 B) per padded cell
+            per = t["r_pad"].astype(np.int64) * (t["n_ablk"].astype(np.int64) * t["a_tile"] * 4 + t["n_alleles"])
+            self.bytes_out = int(per.sum() if key is None else per[~np.asarray(colsum_only, bool)].sum())
         self.be.zero_(self.d_col)
         self.be.launch("gk_likelihood", self.d_table, self.d_lik_items, self.n_lik_items, self.d_mem,
                        self.d_entoff, self.d_ent_word, self.d_ent_pos, self.d_ent_neg, self.d_L, self.d_LT,

@@ -106,6 +106,7 @@ class FakeBackend:
             r0 = int(it["r0"])
             eo = entoff[M["entoff_off"]: M["entoff_off"] + R + 1]
             memv = mem[M["mem_off"]: M["mem_off"] + int(M["n_words"]) * A].reshape(int(M["n_words"]), A)
+            colsum_only = bool(int(it["flags"]) & 1)           # GK_LIK_COLSUM_ONLY: neither L nor LT is written
             for blk in range(int(it["a_blk"]), min(int(it["a_blk"]) + 4, int(M["n_ablk"]))):
                 a0 = blk * a_tile
                 a_hi = min(a0 + a_tile, A)
@@ -118,6 +119,10 @@ class FakeBackend:
                         mw = memv[ent_word[e], a0:a_hi]
                         x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
                         tile[rl, : a_hi - a0] += popcount32(x)
+                for a in range(a0, a_hi):
+                    col[int(M["col_off"]) + a] += np.uint64(tile[:, a - a0].sum())
+                if colsum_only:
+                    continue
                 for rb in range(GK_LIK_READS // GK_RT):      # row-blocked: [r_blk][a_blk][GK_RT][a_tile]
                     base = int(M["L_off"]) + ((r0 // GK_RT + rb) * int(M["n_ablk"]) + blk) * GK_RT * a_tile
                     part = tile[rb * GK_RT:(rb + 1) * GK_RT].reshape(-1)
@@ -129,7 +134,6 @@ class FakeBackend:
                 for a in range(a0, a_hi):
                     o = int(M["LT_off"]) + a * rp + r0
                     LT[o: o + GK_LIK_READS] = tile[:, a - a0].astype(np.uint8)
-                    col[int(M["col_off"]) + a] += np.uint64(tile[:, a - a0].sum())
 
     # --- helpers -------------------------------------------------------------------
     @staticmethod
