@@ -239,6 +239,35 @@ int64_t gk_pack_entries(int64_t n_reads, const int64_t* const* off, const int32_
  * -7 malformed number or Zs item, -8 more than max_seg segments. */
 int gk_sam_walk(const char* line, int64_t len, int32_t* seg, int max_seg, int32_t* meta);
 
+/* Host: name-sorted SAM text -> per read pair the positive / negative variant lists as CSR arrays,
+ * no Python object per record (replaces the loop of extractVariantFromBam
+ * with error_correction = False: readPair graphkir/hisat2.py:228-276, filterRead :541-578,
+ * recordToVariants :657-689, findVariantId :581-606, getVariantsBoundary :692-713,
+ * getPNFromVariantList :716-800, extractVariant :803-844).
+ * Variant table (sorted as the index is, Variant.__lt__ msa2hisat.py:48-53): v_ref = index into the
+ * name table (ref_off / ref_bytes, n_ref names, ids ascending along the table), v_typ = 0 insertion,
+ * 1 single, 2 deletion, v_val_int = deletion length, v_val_off [n_var + 1] / v_val_bytes = base or
+ * inserted sequence.  novel_id = Variant.novel_id at entry; num_editdist = filterRead's bound.
+ * gk_sam_extract returns a handle (never null) and fills sizes[12]:
+ *   [0] pairs kept, [1..4] ids in lpv / lnv / rpv / rnv, [5] novel variants, [6] bytes of their
+ *   values, [7] backbone names (the caller's, then new ones), [8] bytes of the names,
+ *   [9] status (0, or a gk_sam_walk code for the record at line [11]), [10] pairs whose flags are
+ *   not first + second mate ("strange case"), [11] 1-based line of the failing record or -1.
+ * Indices in idx[w] < n_var name table variants, the others novel variant (index - n_var), whose id
+ * is "nv<novel_id + index - n_var>".  span: int64 [pairs][4] = offset, length of the left and of the
+ * right record in `sam`.  gk_sam_extract_fill copies into caller-allocated arrays (off[w] has
+ * pairs + 1 entries); gk_sam_extract_free releases the handle. */
+void* gk_sam_extract(const char* sam, int64_t sam_len, int32_t n_var, const int32_t* v_ref,
+                     const int32_t* v_pos, const int32_t* v_typ, const int32_t* v_val_int,
+                     const int32_t* v_length, const int64_t* v_val_off, const char* v_val_bytes,
+                     int32_t n_ref, const int64_t* ref_off, const char* ref_bytes, int32_t novel_id,
+                     int32_t num_editdist, int64_t* sizes);
+int gk_sam_extract_fill(void* handle, int32_t* multiple, int32_t* backbone, int64_t* span,
+                        int64_t* const* off, int32_t* const* idx, int32_t* nv_ref, int32_t* nv_pos,
+                        int32_t* nv_typ, int32_t* nv_val_int, int32_t* nv_length, int64_t* nv_val_off,
+                        char* nv_val_bytes, int64_t* ref_off, char* ref_bytes);
+void gk_sam_extract_free(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

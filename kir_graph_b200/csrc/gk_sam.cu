@@ -37,9 +37,9 @@ struct ZsEntry {
 
 struct Walker {
     const char* line;
-    std::vector<Span> cols;
-    std::vector<MdTok> md;
-    std::vector<ZsEntry> zs;
+    std::vector<Span>& cols;          // scratch vectors of the calling thread (no allocation per record)
+    std::vector<MdTok>& md;
+    std::vector<ZsEntry>& zs;
     int64_t pos = 0, read_i = 0, md_len = 0, zs_pos = 0;
     size_t md_i = 0, zs_i = 0;
     Span seq{0, 0};
@@ -47,6 +47,12 @@ struct Walker {
     int max_seg;
     int n_seg = 0;
     int status = kOk;
+
+    Walker(std::vector<Span>& c, std::vector<MdTok>& m, std::vector<ZsEntry>& z) : cols(c), md(m), zs(z) {
+        cols.clear();
+        md.clear();
+        zs.clear();
+    }
 
     bool emit(int typ, int64_t p, int64_t length, Span val, Span id) {
         if (n_seg >= max_seg) {
@@ -146,7 +152,10 @@ extern "C" int gk_sam_walk(const char* line, int64_t len, int32_t* seg, int max_
     auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };
     while (b < e && blank(line[b])) ++b;
     while (e > b && blank(line[e - 1])) --e;
-    Walker w;
+    static thread_local std::vector<Span> t_cols;
+    static thread_local std::vector<MdTok> t_md;
+    static thread_local std::vector<ZsEntry> t_zs;
+    Walker w(t_cols, t_md, t_zs);
     w.line = line;
     w.seg = seg;
     w.max_seg = max_seg;
@@ -260,3 +269,392 @@ extern "C" int gk_sam_walk(const char* line, int64_t len, int32_t* seg, int max_
     if (w.zs_i != w.zs.size() || w.md_i != w.md.size() || w.read_i != w.seq.len) return kAssert;
     return w.n_seg;
 }
+
+// ---------------------------------------------------------------------------------------
+// Batch extraction: name-sorted SAM text -> per read pair the positive / negative variant lists
+// as CSR arrays, without a Python object per record (reference: graphkir/hisat2.py, readPair
+// :228-276, filterRead :541-578, findVariantId :581-606, recordToVariants :657-689,
+// getVariantsBoundary :692-713, getPNFromVariantList :716-800, extractVariant :803-844; the
+// pileup-based error correction is off on the CLI path, main.py:149, and not covered).
+// kir_graph_b200/hisat2.py keeps the Python statement of every step; tests compare the two.
+#include <string>
+#include <unordered_map>
+#include <algorithm>
+
+namespace {
+
+struct XVar {                       // a table or novel variant
+    int32_t ref, pos, typ;          // typ: 0 insertion, 1 single, 2 deletion (the order of Variant.__lt__), 3 match
+    int32_t val_int;                // deletion length
+    std::string val;                // base / inserted sequence
+    int32_t length;
+};
+
+struct XKey {
+    int32_t ref, pos, typ, val_int;
+    std::string val;
+    bool operator==(const XKey& o) const {
+        return ref == o.ref && pos == o.pos && typ == o.typ && val_int == o.val_int && val == o.val;
+    }
+};
+
+struct XKeyHash {
+    size_t operator()(const XKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+        mix((uint32_t)k.ref);
+        mix((uint32_t)k.pos);
+        mix((uint32_t)k.typ);
+        mix((uint32_t)k.val_int);
+        for (char c : k.val) mix((unsigned char)c);
+        return (size_t)h;
+    }
+};
+
+struct ReadVar {                    // one segment of a record after findVariantId
+    int32_t pos, typ, val_int, length;
+    std::string val;
+    int32_t index;                  // variant index (table or n_table + novel), -1 for a match segment
+    bool novel;
+};
+
+struct Extract {
+    std::vector<XVar> table;        // sorted index variants, then the novel ones in creation order
+    int32_t n_table = 0;
+    std::unordered_map<XKey, int32_t, XKeyHash> by_key;
+    std::vector<std::string> refs;
+    std::unordered_map<std::string, int32_t> ref_index;
+    std::vector<int32_t> multiple, backbone;
+    std::vector<int64_t> span;      // per pair: offset, length of the left record and of the right record
+    std::vector<int64_t> off[4];    // lpv, lnv, rpv, rnv
+    std::vector<int32_t> idx[4];
+    int64_t n_strange = 0;
+    int status = 0;
+    int64_t bad_line = -1;
+
+    int32_t ref_id(const std::string& name) {
+        auto it = ref_index.find(name);
+        if (it != ref_index.end()) return it->second;
+        const int32_t id = (int32_t)refs.size();
+        refs.push_back(name);
+        ref_index.emplace(name, id);
+        return id;
+    }
+};
+
+// Variant.__lt__ on (ref, pos, typ rank, val) for variants of one reference
+bool var_less(int32_t pos_a, int32_t typ_a, int32_t vi_a, const std::string& vs_a, int32_t pos_b, int32_t typ_b,
+              int32_t vi_b, const std::string& vs_b) {
+    if (pos_a != pos_b) return pos_a < pos_b;
+    if (typ_a != typ_b) return typ_a < typ_b;
+    if (typ_a == 2) return vi_a < vi_b;
+    return vs_a < vs_b;
+}
+
+struct Line {
+    const char* s;
+    int64_t n;
+};
+
+void split_tabs(const char* s, int64_t n, std::vector<Span>& cols, size_t limit) {
+    cols.clear();
+    int64_t start = 0;
+    for (int64_t i = 0; i <= n && cols.size() < limit; ++i)
+        if (i == n || s[i] == '\t') {
+            cols.push_back(Span{(int32_t)start, (int32_t)(i - start)});
+            start = i + 1;
+        }
+}
+
+// filterRead (:541-578): flag & 2 and an NM tag <= num_editdist; -1 on a malformed number
+int filter_read(const Line& ln, int num_editdist, std::vector<Span>& cols) {
+    int64_t b = 0, e = ln.n;
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };
+    while (b < e && blank(ln.s[b])) ++b;
+    while (e > b && blank(ln.s[e - 1])) --e;
+    split_tabs(ln.s + b, e - b, cols, (size_t)-1);
+    if (cols.size() < 2) return -2;
+    int64_t flag;
+    if (!parse_int(ln.s + b + cols[1].off, cols[1].len, flag)) return -1;
+    if ((flag & 2) == 0) return 0;
+    bool has_nm = false;
+    int64_t nm = 0;
+    for (size_t c = 11; c < cols.size(); ++c) {
+        const char* s = ln.s + b + cols[c].off;
+        if (cols[c].len >= 2 && s[0] == 'N' && s[1] == 'M') {
+            const int32_t skip = cols[c].len < 5 ? cols[c].len : 5;
+            if (!parse_int(s + skip, cols[c].len - skip, nm)) return -1;
+            has_nm = true;
+        }
+    }
+    return has_nm && nm <= num_editdist ? 1 : 0;
+}
+
+// NH tag of a record, 1 when absent: re.search(r"NH:i:(\d+)")
+int32_t get_nh(const Line& ln) {
+    for (int64_t i = 0; i + 5 < ln.n; ++i)
+        if (ln.s[i] == 'N' && ln.s[i + 1] == 'H' && ln.s[i + 2] == ':' && ln.s[i + 3] == 'i' && ln.s[i + 4] == ':' &&
+            ln.s[i + 5] >= '0' && ln.s[i + 5] <= '9') {
+            int64_t v = 0;
+            for (int64_t j = i + 5; j < ln.n && ln.s[j] >= '0' && ln.s[j] <= '9'; ++j) v = v * 10 + (ln.s[j] - '0');
+            return (int32_t)v;
+        }
+    return 1;
+}
+
+// recordToVariants (:657-689): walk, findVariantId in walk order, sort; empty for a soft-clipped record
+bool record_variants(Extract& ex, const Line& ln, std::vector<ReadVar>& out, int32_t& novel_id,
+                     std::vector<int32_t>& seg) {
+    out.clear();
+    int32_t meta[4];
+    int n = gk_sam_walk(ln.s, ln.n, seg.data(), (int)(seg.size() / 7), meta);
+    if (n == kSpace) {
+        seg.resize((size_t)(ln.n + 1) * 7);
+        n = gk_sam_walk(ln.s, ln.n, seg.data(), (int)(seg.size() / 7), meta);
+    }
+    if (n < 0) {
+        ex.status = n;
+        return false;
+    }
+    if (meta[0] + meta[1] > 0) return true;
+    const int32_t ref = ex.ref_id(std::string(ln.s + meta[2], (size_t)meta[3]));
+    for (int i = 0; i < n; ++i) {
+        const int32_t* s = seg.data() + 7 * i;
+        ReadVar rv;
+        rv.pos = s[1];
+        rv.length = s[2];
+        rv.val_int = 0;
+        rv.index = -1;
+        rv.novel = false;
+        switch (s[0]) {                                  // walker types -> order of Variant.__lt__
+            case 0: rv.typ = 3; break;
+            case 1: rv.typ = 1; rv.val.assign(ln.s + s[3], (size_t)s[4]); break;
+            case 2: rv.typ = 0; rv.val.assign(ln.s + s[3], (size_t)s[4]); break;
+            default: rv.typ = 2; rv.val_int = s[2]; break;
+        }
+        if (rv.typ != 3) {                               // findVariantId (:581-606)
+            XKey key{ref, rv.pos, rv.typ, rv.val_int, rv.val};
+            auto it = ex.by_key.find(key);
+            if (it != ex.by_key.end()) {
+                rv.index = it->second;
+                rv.novel = rv.index >= ex.n_table;
+                rv.length = ex.table[rv.index].length;   // the map's object replaces the segment (:594-595)
+            } else {
+                rv.index = (int32_t)ex.table.size();
+                rv.novel = true;
+                ex.table.push_back(XVar{ref, rv.pos, rv.typ, rv.val_int, rv.val, rv.length});
+                ex.by_key.emplace(std::move(key), rv.index);
+                ++novel_id;
+            }
+        }
+        out.push_back(std::move(rv));
+    }
+    std::stable_sort(out.begin(), out.end(), [](const ReadVar& a, const ReadVar& b) {
+        return var_less(a.pos, a.typ, a.val_int, a.val, b.pos, b.typ, b.val_int, b.val);
+    });
+    return true;
+}
+
+// getPNFromVariantList (:716-800) with exon_only = False, discard_novel_index = True
+void positives_negatives(Extract& ex, int32_t ref, const std::vector<ReadVar>& rv, int which_pos, int which_neg,
+                         const std::vector<int32_t>& ref_begin) {
+    if (rv.empty()) return;
+    for (const ReadVar& v : rv)
+        if ((v.typ == 0 || v.typ == 2) && v.novel) return;          // a novel indel is taken as a mapping error
+    // window of the sorted table: bisect_left with the probes (first.pos, single, "A") and
+    // (last.pos + last.length, single, "T"); the table is sorted by (ref, pos, typ, val), so the
+    // search runs over the slice of this reference
+    const int32_t lo_i = ref < (int32_t)ref_begin.size() - 1 ? ref_begin[ref] : ex.n_table;
+    const int32_t hi_i = ref < (int32_t)ref_begin.size() - 1 ? ref_begin[ref + 1] : ex.n_table;
+    auto lower = [&](int32_t pos, const std::string& base) {
+        int32_t a = lo_i, b = hi_i;
+        while (a < b) {
+            const int32_t m = a + (b - a) / 2;
+            const XVar& t = ex.table[m];
+            if (var_less(t.pos, t.typ, t.val_int, t.val, pos, 1, 0, base)) a = m + 1;
+            else b = m;
+        }
+        return a;
+    };
+    const int32_t read_end = rv.back().pos + rv.back().length;
+    const int32_t left = lower(rv.front().pos, "A"), right = lower(read_end, "T");
+    std::vector<XKey> excluded;
+    for (const ReadVar& v : rv) {
+        if (v.typ != 2 && v.val == "N")                              // a masked base matches every base
+            for (const char* base : {"A", "T", "C", "G"}) excluded.push_back(XKey{ref, v.pos, v.typ, v.val_int, base});
+        if (v.typ != 3) {
+            excluded.push_back(XKey{ref, v.pos, v.typ, v.val_int, v.val});
+            ex.idx[which_pos].push_back(v.index);
+        }
+    }
+    for (int32_t i = left; i < right; ++i) {
+        const XVar& t = ex.table[i];
+        bool skip = false;
+        for (const XKey& k : excluded)
+            if (k.pos == t.pos && k.typ == t.typ && k.val_int == t.val_int && k.val == t.val) {
+                skip = true;
+                break;
+            }
+        if (skip) continue;
+        if (t.typ == 2 && t.pos + t.val_int + 10 >= read_end) continue;   // ambiguous near the read end
+        ex.idx[which_neg].push_back(i);
+    }
+}
+
+}  // namespace
+
+// See include/gk_typing.h.
+extern "C" void* gk_sam_extract(const char* sam, int64_t sam_len, int32_t n_var, const int32_t* v_ref,
+                                const int32_t* v_pos, const int32_t* v_typ, const int32_t* v_val_int,
+                                const int32_t* v_length, const int64_t* v_val_off, const char* v_val_bytes,
+                                int32_t n_ref, const int64_t* ref_off, const char* ref_bytes, int32_t novel_id,
+                                int32_t num_editdist, int64_t* sizes) {
+    Extract* ex = new Extract();
+    for (int32_t i = 0; i < n_ref; ++i) ex->ref_id(std::string(ref_bytes + ref_off[i], (size_t)(ref_off[i + 1] - ref_off[i])));
+    ex->n_table = n_var;
+    std::vector<int32_t> ref_begin(ex->refs.size() + 1, n_var);      // table slice per reference (refs ascending)
+    for (int32_t i = 0; i < n_var; ++i) {
+        XVar v{v_ref[i], v_pos[i], v_typ[i], v_val_int[i],
+               std::string(v_val_bytes + v_val_off[i], (size_t)(v_val_off[i + 1] - v_val_off[i])), v_length[i]};
+        ex->by_key[XKey{v.ref, v.pos, v.typ, v.val_int, v.val}] = i;   // later duplicates win, as dict() does
+        ex->table.push_back(std::move(v));
+    }
+    for (int32_t i = n_var - 1; i >= 0; --i) ref_begin[v_ref[i]] = i;
+    for (int32_t r = (int32_t)ex->refs.size() - 1; r >= 0; --r)
+        if (ref_begin[r] == n_var && r + 1 <= (int32_t)ex->refs.size()) ref_begin[r] = ref_begin[r + 1];
+    for (int w = 0; w < 4; ++w) ex->off[w].push_back(0);
+
+    struct Pending {
+        Line line;
+        int64_t flag;
+    };
+    std::unordered_map<std::string, Pending> pending;               // key: name \t ref \t pos \t (flag & 256)
+    std::vector<Span> cols, fcols;
+    std::vector<ReadVar> lv, rv;
+    std::vector<int32_t> seg(7 * 64);
+    std::string key, mate_key;
+    int64_t p = 0, line_no = 0;
+    while (p < sam_len && ex->status == 0) {
+        const char* nl = static_cast<const char*>(memchr(sam + p, '\n', (size_t)(sam_len - p)));
+        const int64_t e = nl ? nl - sam : sam_len;
+        Line ln{sam + p, e - p};
+        p = e + 1;
+        ++line_no;
+        if (ln.n == 0 || ln.s[0] == '@' || (ln.n >= 15 && memcmp(ln.s, "[bam_sort_core]", 15) == 0)) continue;
+        split_tabs(ln.s, ln.n, cols, 8);
+        if (cols.size() < 8) {
+            ex->status = kValue;
+            ex->bad_line = line_no;
+            break;
+        }
+        if (!(cols[6].len == 1 && ln.s[cols[6].off] == '=')) continue;
+        int64_t flag;
+        if (!parse_int(ln.s + cols[1].off, cols[1].len, flag)) {
+            ex->status = kValue;
+            ex->bad_line = line_no;
+            break;
+        }
+        auto make_key = [&](std::string& out, const Span& pos) {
+            out.assign(ln.s + cols[0].off, (size_t)cols[0].len);
+            out.push_back('\t');
+            out.append(ln.s + cols[2].off, (size_t)cols[2].len);
+            out.push_back('\t');
+            out.append(ln.s + pos.off, (size_t)pos.len);
+            out.push_back('\t');
+            out.push_back((flag & 256) ? '1' : '0');
+        };
+        make_key(mate_key, cols[7]);
+        auto it = pending.find(mate_key);
+        if (it == pending.end()) {
+            make_key(key, cols[3]);
+            pending[key] = Pending{ln, flag};
+            continue;
+        }
+        if (((it->second.flag | flag) & 192) != 192) {
+            ++ex->n_strange;
+            continue;
+        }
+        const Line left = ln, right = it->second.line;              // (current record, earlier mate), as readPair yields
+        pending.erase(it);
+        const int fl = filter_read(left, num_editdist, fcols);
+        const int fr = fl == 1 ? filter_read(right, num_editdist, fcols) : 0;
+        if (fl < 0 || fr < 0) {
+            ex->status = fl == -2 || fr == -2 ? kIndex : kValue;
+            ex->bad_line = line_no;
+            break;
+        }
+        if (fl != 1 || fr != 1) continue;
+        if (!record_variants(*ex, left, lv, novel_id, seg) || !record_variants(*ex, right, rv, novel_id, seg)) {
+            ex->bad_line = line_no;
+            break;
+        }
+        const int32_t ref = ex->ref_id(std::string(ln.s + cols[2].off, (size_t)cols[2].len));
+        // the reference table may not know this name: ref_begin covers the names given by the caller
+        positives_negatives(*ex, ref, lv, 0, 1, ref_begin);
+        positives_negatives(*ex, ref, rv, 2, 3, ref_begin);
+        ex->multiple.push_back(get_nh(left));
+        ex->backbone.push_back(ref);
+        for (const Line& l : {left, right}) {
+            ex->span.push_back((int64_t)(l.s - sam));
+            ex->span.push_back(l.n);
+        }
+        for (int w = 0; w < 4; ++w) ex->off[w].push_back((int64_t)ex->idx[w].size());
+    }
+    sizes[0] = (int64_t)ex->multiple.size();
+    for (int w = 0; w < 4; ++w) sizes[1 + w] = (int64_t)ex->idx[w].size();
+    sizes[5] = (int64_t)ex->table.size() - n_var;
+    int64_t vb = 0;
+    for (size_t i = (size_t)n_var; i < ex->table.size(); ++i) vb += (int64_t)ex->table[i].val.size();
+    sizes[6] = vb;
+    sizes[7] = (int64_t)ex->refs.size();
+    int64_t rb = 0;
+    for (const auto& r : ex->refs) rb += (int64_t)r.size();
+    sizes[8] = rb;
+    sizes[9] = ex->status;
+    sizes[10] = ex->n_strange;
+    sizes[11] = ex->bad_line;
+    return ex;
+}
+
+extern "C" int gk_sam_extract_fill(void* handle, int32_t* multiple, int32_t* backbone, int64_t* span, int64_t* const* off,
+                                   int32_t* const* idx, int32_t* nv_ref, int32_t* nv_pos, int32_t* nv_typ,
+                                   int32_t* nv_val_int, int32_t* nv_length, int64_t* nv_val_off, char* nv_val_bytes,
+                                   int64_t* ref_off, char* ref_bytes) {
+    GK_REQUIRE(handle != nullptr, "gk_sam_extract_fill: null handle%s", "");
+    const Extract* ex = static_cast<const Extract*>(handle);
+    const size_t n = ex->multiple.size();
+    if (n) {
+        memcpy(multiple, ex->multiple.data(), n * sizeof(int32_t));
+        memcpy(backbone, ex->backbone.data(), n * sizeof(int32_t));
+        memcpy(span, ex->span.data(), 4 * n * sizeof(int64_t));
+    }
+    for (int w = 0; w < 4; ++w) {
+        memcpy(off[w], ex->off[w].data(), ex->off[w].size() * sizeof(int64_t));
+        if (!ex->idx[w].empty()) memcpy(idx[w], ex->idx[w].data(), ex->idx[w].size() * sizeof(int32_t));
+    }
+    int64_t o = 0;
+    size_t j = 0;
+    for (size_t i = (size_t)ex->n_table; i < ex->table.size(); ++i, ++j) {
+        const XVar& v = ex->table[i];
+        nv_ref[j] = v.ref;
+        nv_pos[j] = v.pos;
+        nv_typ[j] = v.typ;
+        nv_val_int[j] = v.val_int;
+        nv_length[j] = v.length;
+        nv_val_off[j] = o;
+        memcpy(nv_val_bytes + o, v.val.data(), v.val.size());
+        o += (int64_t)v.val.size();
+    }
+    nv_val_off[j] = o;
+    o = 0;
+    j = 0;
+    for (const auto& r : ex->refs) {
+        ref_off[j++] = o;
+        memcpy(ref_bytes + o, r.data(), r.size());
+        o += (int64_t)r.size();
+    }
+    ref_off[j] = o;
+    return 0;
+}
+
+extern "C" void gk_sam_extract_free(void* handle) { delete static_cast<Extract*>(handle); }

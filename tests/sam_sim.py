@@ -134,3 +134,36 @@ def simulate_pairs(seed: int, n_pairs: int = 60) -> tuple[str, list[Variant], li
         right = simulate_record(rng, f"read{i}", 147, ref_name, seq, variants, s2, nh=nh)
         pairs.append((left, right))
     return seq, variants, pairs
+
+
+def sam_text(pairs, header=True):
+    """Name-sorted SAM of (left, right) pairs with PNEXT set to the mate position; the right record
+    comes first so that readPair yields (left, right) (it yields the later record first, :266)."""
+    lines = ["@HD\tVN:1.0\tSO:queryname", "[bam_sort_core] merging from 0 files"] if header else []
+    for left, right in pairs:
+        lf, rf = left.split("\t"), right.split("\t")
+        lf[7], rf[7] = rf[3], lf[3]
+        lines += ["\t".join(rf), "\t".join(lf)]
+    return "\n".join(lines) + "\n"
+
+
+def multi_gene(seed, n_pairs=80, novel=0.03):
+    """Two backbones in one sorted table, pairs of both interleaved, plus records that readPair skips."""
+    rng = np.random.default_rng(seed)
+    table, pairs = [], []
+    for g, name in enumerate(("KIRA*BACKBONE", "KIRB*BACKBONE")):
+        seq, variants = make_table(rng, name, n_single=50, n_del=10)
+        for i, v in enumerate(variants):
+            v.id = f"hv{1000 * g + i}"
+        # an insertion in the table exercises the type order ins < single < del at one position
+        table += variants + [Variant(pos=variants[3].pos, typ="insertion", ref=name, val="AC",
+                                     id=f"hv{1000 * g + 900}", length=2)]
+        for i in range(n_pairs):
+            s1 = int(rng.integers(0, len(seq) - 200))
+            s2 = s1 + int(rng.integers(40, 110))
+            nh = 3 if rng.random() < 0.1 else 1
+            pairs.append((simulate_record(rng, f"g{g}r{i}", 99, name, seq, variants, s1, nh=nh, novel=novel),
+                          simulate_record(rng, f"g{g}r{i}", 147, name, seq, variants, s2, nh=nh, novel=novel)))
+    table.sort()
+    order = rng.permutation(len(pairs))
+    return table, [pairs[i] for i in order]

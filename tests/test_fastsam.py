@@ -1,0 +1,205 @@
+"""Native batch extraction SAM text -> CSR variant lists (kir_graph_b200/fastsam.py, gk_sam_extract)
+against the reference's outputs (tests/golden/sam_walk.json.gz) and against the Python statement of
+the same loop (hisat2.pairRecords / filterRead / extractVariant) on simulated and damaged SAM text."""
+import copy
+from dataclasses import asdict
+
+import numpy as np
+import pytest
+
+from kir_graph_b200 import fastjson, fastsam, hisat2
+from kir_graph_b200.msa2hisat import Variant
+from tests import sam_sim
+from tests.helpers import load_golden
+
+
+_sam_text = sam_sim.sam_text
+_multi_gene = sam_sim.multi_gene
+
+
+def _python_path(sam: str, table, nm: int = 4):
+    pairs = hisat2.pairRecords(sam.split("\n"))
+    pairs = filter(lambda lr: hisat2.filterRead(lr[0], nm) and hisat2.filterRead(lr[1], nm), pairs)
+    return hisat2.extractVariant(pairs, table)
+
+
+def _as_dicts(data):
+    return [asdict(v) for v in data["variants"]], [asdict(r) for r in data["reads"]]
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_golden_pairs_match_reference(case):
+    data = load_golden("sam_walk")["cases"][case]
+    table = [Variant(**v) for v in data["variants"]]
+    pairs = [tuple(p) for p in data["pairs"]]
+    sam = _sam_text(pairs)
+    Variant.novel_id = 0
+    ext = fastsam.extract(sam, table)
+    # the reference's extractVariant saw every pair; the batch path also applies filterRead to both mates.
+    # Dropping a pair changes the numbering of the novel variants after it, so compare with the
+    # reference's rows only when nothing was filtered, else with the Python statement (below)
+    keep = [data["records"][2 * i]["filter"] and data["records"][2 * i + 1]["filter"] for i in range(len(pairs))]
+    got = ext.reads_data()
+    rows = [{"lpv": r.lpv, "lnv": r.lnv, "rpv": r.rpv, "rnv": r.rnv, "multiple": r.multiple, "backbone": r.backbone}
+            for r in got["reads"]]
+    assert len(rows) == sum(keep)
+    if all(keep):
+        assert rows == data["reads"]
+        assert [v.id for v in got["variants"]] == data["variant_ids_after"]
+    else:
+        strip = lambda row: {k: ([i for i in v if not i.startswith("nv")] if isinstance(v, list) else v)
+                             for k, v in row.items()}
+        assert [strip(r) for r in rows] == [strip(r) for r, k in zip(data["reads"], keep) if k]
+    n_novel = Variant.novel_id
+    Variant.novel_id = 0
+    want = _python_path(sam, copy.deepcopy(table))
+    assert Variant.novel_id == n_novel
+    assert _as_dicts(got) == _as_dicts(want)
+
+
+def test_unfiltered_golden_rows():
+    """With the edit-distance bound lifted and every record flagged as a proper pair nothing is
+    filtered, so every row of the reference's extractVariant output must be reproduced."""
+    for case in (0, 1):
+        data = load_golden("sam_walk")["cases"][case]
+        table = [Variant(**v) for v in data["variants"]]
+        if not all(int(rec.split("\t")[1]) & 2 and "NM:i:" in rec for pair in data["pairs"] for rec in pair):
+            continue
+        Variant.novel_id = 0
+        ext = fastsam.extract(_sam_text([tuple(p) for p in data["pairs"]]), table, num_editdist=10 ** 6)
+        got = ext.reads_data()
+        rows = [{"lpv": r.lpv, "lnv": r.lnv, "rpv": r.rpv, "rnv": r.rnv, "multiple": r.multiple,
+                 "backbone": r.backbone} for r in got["reads"]]
+        assert rows == data["reads"]
+        assert [v.id for v in got["variants"]] == data["variant_ids_after"]
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_whole_loop_matches_reference(case):
+    """tests/golden/sam_extract.json.gz: the reference's readPair -> filterRead -> extractVariant over
+    a two-gene name-sorted SAM text (make_golden_sam_extract.py); every field of the .json it would
+    write must come out the same, and so must the Python statement of the loop."""
+    data = load_golden("sam_extract")["cases"][case]
+    table = [Variant(**v) for v in data["table"]]
+    Variant.novel_id = 0
+    got = fastsam.extract(data["sam"], table, data["num_editdist"]).reads_data()
+    assert Variant.novel_id == data["novel_id_after"]
+    assert _as_dicts(got) == (data["variants"], data["reads"])
+    Variant.novel_id = 0
+    want = _python_path(data["sam"], copy.deepcopy(table), data["num_editdist"])
+    assert _as_dicts(want) == (data["variants"], data["reads"])
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_multi_gene_equals_python_statement(seed):
+    table, pairs = _multi_gene(seed)
+    sam = _sam_text(pairs)
+    lines = sam.rstrip("\n").split("\n")
+    first = lines[2].split("\t")
+    extra = [
+        "\t".join(["lonely", "99", first[2], "10", "60", "*", "chrX", "50"] + first[8:]),       # mate elsewhere
+        "\t".join(["single", "73", first[2], "10", "60"] + first[5:]),                          # never paired
+        "\t".join(["odd", "99"] + first[2:]), "\t".join(["odd", "99", first[2], first[7]] + first[4:7] + [first[3]] + first[8:]),
+        "",
+    ]
+    # secondary alignments pair among themselves (flag & 256 is part of the key)
+    sec_l, sec_r = lines[4].split("\t"), lines[5].split("\t")
+    sec_l[1], sec_r[1] = str(int(sec_l[1]) | 256), str(int(sec_r[1]) | 256)
+    extra += ["\t".join(sec_l), "\t".join(sec_r)]
+    sam = "\n".join(lines[:40] + extra + lines[40:]) + "\n"
+    Variant.novel_id = 7
+    ext = fastsam.extract(sam, table, num_editdist=9)
+    got = ext.reads_data()
+    n_after = Variant.novel_id
+    Variant.novel_id = 7
+    want = _python_path(sam, copy.deepcopy(table), 9)
+    assert Variant.novel_id == n_after > 7
+    assert _as_dicts(got) == _as_dicts(want)
+    assert ext.n_strange == 1                                 # "odd": both records carry the first-mate flag
+    assert ext.n_reads > 40 and set(ext.refs) == {"KIRA*BACKBONE", "KIRB*BACKBONE"}
+    assert len({r.backbone for r in got["reads"]}) == 2
+    assert any(r.multiple == 3 for r in got["reads"]) and any(v.id.startswith("nv") for v in got["variants"])
+
+
+def test_scan_feeds_the_packing_path(tmp_path):
+    """SAM text -> GenePack without JSON equals SAM text -> reference .json -> fastjson -> GenePack."""
+    table, pairs = _multi_gene(21, n_pairs=120)
+    alleles = [f"KIR*{i:03d}" for i in range(9)]
+    rng = np.random.default_rng(5)
+    for v in table:
+        v.allele = [a for a in alleles if rng.random() < 0.4] or [alleles[0]]
+    sam = _sam_text(pairs)
+    Variant.novel_id = 0
+    ext = fastsam.extract(sam, table, num_editdist=9)
+    direct = fastjson.packs_from_scan(ext.scan())
+    path = str(tmp_path / "s.variant.json")
+    hisat2.writeReadsAndVariantsData(ext.reads_data(), path)
+    via_json = fastjson.load_packs(path)
+    assert list(direct) == list(via_json) and len(direct) == 2
+    from tests.test_fastjson import _assert_same_pack
+    for gene in direct:
+        assert direct[gene].csr.n_reads > 10
+        _assert_same_pack(direct[gene], via_json[gene])
+
+
+def _outcome(fn):
+    start = Variant.novel_id = 0
+    try:
+        data = fn()
+        return _as_dicts(data), Variant.novel_id - start
+    except (NotImplementedError, AssertionError, IndexError, ValueError) as exc:
+        return type(exc).__name__, Variant.novel_id - start
+
+
+def test_damaged_sam_text_same_result_or_same_exception():
+    table, pairs = _multi_gene(31, n_pairs=12)
+    rng = np.random.default_rng(32)
+    sam = _sam_text(pairs, header=False)
+    lines = sam.rstrip("\n").split("\n")
+    alphabet = "0123456789MIDSNHX=^ACGT|,*Zs:\t"
+    n_err = n_ok = 0
+    for trial in range(400):
+        bad = list(lines)
+        for _ in range(int(rng.integers(1, 3))):
+            j = int(rng.integers(len(bad)))
+            cols = bad[j].split("\t")
+            c = int(rng.choice([1, 3, 5, 7, 9] + list(range(11, len(cols)))))
+            s = cols[c]
+            if not s:
+                continue
+            i = int(rng.integers(len(s)))
+            kind = int(rng.integers(3))
+            ch = alphabet[int(rng.integers(len(alphabet)))]
+            cols[c] = s[:i] + ch + s[i + 1:] if kind == 0 else s[:i] + s[i + 1:] if kind == 1 else s[:i] + ch + s[i:]
+            bad[j] = "\t".join(cols)
+        text = "\n".join(bad) + "\n"
+        a = _outcome(lambda: fastsam.extract(text, table, 9).reads_data())
+        b = _outcome(lambda: _python_path(text, copy.deepcopy(table), 9))
+        assert a == b, (trial, a if isinstance(a[0], str) else "data", b if isinstance(b[0], str) else "data")
+        n_err += isinstance(a[0], str)
+        n_ok += not isinstance(a[0], str)
+    assert n_err > 30 and n_ok > 30
+
+
+def test_edges():
+    table, pairs = _multi_gene(41, n_pairs=4)
+    for text in ("", "\n", "@HD\tVN:1.0\n", "@HD\tVN:1.0"):
+        ext = fastsam.extract(text, table)
+        assert ext.n_reads == 0 and ext.novel == [] and ext.reads_data()["reads"] == []
+        assert all(len(ext.offsets[k]) == 1 for k in fastjson.SCAN_LISTS)
+    Variant.novel_id = 0
+    got = _as_dicts(fastsam.extract(_sam_text(pairs), []).reads_data())   # empty table: every positive is novel
+    Variant.novel_id = 0
+    assert got == _as_dicts(_python_path(_sam_text(pairs), []))
+    with pytest.raises(ValueError):
+        fastsam.extract("", list(reversed(table)))                # unsorted table
+    with pytest.raises(ValueError):
+        fastsam.extract("a\tb\tc\n", table)                       # fewer than 8 columns
+    with pytest.raises(ValueError):
+        fastsam.extract("a\tx\tc\t1\t60\t4M\t=\t5\n", table)      # flag is not a number
+    # no trailing newline, CRLF line ends are kept in the record as the reference keeps them
+    text = _sam_text(pairs).rstrip("\n")
+    Variant.novel_id = 0
+    a = _as_dicts(fastsam.extract(text, table).reads_data())
+    Variant.novel_id = 0
+    assert a == _as_dicts(_python_path(text, copy.deepcopy(table)))
