@@ -360,6 +360,29 @@ def extractVariant(pair_reads: Iterable[tuple[str, str]], variants: list[Variant
     return {"variants": list(variants_map.values()), "reads": reads}
 
 
+def extractVariantFromSam(index: str | list[Variant], sam_file: str, output_prefix: str | None,
+                          error_correction: bool = False, num_editdist: int = 4):
+    """``extractVariantFromBam`` (:904-940) over a name-sorted SAM file (what the reference's
+    ``readBam`` pipes out of ``samtools sort -n | samtools view -h``, :205-225; running samtools stays
+    in the reference): filter, call, annotate, and write ``{output_prefix}.json`` in the reference's
+    layout.  The loop itself is the native batch routine (:mod:`kir_graph_b200.fastsam`); the
+    returned ``SamExtract`` holds the same reads as arrays (``.scan()`` feeds the typing driver
+    directly, ``output_prefix=None`` skips the JSON).  ``index``: HISAT2 index prefix, or the sorted
+    variant table itself.  The ``.bam`` copies the reference also writes (:937-940) need samtools and
+    are not produced."""
+    if error_correction:
+        raise NotImplementedError("pileup-based read error correction stays in the reference "
+                                  "(the CLI path passes error_correction=False, main.py:149)")
+    from . import fastsam
+    variants = getVariants(index) if isinstance(index, str) else index
+    ext = fastsam.extract_file(sam_file, variants, num_editdist)
+    logger.info(f"[Graph] Filterd pairs: {ext.n_reads}")
+    if output_prefix is not None:
+        logger.debug(f"[Graph] Save allele per reads in {output_prefix}.json")
+        writeReadsAndVariantsData(ext.reads_data(), f"{output_prefix}.json")
+    return ext
+
+
 def pairRecords(lines: Iterable[str]) -> Iterable[tuple[str, str]]:
     """Pair up name-sorted SAM records (the body of the reference's readPair, :228-276; the
     ``samtools sort -n`` subprocess that feeds it stays in the reference)."""

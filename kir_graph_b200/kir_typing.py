@@ -85,16 +85,20 @@ class TypingWithPosNegAllele(Typing):
 
     def __init__(self, filename_variant_json: str, top_n: int = 300, multiple: bool = False,
                  exon_first: bool = False, exon_only: bool = False, exon_candidate_threshold: float = .9,
-                 variant_correction: bool = False, _backend=None, _fast: bool = False):
+                 variant_correction: bool = False, _backend=None, _fast: bool = False, _scan=None):
         """``_fast`` (not in the reference): read the ``.variant.json`` with the C++ scanner and pack
         the genes from arrays (:mod:`kir_graph_b200.fastjson`) instead of building a ``PairRead`` per
         read pair; same calls, ~3.5x less host time per sample.  The read objects are then not kept
-        (``_gene_reads`` is empty), so it applies to the full-variant strategy only."""
+        (``_gene_reads`` is empty), so it applies to the full-variant strategy only.  ``_scan``: the
+        reads as arrays already in memory (``fastsam.extract(sam, variants).scan()``: SAM text ->
+        calls without writing or reading the JSON); ``filename_variant_json`` is then not opened."""
         super().__init__()
         self._packs = None
-        if _fast and not exon_first and not exon_only:
+        if _scan is not None and (exon_first or exon_only):
+            raise ValueError("_scan holds no read objects: full-variant strategy only")
+        if (_fast or _scan is not None) and not exon_first and not exon_only:
             from . import fastjson
-            sc = fastjson.scan(filename_variant_json)
+            sc = _scan if _scan is not None else fastjson.scan(filename_variant_json)
             self._packs = fastjson.packs_from_scan(sc, variant_correction=variant_correction,
                                                    single_mapped_only=not multiple)
             self._gene_reads = {}

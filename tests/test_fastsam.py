@@ -203,3 +203,34 @@ def test_edges():
     a = _as_dicts(fastsam.extract(text, table).reads_data())
     Variant.novel_id = 0
     assert a == _as_dicts(_python_path(text, copy.deepcopy(table)))
+
+
+def test_sam_to_calls_without_json(tmp_path):
+    """extractVariantFromSam + selectKirTypingModel(_scan=...) call the same alleles as the reference's
+    route: write the .json, load it into objects, type from the objects."""
+    from kir_graph_b200.kir_typing import selectKirTypingModel
+    from tests.fake_backend import FakeBackend
+    table, pairs = _multi_gene(61, n_pairs=250, novel=0.002)
+    alleles = {g: [f"{g.split('*')[0]}*{i:03d}" for i in range(7)] for g in ("KIRA*BACKBONE", "KIRB*BACKBONE")}
+    rng = np.random.default_rng(6)
+    for v in table:
+        v.allele = [a for a in alleles[v.ref] if rng.random() < 0.4] or [alleles[v.ref][0]]
+    sam_path = str(tmp_path / "s.sam")
+    with open(sam_path, "w") as f:
+        f.write(_sam_text(pairs))
+    Variant.novel_id = 0
+    ext = hisat2.extractVariantFromSam(table, sam_path, str(tmp_path / "s.variant"), num_editdist=9)
+    gene_cn = {"KIRA*BACKBONE": 2, "KIRB*BACKBONE": 1}
+    slow = selectKirTypingModel("full", str(tmp_path / "s.variant.json"), top_n=30, variant_correction=True,
+                                _backend=FakeBackend())
+    fast = selectKirTypingModel("full", "unused", top_n=30, variant_correction=True, _backend=FakeBackend(),
+                                _scan=ext.scan())
+    a_slow, w_slow = slow.typing(gene_cn)
+    a_fast, w_fast = fast.typing(gene_cn)
+    assert a_fast == a_slow and w_fast == w_slow and len(a_fast) == 3
+    assert fast.getAllPossibleTyping() == slow.getAllPossibleTyping()
+    with pytest.raises(ValueError):
+        selectKirTypingModel("exonfirst_1", "unused", _scan=ext.scan())
+    with pytest.raises(NotImplementedError):
+        hisat2.extractVariantFromSam(table, sam_path, None, error_correction=True)
+    assert hisat2.extractVariantFromSam(table, sam_path, None, num_editdist=9).n_reads == ext.n_reads
