@@ -251,6 +251,10 @@ def main():
     ap.add_argument("--no-deep", action="store_true",
                     help="skip the nested cfg4 deep-sample measurement of the default 1-GPU cohort run")
     ap.add_argument("--parts", type=int, default=1, help="sub-batches (streams) of the resident pass")
+    ap.add_argument("--pipeline-depth", type=int, default=2,
+                    help="consecutive passes (steps) in flight: pass i+1 is enqueued on a replica of the typer "
+                         "(device buffers and streams of its own) before the host reads back pass i; 1 = one "
+                         "pass at a time")
     ap.add_argument("--e2e-parts", type=int, default=6,
                     help="sub-batches (streams) of the end-to-end pass: the host->device copies of one overlap "
                          "the kernels of the others")
@@ -300,9 +304,11 @@ def main():
 
         def reduce_scores(d_S):                      # one small collective per copy-number step
             dist.all_reduce(d_S)
+    group_size = 17 if args.workload != "deep" else 1
+    depth = max(1, args.pipeline_depth) if col_shard is None else 1
     typer = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=args.parts,
-                               group_size=17 if args.workload != "deep" else 1, col_shard=col_shard,
-                               reduce_scores=reduce_scores)
+                               group_size=group_size, col_shard=col_shard,
+                               reduce_scores=reduce_scores, own_stream=depth > 1)
     typer.pin()
     # The packed cohort is a large, long-lived heap (thousands of arrays); keep the cyclic garbage
     # collector from re-traversing it every time the per-run result objects trigger a collection
@@ -316,13 +322,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """CUDA events on the launching stream around `steps` calls; max over ranks."""
+    def timed(fn, steps, finalize=None):
+        """CUDA events on the launching stream around `steps` calls (and `finalize`, which ends the
+        passes still in flight: its streams are joined into the launching one); max over ranks."""
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         for _ in range(steps):
             fn()
+        if finalize is not None:
+            finalize()
         end.record()
         torch.cuda.synchronize()
         ms = start.elapsed_time(end)
@@ -343,10 +352,50 @@ def main():
     lik_cells = sum(p.batch.n_cells for p in typer.parts)
     lik_bytes = sum(p.batch.bytes_out for p in typer.parts)
     n_parts = len(typer.parts)
+    key = lambda cs: [(c.gene, c.alleles, c.score) for c in cs]
+    pipe_ok = True
+
+    def pipelined(typers, upload):
+        """(step, finalize) of a PassPipeline over `typers`; every pass's calls are checked against
+        the warm-up pass outside the timed region."""
+        pipe = cohort.PassPipeline(typers, upload=upload)
+        results = []
+
+        def step():
+            done = pipe.submit()
+            if done is not None:
+                results.append(done)
+
+        def finalize():
+            results.extend(pipe.drain())
+        return step, finalize, results
+
+    replicas = [typer]
+    for _ in range(depth - 1):
+        twin = typer.replica(packs, cns, args.top_n, group_size)
+        twin.upload()
+        for _ in range(3):                       # the third pass records the CUDA graph
+            twin.run()
+        replicas.append(twin)
+    gc.collect()
+    gc.freeze()
     launches0 = be.launches
-    ms_total = timed(typer.run, args.steps)
+    if depth > 1:
+        step, finalize, results = pipelined(replicas, upload=False)
+        for _ in range(depth):                   # fill and drain once untimed
+            step()
+        finalize()
+        results.clear()
+        launches0 = be.launches
+        ms_total = timed(step, args.steps, finalize)
+        pipe_ok = len(results) == args.steps and all(key(r) == key(calls) for r in results)
+        del results[:]
+    else:
+        ms_total = timed(typer.run, args.steps)
     launches = be.launches - launches0
     clocks = sampler.stop()
+    mem_resident = torch.cuda.max_memory_allocated() / 2 ** 30
+    del replicas[1:]
     # kernel timing pass: same work, sub-batches one after the other on one stream so that the
     # CUDA events around each launch do not overlap other kernels
     torch.cuda.synchronize()
@@ -365,21 +414,46 @@ def main():
         # copy/compute overlap returns
         e2e_parts = max(1, min(args.e2e_parts, n_samples_local // 12))
         cand = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=e2e_parts,
-                                  group_size=17 if args.workload != "deep" else 1)
+                                  group_size=group_size, own_stream=depth > 1)
         if len(cand.parts) != len(typer.parts):
             e2e_typer = cand
             e2e_typer.pin()
             gc.collect()
             gc.freeze()
+    twin = None
+    if e2e_typer is not typer:                   # the resident typers' device buffers are not needed any more
+        replicas.clear()
+        typer = None
+        gc.unfreeze()
+        gc.collect()
+        gc.freeze()
+    torch.cuda.empty_cache()
 
-    def e2e_step():
-        e2e_typer.upload_and_run()
-    for _ in range(max(3, args.warmup)):         # the third pass of a batch records its CUDA graph
-        e2e_step()
-    h0, d0 = be.h2d_bytes, be.d2h_bytes
-    ms_e2e = timed(e2e_step, args.steps)
+    e2e_replicas = [e2e_typer]
+    for _ in range(depth - 1):
+        e2e_replicas.append(e2e_typer.replica(packs, cns, args.top_n, group_size))
+    for t in e2e_replicas:
+        for _ in range(max(3, args.warmup)):     # the third pass of a batch records its CUDA graph
+            t.upload_and_run()
+    gc.collect()
+    gc.freeze()
+    e2e_ok = True
+    if depth > 1:
+        step, finalize, results = pipelined(e2e_replicas, upload=True)
+        for _ in range(depth):
+            step()
+        finalize()
+        results.clear()
+        h0, d0 = be.h2d_bytes, be.d2h_bytes
+        ms_e2e = timed(step, args.steps, finalize)
+        e2e_ok = len(results) == args.steps and all(key(r) == key(calls) for r in results)
+        del results[:]
+    else:
+        h0, d0 = be.h2d_bytes, be.d2h_bytes
+        ms_e2e = timed(e2e_typer.upload_and_run, args.steps)
     h2d = (be.h2d_bytes - h0) / args.steps
     d2h = (be.d2h_bytes - d0) / args.steps
+    mem_e2e = torch.cuda.max_memory_allocated() / 2 ** 30
 
     # ---- aggregate over ranks --------------------------------------------------------------
     agg = torch.tensor([cells_per_step, lik_cells, launches, h2d, d2h, n_samples_local], dtype=torch.float64,
@@ -425,7 +499,11 @@ def main():
             "vs_baseline": None, "dtype": "u16" if packed else "f32", "data": "synthetic",
             "config": {"workload": desc, "top_n": args.top_n, "l2": "inputs larger than L2 (no flush needed)",
                        "timed_region": "likelihood build + all CN steps + calls, packed inputs resident in HBM",
-                       "concurrent_sub_batches": n_parts, "e2e_sub_batches": len(e2e_typer.parts)},
+                       "concurrent_sub_batches": n_parts, "e2e_sub_batches": len(e2e_typer.parts),
+                       "passes_in_flight": depth,
+                       "pipelining": ("step i+1 is enqueued on a second set of device buffers and streams before the "
+                                      "host reads back step i (double-buffered passes; every step's copies, kernels, "
+                                      "read-back and calls lie inside the timed region)") if depth > 1 else "none"},
             "samples_per_s": samples_all / (step_ms * 1e-3),
             "e2e": {"value": cells_all / (e2e_ms * 1e-3) / 1e9, "unit": "GCells/s",
                     "samples_per_s": samples_all / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
@@ -445,12 +523,14 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
             },
             "kernel_ms_per_step": {k: kernel_stats(k)[0] / roof_steps for k in timing},
-            "parity": {"genes_matching_generator_truth": truth_ok, "genes": len(truth)},
+            "parity": {"genes_matching_generator_truth": truth_ok, "genes": len(truth),
+                       "every_timed_pass_equals_warmup_calls": bool(pipe_ok and e2e_ok)},
+            "device_mem_gib": {"after_resident": mem_resident, "after_e2e": mem_e2e},
             "build_s": t_build,
         }
         if world == 1 and args.workload == "cohort" and not args.no_deep:
             # second shape of the same path: one very deep sample (cfg4), scoring kernel dominated
-            del typer, e2e_typer
+            del typer, e2e_typer, e2e_replicas, replicas
             torch.cuda.empty_cache()
             d_packs, d_cns, d_truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
             deep = cohort.CohortTyper(d_packs, d_cns, top_n=args.top_n, backend=be, n_parts=1)

@@ -15,6 +15,8 @@ process per GPU; rank r takes samples r, r + world, ...).
 ``CohortTyper``  sub-batches on their own streams, all started before the first is
                  finished, so that host->device copies and the host-side call phase
                  of one overlap the kernels of the others.
+``PassPipeline`` consecutive passes with two (or more) in flight over replicas of a
+                 typer: double buffering of whole passes.
 """
 from __future__ import annotations
 
@@ -177,9 +179,9 @@ class BatchTyper:
         self.upload()
         return self.run()
 
-    def upload_and_start(self) -> None:
+    def upload_and_start(self):
         self.upload()
-        self.start()
+        return self.start()
 
     def run(self) -> list[GeneCall]:
         """Likelihood build + greedy search + calls for every problem of the batch."""
@@ -211,9 +213,16 @@ class BatchTyper:
         if self.pipelined:
             self._pending = self.group.run_pipeline_start(steps)
 
-    def start(self) -> None:
+    def start(self):
         """Enqueue the likelihood build and (pipelined mode) every search launch on the current
-        stream without waiting for the device; ``finish`` reads back and forms the calls."""
+        stream without waiting for the device; ``finish`` reads back and forms the calls.  Returns
+        the token of this pass (``finish(token)``): a second pass may be started before the first
+        is finished - the launches of both are ordered on the stream and every pass has its own
+        page-locked read-back buffer."""
+        self._start()
+        return self._pending
+
+    def _start(self) -> None:
         if self.batch is None:
             self.upload()
         graphable = (self.use_graph and self.pipelined and self.col_shard is None and self.group is not None
@@ -261,7 +270,10 @@ class BatchTyper:
             self.be.capturing = False
         self.be.launches = launches0
 
-    def finish(self) -> list[GeneCall]:
+    def finish(self, pending=None) -> list[GeneCall]:
+        """Read back and form the calls of the pass ``pending`` (default: the last one started)."""
+        if pending is None:
+            pending = self._pending
         group = self.group
         cn_live = self.cns[self.live]
         homo_live = self.homo[self.live]
@@ -273,8 +285,9 @@ class BatchTyper:
         score = np.zeros(n_live, dtype=np.int64)
         flags = np.zeros(n_live, dtype=np.int64)
         called = np.full((n_live, max(int(cn_live.max(initial=1)), 1)), -1, dtype=np.int64)
-        piped = group.run_pipeline_finish(self._pending) if self._pending is not None else None
-        self._pending = None
+        piped = group.run_pipeline_finish(pending) if pending is not None else None
+        if pending is self._pending:
+            self._pending = None
         if piped is not None:
             ids, score, info = piped
             kept = info["n_kept"].astype(np.int64)
@@ -337,8 +350,11 @@ class CohortTyper:
 
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
                  n_parts: int = 2, group_size: int = 1, col_shard: tuple[int, int] | None = None,
-                 reduce_scores=None):
-        """``group_size`` consecutive problems (e.g. the 17 genes of a sample) stay in one part."""
+                 reduce_scores=None, own_stream: bool = False, host_batches: list | None = None):
+        """``group_size`` consecutive problems (e.g. the 17 genes of a sample) stay in one part.
+        ``own_stream``: a stream of its own even for a single part (replicas of a ``PassPipeline``
+        overlap on the device only if they do not share the current stream).  ``host_batches``: the
+        packed host pools of another typer over the same problems and parts (shared, read only)."""
         self.be = backend if backend is not None else engine.CudaBackend()
         if col_shard is not None and col_shard[1] > 1:
             n_parts = 1                          # one collective stream: keep the parts serial
@@ -347,10 +363,14 @@ class CohortTyper:
         n_parts = max(1, min(n_parts, n_groups))
         bounds = [(g * n_groups // n_parts) * group_size for g in range(n_parts)] + [n]
         self.slices = [slice(bounds[i], min(bounds[i + 1], n)) for i in range(n_parts)]
+        if host_batches is not None and len(host_batches) != n_parts:
+            raise ValueError("host_batches must hold one HostBatch per part")
         self.parts = [BatchTyper(packs[sl], list(cns)[sl], top_n=top_n, backend=self.be, col_shard=col_shard,
-                                 reduce_scores=reduce_scores) for sl in self.slices]
+                                 reduce_scores=reduce_scores,
+                                 host_batch=host_batches[i] if host_batches is not None else None)
+                      for i, sl in enumerate(self.slices)]
         self.streams = None
-        if n_parts > 1 and hasattr(self.be, "torch"):
+        if (n_parts > 1 or own_stream) and col_shard is None and hasattr(self.be, "torch"):
             self.streams = [self.be.torch.cuda.Stream(device=self.be.device) for _ in self.parts]
 
     @property
@@ -365,17 +385,18 @@ class CohortTyper:
         for p in self.parts:
             p.host.pin(self.be)
 
-    def _each(self, fn_name: str) -> list:
+    def _each(self, fn_name: str, args: list | None = None) -> list:
         """``fn_name`` of every part, each under its own stream (no synchronisation)."""
+        args = [()] * len(self.parts) if args is None else [(a,) for a in args]
         if self.streams is None:
-            return [getattr(part, fn_name)() for part in self.parts]
+            return [getattr(part, fn_name)(*a) for part, a in zip(self.parts, args)]
         torch = self.be.torch
         cur = torch.cuda.current_stream(self.be.device)
         out = []
-        for part, st in zip(self.parts, self.streams):
+        for part, st, a in zip(self.parts, self.streams, args):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                out.append(getattr(part, fn_name)())
+                out.append(getattr(part, fn_name)(*a))
         return out
 
     def _join(self) -> None:
@@ -412,6 +433,60 @@ class CohortTyper:
             calls.extend(part)
         self._join()
         return calls
+
+    def start_pass(self, upload: bool = False) -> list:
+        """Enqueue one pass of every part (with ``upload``: the host->device copies first) and
+        return its token without blocking; ``finish_pass(token)`` yields the calls."""
+        return self._each("upload_and_start" if upload else "start")
+
+    def finish_pass(self, token: list) -> list[GeneCall]:
+        calls: list[GeneCall] = []
+        for part in self._each("finish", token):
+            calls.extend(part)
+        self._join()
+        return calls
+
+    def replica(self, packs: list[GenePack], cns: list[int], top_n: int, group_size: int = 1) -> "CohortTyper":
+        """A second typer over the same problems: same parts and host pools (shared, page-locked
+        once), device buffers and streams of its own."""
+        return CohortTyper(packs, cns, top_n=top_n, backend=self.be, n_parts=len(self.parts), group_size=group_size,
+                           own_stream=True, host_batches=[p.host for p in self.parts])
+
+
+class PassPipeline:
+    """Consecutive passes of a cohort with ``len(typers)`` of them in flight: pass ``i`` runs on
+    ``typers[i % depth]``, and the host blocks on a pass only when its typer is needed again (or at
+    ``drain``).  With one typer used twice in a row the host-side call phase of a pass overlaps the
+    kernels of the next; with replicas (device buffers and streams of their own) the next pass's
+    host->device copies and kernels also overlap the latency-bound tail of the current one
+    (selection and ranking are short serial chains) - double buffering of whole passes.  Calls come
+    back in submission order."""
+
+    def __init__(self, typers: list[CohortTyper], upload: bool = False, depth: int | None = None):
+        self.typers = typers
+        self.upload = upload
+        self.depth = max(1, depth if depth is not None else len(typers))
+        self._in_flight: list[tuple[CohortTyper, list]] = []
+        self._next = 0
+
+    def submit(self) -> list[GeneCall] | None:
+        """Enqueue the next pass; returns the calls of the oldest pass if it had to be finished
+        to make room, else ``None``."""
+        done = None
+        if len(self._in_flight) >= self.depth:
+            typer, token = self._in_flight.pop(0)
+            done = typer.finish_pass(token)
+        typer = self.typers[self._next % len(self.typers)]
+        self._next += 1
+        self._in_flight.append((typer, typer.start_pass(self.upload)))
+        return done
+
+    def drain(self) -> list[list[GeneCall]]:
+        out = []
+        while self._in_flight:
+            typer, token = self._in_flight.pop(0)
+            out.append(typer.finish_pass(token))
+        return out
 
 
 def shard(items: list, rank: int, world: int) -> list:

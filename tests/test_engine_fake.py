@@ -209,3 +209,37 @@ def test_pipelined_batch_equals_stepwise_and_falls_back(monkeypatch):
     slow = cohort.BatchTyper(packs, cns, top_n=25, backend=be)
     got = slow.run()
     assert [(c.alleles, c.score) for c in got] == [(c.alleles, c.score) for c in want]
+
+
+def test_pass_pipeline_equals_serial_passes():
+    """PassPipeline (passes in flight over replicas that share the host pools) returns, pass by pass
+    and in order, what typer.run() returns; a single typer used with depth 2 as well."""
+    from kir_graph_b200 import cohort
+    genes = (synthetic.make_wgs30x_sample(seed=14, total_reads=900) + synthetic.make_wgs30x_sample(seed=15, total_reads=900))
+    genes = [g for g in genes if g.n_alleles <= 40][:8]
+    packs = [packing.pack_synthetic(g) for g in genes]
+    cns = [g.cn for g in genes]
+    key = lambda calls: [(c.gene, c.alleles, c.score, c.best_rank, c.tie_flags) for c in calls]
+    typer = cohort.CohortTyper(packs, cns, top_n=25, backend=FakeBackend(), n_parts=2, group_size=4)
+    want = key(typer.run())
+    assert len(want) == len(packs)
+    twin = typer.replica(packs, cns, top_n=25, group_size=4)
+    assert all(a.host is b.host for a, b in zip(typer.parts, twin.parts))
+    for typers, depth, upload in (([typer, twin], None, False), ([typer, twin], None, True), ([typer], 2, False),
+                                  ([typer], 1, True)):
+        pipe = cohort.PassPipeline(typers, upload=upload, depth=depth)
+        out = []
+        for i in range(3):
+            done = pipe.submit()
+            assert (done is None) == (i < pipe.depth)
+            if done is not None:
+                out.append(done)
+        out += pipe.drain()
+        assert len(out) == 3 and all(key(calls) == want for calls in out)
+        assert pipe.drain() == []
+    # a typer whose passes are not pipelined (read-back per step) still gives the same calls
+    for part in typer.parts:
+        part.pipelined = False
+    pipe = cohort.PassPipeline([typer], depth=2)
+    pipe.submit(), pipe.submit()
+    assert [key(c) for c in pipe.drain()] == [want, want]

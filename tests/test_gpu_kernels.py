@@ -270,6 +270,36 @@ def test_two_batches_in_flight_on_one_stream(cuda):
         assert key(typers[1].finish()) == want[1]
 
 
+def test_pass_pipeline_over_replicas(cuda):
+    """Consecutive passes with two in flight (cohort.PassPipeline): replicas with device buffers and
+    streams of their own, resident and with the host->device copies inside every pass; and two passes
+    of ONE typer in flight on its stream.  Every pass must give the calls of a plain run()."""
+    from kir_graph_b200 import cohort
+    key = lambda calls: [(c.gene, tuple(c.alleles), c.best_rank, c.score, c.tie_flags) for c in calls]
+    packs, cns = [], []
+    for seed in (21, 22, 23):
+        genes = synthetic.make_wgs30x_sample(seed=seed, total_reads=15000)
+        packs += [packing.pack_synthetic(g) for g in genes]
+        cns += [g.cn for g in genes]
+    want = key(cohort.BatchTyper(packs, cns, top_n=300, backend=cuda).run())
+    for n_parts in (1, 3):
+        typer = cohort.CohortTyper(packs, cns, top_n=300, backend=cuda, n_parts=n_parts, group_size=17, own_stream=True)
+        assert typer.streams is not None and len(typer.streams) == n_parts
+        twin = typer.replica(packs, cns, top_n=300, group_size=17)
+        assert all(a.host is b.host for a, b in zip(typer.parts, twin.parts))
+        for typers, depth, upload in (([typer, twin], None, False), ([typer, twin], None, True), ([typer], 2, False)):
+            pipe = cohort.PassPipeline(typers, upload=upload, depth=depth)
+            out = []
+            for _ in range(7):                           # eager passes, graph capture, replays
+                done = pipe.submit()
+                if done is not None:
+                    out.append(done)
+            out += pipe.drain()
+            assert len(out) == 7 and all(key(calls) == want for calls in out), (n_parts, depth, upload)
+        assert all(getattr(p, "graph_error", None) is None for t in (typer, twin) for p in t.parts)
+        assert all(p._graph is not None for t in (typer, twin) for p in t.parts)
+
+
 @pytest.mark.parametrize("packed", [False, True])
 def test_many_observations_per_read(cuda, packed):
     """Up to 255 observations per read pair stay exact on both scoring paths."""
