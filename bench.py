@@ -251,10 +251,11 @@ def main():
     ap.add_argument("--no-deep", action="store_true",
                     help="skip the nested cfg4 deep-sample measurement of the default 1-GPU cohort run")
     ap.add_argument("--parts", type=int, default=1, help="sub-batches (streams) of the resident pass")
-    ap.add_argument("--pipeline-depth", type=int, default=2,
+    ap.add_argument("--pipeline-depth", type=int, default=0,
                     help="consecutive passes (steps) in flight: pass i+1 is enqueued on a replica of the typer "
                          "(device buffers and streams of its own) before the host reads back pass i; 1 = one "
-                         "pass at a time")
+                         "pass at a time; 0 = 3, or 4 when this rank holds fewer than 16 samples (the "
+                         "selection / ranking chains of a small batch leave more of the GPU idle)")
     ap.add_argument("--e2e-parts", type=int, default=6,
                     help="sub-batches (streams) of the end-to-end pass: the host->device copies of one overlap "
                          "the kernels of the others")
@@ -305,7 +306,11 @@ def main():
         def reduce_scores(d_S):                      # one small collective per copy-number step
             dist.all_reduce(d_S)
     group_size = 17 if args.workload != "deep" else 1
-    depth = max(1, args.pipeline_depth) if col_shard is None else 1
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else (4 if n_samples_local < 16 else 3)
+    if args.workload == "deep" and args.pipeline_depth <= 0:
+        depth = 2                                # 150 ms of saturated kernels per pass: only the host phase to hide
+    if col_shard is not None:
+        depth = 1                                # one collective stream: passes stay serial
     typer = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=args.parts,
                                group_size=group_size, col_shard=col_shard,
                                reduce_scores=reduce_scores, own_stream=depth > 1)
