@@ -267,6 +267,16 @@ int gk_sam_extract_fill(void* handle, int32_t* multiple, int32_t* backbone, int6
                         int32_t* nv_typ, int32_t* nv_val_int, int32_t* nv_length, int64_t* nv_val_off,
                         char* nv_val_bytes, int64_t* ref_off, char* ref_bytes);
 void gk_sam_extract_free(void* handle);
+/* The "reads" array of the reference's {prefix}.json (writeReadsAndVariantsData, hisat2.py:847-857)
+ * for the pairs of a gk_sam_extract handle, byte for byte what json.dump writes for
+ * [asdict(PairRead), ...] without the enclosing brackets: {"l_sam": ..., "r_sam": ..., "multiple": ...,
+ * "backbone": ..., "lpv": [...], "lnv": [...], "rpv": [...], "rnv": [...]} joined by ", ", strings
+ * escaped as ensure_ascii does.  sam = the text given to gk_sam_extract; id_off [n_var + 1] /
+ * id_bytes = ids of the table variants; novel variants are written as "nv<novel_id + k>".  *out points
+ * into the handle (valid until the next call on it or gk_sam_extract_free).  -1 if a string is not
+ * UTF-8. */
+int gk_sam_extract_json(void* handle, const char* sam, const int64_t* id_off, const char* id_bytes,
+                        int32_t novel_id, const char** out, int64_t* out_len);
 
 #ifdef __cplusplus
 }

@@ -326,6 +326,7 @@ struct Extract {
     std::unordered_map<std::string, int32_t> ref_index;
     std::vector<int32_t> multiple, backbone;
     std::vector<int64_t> span;      // per pair: offset, length of the left record and of the right record
+    std::string json;               // gk_sam_extract_json: the "reads" array, owned by the handle
     std::vector<int64_t> off[4];    // lpv, lnv, rpv, rnv
     std::vector<int32_t> idx[4];
     int64_t n_strange = 0;
@@ -654,6 +655,124 @@ extern "C" int gk_sam_extract_fill(void* handle, int32_t* multiple, int32_t* bac
         o += (int64_t)r.size();
     }
     ref_off[j] = o;
+    return 0;
+}
+
+namespace {
+
+// json.dumps(str) with ensure_ascii=True: the escapes of Python's encoder (py_encode_basestring_ascii)
+bool json_string(std::string& out, const char* s, int64_t n) {
+    static const char hex[] = "0123456789abcdef";
+    auto u16 = [&](uint32_t c) {
+        out += "\\u";
+        out.push_back(hex[(c >> 12) & 15]);
+        out.push_back(hex[(c >> 8) & 15]);
+        out.push_back(hex[(c >> 4) & 15]);
+        out.push_back(hex[c & 15]);
+    };
+    out.push_back('"');
+    for (int64_t i = 0; i < n;) {
+        int64_t j = i;                                      // run of characters the encoder copies as they are
+        while (j < n && s[j] >= ' ' && s[j] <= '~' && s[j] != '"' && s[j] != '\\') ++j;
+        if (j > i) {
+            out.append(s + i, (size_t)(j - i));
+            i = j;
+            continue;
+        }
+        const unsigned char c = (unsigned char)s[i];
+        if (c < 0x80) {
+            switch (c) {
+                case '"': out += "\\\""; break;
+                case '\\': out += "\\\\"; break;
+                case '\n': out += "\\n"; break;
+                case '\r': out += "\\r"; break;
+                case '\t': out += "\\t"; break;
+                case '\b': out += "\\b"; break;
+                case '\f': out += "\\f"; break;
+                default:
+                    if (c < 0x20 || c == 0x7f) u16(c);              // the encoder keeps ' ' .. '~' only
+                    else out.push_back((char)c);
+            }
+            ++i;
+            continue;
+        }
+        // UTF-8 -> code point (what bytes.decode("utf-8") accepts), then \uXXXX / a surrogate pair
+        int len = c >= 0xf0 ? 4 : c >= 0xe0 ? 3 : c >= 0xc2 ? 2 : 0;
+        if (len == 0 || c > 0xf4 || i + len > n) return false;
+        uint32_t cp = len == 2 ? c & 0x1f : len == 3 ? c & 0x0f : c & 0x07;
+        for (int k = 1; k < len; ++k) {
+            const unsigned char t = (unsigned char)s[i + k];
+            if ((t & 0xc0) != 0x80) return false;
+            cp = (cp << 6) | (t & 0x3f);
+        }
+        if ((len == 3 && (cp < 0x800 || (cp >= 0xd800 && cp <= 0xdfff))) || (len == 4 && (cp < 0x10000 || cp > 0x10ffff)))
+            return false;
+        if (cp >= 0x10000) {
+            cp -= 0x10000;
+            u16(0xd800 + (cp >> 10));
+            u16(0xdc00 + (cp & 0x3ff));
+        } else {
+            u16(cp);
+        }
+        i += len;
+    }
+    out.push_back('"');
+    return true;
+}
+
+}  // namespace
+
+// See include/gk_typing.h.
+extern "C" int gk_sam_extract_json(void* handle, const char* sam, const int64_t* id_off, const char* id_bytes,
+                                   int32_t novel_id, const char** out, int64_t* out_len) {
+    GK_REQUIRE(handle != nullptr && out != nullptr && out_len != nullptr, "gk_sam_extract_json: null argument%s", "");
+    Extract* ex = static_cast<Extract*>(handle);
+    std::string& js = ex->json;
+    js.clear();
+    js.reserve(ex->span.size() / 4 * 1024);
+    static const char* const names[4] = {"\"lpv\": [", "\"lnv\": [", "\"rpv\": [", "\"rnv\": ["};
+    char num[32];
+    const size_t n = ex->multiple.size();
+    for (size_t r = 0; r < n; ++r) {
+        js += r ? ", {\"l_sam\": " : "{\"l_sam\": ";
+        if (!json_string(js, sam + ex->span[4 * r], ex->span[4 * r + 1])) {
+            gk_set_error("gk_sam_extract_json: record of pair %lld is not UTF-8", (long long)r);
+            return -1;
+        }
+        js += ", \"r_sam\": ";
+        if (!json_string(js, sam + ex->span[4 * r + 2], ex->span[4 * r + 3])) {
+            gk_set_error("gk_sam_extract_json: record of pair %lld is not UTF-8", (long long)r);
+            return -1;
+        }
+        js += ", \"multiple\": ";
+        js.append(num, (size_t)snprintf(num, sizeof num, "%d", ex->multiple[r]));
+        js += ", \"backbone\": ";
+        const std::string& ref = ex->refs[(size_t)ex->backbone[r]];
+        if (!json_string(js, ref.data(), (int64_t)ref.size())) {
+            gk_set_error("gk_sam_extract_json: backbone name of pair %lld is not UTF-8", (long long)r);
+            return -1;
+        }
+        for (int w = 0; w < 4; ++w) {
+            js += ", ";
+            js += names[w];
+            for (int64_t j = ex->off[w][r]; j < ex->off[w][r + 1]; ++j) {
+                if (j > ex->off[w][r]) js += ", ";
+                const int32_t v = ex->idx[w][(size_t)j];
+                if (v < ex->n_table) {
+                    if (!json_string(js, id_bytes + id_off[v], id_off[v + 1] - id_off[v])) {
+                        gk_set_error("gk_sam_extract_json: id of variant %d is not UTF-8", v);
+                        return -1;
+                    }
+                } else {
+                    js.append(num, (size_t)snprintf(num, sizeof num, "\"nv%d\"", novel_id + (v - ex->n_table)));
+                }
+            }
+            js.push_back(']');
+        }
+        js.push_back('}');
+    }
+    *out = js.data();
+    *out_len = (int64_t)js.size();
     return 0;
 }
 

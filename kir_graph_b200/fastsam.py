@@ -7,7 +7,8 @@ recordToVariants -> getPNFromVariantList, graphkir/hisat2.py:228-276, :541-578, 
 routine ``gk_sam_extract`` of ``libgk_typing.so`` does the whole loop over the SAM text and returns
 the four variant lists of every kept pair as CSR arrays plus the novel variants it met; objects are
 built only on request (:meth:`SamExtract.reads_data`, used by the tests to compare with the object
-path and to write the reference's ``.json``).  :meth:`SamExtract.scan` presents the result as the
+path); the reference's ``.json`` is written natively as well (:meth:`SamExtract.write_json`, byte
+for byte what ``writeReadsAndVariantsData`` writes).  :meth:`SamExtract.scan` presents the result as the
 ``fastjson.JsonScan`` the packing code takes, so SAM text -> ``GenePack`` needs no JSON at all.
 
 Pileup-based read error correction is not covered (the CLI path runs with it off, main.py:149).
@@ -44,6 +45,7 @@ class SamExtract:
     offsets: dict[str, np.ndarray]       # list name -> int64 [R + 1]
     indices: dict[str, np.ndarray]       # list name -> int32
     n_strange: int                       # pairs skipped because the flags are not first + second mate
+    reads_json: bytes | None = None      # the "reads" array of the .json, written natively (json_reads=True)
 
     @property
     def n_reads(self) -> int:
@@ -68,6 +70,24 @@ class SamExtract:
             reads.append(PairRead(l_sam=self.sam[lo:lo + ln].decode("utf-8"), r_sam=self.sam[ro:ro + rn].decode("utf-8"),
                                   multiple=int(self.multiple[r]), backbone=self.refs[int(self.backbone[r])], **lists))
         return {"variants": self.variants(), "reads": reads}
+
+    def write_json(self, filename: str) -> None:
+        """``writeReadsAndVariantsData(self.reads_data(), filename)`` (hisat2.py:847-857), byte for byte,
+        without building the read objects: the "reads" array comes from the native writer (needs
+        ``extract(..., json_reads=True)``), only the variant table goes through ``json``."""
+        if self.reads_json is None:
+            raise ValueError("extract(..., json_reads=True) is needed for write_json")
+        import json
+        # asdict(v) field by field (the dataclass order of msa2hisat.Variant), without its deep copies
+        rows = [{"pos": v.pos, "typ": v.typ, "ref": v.ref, "val": v.val, "id": v.id, "length": v.length,
+                 "allele": list(v.allele), "freq": v.freq, "ignore": v.ignore, "in_exon": v.in_exon}
+                for v in self.variants()]
+        with open(filename, "wb") as handle:
+            handle.write(b'{"variants": ')
+            handle.write(json.dumps(rows).encode("ascii"))
+            handle.write(b', "reads": [')
+            handle.write(self.reads_json)
+            handle.write(b"]}")
 
     def scan(self) -> JsonScan:
         """The same reads as the array form ``fastjson`` produces from a ``.variant.json``."""
@@ -117,7 +137,8 @@ def _strings(off: np.ndarray, blob: bytes) -> list[str]:
     return [blob[off[i]:off[i + 1]].decode("utf-8") for i in range(len(off) - 1)]
 
 
-def extract(sam: bytes | str, variants: list[Variant], num_editdist: int = 4) -> SamExtract:
+def extract(sam: bytes | str, variants: list[Variant], num_editdist: int = 4, json_reads: bool = False
+            ) -> SamExtract:
     """Name-sorted SAM text (header lines allowed) + sorted index variants -> :class:`SamExtract`.
 
     Equivalent to ``extractVariant(filter(filterRead both, readPair(...)), variants)`` of the
@@ -168,6 +189,17 @@ def extract(sam: bytes | str, variants: list[Variant], num_editdist: int = 4) ->
                                      out_ref_off.ctypes.data, out_ref_blob)
         if rc != 0:
             raise ValueError(lib.gk_last_error().decode())
+        reads_json = None
+        if json_reads:
+            id_off, id_blob = _blob([str(v.id).encode("utf-8") for v in variants])
+            out, out_len = ctypes.c_char_p(), ctypes.c_int64()
+            lib.gk_sam_extract_json.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p,
+                                                ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p),
+                                                ctypes.POINTER(ctypes.c_int64)]
+            if lib.gk_sam_extract_json(handle, sam, id_off.ctypes.data, id_blob, novel_base, ctypes.byref(out),
+                                       ctypes.byref(out_len)) != 0:
+                raise UnicodeDecodeError("utf-8", b"", 0, 1, lib.gk_last_error().decode())
+            reads_json = ctypes.string_at(out, out_len.value)
     finally:
         lib.gk_sam_extract_free(handle)
     all_refs = _strings(out_ref_off, out_ref_blob.raw)
@@ -181,11 +213,13 @@ def extract(sam: bytes | str, variants: list[Variant], num_editdist: int = 4) ->
     Variant.novel_id = novel_base + n_novel
     return SamExtract(sam, variants, novel, all_refs, backbone, multiple, span,
                       {name: offs[w] for w, name in enumerate(SCAN_LISTS)},
-                      {name: idxs[w][: int(sizes[1 + w])] for w, name in enumerate(SCAN_LISTS)}, int(sizes[10]))
+                      {name: idxs[w][: int(sizes[1 + w])] for w, name in enumerate(SCAN_LISTS)}, int(sizes[10]),
+                      reads_json)
 
 
-def extract_file(filename: str, variants: list[Variant], num_editdist: int = 4) -> SamExtract:
+def extract_file(filename: str, variants: list[Variant], num_editdist: int = 4, json_reads: bool = False
+                 ) -> SamExtract:
     """:func:`extract` over a name-sorted ``.sam`` file (``samtools sort -n | samtools view -h``
     output; running samtools stays in the reference, hisat2.py:205-225)."""
     with open(filename, "rb") as handle:
-        return extract(handle.read(), variants, num_editdist)
+        return extract(handle.read(), variants, num_editdist, json_reads)

@@ -375,11 +375,11 @@ def extractVariantFromSam(index: str | list[Variant], sam_file: str, output_pref
                                   "(the CLI path passes error_correction=False, main.py:149)")
     from . import fastsam
     variants = getVariants(index) if isinstance(index, str) else index
-    ext = fastsam.extract_file(sam_file, variants, num_editdist)
+    ext = fastsam.extract_file(sam_file, variants, num_editdist, json_reads=output_prefix is not None)
     logger.info(f"[Graph] Filterd pairs: {ext.n_reads}")
     if output_prefix is not None:
         logger.debug(f"[Graph] Save allele per reads in {output_prefix}.json")
-        writeReadsAndVariantsData(ext.reads_data(), f"{output_prefix}.json")
+        ext.write_json(f"{output_prefix}.json")               # == writeReadsAndVariantsData(ext.reads_data(), ...)
     return ext
 
 

@@ -234,3 +234,46 @@ def test_sam_to_calls_without_json(tmp_path):
     with pytest.raises(NotImplementedError):
         hisat2.extractVariantFromSam(table, sam_path, None, error_correction=True)
     assert hisat2.extractVariantFromSam(table, sam_path, None, num_editdist=9).n_reads == ext.n_reads
+
+
+def test_native_json_is_byte_identical(tmp_path):
+    """SamExtract.write_json == writeReadsAndVariantsData(reads_data()) byte for byte, including
+    the escapes json.dump applies (quotes and backslashes in quality strings, control characters,
+    non-ASCII read names as \\uXXXX / surrogate pairs), and the file loads back into equal objects."""
+    table, pairs = _multi_gene(71, n_pairs=60, novel=0.004)
+    table[0].id = 'hv"0\\x'                                  # an id that needs escaping
+    lines = _sam_text(pairs).rstrip("\n").split("\n")
+    out = []
+    for i, line in enumerate(lines):
+        f = line.split("\t")
+        if len(f) > 10 and i % 3 == 0:
+            f[10] = ('"\\/' + "\x7f\x01" + f[10])[: len(f[10])] if len(f[10]) > 6 else f[10]
+        if len(f) > 10 and i % 5 < 2:
+            # both mates of a pair must keep one name: rename by the name itself
+            f[0] = f[0] + "é€😀"
+        out.append("\t".join(f))
+    sam = "\n".join(out) + "\n"
+    Variant.novel_id = 3
+    ext = fastsam.extract(sam, table, num_editdist=9, json_reads=True)
+    assert ext.n_reads > 20
+    a, b = str(tmp_path / "a.json"), str(tmp_path / "b.json")
+    ext.write_json(a)
+    hisat2.writeReadsAndVariantsData(ext.reads_data(), b)
+    raw_a, raw_b = open(a, "rb").read(), open(b, "rb").read()
+    assert raw_a == raw_b
+    assert b"\\u00e9\\u20ac\\ud83d\\ude00" in raw_a and b'\\"\\\\/\\u007f\\u0001' in raw_a
+    back = hisat2.loadReadsAndVariantsData(a)
+    assert _as_dicts(back) == _as_dicts(ext.reads_data())
+    # the scanner of the fast typing path reads the natively written file
+    sc = fastjson.scan(a)
+    assert sc.n_reads == ext.n_reads and sc.multiple.tolist() == ext.multiple.tolist()
+    with pytest.raises(ValueError):
+        fastsam.extract(sam, table, num_editdist=9).write_json(a)          # json_reads not requested
+    # empty result and invalid UTF-8
+    empty = fastsam.extract("", table, json_reads=True)
+    empty.write_json(a)
+    hisat2.writeReadsAndVariantsData(empty.reads_data(), b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    bad = sam.encode("utf-8").replace("é".encode("utf-8"), b"\xff\xfe")
+    with pytest.raises(UnicodeDecodeError):
+        fastsam.extract(bad, table, num_editdist=9, json_reads=True)

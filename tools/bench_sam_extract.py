@@ -48,6 +48,19 @@ got = ext.reads_data()
 assert [(r.lpv, r.lnv, r.rpv, r.rnv, r.multiple, r.backbone) for r in got["reads"]] == \
        [(r.lpv, r.lnv, r.rpv, r.rnv, r.multiple, r.backbone) for r in want["reads"]]
 n = len(pairs)
+import tempfile
+with tempfile.TemporaryDirectory() as d:
+    Variant.novel_id = 0
+    t5 = time.perf_counter()
+    fastsam.extract(raw, table, json_reads=True).write_json(os.path.join(d, "a.json"))
+    t6 = time.perf_counter()
+    hisat2.writeReadsAndVariantsData(want, os.path.join(d, "b.json"))
+    t7 = time.perf_counter()
+    assert open(os.path.join(d, "a.json"), "rb").read() == open(os.path.join(d, "b.json"), "rb").read()
+    size = os.path.getsize(os.path.join(d, "a.json"))
+print(f"SAM -> .json ({size / 1e6:.1f} MB, byte-identical): object path {t4 - t3 + t7 - t6:.2f} s "
+      f"({1e6 * (t4 - t3 + t7 - t6) / n:.1f} us per pair), native {t6 - t5:.3f} s ({1e6 * (t6 - t5) / n:.2f} us per pair)"
+      f"  -> {(t4 - t3 + t7 - t6) / (t6 - t5):.0f}x")
 print(f"kept {ext.n_reads} pairs, {len(ext.novel)} novel variants")
 print(f"object path : {t4 - t3:.2f} s ({1e6 * (t4 - t3) / n:.1f} us per pair)")
 print(f"native path : {t1 - t0:.3f} s ({1e6 * (t1 - t0) / n:.2f} us per pair, {len(raw) / (t1 - t0) / 1e6:.0f} MB/s)"
