@@ -69,6 +69,7 @@ def removeMultipleMapped(reads_data: ReadsAndVariantsData) -> ReadsAndVariantsDa
 # ---------------------------------------------------------------------------
 import bisect
 import copy
+import os
 import re
 from typing import Iterable
 
@@ -380,6 +381,50 @@ def extractVariantFromSam(index: str | list[Variant], sam_file: str, output_pref
     if output_prefix is not None:
         logger.debug(f"[Graph] Save allele per reads in {output_prefix}.json")
         ext.write_json(f"{output_prefix}.json")               # == writeReadsAndVariantsData(ext.reads_data(), ...)
+    return ext
+
+
+def _samtools(args: list[str], capture: bool = False) -> str:
+    """One local ``samtools`` call (the reference's runTool with the local engine,
+    external_tools.py:161-186 -> utils.py:88-103); containers stay in the reference."""
+    import subprocess
+    try:
+        proc = subprocess.run(["samtools", *args], capture_output=True, check=True, universal_newlines=True)
+    except FileNotFoundError as exc:
+        raise FileNotFoundError("samtools is not on PATH: pass a name-sorted SAM file to "
+                                "extractVariantFromSam instead (mapping and BAM handling stay in the "
+                                "reference)") from exc
+    return proc.stdout if capture else ""
+
+
+def extractVariantFromBam(index: str | list[Variant], bam_file: str, output_prefix: str,
+                          error_correction: bool = True, num_editdist: int = 4):
+    """The reference's entry point (:904-940), same arguments: reads ``samtools sort -n bam -O SAM``
+    (readBam, :103-110), runs the native extraction loop, writes ``{output_prefix}.json`` and - as the
+    reference does through samtools - ``{output_prefix}.bam`` and ``{output_prefix}.no_multi.bam``
+    (saveReadsToBam, :884-901).  ``error_correction`` defaults to True as in the reference, which this
+    implementation refuses (the CLI path passes False, main.py:149)."""
+    if error_correction:
+        raise NotImplementedError("pileup-based read error correction stays in the reference "
+                                  "(the CLI path passes error_correction=False, main.py:149)")
+    from . import fastsam
+    variants = getVariants(index) if isinstance(index, str) else index
+    text = _samtools(["sort", "-n", bam_file, "-O", "SAM"], capture=True)
+    ext = fastsam.extract(text, variants, num_editdist, json_reads=True)
+    logger.info(f"[Graph] Filterd pairs: {ext.n_reads}")
+    logger.debug(f"[Graph] Save allele per reads in {output_prefix}.json")
+    ext.write_json(f"{output_prefix}.json")
+    header = _samtools(["view", "-H", bam_file], capture=True)
+    for prefix, keep in ((output_prefix, None), (output_prefix + ".no_multi", ext.multiple == 1)):
+        with open(prefix + ".sam", "wb") as handle:                   # saveSam (:869-881)
+            handle.write(header.encode("utf-8"))
+            for r in range(ext.n_reads):
+                if keep is None or keep[r]:
+                    lo, ln, ro, rn = (int(x) for x in ext.span[r])
+                    handle.write(ext.sam[lo:lo + ln] + b"\n" + ext.sam[ro:ro + rn] + b"\n")
+        _samtools(["sort", prefix + ".sam", "-o", prefix + ".bam"])    # samtobam (utils.py:106-116)
+        _samtools(["index", prefix + ".bam"])
+        os.remove(prefix + ".sam")
     return ext
 
 

@@ -277,3 +277,43 @@ def test_native_json_is_byte_identical(tmp_path):
     bad = sam.encode("utf-8").replace("é".encode("utf-8"), b"\xff\xfe")
     with pytest.raises(UnicodeDecodeError):
         fastsam.extract(bad, table, num_editdist=9, json_reads=True)
+
+
+def test_extract_variant_from_bam_with_a_samtools_shim(tmp_path, monkeypatch):
+    """extractVariantFromBam (the reference's name and arguments) end to end; samtools is replaced by
+    a shim on PATH that serves the name-sorted SAM text ("sort -n X -O SAM"), the header ("view -H")
+    and copies for "sort X.sam -o X.bam" / "index"."""
+    import os
+    import stat
+    table, pairs = _multi_gene(81, n_pairs=50, novel=0.002)
+    sam = _sam_text(pairs)
+    (tmp_path / "in.bam").write_text(sam)                     # the shim treats the "bam" as SAM text
+    shim = tmp_path / "bin" / "samtools"
+    shim.parent.mkdir()
+    shim.write_text("""#!/bin/sh
+if [ "$1" = sort ] && [ "$2" = -n ]; then cat "$3"; exit 0; fi
+if [ "$1" = view ] && [ "$2" = -H ]; then grep '^@' "$3"; exit 0; fi
+if [ "$1" = sort ]; then cp "$2" "$4"; exit 0; fi
+if [ "$1" = index ]; then : > "$2.bai"; exit 0; fi
+exit 1
+""")
+    shim.chmod(shim.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{shim.parent}{os.pathsep}{os.environ['PATH']}")
+    with pytest.raises(NotImplementedError):
+        hisat2.extractVariantFromBam(table, str(tmp_path / "in.bam"), str(tmp_path / "out"))   # default: pileup
+    Variant.novel_id = 0
+    ext = hisat2.extractVariantFromBam(table, str(tmp_path / "in.bam"), str(tmp_path / "out"), error_correction=False,
+                                       num_editdist=9)
+    Variant.novel_id = 0
+    want = _python_path(sam, copy.deepcopy(table), 9)
+    got = hisat2.loadReadsAndVariantsData(str(tmp_path / "out.json"))
+    assert _as_dicts(got) == _as_dicts(want) and ext.n_reads == len(want["reads"]) > 10
+    # the two "bam" files: header + the kept records, all pairs / single-mapped pairs only (:937-940)
+    body = lambda path: [l for l in open(path).read().split("\n") if l and not l.startswith("@")]
+    assert body(tmp_path / "out.bam") == [x for r in want["reads"] for x in (r.l_sam, r.r_sam)]
+    assert body(tmp_path / "out.no_multi.bam") == [x for r in want["reads"] if r.multiple == 1 for x in (r.l_sam, r.r_sam)]
+    assert open(tmp_path / "out.bam").read().startswith("@HD") and os.path.exists(tmp_path / "out.bam.bai")
+    assert not os.path.exists(tmp_path / "out.sam")
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    with pytest.raises(FileNotFoundError):
+        hisat2.extractVariantFromBam(table, str(tmp_path / "in.bam"), str(tmp_path / "out"), error_correction=False)
