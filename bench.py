@@ -12,9 +12,15 @@ copy-number step of the greedy search (kernels b, c) and the allele calls.
 
   value   whole-job scoring GCells/s with the packed inputs already resident in HBM (a batch that is
           typed repeatedly replays its launches as one CUDA graph from the third pass on)
-  e2e     the same pass through the public host API (``CohortTyper.upload_and_run()``): packed host
-          arrays in pinned memory -> device, results back to the host, every step; sub-batches on
-          their own streams so that the copies of one overlap the kernels of the others
+  e2e     the same pass through the public host API (``CohortTyper.start_pass(upload=True)`` /
+          ``finish_pass``): packed host arrays in pinned memory -> device, results back to the host,
+          every step; sub-batches on their own streams so that the copies of one overlap the kernels
+          of the others
+  Consecutive steps are pipelined (``cohort.PassPipeline``, ``--pipeline-depth``): step i+1 is enqueued
+  on a replica of the typer - device buffers and streams of its own - before the host reads back
+  step i, as a prefetching input pipeline would; all K steps, with their copies, kernels, read-backs
+  and host-side calls, complete inside the timed region, and every step's calls are compared with the
+  warm-up pass afterwards (``parity.every_timed_pass_equals_warmup_calls``).
   roofline        dominant kernel (gk_score), CUDA events around every launch of extra passes run
                   right after the timed region (eager launches, one stream)
   cpu_baseline    the oracle (kind "port": reference NumPy expressions, read-chunked) on host cores
