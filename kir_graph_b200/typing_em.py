@@ -49,6 +49,23 @@ class GeneEmReads:
         return self.n_reads
 
 
+def readAlleleLength(file_fasta: str) -> dict[str, int]:
+    """Sequence length per record id of a fasta file (typing_em.py:32-34; the reference goes through
+    Bio.SeqIO, whose record id is the header up to the first blank); feeds ``hisatEMnp(seq_len=...)``."""
+    lengths: dict[str, int] = {}
+    name = None
+    with open(file_fasta) as handle:
+        for line in handle:
+            line = line.rstrip("\r\n")
+            if line.startswith(">"):
+                fields = line[1:].split(None, 1)
+                name = fields[0] if fields else ""
+                lengths[name] = 0
+            elif name is not None:
+                lengths[name] += len(line.strip())
+    return lengths
+
+
 def _gene_em_reads(per_read: list[dict[str, list[list[str]]]]) -> GeneEmReads:
     """Reference format (list of {'lp','ln','rp','rn': list of allele-name lists}) -> packed."""
     set_id: dict[tuple[str, ...], int] = {}

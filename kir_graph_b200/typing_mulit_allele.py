@@ -31,7 +31,7 @@ from typing import Iterable, Optional
 import numpy as np
 
 from . import engine
-from .packing import GenePack, pack_gene, site_tallies
+from .packing import GenePack, csr_from_reads, error_correction_masks, pack_gene, site_tallies
 from .utils import logger
 
 C_HIT = float(np.log10(0.999))
@@ -294,6 +294,54 @@ class AlleleTyping:
 
     def mapAlleleIDs(self, list_ids) -> list[list[str]]:
         return [[self.id_to_allele[int(i)] for i in ids] for ids in list_ids]
+
+    # The constructor does the work of the four methods below in packed form (packing.pack_gene +
+    # the likelihood kernel); they are kept under the reference's names for callers that use them
+    # on their own.
+    def read2Onehot(self, variant) -> np.ndarray:
+        """Alleles carrying ``variant`` as a boolean vector over the allele columns (:287-292)."""
+        onehot = np.zeros(len(self.allele_to_id), dtype=bool)
+        for allele in variant.allele:
+            onehot[self.allele_to_id[allele]] = True
+        return onehot
+
+    @staticmethod
+    def onehot2Prob(onehot: np.ndarray) -> np.ndarray:
+        """0.999 where set, 0.001 elsewhere (:294-300)."""
+        prob = np.ones(onehot.shape) * 0.001
+        prob[onehot] = 0.999
+        return prob
+
+    def errorCorrection(self, reads):
+        """Drop shallow (< 3 observations) variants and minor (< 0.2) polarities from the reads'
+        id lists, in place (:302-338); returns ``reads``."""
+        ids = list(self.variants)
+        csr = csr_from_reads(reads, {vid: i for i, vid in enumerate(ids)})
+        drop_pos, drop_neg = error_correction_masks(csr, len(ids))
+        bad_pos = {ids[i] for i in np.flatnonzero(drop_pos)}
+        bad_neg = {ids[i] for i in np.flatnonzero(drop_neg)}
+        for read in reads:
+            read.lpv = [v for v in read.lpv if v not in bad_pos]
+            read.rpv = [v for v in read.rpv if v not in bad_pos]
+            read.lnv = [v for v in read.lnv if v not in bad_neg]
+            read.rnv = [v for v in read.rnv if v not in bad_neg]
+        return reads
+
+    def reads2AlleleProb(self, reads) -> np.ndarray:
+        """probs[r, a] of arbitrary reads of this gene (:340-381) through the likelihood kernel:
+        0.999^(K_r - m) * 0.001^m.  As in the reference: no reads -> warning and ``np.array([])``;
+        a read without observations is a row of 0.999 when ``no_empty`` is off and a ValueError
+        (``np.stack`` of nothing) when it is on."""
+        if not reads:
+            logger.warning("[Allele] Error: Empty reads for typing (or Maybe read depth is too low)")
+            return np.array([])
+        pack = pack_gene(reads, list(self.variants.values()), variant_correction=False, no_empty=False,
+                         mutate_reads=False)
+        if self._no_empty and bool((pack.k_obs == 0).any()):
+            raise ValueError("need at least one array to stack")
+        m = engine.MatrixBatch([pack], backend=self._backend).mismatch_counts(0).astype(np.float64)
+        k_eff = np.where(pack.k_obs == 0, 1, pack.k_obs).astype(np.float64)
+        return np.power(10.0, (k_eff[:, None] - m) * C_HIT + m * C_MISS)
 
     # --- typing ----------------------------------------------------------------------
     def typing(self, cn: int) -> TypingResult:

@@ -60,3 +60,10 @@ def test_select_kir_typing_model_matches_reference(tmp_path, method):
 def test_unknown_method():
     with pytest.raises(NotImplementedError):
         kir_typing.selectKirTypingModel("report", "nothing.json")
+
+
+def test_read_allele_length(tmp_path):
+    from kir_graph_b200.typing_em import readAlleleLength
+    path = tmp_path / "a.fa"
+    path.write_text(">KIR2DL1*001 some description\nACGT\nAC\n\n>KIR2DL1*002\nAAAA\r\n>empty\n")
+    assert readAlleleLength(str(path)) == {"KIR2DL1*001": 6, "KIR2DL1*002": 4, "empty": 0}

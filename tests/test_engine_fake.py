@@ -158,6 +158,40 @@ def test_deepcopy_continues_search():
     assert len(a.result) == len(b.result) == 2
 
 
+@pytest.mark.parametrize("name", ["syn_a6_cn2", "syn_a12_cn4_nocorr", "worked_example_corr"])
+def test_reference_named_likelihood_methods(name):
+    """read2Onehot / onehot2Prob / errorCorrection / reads2AlleleProb under the reference's names
+    (typing_mulit_allele.py:287-381): same lists after correction and the reference's probs, also
+    when called on their own; the reference's ordered product restated from the one-hot helpers."""
+    import copy
+    from kir_graph_b200.hisat2 import PairRead
+    case = load_golden(name)
+    reads, variants = objects_from_input(case["input"])
+    raw = copy.deepcopy(reads)
+    typ = AlleleTyping(reads, variants, force_homo=case["force_homo"], top_n=case["top_n"],
+                       variant_correction=case["variant_correction"], _backend=FakeBackend())
+    if case["variant_correction"]:
+        fixed = typ.errorCorrection(raw)
+        assert fixed is raw
+        kept = AlleleTyping.removeEmptyReads(raw)
+        assert [{"lpv": r.lpv, "rpv": r.rpv, "lnv": r.lnv, "rnv": r.rnv} for r in kept] == case["reads_after"]
+    probs = typ.reads2AlleleProb(typ.reads)
+    np.testing.assert_allclose(probs, np.array(case["probs"]), rtol=1e-9)
+    for r, read in list(enumerate(typ.reads))[:25]:
+        factors = [typ.onehot2Prob(typ.read2Onehot(typ.variants[i])) for i in read.lpv + read.rpv] + \
+                  [typ.onehot2Prob(np.logical_not(typ.read2Onehot(typ.variants[i]))) for i in read.lnv + read.rnv]
+        np.testing.assert_allclose(probs[r], np.stack(factors).prod(axis=0), rtol=1e-12)
+    assert typ.reads2AlleleProb([]).shape == (0,)
+    blank = PairRead(backbone=str(variants[0].ref))
+    with pytest.raises(ValueError):
+        typ.reads2AlleleProb([typ.reads[0], blank])              # no_empty: np.stack of nothing
+    loose = AlleleTyping(copy.deepcopy(typ.reads), variants, no_empty=False, variant_correction=False,
+                         _backend=FakeBackend())
+    rows = loose.reads2AlleleProb([typ.reads[0], blank])
+    np.testing.assert_allclose(rows[1], np.full(len(typ.allele_to_id), 0.999), rtol=1e-12)
+    np.testing.assert_allclose(rows[0], probs[0], rtol=1e-12)
+
+
 def test_errors_and_empty():
     gene = synthetic.make_gene([3, 4], "KIRY*BACKBONE", 8, 64, 2, 50)
     reads, variants = gene.to_objects()
