@@ -397,6 +397,41 @@ def _samtools(args: list[str], capture: bool = False) -> str:
     return proc.stdout if capture else ""
 
 
+def readBam(bam_file: str) -> list[str]:
+    """Name-sorted SAM lines of a bam file via a local samtools (:103-110)."""
+    return _samtools(["sort", "-n", bam_file, "-O", "SAM"], capture=True).split("\n")
+
+
+def readBamHeader(bam_file: str) -> str:
+    """Header of a bam file via a local samtools (:113-118)."""
+    return _samtools(["view", "-H", bam_file], capture=True)
+
+
+def readPair(bam_file: str) -> Iterable[tuple[str, str]]:
+    """(left record, right record) of every proper pair of a bam file (:228-276)."""
+    return pairRecords(readBam(bam_file))
+
+
+def saveSam(filename: str, header: str, reads: Iterable[PairRead]) -> None:
+    """Header + both records of every read pair (:869-881)."""
+    with open(filename, "w") as handle:
+        handle.writelines(header)
+        handle.writelines(r.l_sam + "\n" + r.r_sam + "\n" for r in reads)
+
+
+def saveReadsToBam(reads_data: ReadsAndVariantsData, filename_prefix: str, bam_file: str,
+                   filter_multi_mapped: bool = False) -> None:
+    """``{filename_prefix}.bam`` (sorted, indexed) of the kept pairs, header taken from ``bam_file``
+    (:884-901, samtobam utils.py:106-116)."""
+    reads = reads_data["reads"]
+    if filter_multi_mapped:
+        reads = [r for r in reads if r.multiple == 1]
+    saveSam(filename_prefix + ".sam", readBamHeader(bam_file), reads)
+    _samtools(["sort", filename_prefix + ".sam", "-o", filename_prefix + ".bam"])
+    _samtools(["index", filename_prefix + ".bam"])
+    os.remove(filename_prefix + ".sam")
+
+
 def extractVariantFromBam(index: str | list[Variant], bam_file: str, output_prefix: str,
                           error_correction: bool = True, num_editdist: int = 4):
     """The reference's entry point (:904-940), same arguments: reads ``samtools sort -n bam -O SAM``

@@ -314,6 +314,11 @@ exit 1
     assert body(tmp_path / "out.no_multi.bam") == [x for r in want["reads"] if r.multiple == 1 for x in (r.l_sam, r.r_sam)]
     assert open(tmp_path / "out.bam").read().startswith("@HD") and os.path.exists(tmp_path / "out.bam.bai")
     assert not os.path.exists(tmp_path / "out.sam")
+    # the object-level functions of the reference over the same shim
+    pr = list(hisat2.readPair(str(tmp_path / "in.bam")))
+    assert len(pr) == len(pairs) and hisat2.readBamHeader(str(tmp_path / "in.bam")).startswith("@HD")
+    hisat2.saveReadsToBam(want, str(tmp_path / "obj"), str(tmp_path / "in.bam"), filter_multi_mapped=True)
+    assert open(tmp_path / "obj.bam").read() == open(tmp_path / "out.no_multi.bam").read()
     monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
     with pytest.raises(FileNotFoundError):
         hisat2.extractVariantFromBam(table, str(tmp_path / "in.bam"), str(tmp_path / "out"), error_correction=False)
