@@ -121,9 +121,13 @@ class TypingWithPosNegAllele(Typing):
         logger.debug(f"[Allele] {gene=} {cn=}")
         force_homo = False if isHetrozygous(gene) else None
         if self._packs is not None:
-            typ = AlleleTyping(None, self._gene_variants[gene], force_homo=force_homo, top_n=self._top_n,
+            pack = self._packs.get(gene)
+            if pack is None:                     # no variants, no reads: the reference's defaultdicts give []
+                from .packing import pack_gene
+                pack = pack_gene([], [], gene=gene)
+            typ = AlleleTyping(None, self._gene_variants.get(gene, []), force_homo=force_homo, top_n=self._top_n,
                                variant_correction=self._variant_correction, _backend=self._backend,
-                               _pack=self._packs[gene])
+                               _pack=pack)
         elif not self._exon_first and not self._exon_only:
             typ = AlleleTyping(self._gene_reads[gene], self._gene_variants[gene], force_homo=force_homo,
                                top_n=self._top_n, variant_correction=self._variant_correction,

@@ -1,0 +1,132 @@
+"""
+The callers of the typing path: per-sample allele typing with the reference's outputs, and a
+cohort entry that types every sample's genes as one GPU batch.
+
+``alleleTyping`` mirrors the reference function of that name (graphkir/main.py:171-220): per sample
+``selectKirTypingModel(method, name + ".json", top_n=600, variant_correction=True)``, ``loadCN``,
+``typing``, then ``{name}{suffix}.tsv`` (name / alleles / warnings) and ``.possible.tsv``; file names,
+columns and formatting come from the same pandas calls, so the files are interchangeable.
+``mergeAllele`` (utils.py:161-165) concatenates them into ``cohort.allele.tsv``.
+
+``cohortAlleleTyping`` is new: the (sample, gene) problems of all samples of
+this rank go through ``cohort.CohortTyper`` in one pass - samples are independent, so ranks take
+samples ``rank, rank + world, ...`` with no data-path communication and write their own ``.tsv``
+files; the caller merges on rank 0 in input order.  It covers the ``full`` strategy (the only one
+that needs no per-gene Python objects) and writes no ``.possible.tsv`` (only the called set is read
+back from the device); other strategies go through ``alleleTyping``.
+
+Everything upstream (mapping, BAM handling, copy-number estimation) stays in the reference; the CLI
+itself is not rebuilt.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import pandas as pd
+
+from .kir_typing import selectKirTypingModel
+from .utils import logger
+
+
+def getCommonName(r1: str, r2: str) -> str:
+    """Longest common dot-separated prefix of two file names (main.py:223-250)."""
+    name = ""
+    for s1, s2 in zip(r1.split("."), r2.split(".")):
+        if s1 != s2:
+            return name
+        name = name + "." + s1 if name else s1
+    return name
+
+
+def loadCN(filename_cn: str) -> dict[str, int]:
+    """gene -> copy number of a ``.cn.tsv`` (kir_cn.py:234-243)."""
+    data = pd.read_csv(filename_cn, sep="\t", index_col=[0])
+    return dict(data.to_dict()["cn"])
+
+
+def mergeAllele(allele_result_files: list[str], final_result_file: str) -> pd.DataFrame:
+    """Per-sample ``.tsv`` files -> ``cohort.allele.tsv`` (utils.py:161-165)."""
+    df = pd.concat(pd.read_csv(f, sep="\t") for f in allele_result_files)
+    df.to_csv(final_result_file, index=False, sep="\t")
+    return df
+
+
+def _suffix(name: str, cn_file: str, method: str) -> str:
+    """``.cn<rest of the CN file name>.<method>`` (main.py:182-192)."""
+    return (".cn" + cn_file[len(getCommonName(name, cn_file)):].replace("/", "_").replace(".", "_") + "."
+            + method)
+
+
+def _write_sample(name: str, called_alleles: list[str], warning_genes: list[str]) -> str:
+    df = pd.DataFrame({"name": [name], "alleles": ["_".join(called_alleles)],
+                       "warnings": ["_".join(warning_genes)]})
+    df.to_csv(name + ".tsv", sep="\t", index=False)
+    return name + ".tsv"
+
+
+def alleleTyping(processed_bam: list[str], cn_files: list[str], method: str = "full", **kwargs: Any) -> list[str]:
+    """Allele typing sample by sample (main.py:171-220).  ``kwargs`` reach the typing model
+    (``_backend``, ``_fast``)."""
+    allele_files = []
+    for name, cn_file in zip(processed_bam, cn_files):
+        logger.debug(f"[Allele] Allele typing ({method}) with CN {cn_file} ({name})")
+        if method == "exonfirst":
+            method += "_1"
+        suffix = _suffix(name, cn_file, method)
+        t = selectKirTypingModel(method, name + ".json", top_n=600, variant_correction=True, **kwargs)
+        called_alleles, warning_genes = t.typing(loadCN(cn_file))
+        logger.info(f"[Allele] {called_alleles} ({name})")
+        name += suffix
+        allele_files.append(_write_sample(name, called_alleles, warning_genes))
+        logger.info("[Allele] All possible allele set in Allele typing saved in [name].possible.tsv")
+        pd.DataFrame(t.getAllPossibleTyping()).fillna("").to_csv(name + ".possible.tsv", index=False, sep="\t")
+    return allele_files
+
+
+def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: str = "full", top_n: int = 600,
+                       min_reads_num: int = 100, rank: int = 0, world: int = 1, n_parts: int = 6,
+                       _backend=None) -> list[str]:
+    """The samples ``rank, rank + world, ...`` typed as one batch on this rank's GPU; writes the
+    ``{name}{suffix}.tsv`` of each (same bytes as ``alleleTyping``) and returns the names of ALL
+    samples' files in input order, so that rank 0 can ``mergeAllele`` them once every rank is done."""
+    if method != "full":
+        raise NotImplementedError("cohortAlleleTyping covers the full-variant strategy; use alleleTyping")
+    from . import cohort, fastjson
+    mine = list(range(len(processed_bam)))[rank::world]
+    packs, cns = [], []
+    plans = {}
+    for i in mine:
+        name, cn_file = processed_bam[i], cn_files[i]
+        gene_cn = loadCN(cn_file)
+        by_gene = fastjson.load_packs(name + ".json", variant_correction=True)
+        # CN-file order, as Typing.typing; the flag says whether the gene goes to the device
+        plans[i] = [(g, int(c), g in by_gene) for g, c in gene_cn.items() if c]
+        for gene, cn, known in plans[i]:
+            if known:
+                packs.append(by_gene[gene])
+                cns.append(cn)
+    calls = []
+    if packs:
+        typer = cohort.CohortTyper(packs, cns, top_n=top_n, backend=_backend, n_parts=n_parts)
+        calls = typer.upload_and_run()
+    at = 0
+    for i in mine:
+        alleles, warnings = [], []
+        for gene, cn, known in plans[i]:
+            pure_gene = gene.split("*")[0]
+            if known:
+                call = calls[at]
+                at += 1
+                alleles.extend(a if a != "fail" else f"{pure_gene}*" for a in call.alleles)
+                n_reads = call.n_reads
+            else:
+                # a gene without variants or reads never reaches the device: the reference's
+                # defaultdict grouping (kir_typing.py:15-28) gives it no reads -> ["fail"] * cn
+                alleles.extend([f"{pure_gene}*"] * cn)
+                n_reads = 0
+            if n_reads < min_reads_num:
+                warnings.append(gene)
+        name = processed_bam[i] + _suffix(processed_bam[i], cn_files[i], method)
+        logger.info(f"[Allele] {alleles} ({processed_bam[i]})")
+        _write_sample(name, alleles, warnings)
+    return [n + _suffix(n, c, method) + ".tsv" for n, c in zip(processed_bam, cn_files)]

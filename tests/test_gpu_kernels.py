@@ -373,3 +373,29 @@ def test_full_size_wgs30x_sample_properties(cuda):
         if a[i].homozygous:
             want = m[:, a[i].ids[0]].sum() * cns[i]
         assert a[i].score == want
+
+
+def test_caller_side_files_equal_the_references(cuda, tmp_path, monkeypatch):
+    """kir_graph_b200.main on the GPU: per-sample alleleTyping and the batched cohortAlleleTyping write
+    the .tsv files of the reference's graphkir.main.alleleTyping (tests/golden/main_tsv.json.gz)."""
+    import pandas as pd
+    from kir_graph_b200 import main
+    from kir_graph_b200.hisat2 import PairRead, writeReadsAndVariantsData
+    from kir_graph_b200.msa2hisat import Variant
+    data = load_golden("main_tsv")
+    monkeypatch.chdir(tmp_path)
+    names, cn_files = [], []
+    for inp in data["inputs"]:
+        writeReadsAndVariantsData({"variants": [Variant(**v) for v in inp["variants"]],
+                                   "reads": [PairRead(**r) for r in inp["reads"]]}, inp["name"] + ".json")
+        pd.DataFrame({"gene": list(inp["cn"]), "cn": list(inp["cn"].values())}).to_csv(
+            inp["name"] + ".depth.cn.tsv", sep="\t", index=False)
+        names.append(inp["name"])
+        cn_files.append(inp["name"] + ".depth.cn.tsv")
+    want = data["methods"]["full"]
+    files = main.cohortAlleleTyping(names, cn_files, "full", n_parts=2, _backend=cuda)
+    assert files == want["files"] and [open(f).read() for f in files] == want["tsv"]
+    files = main.alleleTyping(names, cn_files, "full", _backend=cuda, _fast=True)
+    assert files == want["files"] and [open(f).read() for f in files] == want["tsv"]
+    files = main.alleleTyping(names, cn_files, "exonfirst", _backend=cuda)
+    assert [open(f).read() for f in files] == data["methods"]["exonfirst"]["tsv"]

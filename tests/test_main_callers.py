@@ -1,0 +1,101 @@
+"""The callers of the typing path (kir_graph_b200/main.py): alleleTyping writes the reference's
+per-sample files, cohortAlleleTyping types all samples as one batch and writes the same bytes;
+sharded over ranks the merged cohort.allele.tsv is the same."""
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from kir_graph_b200 import main
+from kir_graph_b200.hisat2 import PairRead, writeReadsAndVariantsData
+from kir_graph_b200.msa2hisat import Variant
+from tests.cohort_sim import write_cohort
+from tests.fake_backend import FakeBackend
+from tests.helpers import load_golden
+
+
+def _cohort(tmp_path, n_samples=3):
+    names, cn_files, _ = write_cohort(str(tmp_path), n_samples)
+    return names, cn_files
+
+
+@pytest.mark.parametrize("method", ["full", "exonfirst"])
+def test_allele_typing_files_equal_the_references(tmp_path, monkeypatch, method):
+    """tests/golden/main_tsv.json.gz: graphkir.main.alleleTyping + mergeAllele of the reference on a
+    three-sample cohort (make_golden_main.py).  Same file names and bytes for {name}.tsv and the merged
+    cohort file; the .possible.tsv rows equal up to the order of exactly tied sets."""
+    data = load_golden("main_tsv")
+    monkeypatch.chdir(tmp_path)
+    names, cn_files = [], []
+    for inp in data["inputs"]:
+        writeReadsAndVariantsData({"variants": [Variant(**v) for v in inp["variants"]],
+                                   "reads": [PairRead(**r) for r in inp["reads"]]}, inp["name"] + ".json")
+        pd.DataFrame({"gene": list(inp["cn"]), "cn": list(inp["cn"].values())}).to_csv(
+            inp["name"] + ".depth.cn.tsv", sep="\t", index=False)
+        names.append(inp["name"])
+        cn_files.append(inp["name"] + ".depth.cn.tsv")
+    want = data["methods"][method]
+    files = main.alleleTyping(names, cn_files, method, _backend=FakeBackend())
+    assert files == want["files"]
+    assert [open(f).read() for f in files] == want["tsv"]
+    main.mergeAllele(files, "cohort.allele.tsv")
+    assert open("cohort.allele.tsv").read() == want["merged"]
+    for f, ref in zip(files, want["possible"]):
+        got = pd.read_csv(f[:-4] + ".possible.tsv", sep="\t").fillna("")
+        exp = pd.read_csv(io.StringIO(ref), sep="\t").fillna("")
+        assert list(got.columns) == list(exp.columns) and len(got) == len(exp)
+        np.testing.assert_allclose(got["value"], exp["value"], rtol=1e-11)
+        cols = [c for c in got.columns if c.isdigit()]
+        rows = lambda df: sorted((g, round(v, 6), tuple(sorted(map(str, r)))) for g, v, r in
+                                 zip(df["gene"], df["value"], df[cols].values.tolist()))
+        assert rows(got) == rows(exp)
+    if method == "full":
+        for f in files:
+            os.remove(f)
+        assert main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend()) == want["files"]
+        assert [open(f).read() for f in files] == want["tsv"]
+
+
+def test_helpers():
+    assert main.getCommonName("data/x_30x.00.read.r1.fq", "data/x_30x.00.read.r2.fq") == "data/x_30x.00.read"
+    assert main.getCommonName("a.b.c", "a.b.c") == "a.b.c" and main.getCommonName("a.b", "c.b") == ""
+    assert main._suffix("d/s.00.variant", "d/s.00.variant.depth.cn.tsv", "full") == ".cn_depth_cn_tsv.full"
+
+
+def test_cohort_entry_writes_the_same_files(tmp_path):
+    names, cn_files = _cohort(tmp_path)
+    assert main.loadCN(cn_files[0])["KIRM0*BACKBONE"] == 2
+    per_sample = main.alleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    want = [open(f, "rb").read() for f in per_sample]
+    assert all(os.path.exists(f[:-4] + ".possible.tsv") for f in per_sample)
+    rows = [pd.read_csv(f, sep="\t").fillna("") for f in per_sample]
+    assert rows[0]["alleles"][0].endswith("KIRNONE*") and "KIRNONE*BACKBONE" in rows[0]["warnings"][0]
+    assert "KIRM1*BACKBONE" in rows[1]["warnings"][0] and rows[2]["warnings"][0] == ""
+    assert len(rows[2]["alleles"][0].split("_")) == 5 and len(rows[1]["alleles"][0].split("_")) == 6
+    merged = main.mergeAllele(per_sample, str(tmp_path / "cohort.allele.tsv"))
+    assert list(merged.columns) == ["name", "alleles", "warnings"] and len(merged) == 3
+    want_merged = open(tmp_path / "cohort.allele.tsv", "rb").read()
+    for f in per_sample:
+        os.remove(f)
+    # one rank
+    files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend(), n_parts=2)
+    assert files == per_sample and [open(f, "rb").read() for f in files] == want
+    for f in per_sample:
+        os.remove(f)
+    # two ranks: each writes its own samples, rank 0 merges in input order
+    for rank in (1, 0):
+        files = main.cohortAlleleTyping(names, cn_files, "full", rank=rank, world=2, _backend=FakeBackend())
+        assert files == per_sample
+    assert [open(f, "rb").read() for f in files] == want
+    main.mergeAllele(files, str(tmp_path / "cohort2.allele.tsv"))
+    assert open(tmp_path / "cohort2.allele.tsv", "rb").read() == want_merged
+    # the fast per-sample driver gives the same files too (a gene without variants included)
+    for f in per_sample:
+        os.remove(f)
+    assert main.alleleTyping(names, cn_files, "full", _backend=FakeBackend(), _fast=True) == per_sample
+    assert [open(f, "rb").read() for f in per_sample] == want
+    with pytest.raises(NotImplementedError):
+        main.cohortAlleleTyping(names, cn_files, "exonfirst_1", _backend=FakeBackend())
+    assert main.cohortAlleleTyping([], [], "full", _backend=FakeBackend()) == []
