@@ -1,0 +1,38 @@
+"""bench.py --impl reference (the CPU arm the driver runs beside the GPU arm): one JSON line with
+the contract's keys, printed by rank 0 only."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-scale", "0.01", "--cpu-cores", "2"]
+
+
+def _lines(out: str) -> list[dict]:
+    return [json.loads(line) for line in out.splitlines() if line.startswith("{")]
+
+
+def test_reference_arm_prints_one_contract_line():
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *ARGS], capture_output=True, text=True,
+                          timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = _lines(proc.stdout)
+    assert len(lines) == 1
+    line = lines[0]
+    assert line["impl"] == "reference" and line["unit"] == "GCells/s" and line["value"] > 0
+    assert line["metric"] == "allele-typing read x candidate GCells/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and line["gpu_launches"] == 0
+
+
+def test_reference_arm_under_torchrun_rank0_only():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(ROOT, "bench.py"),
+                           "--gpus", "2", *ARGS], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = _lines(proc.stdout)
+    assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2
