@@ -93,3 +93,59 @@ def test_column_sharding_and_cohort_sharding_world2():
         packs = [packing.pack_synthetic(g) for g in genes]
         want = cohort.BatchTyper(packs, [g.cn for g in genes], top_n=20, backend=FakeBackend()).run()
         assert got == [c.alleles for c in want]
+
+
+def _cohort_worker(rank, world, port, folder, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import json
+        from kir_graph_b200 import main
+        os.chdir(folder)
+        names = json.load(open("names.json"))
+        files = main.cohortAlleleTyping(names, [n + ".depth.cn.tsv" for n in names], "full", rank=dist.get_rank(),
+                                        world=dist.get_world_size(), _backend=FakeBackend())
+        dist.barrier()                       # every rank has written its samples' files
+        if rank == 0:
+            main.mergeAllele(files, "cohort.allele.tsv")
+        out.put(("ok", files))
+    except Exception as exc:  # pragma: no cover
+        out.put(("error", repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_cohort_entry_world2_merges_the_references_file(tmp_path):
+    """main.cohortAlleleTyping on two ranks (samples 0, 2 / sample 1), rank 0 merges after a barrier:
+    cohort.allele.tsv equals the file the reference's alleleTyping + mergeAllele wrote
+    (tests/golden/main_tsv.json.gz)."""
+    import json
+    import pandas as pd
+    from kir_graph_b200.hisat2 import PairRead, writeReadsAndVariantsData
+    from kir_graph_b200.msa2hisat import Variant
+    from tests.helpers import load_golden
+    data = load_golden("main_tsv")
+    names = []
+    for inp in data["inputs"]:
+        base = str(tmp_path / inp["name"])
+        writeReadsAndVariantsData({"variants": [Variant(**v) for v in inp["variants"]],
+                                   "reads": [PairRead(**r) for r in inp["reads"]]}, base + ".json")
+        pd.DataFrame({"gene": list(inp["cn"]), "cn": list(inp["cn"].values())}).to_csv(
+            base + ".depth.cn.tsv", sep="\t", index=False)
+        names.append(inp["name"])
+    json.dump(names, open(tmp_path / "names.json", "w"))
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cohort_worker, args=(r, 2, port, str(tmp_path), out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[0] == "ok" for r in results), results
+    want = data["methods"]["full"]
+    assert all(r[1] == want["files"] for r in results)
+    assert open(tmp_path / "cohort.allele.tsv").read() == want["merged"]
+    assert [open(tmp_path / f).read() for f in want["files"]] == want["tsv"]
