@@ -146,3 +146,15 @@ def test_fast_driver_equals_object_driver(tmp_path, method):
     a_fast, w_fast = fast.typing(gene_cn)
     assert a_fast == a_slow and w_fast == w_slow
     assert fast.getAllPossibleTyping() == slow.getAllPossibleTyping()
+
+
+def test_scanner_fuzz_against_json_loads():
+    """tools/fuzz_json_scan.py for a few seconds: shuffled / missing keys, unknown nested values, escapes,
+    non-ASCII text, every json.dumps layout - the scanner must agree with json.loads on every case."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_json_scan.py"), "11", "4"],
+                          capture_output=True, text=True, timeout=120)
+    assert proc.returncode == 0 and " bad 0" in proc.stdout, proc.stdout[-1500:] + proc.stderr[-1500:]
