@@ -543,6 +543,15 @@ class AlleleTypingExonFirst(AlleleTyping):
             return self.full_model.typing(cn)
 
         ranks = list(result.topRank(threshold=self.candidate_set_threshold))
+        if self.full_model.top_n < 1:
+            # top_n < 5 leaves the restricted model with top_n // 5 == 0 kept sets (:716): the reference's
+            # first step then keeps nothing (the merged result is empty: "fail") and a second step
+            # indexes with an empty float array
+            if cn > 1:
+                raise IndexError("arrays used as indices must be of integer (or boolean) type")
+            self.result.extend(_empty_result(1) for _ in ranks)
+            self.result.append(_empty_result(1))
+            return self.result[-1]
         candidate_result = self._typing_intron_batched([result.allele_name_group[i] for i in ranks])
         logger.debug(f"[Allele] Intron Candidate {len(candidate_result)} Done")
         cat = lambda xs: None if any(x is None for x in xs) else np.concatenate(xs)

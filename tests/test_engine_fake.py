@@ -277,3 +277,22 @@ def test_pass_pipeline_equals_serial_passes():
     pipe = cohort.PassPipeline([typer], depth=2)
     pipe.submit(), pipe.submit()
     assert [key(c) for c in pipe.drain()] == [want, want]
+
+
+def test_exon_first_with_top_n_below_five_follows_the_reference():
+    """top_n < 5 leaves the restricted model of exon-first with top_n // 5 == 0 kept sets
+    (typing_mulit_allele.py:716): the reference then answers "fail" for one step and raises IndexError
+    (an empty float array used as an index, :540) for more - checked against the imported reference
+    on random genes; the mirror does the same instead of its own ValueError."""
+    gene = synthetic.make_gene([380855173, 0], "KIRQ*BACKBONE", 22, 176, 3, 143, hierarchical=True)
+    reads, variants = gene.to_objects()
+    typ = AlleleTypingExonFirst(reads, variants, force_homo=None, top_n=3, candidate_set_threshold=0.0,
+                                _backend=FakeBackend())
+    with pytest.raises(IndexError):
+        typ.typing(3)
+    gene = synthetic.make_gene([237585442, 0], "KIRQ*BACKBONE", 10, 80, 1, 24, hierarchical=True)
+    reads, variants = gene.to_objects()
+    typ = AlleleTypingExonFirst(reads, variants, force_homo=None, top_n=3, candidate_set_threshold=0.0,
+                                _backend=FakeBackend())
+    res = typ.typing(1)
+    assert res.isFail() and res.selectBest() == ["fail"]

@@ -1,0 +1,53 @@
+"""Differential run against the UNMODIFIED reference (imported from /root/reference with the stubs of
+tests/golden/make_golden.py - build container only): random small genes through AlleleTyping /
+AlleleTypingExonFirst of both implementations (ours on the NumPy test double of the kernels), called
+alleles or exception type compared; differences covered by tie flags are counted, others printed.
+
+    python tools/fuzz_vs_reference.py <seed> <seconds>
+"""
+import sys, time, copy, logging
+import numpy as np
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden')); sys.path.insert(0, ROOT)
+from make_golden import import_reference, ref_objects
+tma, tem, kt, h2, m2h = import_reference()
+logging.getLogger("graphkir").setLevel(logging.ERROR)
+from kir_graph_b200 import synthetic
+from kir_graph_b200.typing_mulit_allele import AlleleTyping, AlleleTypingExonFirst
+from tests.fake_backend import FakeBackend
+rng = np.random.default_rng(int(sys.argv[1])); T = float(sys.argv[2])
+t0 = time.time(); n = 0; bad = 0; tie = 0
+while time.time() - t0 < T:
+    a = int(rng.integers(2, 28)); cn = int(rng.integers(1, 5)); r = int(rng.integers(5, 220)); top_n = int(rng.choice([3, 10, 30, 60]))
+    seed = int(rng.integers(1 << 30)); hier = bool(rng.integers(2)); mode = rng.choice(["full", "exon", "exon_thr"])
+    gene = synthetic.make_gene([seed, 0], "KIRQ*BACKBONE", a, max(64, 8 * a), cn, r, hierarchical=hier)
+    reads, variants = gene.to_objects()
+    rr, rv = ref_objects(h2, m2h, copy.deepcopy(reads), copy.deepcopy(variants))
+    force = rng.choice([None, False])
+    force = None if force is None else False
+    def outcome(fn):
+        try:
+            return fn()
+        except Exception as e:
+            return "EXC:" + type(e).__name__
+    if mode == "full":
+        vc = bool(rng.integers(2))
+        mk_ref = lambda: tma.AlleleTyping(rr, rv, force_homo=force, top_n=top_n, variant_correction=vc)
+        mk_ours = lambda: AlleleTyping(reads, variants, force_homo=force, top_n=top_n, variant_correction=vc, _backend=FakeBackend())
+    else:
+        thr = 0.0 if mode == "exon" else 1.0
+        mk_ref = lambda: tma.AlleleTypingExonFirst(rr, rv, force_homo=force, top_n=top_n, candidate_set_threshold=thr)
+        mk_ours = lambda: AlleleTypingExonFirst(reads, variants, force_homo=force, top_n=top_n, candidate_set_threshold=thr, _backend=FakeBackend())
+    want = outcome(lambda: mk_ref().typing(cn).selectBest())
+    holder = {}
+    def run_ours():
+        holder["m"] = mk_ours(); holder["r"] = holder["m"].typing(cn); return holder["r"].selectBest()
+    got = outcome(run_ours)
+    n += 1
+    if got != want:
+        flags = getattr(holder.get("r"), "tie_flags", 0) or getattr(holder.get("m"), "tie_report", None)
+        if flags and not isinstance(got, str) and not isinstance(want, str): tie += 1
+        else:
+            print("MISMATCH", mode, seed, a, cn, r, top_n, hier, force, got, want); bad += 1
+print("cases", n, "bad", bad, "tie-explained", tie)
