@@ -84,6 +84,11 @@ def test_cohort_entry_writes_the_same_files(tmp_path):
     assert files == per_sample and [open(f, "rb").read() for f in files] == want
     for f in per_sample:
         os.remove(f)
+    # host preparation in worker processes
+    files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend(), workers=2)
+    assert files == per_sample and [open(f, "rb").read() for f in files] == want
+    for f in per_sample:
+        os.remove(f)
     # two ranks: each writes its own samples, rank 0 merges in input order
     for rank in (1, 0):
         files = main.cohortAlleleTyping(names, cn_files, "full", rank=rank, world=2, _backend=FakeBackend())
