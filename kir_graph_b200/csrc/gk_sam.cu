@@ -184,18 +184,20 @@ extern "C" int gk_sam_walk(const char* line, int64_t len, int32_t* seg, int max_
             while (true) {                                  // items separated by ',', fields by '|'
                 int32_t j = i;
                 while (j < n && s[j] != ',') ++j;
-                int32_t bars[2], nb = 0;
+                // item.split("|") -> (int(f[0]), f[1], f[2]): the gap is parsed first (ValueError), a missing
+                // second or third field is an IndexError, fields beyond the third are ignored
+                int32_t bars[3] = {j, j, j}, nb = 0;
                 for (int32_t k = i; k < j; ++k)
                     if (s[k] == '|') {
-                        if (nb < 2) bars[nb] = k;
+                        if (nb < 3) bars[nb] = k;
                         ++nb;
                     }
-                if (nb != 2) return kValue;
                 ZsEntry z;
                 if (!parse_int(s + i, bars[0] - i, z.gap)) return kValue;
+                if (nb < 2) return kIndex;
                 z.kind_len = bars[1] - bars[0] - 1;
                 z.kind = z.kind_len > 0 ? s[bars[0] + 1] : '\0';
-                z.id = Span{(int32_t)(w.cols[c].off + bars[1] + 1), (int32_t)(j - bars[1] - 1)};
+                z.id = Span{(int32_t)(w.cols[c].off + bars[1] + 1), (int32_t)(bars[2] - bars[1] - 1)};
                 w.zs.push_back(z);
                 if (j >= n) break;
                 i = j + 1;

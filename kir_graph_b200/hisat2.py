@@ -91,8 +91,10 @@ def readZs(cols: list[str]) -> list[tuple[int, str, str]]:
         if col.startswith("Zs"):
             out = []
             for item in col[5:].split(","):
-                gap, kind, vid = item.split("|")
-                out.append((int(gap), kind, vid))
+                # fields beyond the third are ignored and a missing one is an IndexError after the gap
+                # has been parsed, as in the reference's (int(i[0]), i[1], i[2])
+                fields = item.split("|")
+                out.append((int(fields[0]), fields[1], fields[2]))
             return out
     return []
 
