@@ -106,3 +106,20 @@ def test_native_walk_equals_python_statement_on_mutated_records():
     for rec in ("r\t99\tG\t5\t60\t*\t=\t1\t0\tACGT\tFFFF", "r\t99\tG\t5\t60\t4M\t=\t1\t0\tACGT\tFFFF\tMD:Z:4",
                 "r\t99\tG\t5\t60\t2S2M\t=\t1\t0\tACGT\tFFFF\tMD:Z:2\tZs:Z:", "r\t99\tG\tx\t60\t4M", ""):
         assert _outcome(hisat2.recordToRawVariant, rec) == _outcome(hisat2.recordToRawVariantPy, rec), rec
+
+
+def test_zs_items_follow_the_references_tuple_indexing():
+    """readZs builds (int(f[0]), f[1], f[2]) from item.split("|") (hisat2.py:518-527): the gap is parsed
+    first (ValueError), a missing field is an IndexError, fields beyond the third are ignored - found
+    by tools/fuzz_sam_vs_reference.py against the imported reference."""
+    line = load_golden("sam_walk")["kats"]["k5"]["line"]          # ... Zs:Z:10|S|hv0
+    assert "Zs:Z:10|S|hv0" in line
+    for walk in (hisat2.recordToRawVariant, hisat2.recordToRawVariantPy):
+        good = _outcome(walk, line)
+        assert not isinstance(good, str)
+        assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:10|S|hv0|more|fields")) == good
+        assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:10|Shv0")) == "IndexError"
+        assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:10")) == "IndexError"
+        assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:x|S")) == "ValueError"
+        assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:")) == "ValueError"
+        assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:10|S|hv0,")) == "ValueError"
