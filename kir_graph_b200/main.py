@@ -13,7 +13,10 @@ this rank go through ``cohort.CohortTyper`` in one pass - samples are independen
 samples ``rank, rank + world, ...`` with no data-path communication and write their own ``.tsv``
 files; the caller merges on rank 0 in input order.  It covers the ``full`` strategy (the only one
 that needs no per-gene Python objects) and writes no ``.possible.tsv`` (only the called set is read
-back from the device); other strategies go through ``alleleTyping``.
+back from the device); other strategies go through ``alleleTyping``.  One deliberate difference: a
+gene with copy number >= 2 and no usable reads is called ``<gene>*`` (fail) here, where the reference
+- and the per-sample mirror - end in numpy's AxisError (``createHomoResult`` on the empty first-step
+result, typing_mulit_allele.py:441) unless the gene is one of the always-heterozygous ones.
 
 Everything upstream (mapping, BAM handling, copy-number estimation) stays in the reference; the CLI
 itself is not rebuilt.
