@@ -23,7 +23,7 @@ There is no CPU implementation of any kernel in this package.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

@@ -23,7 +23,6 @@ import numpy as np
 from . import engine
 from ._cabi import EM_PROBLEM_DTYPE
 from .hisat2 import ReadsAndVariantsData, loadReadsAndVariantsData, removeMultipleMapped
-from .utils import logger
 
 
 @dataclass
