@@ -363,14 +363,24 @@ def extractVariant(pair_reads: Iterable[tuple[str, str]], variants: list[Variant
     return {"variants": list(variants_map.values()), "reads": reads}
 
 
+def _write_sidecar(ext, output_prefix: str) -> None:
+    """``{output_prefix}.gkpack.npz``: the genes of an extraction packed as the typing step wants them
+    (variant correction on, single-mapped pairs: what main.alleleTyping asks for), so that typing a
+    cohort does not parse the ``.json`` again."""
+    from . import fastjson, packio
+    packs = fastjson.packs_from_scan(ext.scan(), variant_correction=True, single_mapped_only=True)
+    packio.save_packs(packio.sidecar_path(output_prefix), packs, packio.sidecar_meta(output_prefix))
+
+
 def extractVariantFromSam(index: str | list[Variant], sam_file: str, output_prefix: str | None,
-                          error_correction: bool = False, num_editdist: int = 4):
+                          error_correction: bool = False, num_editdist: int = 4, write_pack: bool = False):
     """``extractVariantFromBam`` (:904-940) over a name-sorted SAM file (what the reference's
     ``readBam`` pipes out of ``samtools sort -n | samtools view -h``, :205-225; running samtools stays
     in the reference): filter, call, annotate, and write ``{output_prefix}.json`` in the reference's
     layout.  The loop itself is the native batch routine (:mod:`kir_graph_b200.fastsam`); the
     returned ``SamExtract`` holds the same reads as arrays (``.scan()`` feeds the typing driver
-    directly, ``output_prefix=None`` skips the JSON).  ``index``: HISAT2 index prefix, or the sorted
+    directly, ``output_prefix=None`` skips the JSON; ``write_pack`` adds the ``.gkpack.npz`` sidecar that
+    ``main.cohortAlleleTyping`` loads instead of the JSON).  ``index``: HISAT2 index prefix, or the sorted
     variant table itself.  The ``.bam`` copies the reference also writes (:937-940) need samtools and
     are not produced."""
     if error_correction:
@@ -383,6 +393,8 @@ def extractVariantFromSam(index: str | list[Variant], sam_file: str, output_pref
     if output_prefix is not None:
         logger.debug(f"[Graph] Save allele per reads in {output_prefix}.json")
         ext.write_json(f"{output_prefix}.json")               # == writeReadsAndVariantsData(ext.reads_data(), ...)
+        if write_pack:
+            _write_sidecar(ext, output_prefix)
     return ext
 
 
@@ -435,7 +447,7 @@ def saveReadsToBam(reads_data: ReadsAndVariantsData, filename_prefix: str, bam_f
 
 
 def extractVariantFromBam(index: str | list[Variant], bam_file: str, output_prefix: str,
-                          error_correction: bool = True, num_editdist: int = 4):
+                          error_correction: bool = True, num_editdist: int = 4, write_pack: bool = False):
     """The reference's entry point (:904-940), same arguments: reads ``samtools sort -n bam -O SAM``
     (readBam, :103-110), runs the native extraction loop, writes ``{output_prefix}.json`` and - as the
     reference does through samtools - ``{output_prefix}.bam`` and ``{output_prefix}.no_multi.bam``
@@ -451,6 +463,8 @@ def extractVariantFromBam(index: str | list[Variant], bam_file: str, output_pref
     logger.info(f"[Graph] Filterd pairs: {ext.n_reads}")
     logger.debug(f"[Graph] Save allele per reads in {output_prefix}.json")
     ext.write_json(f"{output_prefix}.json")
+    if write_pack:
+        _write_sidecar(ext, output_prefix)
     header = _samtools(["view", "-H", bam_file], capture=True)
     for prefix, keep in ((output_prefix, None), (output_prefix + ".no_multi", ext.multiple == 1)):
         with open(prefix + ".sam", "wb") as handle:                   # saveSam (:869-881)

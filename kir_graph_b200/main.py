@@ -98,15 +98,16 @@ def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: st
     if method != "full":
         raise NotImplementedError("cohortAlleleTyping covers the full-variant strategy; use alleleTyping")
     import functools
-    from . import cohort, fastjson
+    from . import cohort, packio
     mine = list(range(len(processed_bam)))[rank::world]
     jsons = [processed_bam[i] + ".json" for i in mine]
-    load = functools.partial(fastjson.load_packs, variant_correction=True)     # one sample's .json -> packed genes
+    # one sample's packed genes: the .gkpack.npz sidecar when it is fresh, else the .json through the scanner
+    load = functools.partial(packio.load_sample_packs, variant_correction=True)
     if workers > 1 and len(mine) > 1:
         import multiprocessing
         from concurrent.futures import ProcessPoolExecutor
         # spawn: the parent may hold a CUDA context, which a forked child must not inherit; the workers
-        # import kir_graph_b200.fastjson only (numpy + the C++ scanner, no pandas / torch)
+        # import kir_graph_b200.packio / fastjson only (numpy + the C++ scanner, no pandas / torch)
         with ProcessPoolExecutor(max_workers=min(workers, len(mine)),
                                  mp_context=multiprocessing.get_context("spawn")) as pool:
             packed = list(pool.map(load, jsons))

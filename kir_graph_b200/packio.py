@@ -11,6 +11,7 @@ the packing options.
 from __future__ import annotations
 
 import json
+import os
 
 import numpy as np
 
@@ -53,6 +54,42 @@ def load_packs(path: str) -> tuple[dict[str, GenePack], dict]:
         p.var_val = names["var_val"]
         packs[g] = p
     return packs, json.loads(str(data["__meta__"]))
+
+
+SIDECAR_SUFFIX = ".gkpack.npz"
+
+
+def sidecar_path(filename_variant_json: str) -> str:
+    """``{prefix}.json`` (or ``{prefix}``) -> ``{prefix}.gkpack.npz``."""
+    prefix = filename_variant_json[:-5] if filename_variant_json.endswith(".json") else filename_variant_json
+    return prefix + SIDECAR_SUFFIX
+
+
+def sidecar_meta(filename_variant_json: str, variant_correction: bool = True, multiple: bool = False) -> dict:
+    """What a sidecar records about how and from what it was packed; ``json_size`` ties it to the
+    ``.json`` it sits next to (a rewritten ``.json`` of another size invalidates it)."""
+    path = filename_variant_json if filename_variant_json.endswith(".json") else filename_variant_json + ".json"
+    return {"variant_correction": bool(variant_correction), "multiple": bool(multiple),
+            "json_size": os.path.getsize(path) if os.path.exists(path) else -1}
+
+
+def load_sample_packs(filename_variant_json: str, variant_correction: bool = True, multiple: bool = False
+                      ) -> dict[str, GenePack]:
+    """Packed genes of one sample: from ``{prefix}.gkpack.npz`` when it is there and was packed with
+    the same options from a ``.json`` of the same size, else from the ``.json`` through the C++
+    scanner (:mod:`kir_graph_b200.fastjson`).  Module-level and cheap to import: it is what the worker
+    processes of ``main.cohortAlleleTyping`` run."""
+    side = sidecar_path(filename_variant_json)
+    if os.path.exists(side):
+        try:
+            packs, meta = load_packs(side)
+            if meta == sidecar_meta(filename_variant_json, variant_correction, multiple):
+                return packs
+        except (OSError, ValueError, KeyError):
+            pass                                  # unreadable sidecar: fall through to the .json
+    from . import fastjson
+    return fastjson.load_packs(filename_variant_json, variant_correction=variant_correction,
+                               single_mapped_only=not multiple)
 
 
 def pack_variant_json(filename_variant_json: str, variant_correction: bool = True,

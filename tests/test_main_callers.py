@@ -104,3 +104,46 @@ def test_cohort_entry_writes_the_same_files(tmp_path):
     with pytest.raises(NotImplementedError):
         main.cohortAlleleTyping(names, cn_files, "exonfirst_1", _backend=FakeBackend())
     assert main.cohortAlleleTyping([], [], "full", _backend=FakeBackend()) == []
+
+
+def test_sidecar_written_at_extraction_feeds_the_cohort_entry(tmp_path):
+    """extractVariantFromSam(write_pack=True) leaves {prefix}.gkpack.npz next to the .json; the cohort
+    entry types from it (the .json is not parsed: here it is blanked, same size), falls back to the
+    .json when the sidecar does not belong to it, and the calls are those of the .json route."""
+    from kir_graph_b200 import hisat2, packio
+    from tests import sam_sim
+    names, cn_files = [], []
+    for s in range(2):
+        table, pairs = sam_sim.multi_gene(90 + s, n_pairs=260, novel=0.002)
+        alleles = {g: [f"{g.split('*')[0]}*{i:03d}" for i in range(6)] for g in ("KIRA*BACKBONE", "KIRB*BACKBONE")}
+        rng = np.random.default_rng(7 + s)
+        for v in table:
+            v.allele = [a for a in alleles[v.ref] if rng.random() < 0.4] or [alleles[v.ref][0]]
+        name = str(tmp_path / f"c.{s:02d}.variant")
+        with open(name + ".sam", "w") as f:
+            f.write(sam_sim.sam_text(pairs))
+        Variant.novel_id = 0
+        hisat2.extractVariantFromSam(table, name + ".sam", name, num_editdist=9, write_pack=True)
+        assert os.path.exists(name + ".gkpack.npz")
+        pd.DataFrame({"gene": ["KIRA*BACKBONE", "KIRB*BACKBONE"], "cn": [2, 1]}).to_csv(
+            name + ".cn.tsv", sep="\t", index=False)
+        names.append(name)
+        cn_files.append(name + ".cn.tsv")
+    want_files = main.alleleTyping(names, cn_files, "full", _backend=FakeBackend())          # the .json route
+    want = [open(f, "rb").read() for f in want_files]
+    assert all(len(pd.read_csv(f, sep="\t")["alleles"][0].split("_")) == 3 for f in want_files)
+    for f in want_files:
+        os.remove(f)
+    sizes = [os.path.getsize(n + ".json") for n in names]
+    for n, size in zip(names, sizes):                       # blank the .json: only the sidecar can answer now
+        with open(n + ".json", "wb") as f:
+            f.write(b" " * size)
+    files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    assert files == want_files and [open(f, "rb").read() for f in files] == want
+    # a .json of another size does not belong to the sidecar: the scanner is asked (and finds no reads)
+    with open(names[0] + ".json", "wb") as f:
+        f.write(b"{}")
+    assert packio.load_sample_packs(names[0] + ".json") == {}
+    side, meta = packio.load_packs(packio.sidecar_path(names[1] + ".json"))
+    assert meta == {"variant_correction": True, "multiple": False, "json_size": sizes[1]} and len(side) == 2
+    assert list(packio.load_sample_packs(names[1] + ".json", variant_correction=True)) == list(side)
