@@ -15,7 +15,8 @@ runs on the GPU through :mod:`kir_graph_b200.engine`:
 Tie policy: the reference orders exactly-tied
 candidates by float rounding noise and an unstable ``argsort``; here ties are
 exact and broken by the documented secondary keys, then by candidate order.
-Whenever a tie group touches a cut or the best rank, ``TypingResult.tie_flags``
+Whenever a tie group touches a cut or the best rank, or a member fraction that
+``selectBest`` examines lies within 0.01 of its threshold, ``TypingResult.tie_flags``
 is set and ``AlleleTyping.tie_report`` records it.
 """
 from __future__ import annotations
@@ -36,6 +37,9 @@ from .utils import logger
 
 C_HIT = float(np.log10(0.999))
 C_MISS = float(np.log10(0.001))
+
+
+TIE_FRACTION_NEAR_THRESHOLD = 8      # TypingResult.tie_flags bit3 (host side; bits 0-2: GkStepInfo.tie_flags)
 
 
 def _lcm_upto(n: int) -> int:
@@ -444,6 +448,18 @@ def step_to_result(out: engine.StepOutput, colsum: np.ndarray, k_total: int, k_e
         p = p_loader().astype(np.float64)
         return (k_eff[:, None] - p) * C_HIT + p * C_MISS
 
+    # bit3: a fraction that selectBest looks at lies within 0.01 of its threshold 1 / (2n).  The
+    # reference's fractions carry float noise of that order (a read tied between two members can
+    # go to one of them when their log-probabilities differ in the last bit, :575-580),
+    # so its choice of the best rank may differ there.
+    tie_flags = int(out.tie_flags)
+    if len(fraction):
+        floor = 0.5 / n
+        passing = np.flatnonzero((fraction >= floor).all(axis=1))
+        looked_at = fraction[: int(passing[0]) + 1] if len(passing) else fraction
+        if bool((np.abs(looked_at - floor) < 0.01).any()):
+            tie_flags |= TIE_FRACTION_NEAR_THRESHOLD
+
     return TypingResult(
         n=n,
         value=k_total * C_HIT + out.score.astype(np.float64) * (C_MISS - C_HIT),
@@ -454,7 +470,7 @@ def step_to_result(out: engine.StepOutput, colsum: np.ndarray, k_total: int, k_e
         fraction=fraction,
         fraction_uniq=np.ones(fraction.shape),                                      # "fake" in the reference (:584)
         score=out.score, member_colsum=member_colsum, frac_num=frac_num,
-        tie_flags=out.tie_flags, n_unique=out.n_unique, p_colsum=out.score.copy())
+        tie_flags=tie_flags, n_unique=out.n_unique, p_colsum=out.score.copy())
 
 
 class AlleleTypingExonFirst(AlleleTyping):

@@ -296,3 +296,26 @@ def test_exon_first_with_top_n_below_five_follows_the_reference():
                                 _backend=FakeBackend())
     res = typ.typing(1)
     assert res.isFail() and res.selectBest() == ["fail"]
+
+
+def test_fraction_near_the_select_best_threshold_is_reported():
+    """A member fraction within 0.01 of 1 / (2n) sets tie_flags bit3: the reference's fractions carry
+    float noise of that size (typing_mulit_allele.py:575-580), so its best rank may be another one -
+    this gene is the case a differential run against the imported reference found (the reference
+    computes 31/122 = 0.254 for the second member of rank 0 and keeps it, exact arithmetic gives
+    30/122 = 0.246 and moves on to rank 1)."""
+    from kir_graph_b200.typing_mulit_allele import TIE_FRACTION_NEAR_THRESHOLD
+    gene = synthetic.make_gene([257500406, 1], "KIRE1*BACKBONE", 3, 64, 4, 122, hierarchical=False,
+                               variant_id_base=1000)
+    reads, variants = gene.to_objects()
+    typ = AlleleTyping(reads, variants, force_homo=None, top_n=40, _backend=FakeBackend())
+    res = typ.typing(2)
+    assert res.tie_flags & TIE_FRACTION_NEAR_THRESHOLD
+    assert abs(res.fraction[0].min() - 0.25) < 0.01 and res.selectBest() == res.allele_name[1]
+    assert any(r["tie_flags"] & TIE_FRACTION_NEAR_THRESHOLD for r in typ.tie_report)
+    # far from the threshold: not set
+    gene = synthetic.make_gene([3, 4], "KIRY*BACKBONE", 8, 64, 2, 300)
+    reads, variants = gene.to_objects()
+    typ = AlleleTyping(reads, variants, force_homo=False, top_n=10, _backend=FakeBackend())
+    res = typ.typing(2)
+    assert not res.tie_flags & TIE_FRACTION_NEAR_THRESHOLD or abs(res.fraction[0].min() - 0.25) < 0.01
