@@ -18,7 +18,7 @@ from kir_graph_b200 import synthetic, kir_typing
 from kir_graph_b200.hisat2 import writeReadsAndVariantsData
 from tests.fake_backend import FakeBackend
 rng = np.random.default_rng(int(sys.argv[1])); T = float(sys.argv[2])
-t0 = time.time(); n = 0; bad = 0
+t0 = time.time(); n = 0; bad = 0; em_ties = 0
 tmp = tempfile.mkdtemp()
 while time.time() - t0 < T:
     seed = int(rng.integers(1 << 30))
@@ -47,5 +47,15 @@ while time.time() - t0 < T:
         tie = getattr(holder.get("t"), "tie_report", None)
         if method == "em" and same_sets: continue
         if tie or same_sets: continue
+        if method == "em" and not isinstance(got, str) and not isinstance(want, str) and got[1] == want[1]:
+            # an exact tie of two abundances at the last copy of a gene: the reference orders those by a
+            # set's iteration order, the mirror by name
+            probs = {x.allele: x.prob for g in holder["t"]._result.values() for x in g}
+            only_a = [a for a in got[0] if a not in want[0]]
+            only_b = [a for a in want[0] if a not in got[0]]
+            if len(only_a) == len(only_b) and all(abs(probs.get(x, -1) - probs.get(y, -2)) <= 1e-12 * max(probs.get(x, 1), 1e-300)
+                                                 for x, y in zip(sorted(only_a), sorted(only_b))):
+                em_ties += 1
+                continue
         print("MISMATCH", method, seed, cn, kw, got, want); bad += 1
-print("cases", n, "bad", bad)
+print("cases", n, "bad", bad, "exact EM ties", em_ties)
