@@ -123,3 +123,18 @@ def test_zs_items_follow_the_references_tuple_indexing():
         assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:x|S")) == "ValueError"
         assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:")) == "ValueError"
         assert _outcome(walk, line.replace("Zs:Z:10|S|hv0", "Zs:Z:10|S|hv0,")) == "ValueError"
+
+
+def test_index_readers_match_reference(tmp_path):
+    """getVariants (readVariants / readLink / readExons / isInExon) over .snp / .link / .locus files:
+    tests/golden/index_readers.json.gz holds what the reference's getVariants returned
+    (make_golden_index.py) - order, allele lists and exon flags included."""
+    from dataclasses import asdict
+    for i, case in enumerate(load_golden("index_readers")["cases"]):
+        index = str(tmp_path / f"kir{i}")
+        for ext, text in case["files"].items():
+            with open(f"{index}.{ext}", "w") as handle:
+                handle.write(text)
+        got = hisat2.getVariants(index)
+        assert [asdict(v) for v in got] == case["variants"]
+        assert got == sorted(got) and any(v.in_exon for v in got) and any(not v.allele for v in got)
