@@ -408,6 +408,13 @@ class AlleleTyping:
             logger.warning("[Allele] Empty reads for typing. Skip")
             self.result.append(_empty_result(len(self.result) + 1))
             return self.result[-1]
+        if self.top_n < 1:
+            # top_n == 0 (the restricted model of exon-first with top_n < 5, :716): the reference's
+            # first step keeps nothing, a further step indexes with the empty float id array (:540)
+            if self.result:
+                raise IndexError("arrays used as indices must be of integer (or boolean) type")
+            self.result.append(_empty_result(1))
+            return self.result[-1]
         cand = None
         if candidate_allele is not None:
             cand = np.array([self.allele_to_id[a] for a in candidate_allele], dtype=np.int32)

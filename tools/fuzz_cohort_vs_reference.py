@@ -78,5 +78,10 @@ while time.time() - t0 < seconds:
             continue
         bad += 1
         print("MISMATCH", seed, gene, cn[gene], top_n, got, want, call.n_reads, want_reads)
+        if os.environ.get("FUZZ_KEEP"):
+            import shutil
+            shutil.copy(path, os.environ["FUZZ_KEEP"])
+            print("kept", os.environ["FUZZ_KEEP"], "cn", cn, "top_n", top_n)
+            sys.exit(1)
 print("genes", n_genes, "bad", bad, "explained by ties", explained)
 sys.exit(1 if bad else 0)

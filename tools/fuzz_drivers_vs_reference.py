@@ -58,4 +58,7 @@ while time.time() - t0 < T:
                 em_ties += 1
                 continue
         print("MISMATCH", method, seed, cn, kw, got, want); bad += 1
+        if os.environ.get("FUZZ_KEEP"):
+            import shutil
+            shutil.copy(path, os.environ["FUZZ_KEEP"]); print("kept", os.environ["FUZZ_KEEP"]); sys.exit(1)
 print("cases", n, "bad", bad, "exact EM ties", em_ties)
