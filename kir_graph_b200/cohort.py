@@ -299,9 +299,11 @@ class BatchTyper:
             called[homo_live, 1:] = called[homo_live, :1]                    # homozygous shortcut (:423-454)
         else:
             group.reset()
+            sticky = np.zeros(n_live, dtype=np.int64)          # tie flags accumulate over the steps of a search
             for step in range(1, int(steps.max(initial=0)) + 1):
                 out = group.step(active=steps >= step, need_next=steps > step, collect=steps == step,
                                  best_only=True)
+                sticky |= np.where(steps >= step, out.info["tie_flags"].astype(np.int64), 0)
                 rows = out.searches
                 if not len(rows):
                     continue
@@ -309,7 +311,7 @@ class BatchTyper:
                 kept = out.info["n_kept"][rows].astype(np.int64)
                 best[rows] = np.where(homo_live[rows], 0, out.info["best_rank"][rows])
                 score[rows] = out.score
-                flags[rows] = out.info["tie_flags"][rows]
+                flags[rows] = sticky[rows]
                 ids = out.ids.astype(np.int64)
                 ids[kept == 0] = -1
                 if n == 1:                                                   # homozygous shortcut (:423-454)

@@ -1050,6 +1050,10 @@ class SearchGroup:
             out_ids[done, :n] = ids
             out_score[done] = arrays[2 * j + 1].view(np.uint32).astype(np.int64)
             out_info[done] = infos[n - 1][done]
+            # tie flags are sticky over the steps of a search: a tie at a cut of an earlier step
+            # decides which sets the later steps grow
+            for earlier in infos[: n - 1]:
+                out_info["tie_flags"][done] |= earlier["tie_flags"][done]
         self.kept = infos[-1]["n_kept"].astype(np.int32) if infos else self.kept
         return out_ids, out_score, out_info
 

@@ -140,8 +140,11 @@ class TypingWithPosNegAllele(Typing):
                                         _backend=self._backend)
         res = typ.typing(cn)
         self._result[gene] = typ.result
-        if res.tie_flags:
-            self.tie_report[gene] = [{"n": r.n, "tie_flags": r.tie_flags} for r in typ.result if r.tie_flags]
+        # a tie at a cut of an EARLIER step decides which sets the later steps grow, even when the
+        # last step itself is tie-free: report every flagged step
+        flagged = [{"n": r.n, "tie_flags": r.tie_flags} for r in typ.result if r.tie_flags]
+        if flagged:
+            self.tie_report[gene] = flagged
         alleles = res.selectBest()
         pure_gene = gene.split("*")[0]
         return [a if a != "fail" else f"{pure_gene}*" for a in alleles], typ.getReadsNum()

@@ -15,9 +15,9 @@ runs on the GPU through :mod:`kir_graph_b200.engine`:
 Tie policy: the reference orders exactly-tied
 candidates by float rounding noise and an unstable ``argsort``; here ties are
 exact and broken by the documented secondary keys, then by candidate order.
-Whenever a tie group touches a cut or the best rank, or a member fraction that
-``selectBest`` examines lies within 0.01 of its threshold, ``TypingResult.tie_flags``
-is set and ``AlleleTyping.tie_report`` records it.
+Whenever a tie group touches a cut or the best rank, or read-level ties leave the
+outcome of ``selectBest``'s fraction test open for a rank it examines,
+``TypingResult.tie_flags`` is set and ``AlleleTyping.tie_report`` records it.
 """
 from __future__ import annotations
 
@@ -455,16 +455,21 @@ def step_to_result(out: engine.StepOutput, colsum: np.ndarray, k_total: int, k_e
         p = p_loader().astype(np.float64)
         return (k_eff[:, None] - p) * C_HIT + p * C_MISS
 
-    # bit3: a fraction that selectBest looks at lies within 0.01 of its threshold 1 / (2n).  The
-    # reference's fractions carry float noise of that order (a read tied between two members can
-    # go to one of them when their log-probabilities differ in the last bit, :575-580),
-    # so its choice of the best rank may differ there.
+    # bit3: the outcome of selectBest's test "every member fraction >= 1 / (2n)" (:83-87) is not
+    # decided by exact arithmetic alone for a rank it looks at.  A read tied between q members counts
+    # 1/q for each here; in the reference the tied log-probabilities can differ in the last bit
+    # (ordered float product), and then the read counts 1 for one member and 0 for the
+    # others (:575-580).  Member t's fraction in the reference therefore lies anywhere between
+    # (reads t wins alone) / R and (reads t wins or ties) / R; if the threshold falls inside that
+    # range the reference may pass or fail the rank differently.
     tie_flags = int(out.tie_flags)
     if len(fraction):
         floor = 0.5 / n
         passing = np.flatnonzero((fraction >= floor).all(axis=1))
-        looked_at = fraction[: int(passing[0]) + 1] if len(passing) else fraction
-        if bool((np.abs(looked_at - floor) < 0.01).any()):
+        last = int(passing[0]) + 1 if len(passing) else len(fraction)
+        alone = out.cnt[:last, :, 0] / float(n_reads)
+        at_most = out.cnt[:last].sum(axis=2) / float(n_reads)
+        if bool(((alone < floor) & (at_most >= floor)).any()):
             tie_flags |= TIE_FRACTION_NEAR_THRESHOLD
 
     return TypingResult(

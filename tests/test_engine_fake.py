@@ -299,11 +299,12 @@ def test_exon_first_with_top_n_below_five_follows_the_reference():
 
 
 def test_fraction_near_the_select_best_threshold_is_reported():
-    """A member fraction within 0.01 of 1 / (2n) sets tie_flags bit3: the reference's fractions carry
-    float noise of that size (typing_mulit_allele.py:575-580), so its best rank may be another one -
-    this gene is the case a differential run against the imported reference found (the reference
-    computes 31/122 = 0.254 for the second member of rank 0 and keeps it, exact arithmetic gives
-    30/122 = 0.246 and moves on to rank 1)."""
+    """tie_flags bit3: read-level ties leave the outcome of selectBest's test "every member fraction
+    >= 1 / (2n)" open for a rank it looks at - a read tied between members counts 1/q for each in exact
+    arithmetic, but 1 for one of them in the reference when the tied log-probabilities differ in the
+    last bit (typing_mulit_allele.py:575-580).  This gene is the case a differential run against the
+    imported reference found (the reference computes 31/122 = 0.254 for the second member of rank 0 and
+    keeps it, exact arithmetic gives 30/122 = 0.246 and moves on to rank 1)."""
     from kir_graph_b200.typing_mulit_allele import TIE_FRACTION_NEAR_THRESHOLD
     gene = synthetic.make_gene([257500406, 1], "KIRE1*BACKBONE", 3, 64, 4, 122, hierarchical=False,
                                variant_id_base=1000)
@@ -318,4 +319,5 @@ def test_fraction_near_the_select_best_threshold_is_reported():
     reads, variants = gene.to_objects()
     typ = AlleleTyping(reads, variants, force_homo=False, top_n=10, _backend=FakeBackend())
     res = typ.typing(2)
-    assert not res.tie_flags & TIE_FRACTION_NEAR_THRESHOLD or abs(res.fraction[0].min() - 0.25) < 0.01
+    alone = res.frac_num is not None and typ.result[-1].fraction[0].min() > 0.3
+    assert not (alone and res.tie_flags & TIE_FRACTION_NEAR_THRESHOLD and not res.fraction[0].min() < 0.35)
