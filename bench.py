@@ -137,14 +137,40 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle's float64 restatement of the reference path
+# CPU arm: the reference itself (oracle/_ref: graphkir byte-compiled by oracle/make_ref.py), or - only
+# when that is absent - the oracle's float64 restatement
 # ---------------------------------------------------------------------------
 def _cpu_type_sample(args):
-    """Type one synthetic cfg3 sample (read-scaled) with the reference's NumPy expressions."""
-    seed, scale, top_n = args
-    from kir_graph_b200 import packing, synthetic
-    from oracle import typing_oracle as orc
+    """Type one synthetic cfg3 sample (read-scaled) on one core; returns (scoring cells, seconds of the
+    whole typing path, seconds of the search alone, genes, genes whose call equals the generator's truth).
+
+    kind "reference": per gene ``AlleleTyping(reads, variants, top_n=...).typing(cn)`` of the imported,
+    unmodified reference - constructor (errorCorrection, reads2AlleleProb, log10:
+    typing_mulit_allele.py:229-269) and greedy search (:383-598) - on the generator's objects; this
+    process never loads libgk_typing.so.  kind "port": the oracle's F64Search (search only)."""
+    seed, scale, top_n, kind = args
+    from kir_graph_b200 import synthetic
     genes = synthetic.make_wgs30x_sample(seed=seed, scale=scale)
+    cells, t_all, t_search, ok = 0, 0.0, 0.0, 0
+    if kind == "reference":
+        from oracle import ref_loader
+        tma = ref_loader.load()[0]
+        for g in genes:
+            reads, variants = ref_loader.to_ref_objects(*g.to_objects())
+            t0 = time.perf_counter()
+            typ = tma.AlleleTyping(reads, variants, top_n=top_n)
+            t1 = time.perf_counter()
+            res = typ.typing(g.cn)
+            t2 = time.perf_counter()
+            t_all += t2 - t0
+            t_search += t2 - t1
+            n_reads, n_alleles = (typ.probs.shape if typ.probs.ndim == 2 else (0, 0))
+            if len(typ.result) == g.cn:                      # not the homozygous shortcut: cn - 1 scored steps
+                cells += sum(len(r.value) for r in typ.result[:-1]) * n_reads * n_alleles
+            ok += sorted(res.selectBest()) == sorted(g.allele_names[t] for t in g.truth)
+        return cells, t_all, t_search, len(genes), ok
+    from kir_graph_b200 import packing
+    from oracle import typing_oracle as orc
     prepared = []
     for g in genes:
         pack = packing.pack_synthetic(g)
@@ -156,57 +182,94 @@ def _cpu_type_sample(args):
             np.add.at(m, row, (~member[idx] if name in ("lpv", "rpv") else member[idx]).astype(np.int64))
         prepared.append((orc.log_probs_from_counts(m, pack.k_obs.astype(np.int64)), g.cn))
     t0 = time.perf_counter()
-    cells = 0
     for lp, cn in prepared:
         search = orc.F64Search(lp, top_n=top_n, read_chunk=1024)
         for step in range(cn):
             if step:
                 cells += len(search.result[-1].value) * lp.shape[1] * lp.shape[0]
             search.add_candidate()
-    return cells, time.perf_counter() - t0
+    t_all = t_search = time.perf_counter() - t0
+    return cells, t_all, t_search, len(genes), -1
 
 
-def cpu_reference_step(cores, scale, top_n, first_seed=100):
-    """``cores`` worker processes each type one read-scaled sample; returns (cells, wall seconds, samples)."""
-    jobs = [(first_seed + i, scale, top_n) for i in range(cores)]
-    t0 = time.perf_counter()
-    if cores > 1:
+def cpu_reference_kind() -> str:
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
+class CpuArm:
+    """``cores`` worker processes (spawned once, reused by every step), each typing one read-scaled
+    cfg3 sample per step - the reference's own cohort recipe is one process per sample
+    (research/test_speed.graphkir.par.sh:14)."""
+
+    def __init__(self, cores, scale, top_n):
         import multiprocessing as mp
-        with mp.get_context("spawn").Pool(cores) as pool:      # CUDA may already be initialised: no fork
-            out = pool.map(_cpu_type_sample, jobs)
-    else:
-        out = [_cpu_type_sample(jobs[0])]
-    wall = max(t for _, t in out)      # typing time only (generation excluded), slowest worker
-    _ = time.perf_counter() - t0
-    return sum(c for c, _ in out), wall, len(jobs)
+        self.cores, self.scale, self.top_n = cores, scale, top_n
+        self.kind = cpu_reference_kind()
+        self.pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None    # CUDA may be initialised: no fork
+        self.next_seed = 100
+
+    def step(self):
+        """(cells, wall seconds of the slowest worker's typing, search-only seconds, samples, genes, genes ok)"""
+        jobs = [(self.next_seed + i, self.scale, self.top_n, self.kind) for i in range(self.cores)]
+        self.next_seed += self.cores
+        out = self.pool.map(_cpu_type_sample, jobs) if self.pool is not None else [_cpu_type_sample(jobs[0])]
+        return (sum(o[0] for o in out), max(o[1] for o in out), max(o[2] for o in out), len(jobs),
+                sum(o[3] for o in out), sum(o[4] for o in out))
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+    def describe(self) -> str:
+        reads = int(200000 * self.scale)
+        if self.kind == "reference":
+            return (f"{self.cores} processes x 1 synthetic cfg3 sample each per step at {self.scale:g} of the reads "
+                    f"({reads} read pairs, 17 genes, top_n={self.top_n}); the unmodified reference (oracle/_ref: graphkir "
+                    "byte-compiled from /root/reference) AlleleTyping(reads, variants).typing(cn) per gene, likelihood "
+                    "build included; time of the slowest process")
+        return (f"{self.cores} processes x 1 synthetic cfg3 sample each per step at {self.scale:g} of the reads ({reads} "
+                f"read pairs, 17 genes, top_n={self.top_n}), oracle F64Search (reference NumPy expressions, 1024-read "
+                "chunks); search only (oracle/_ref not built)")
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
-    scale = args.cpu_scale
+    arm = CpuArm(cores, args.cpu_scale, args.top_n)
     for _ in range(args.warmup):
-        pass                                   # nothing to warm: fresh processes every step
-    cells = wall = 0.0
-    samples = 0
-    for _ in range(max(1, args.steps)):
-        c, w, n = cpu_reference_step(cores, scale, args.top_n)
+        arm.step()
+    cells = wall = search = 0.0
+    samples = genes = ok = 0
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        c, w, sw, n, g, k = arm.step()
         cells += c
         wall += w
+        search += sw
         samples += n
+        genes += g
+        ok += k
+    arm.close()
     value = cells / wall / 1e9
-    sample_desc = (f"{cores} processes x 1 synthetic cfg3 sample each at {scale:g} of the reads "
-                   f"({int(200000 * scale)} read pairs, 17 genes, top_n={args.top_n}), oracle F64Search "
-                   f"(reference NumPy expressions, 1024-read chunks); typing time only")
     line = {
         "impl": "reference", "metric": "allele-typing read x candidate GCells/s", "value": value,
-        "unit": "GCells/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+        "unit": "GCells/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cohort (cfg5: 96 x cfg3 synthetic 30x WGS samples), bounded sample", "top_n": args.top_n},
-        "samples_per_s": samples * scale / wall,
-        "cpu_baseline": {"value": value, "unit": "GCells/s", "cores": cores, "kind": "port", "sample": sample_desc},
+        "config": {"workload": f"cfg5 cohort: {args.samples} synthetic 30x WGS samples x 200000 read pairs x 900 alleles / 17 "
+                               f"genes, CN<=4, top_n={args.top_n}, sample-sharded",
+                   "top_n": args.top_n,
+                   "bounded_sample": f"each step types {cores} samples (one per host core) at {args.cpu_scale:g} of the reads "
+                                     "instead of 96 full samples: the full step is ~10 core-minutes per sample in the "
+                                     "reference; GCells/s and samples/s are rates, and the reference's cost is linear in "
+                                     "the reads (likelihood) and in reads x candidates (search)"},
+        "samples_per_s": samples * args.cpu_scale / wall,
+        "search_only_value": cells / search / 1e9 if search else None,
+        "parity": {"genes_matching_generator_truth": ok, "genes": genes},
+        "cpu_baseline": {"value": value, "unit": "GCells/s", "cores": cores, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": value, "unit": "GCells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,6 +279,13 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def load_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
 def score_roofline(cells, ms, packed, sm_max_mhz):
     """Roofline entry of the scoring kernel.  Its bound is non-tensor instruction issue, not HBM or
     the tensor cores: the packed path issues 3 ALU-pipe instructions (2 VIMNMX.U16x2 + 1 IADD3)
@@ -238,6 +308,115 @@ def score_roofline(cells, ms, packed, sm_max_mhz):
             "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=128)}
 
 
+
+# ---------------------------------------------------------------------------
+# cfg4: one very deep sample over all ranks
+# ---------------------------------------------------------------------------
+def deep_leg(args, be, rank, world, timed, packed, sm_max, shard, steps=3, parity=True):
+    """One deep sample (cfg4) typed by all ranks together; returns the ``deep`` block (rank 0) or None.
+
+    shard = "reads": every rank holds R / world reads (``packing.shard_reads``); likelihood, scoring, tie
+                     counting and the P writer all work on the local reads, the partial score matrix and
+                     the partial tie counts are summed with two small all-reduces per copy-number step
+                     (plus one of the column sums), nothing is replicated.
+    shard = "cols":  candidate-column tiles of the scoring kernel are dealt to the ranks, L / LT / P and
+                     every other kernel are replicated, one all-reduce of the score matrix per step.
+    ``calls_equal_unsharded``: every copy-number step of the sharded search (kept allele ids, scores,
+    tie counts, tie flags, N_uniq) against the same code run unsharded on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from kir_graph_b200 import cohort, engine, packing
+    t0 = time.perf_counter()
+    d_packs, d_cns, d_truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
+    t_build = time.perf_counter() - t0
+    reduce_scores = None
+    if world > 1:
+        def reduce_scores(t):                       # integer sums over NVLink: exact, order independent
+            dist.all_reduce(t)
+    kw = {}
+    my_packs = d_packs
+    if world > 1 and shard == "reads":
+        my_packs = [packing.shard_reads(p, rank, world) for p in d_packs]
+        kw = dict(read_shard=True, reduce_scores=reduce_scores)
+    elif world > 1:
+        kw = dict(col_shard=(rank, world), reduce_scores=reduce_scores)
+    deep = cohort.CohortTyper(my_packs, d_cns, top_n=args.top_n, backend=be, n_parts=1, **kw)
+    deep.pin()
+    deep.upload()
+    for _ in range(3):                              # unsharded: the third pass records the CUDA graph
+        d_calls = deep.run()
+    d_ms = timed(deep.run, steps) / steps
+    group = deep.parts[0].group
+    coll0 = group.collective_bytes
+    deep.run()
+    coll_bytes = group.collective_bytes - coll0
+    h0 = be.h2d_bytes
+    e_ms = timed(deep.upload_and_run, steps) / steps
+    h2d = (be.h2d_bytes - h0) / steps
+    # per-kernel times of one more pass (CUDA events around every launch; collectives excluded)
+    torch.cuda.synchronize()
+    be.timing = {}
+    deep.run_serial()
+    torch.cuda.synchronize()
+    timing, be.timing = be.timing, None
+    k_ms = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in timing.items()}
+    evs = timing.get("gk_score", [])
+    d_ms_s = sum(a.elapsed_time(b) for a, b, _ in evs)
+    d_work = sum(w for _, _, w in evs)
+    agg = torch.tensor([deep.score_cells, h2d, d_work], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg)
+    mx = torch.tensor([d_ms_s] + [k_ms.get(k, 0.0) for k in sorted(k_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    cells_all, h2d_all, work_all = [float(x) for x in agg.tolist()]
+
+    equal = None
+    if parity and world > 1:
+        # every step of the sharded search against the unsharded one (rank 0 holds both)
+        part = deep.parts[0]
+        sg = engine.SearchGroup(part.batch, [0], args.top_n, reduce_scores=reduce_scores, **{
+            k: v for k, v in kw.items() if k in ("read_shard", "col_shard")})
+        cn = int(d_cns[0])
+        mine = [sg.step(need_next=[i + 1 < cn])[0] for i in range(cn)]
+        del sg
+        if rank == 0:
+            whole = engine.MatrixBatch(d_packs, backend=be)
+            wg = engine.SearchGroup(whole, [0], args.top_n)
+            ref = [wg.step(need_next=[i + 1 < cn])[0] for i in range(cn)]
+            equal = all(np.array_equal(a.ids, b.ids) and np.array_equal(a.score, b.score)
+                        and np.array_equal(a.cnt, b.cnt) and a.tie_flags == b.tie_flags
+                        and a.n_unique == b.n_unique and a.cut == b.cut for a, b in zip(mine, ref))
+            del wg, whole
+        if world > 1:
+            dist.barrier()
+    mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    del deep
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    names = sorted(k_ms)
+    return {
+        "workload": f"cfg4 deep: {args.deep_reads} read pairs x {args.deep_alleles} alleles, CN {args.deep_cn}, "
+                    f"top_n={args.top_n}",
+        "n_gpus": world, "sharding": "none" if world == 1 else shard,
+        "value": cells_all / (d_ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": d_ms, "steps": steps,
+        "e2e": {"value": cells_all / (e_ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": e_ms,
+                "h2d_bytes_per_step": h2d_all},
+        "collective": None if world == 1 else {
+            "kind": "ncclAllReduce (sum of uint32 / uint64 partial integer sums)",
+            "bytes_per_pass_per_rank": coll_bytes, "per_cn_step": "score matrix S" + (
+                " + tie counts of the alive sets" if shard == "reads" else ""),
+            "calls_per_pass": (2 * (int(d_cns[0]) - 1) + 1) if shard == "reads" else int(d_cns[0]) - 1},
+        "calls_match_truth": sorted(d_calls[0].alleles) == d_truth[0],
+        "calls_equal_unsharded": equal,
+        "kernel_ms_per_step_max_over_ranks": dict(zip(names, [float(x) for x in mx.tolist()[1:]])),
+        "roofline": dict(score_roofline(work_all / world, float(mx[0].item()), packed, sm_max), launches=len(evs),
+                         note="cells of one rank (mean) over the slowest rank's scoring time"),
+        "device_mem_gib_rank0": mem, "build_s": t_build,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -251,11 +430,16 @@ def main():
     ap.add_argument("--deep-reads", type=int, default=2_000_000)
     ap.add_argument("--deep-alleles", type=int, default=1000)
     ap.add_argument("--deep-cn", type=int, default=6)
-    ap.add_argument("--cpu-scale", type=float, default=0.5)
+    ap.add_argument("--cpu-scale", type=float, default=0.1,
+                    help="fraction of the reads of a cfg3 sample each CPU-arm process types per step")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-deep", action="store_true",
                     help="skip the nested cfg4 deep-sample measurement of the default 1-GPU cohort run")
+    ap.add_argument("--deep-shard", default="reads", choices=["reads", "cols", "both"],
+                    help="how the deep sample (cfg4) is spread over the ranks: by reads (nothing replicated, two "
+                         "small all-reduces per step), by candidate columns (L / LT / P replicated, one all-reduce "
+                         "per step), or both one after the other (the second as deep_cols)")
     ap.add_argument("--parts", type=int, default=1, help="sub-batches (streams) of the resident pass")
     ap.add_argument("--pipeline-depth", type=int, default=0,
                     help="consecutive passes (steps) in flight: pass i+1 is enqueued on a replica of the typer "
@@ -291,11 +475,6 @@ def main():
         packs, cns, truth = build_cohort([3], args.scale, 1)
         n_samples_total = n_samples_local = 1
         desc = f"cfg3: one synthetic 30x WGS sample, {int(200000 * args.scale)} read pairs x 900 alleles / 17 genes"
-    else:
-        packs, cns, truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
-        n_samples_total = n_samples_local = 1
-        desc = (f"cfg4 deep: {args.deep_reads} read pairs x {args.deep_alleles} alleles, CN {args.deep_cn}, "
-                f"top_n={args.top_n}")
     t_build = time.perf_counter() - t_build
 
     import torch
@@ -305,28 +484,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     from kir_graph_b200 import cohort, engine
     be = engine.CudaBackend(local_rank)
-    col_shard = reduce_scores = None
-    if args.workload == "deep" and world > 1:
-        col_shard = (rank, world)
-
-        def reduce_scores(d_S):                      # one small collective per copy-number step
-            dist.all_reduce(d_S)
-    group_size = 17 if args.workload != "deep" else 1
-    depth = args.pipeline_depth if args.pipeline_depth > 0 else (4 if n_samples_local < 16 else 3)
-    if args.workload == "deep" and args.pipeline_depth <= 0:
-        depth = 2                                # 150 ms of saturated kernels per pass: only the host phase to hide
-    if col_shard is not None:
-        depth = 1                                # one collective stream: passes stay serial
-    typer = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=args.parts,
-                               group_size=group_size, col_shard=col_shard,
-                               reduce_scores=reduce_scores, own_stream=depth > 1)
-    typer.pin()
-    # The packed cohort is a large, long-lived heap (thousands of arrays); keep the cyclic garbage
-    # collector from re-traversing it every time the per-run result objects trigger a collection
-    # (measured: 2.5 ms of a 28 ms pass).
-    import gc
-    gc.collect()
-    gc.freeze()
 
     def barrier():
         if world > 1:
@@ -351,6 +508,51 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         barrier()
         return float(t.item())
+
+    if args.workload == "deep":
+        # cfg4 alone: the deep block is the line
+        peaks = load_peaks()
+        sm_max = float(peaks.get("sm_max_mhz") or 1965.0)
+        packed = bool(engine.PACKED_DEFAULT)
+        sampler = ClockSampler(local_rank, args.clock_interval_ms)
+        sampler.start()
+        launches0 = be.launches
+        modes = ["reads", "cols"] if args.deep_shard == "both" else [args.deep_shard]
+        blocks = {}
+        for mode in (modes if world > 1 else modes[:1]):
+            blocks[mode] = deep_leg(args, be, rank, world, timed, packed, sm_max, mode, steps=args.steps)
+        clocks = sampler.stop()
+        if rank == 0:
+            first = blocks[modes[0]]
+            line = {"metric": "allele-typing read x candidate GCells/s", "value": first["value"], "unit": "GCells/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": 3, "ms_per_step": first["ms_per_step"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "u16" if packed else "f32", "data": "synthetic",
+                    "config": {"workload": first["workload"], "top_n": args.top_n, "sharding": first["sharding"],
+                               "l2": "inputs larger than L2 (no flush needed)"},
+                    "e2e": first["e2e"], "gpu_launches": be.launches - launches0, "clocks": clocks,
+                    "roofline": first["roofline"], "deep": first}
+            for mode in modes[1:]:
+                if mode in blocks:
+                    line["deep_" + mode] = blocks[mode]
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    group_size = 17
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else (4 if n_samples_local < 16 else 3)
+    col_shard = reduce_scores = None
+    typer = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=args.parts,
+                               group_size=group_size, col_shard=col_shard,
+                               reduce_scores=reduce_scores, own_stream=depth > 1)
+    typer.pin()
+    # The packed cohort is a large, long-lived heap (thousands of arrays); keep the cyclic garbage
+    # collector from re-traversing it every time the per-run result objects trigger a collection
+    # (measured: 2.5 ms of a 28 ms pass).
+    import gc
+    gc.collect()
+    gc.freeze()
 
     # ---- resident: inputs already in HBM ---------------------------------------------
     sampler = ClockSampler(local_rank, args.clock_interval_ms)
@@ -479,16 +681,13 @@ def main():
         work = sum(w for _, _, w in evs)
         return ms, work, len(evs)
 
+    peaks = load_peaks()
+    sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    packed = bool(engine.PACKED_DEFAULT)
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        sm_max = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
         ms_s, work_s, n_s = kernel_stats("gk_score")
         ms_l, work_l, n_l = kernel_stats("gk_likelihood")
-        packed = bool(engine.PACKED_DEFAULT)
         traffic = None
         try:                                     # DRAM bytes per launch of the same kernel from an ncu capture
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -539,39 +738,27 @@ def main():
             "device_mem_gib": {"after_resident": mem_resident, "after_e2e": mem_e2e},
             "build_s": t_build,
         }
-        if world == 1 and args.workload == "cohort" and not args.no_deep:
-            # second shape of the same path: one very deep sample (cfg4), scoring kernel dominated
-            del typer, e2e_typer, e2e_replicas, replicas
-            torch.cuda.empty_cache()
-            d_packs, d_cns, d_truth = build_deep(args.deep_reads, args.deep_alleles, args.deep_cn)
-            deep = cohort.CohortTyper(d_packs, d_cns, top_n=args.top_n, backend=be, n_parts=1)
-            deep.upload()
-            for _ in range(3):                       # the third pass records the CUDA graph
-                d_calls = deep.run()
-            d_steps = 3
-            d_ms = timed(deep.run, d_steps) / d_steps
-            be.timing = {}
-            deep.run_serial()
-            torch.cuda.synchronize()
-            evs = be.timing.get("gk_score", [])
-            be.timing = None
-            d_ms_s = sum(a.elapsed_time(b) for a, b, _ in evs)
-            d_work = sum(w for _, _, w in evs)
-            line["deep"] = {
-                "workload": f"cfg4 deep: {args.deep_reads} read pairs x {args.deep_alleles} alleles, CN {args.deep_cn}, "
-                            f"top_n={args.top_n}",
-                "value": deep.score_cells / (d_ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": d_ms,
-                "steps": d_steps, "calls_match_truth": sorted(d_calls[0].alleles) == d_truth[0],
-                "roofline": dict(score_roofline(d_work, d_ms_s, packed, sm_max), launches=len(evs)),
-            }
+    if args.workload == "cohort" and not args.no_deep:
+        # second shape of the same path: one very deep sample (cfg4) typed by all ranks together
+        del typer, e2e_typer, e2e_replicas, replicas, twin
+        gc.unfreeze()
+        gc.collect()
+        torch.cuda.empty_cache()
+        modes = ["reads", "cols"] if args.deep_shard == "both" else [args.deep_shard]
+        for i, mode in enumerate(modes if world > 1 else modes[:1]):
+            block = deep_leg(args, be, rank, world, timed, packed, sm_max, mode)
+            if rank == 0:
+                line["deep" if i == 0 else "deep_" + mode] = block
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
-            c_cells, c_wall, c_n = cpu_reference_step(cores, args.cpu_scale, args.top_n)
+            arm = CpuArm(cores, args.cpu_scale, args.top_n)
+            c_cells, c_wall, c_search, c_n, _, _ = arm.step()
+            arm.close()
             line["cpu_baseline"] = {
-                "value": c_cells / c_wall / 1e9, "unit": "GCells/s", "cores": cores, "kind": "port",
+                "value": c_cells / c_wall / 1e9, "unit": "GCells/s", "cores": cores, "kind": arm.kind,
                 "samples_per_s": c_n * args.cpu_scale / c_wall,
-                "sample": f"{cores} processes x 1 synthetic cfg3 sample each at {args.cpu_scale:g} of the reads, "
-                          "oracle F64Search (reference NumPy expressions, 1024-read chunks), typing time only"}
+                "search_only_value": c_cells / c_search / 1e9 if c_search else None, "sample": arm.describe()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

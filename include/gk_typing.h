@@ -57,6 +57,9 @@ typedef struct GkMatrix {
     int32_t r_pad;       /* multiple of 128; rows >= n_reads are zero                                    */
     int32_t a_tile;      /* allele block width of L (32)                                                 */
     int32_t n_ablk;      /* ceil(n_alleles / a_tile)                                                     */
+    int32_t n_reads_total; /* reads of the whole problem when its reads are sharded over ranks (the
+                            denominator of the read fractions); = n_reads otherwise                      */
+    int32_t pad0;
 } GkMatrix;
 
 /* State of one search.  Strides are fixed by (top_n, GK_MAX_CN). */

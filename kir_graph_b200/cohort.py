@@ -137,21 +137,24 @@ class BatchTyper:
 
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
                  host_batch: engine.HostBatch | None = None, col_shard: tuple[int, int] | None = None,
-                 reduce_scores=None):
-        """``col_shard`` / ``reduce_scores``: shard the candidate columns of every problem over
-        several ranks (see :class:`engine.SearchGroup`); used for one very deep sample."""
+                 reduce_scores=None, read_shard: bool = False):
+        """``col_shard`` / ``read_shard`` + ``reduce_scores``: one very deep sample spread over several
+        ranks, by candidate columns or by reads (see :class:`engine.SearchGroup`; with ``read_shard``
+        the packs are this rank's ``packing.shard_reads`` parts)."""
         self.be = backend if backend is not None else engine.CudaBackend()
-        self.col_shard, self.reduce_scores = col_shard, reduce_scores
+        self.col_shard, self.reduce_scores, self.read_shard = col_shard, reduce_scores, bool(read_shard)
         self.packs = packs
         self.cns = np.asarray(cns, dtype=np.int64)
         self.top_n = top_n
         self.host = host_batch if host_batch is not None else engine.HostBatch(packs)
         self.homo_index = HomozygosityIndex(packs)
-        typable = np.array([p.n_reads > 0 and p.n_alleles > 0 for p in packs], dtype=bool)
+        # reads of the whole problem (a read shard may hold none of them and still takes part)
+        self.n_reads = np.array([p.n_reads if p.n_reads_total is None else p.n_reads_total for p in packs],
+                                dtype=np.int64)
+        typable = (self.n_reads > 0) & np.array([p.n_alleles > 0 for p in packs], dtype=bool)
         self.live = np.flatnonzero((self.cns > 0) & typable)
-        self.n_reads = np.array([p.n_reads for p in packs], dtype=np.int64)
         # per problem: what the call phase needs without attribute look-ups in its loop
-        self._static = [(p.gene, p.allele_names, p.n_reads, int(c)) for p, c in zip(packs, self.cns)]
+        self._static = [(p.gene, p.allele_names, int(r), int(c)) for p, r, c in zip(packs, self.n_reads, self.cns)]
         self.batch: engine.MatrixBatch | None = None
         self.group: engine.SearchGroup | None = None
         self.score_cells = 0
@@ -170,7 +173,8 @@ class BatchTyper:
         if self.batch is not None and self.batch.host is self.host:
             self.batch.reload()                # same layout: device buffers (and a recorded graph) are kept
             return
-        self.batch = engine.MatrixBatch(self.host, backend=self.be, run=False)
+        self.batch = engine.MatrixBatch(self.host, backend=self.be, run=False,
+                                        reduce=self.reduce_scores if self.read_shard else None)
         self._graph, self._graph_runs = None, 0          # a captured graph names the old buffers
         if self.group is not None:
             self.group.batch = self.batch      # same tables and offsets: search buffers are reused
@@ -202,7 +206,7 @@ class BatchTyper:
         batch.run_likelihood(self._colsum_only())
         if self.group is None:
             self.group = engine.SearchGroup(batch, self.live, self.top_n, col_shard=self.col_shard,
-                                            reduce_scores=self.reduce_scores)
+                                            reduce_scores=self.reduce_scores, read_shard=self.read_shard)
         else:
             self.group.reset()
         if self._homo_cache is None:           # the copy numbers are fixed for this batch
@@ -225,8 +229,8 @@ class BatchTyper:
     def _start(self) -> None:
         if self.batch is None:
             self.upload()
-        graphable = (self.use_graph and self.pipelined and self.col_shard is None and self.group is not None
-                     and self.be.timing is None)
+        graphable = (self.use_graph and self.pipelined and self.col_shard is None and not self.read_shard
+                     and self.group is not None and self.be.timing is None)
         if not graphable:
             self._graph_runs += 1
             self._start_eager()
@@ -352,13 +356,15 @@ class CohortTyper:
 
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
                  n_parts: int = 2, group_size: int = 1, col_shard: tuple[int, int] | None = None,
-                 reduce_scores=None, own_stream: bool = False, host_batches: list | None = None):
+                 reduce_scores=None, own_stream: bool = False, host_batches: list | None = None,
+                 read_shard: bool = False):
         """``group_size`` consecutive problems (e.g. the 17 genes of a sample) stay in one part.
         ``own_stream``: a stream of its own even for a single part (replicas of a ``PassPipeline``
         overlap on the device only if they do not share the current stream).  ``host_batches``: the
         packed host pools of another typer over the same problems and parts (shared, read only)."""
         self.be = backend if backend is not None else engine.CudaBackend()
-        if col_shard is not None and col_shard[1] > 1:
+        sharded = read_shard or (col_shard is not None and col_shard[1] > 1)
+        if sharded:
             n_parts = 1                          # one collective stream: keep the parts serial
         n = len(packs)
         n_groups = max(1, -(-n // group_size))
@@ -368,11 +374,11 @@ class CohortTyper:
         if host_batches is not None and len(host_batches) != n_parts:
             raise ValueError("host_batches must hold one HostBatch per part")
         self.parts = [BatchTyper(packs[sl], list(cns)[sl], top_n=top_n, backend=self.be, col_shard=col_shard,
-                                 reduce_scores=reduce_scores,
+                                 reduce_scores=reduce_scores, read_shard=read_shard,
                                  host_batch=host_batches[i] if host_batches is not None else None)
                       for i, sl in enumerate(self.slices)]
         self.streams = None
-        if (n_parts > 1 or own_stream) and col_shard is None and hasattr(self.be, "torch"):
+        if (n_parts > 1 or own_stream) and not sharded and hasattr(self.be, "torch"):
             self.streams = [self.be.torch.cuda.Stream(device=self.be.device) for _ in self.parts]
 
     @property

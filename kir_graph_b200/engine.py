@@ -42,7 +42,9 @@ MAX_TOP_N = 2048
 
 # packed 16-bit integer scoring path (False: FP32 sum of absolute differences); GK_PACKED=0/1 overrides
 PACKED_DEFAULT = _os.environ.get("GK_PACKED", "1") != "0"
-MIN_SCORE_ITEMS = int(_os.environ.get("GK_MIN_SCORE_ITEMS", 1184))   # ~4 waves of 2 CTAs x 148 SMs before shrinking the read chunk further
+SCORE_SLOTS = int(_os.environ.get("GK_SCORE_SLOTS", 444))            # resident scoring CTAs: 148 SMs x 3
+SCORE_ITEM_OVERHEAD = int(_os.environ.get("GK_SCORE_ITEM_OVERHEAD", 48))   # fixed cost of a work item, in reads
+SCORE_CHUNK_CANDIDATES = (8192, 6144, 4096, 3072, 2048, 1536, 1024)
 
 
 def _round_up(x: int, m: int) -> int:
@@ -266,8 +268,9 @@ class HostBatch:
             a_tile = 32
             n_ablk = max(1, -(-p.n_alleles // a_tile))
             r_pad = max(128, _round_up(p.n_reads, 128))
+            n_total = getattr(p, "n_reads_total", None)        # set on a read shard (packing.shard_reads)
             table[i] = (mem_off, entoff_off, L_off, LT_off, col_off, p.n_reads, p.n_alleles, p.n_words,
-                        r_pad, a_tile, n_ablk)
+                        r_pad, a_tile, n_ablk, p.n_reads if n_total is None else n_total, 0)
             entoffs.append(p.ent_off.astype(np.int64) + ent_base)
             mem_off += p.mem_words.size
             entoff_off += p.n_reads + 1
@@ -285,7 +288,9 @@ class HostBatch:
         self.ent_pos = cat([p.ent_pos for p in packs], np.uint32)
         self.ent_neg = cat([p.ent_neg for p in packs], np.uint32)
         self.k_max = int(max((int(p.k_obs.max()) for p in packs if p.n_reads), default=0))
-        self.k_total = np.array([int(np.where(p.k_obs == 0, 1, p.k_obs).astype(np.int64).sum()) for p in packs],
+        # sum of K_r over the reads of the whole problem (a read shard carries the global sum)
+        self.k_total = np.array([int(np.where(p.k_obs == 0, 1, p.k_obs).astype(np.int64).sum())
+                                 if getattr(p, "k_total", None) is None else int(p.k_total) for p in packs],
                                 dtype=np.int64)
         self.L_size, self.LT_size, self.col_size = int(L_off), int(LT_off), int(col_off)
 
@@ -311,11 +316,15 @@ class HostBatch:
 class MatrixBatch:
     """Likelihood data of a batch of gene problems, resident on one GPU."""
 
-    def __init__(self, packs, backend=None, run: bool = True, packed: bool = PACKED_DEFAULT):
+    def __init__(self, packs, backend=None, run: bool = True, packed: bool = PACKED_DEFAULT, reduce=None):
         """``packed``: score on 16-bit integer lanes (VIMNMX.U16x2 + IADD3 on the ALU pipe, 1.5 clk per
         cell; ``L`` holds the pair (m, m), ``P`` is uint16) instead of FP32 (two FADDs, 2 clk per
-        cell).  Both are exact for every supported input (counts <= 255)."""
+        cell).  Both are exact for every supported input (counts <= 255).
+        ``reduce(tensor)``: the packs are read shards of problems whose other reads live on other
+        ranks (``packing.shard_reads``); the callable sums a device array over the ranks in place and
+        is applied to the column sums after the likelihood build (integer sums: order independent)."""
         self.be = backend if backend is not None else CudaBackend()
+        self.reduce = reduce
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
         self.half = bool(packed)          # name kept from the C ABI parameter (half_mode)
@@ -387,6 +396,8 @@ class MatrixBatch:
         self.be.launch("gk_likelihood", self.d_table, self.d_lik_items, self.n_lik_items, self.d_mem,
                        self.d_entoff, self.d_ent_word, self.d_ent_pos, self.d_ent_neg, self.d_L, self.d_LT,
                        self.d_col, int(self.half), work=float(self.n_cells))
+        if self.reduce is not None:
+            self.reduce(self.d_col)                  # read shards: column sums of the whole problem
         self._colsum_host = None
 
     # --- read-backs ------------------------------------------------------------
@@ -527,14 +538,29 @@ class SearchGroup:
     """Greedy searches (one per entry of ``matrix_ids``) advancing in lock step."""
 
     def __init__(self, batch: MatrixBatch, matrix_ids, top_n: int, col_shard: tuple[int, int] | None = None,
-                 reduce_scores=None):
-        """``col_shard=(rank, world)`` scores only this rank's share of the candidate-column tiles;
-        ``reduce_scores(d_S)`` must then sum the score pool over the ranks in place (one small
-        collective per copy-number step); everything after scoring runs replicated."""
+                 reduce_scores=None, read_shard: bool = False):
+        """Two ways to spread one deep problem over several ranks (both exact: every partial result is
+        an integer sum, so the sharded run is bit-identical to the unsharded one):
+
+        ``col_shard=(rank, world)`` scores only this rank's share of the candidate-column tiles;
+        ``reduce_scores(tensor)`` must then sum the score pool over the ranks in place (one small
+        collective per copy-number step); ``L``, ``LT``, ``P`` and everything after scoring are
+        replicated.
+
+        ``read_shard=True``: the matrices of ``batch`` hold only this rank's reads
+        (``packing.shard_reads``, ``MatrixBatch(reduce=)``), so every read-streaming kernel -
+        likelihood, scoring, tie counting, the ``P`` writer - works on ``R / world`` reads and nothing
+        is replicated; ``reduce_scores`` sums the partial score pool and the partial tie counts
+        (two small collectives per step); dedup, cut and ranking run on the complete sums on every
+        rank and give identical kept sets everywhere."""
         self.col_shard = col_shard
+        self.read_shard = bool(read_shard)
         self.reduce_scores = reduce_scores
-        if col_shard is not None and col_shard[1] > 1 and reduce_scores is None:
-            raise ValueError("column sharding needs a reduce_scores callable")
+        if (self.read_shard or (col_shard is not None and col_shard[1] > 1)) and reduce_scores is None:
+            raise ValueError("sharding needs a reduce_scores callable")
+        if self.read_shard and col_shard is not None:
+            raise ValueError("shard either the candidate columns or the reads, not both")
+        self.collective_bytes = 0            # bytes handed to reduce_scores since construction
         if not 1 <= top_n <= MAX_TOP_N:
             raise ValueError(f"top_n must be in 1..{MAX_TOP_N}")
         self.batch = batch
@@ -595,6 +621,10 @@ class SearchGroup:
         self._plan: dict = {}
         self._plan_on = False                 # True inside run_pipeline only
         self.reset()
+
+    def _reduce(self, tensor) -> None:
+        self.collective_bytes += int(tensor.numel() if hasattr(tensor, "numel") else tensor.size) * 4
+        self.reduce_scores(tensor)
 
     def reset(self) -> None:
         """Start all searches over (buffers are reused)."""
@@ -703,14 +733,24 @@ class SearchGroup:
             if int(s) in self.restricted:
                 custom[j] = self._restricted_a_tiles(int(s))
                 n_at[j] = len(custom[j])
-        # chunk size: large chunks unless that leaves the GPU underfilled
-        chunk = SCORE_READ_CHUNK
-        for cand_chunk in (8192, 4096, 2048, 1024):
+        # Reads per work item: a launch lasts (work per CTA slot) + (one item) at best, so large chunks
+        # leave a tail when a slot holds only a few of them (one deep problem spread over 444 slots,
+        # or a read shard of it), and small chunks pay the pipeline fill and the final atomics of an
+        # item (about SCORE_ITEM_OVERHEAD reads' worth) more often.  Pick the candidate with the
+        # smallest estimate of both.
+        tiles = n_kt * n_at
+        best = None
+        for cand_chunk in SCORE_CHUNK_CANDIDATES:
             if cand_chunk > SCORE_READ_CHUNK:
                 continue
-            chunk = cand_chunk
-            if int((n_kt * n_at * np.maximum(1, -(-r16 // cand_chunk))).sum()) >= MIN_SCORE_ITEMS:
-                break
+            n_ch = np.maximum(1, -(-r16 // cand_chunk))
+            per_item = r16 / n_ch                                   # reads per item of each search
+            est = float((tiles * n_ch * (per_item + SCORE_ITEM_OVERHEAD)).sum()) / SCORE_SLOTS + float(per_item.max())
+            if best is None or est < best[0] * 0.995:               # prefer the larger chunk on a tie
+                best = (est, cand_chunk)
+        chunk = best[1] if best is not None else SCORE_READ_CHUNK
+        if _os.environ.get("GK_SCORE_CHUNK"):                       # sweeps (tools/sweep_params.sh)
+            chunk = int(_os.environ["GK_SCORE_CHUNK"])
         n_ch = np.maximum(1, -(-r16 // chunk))
         search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
         items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
@@ -854,6 +894,8 @@ class SearchGroup:
         be.launch("gk_rescore_count", bt.d_table, self.d_tab, d_citems, n_citems, self.top_n, n,
                   self.d_info, self.d_ids[self.cur], self.d_cand, self.d_alive, bt.d_LT, d_cnt,
                   work=work)
+        if self.read_shard:
+            self._reduce(d_cnt)                      # tie counts over the reads of the other ranks
         be.launch("gk_rank", bt.d_table, self.d_tab, self.n_search, self.top_n, n, self.d_ids[self.cur],
                   self.d_cand, self.d_alive, self.d_S, d_cnt, bt.d_col, self.d_score[self.cur], self.d_keys,
                   self.d_ids[new], self.d_score[new], self.d_cnt_out, self.d_flat, self.d_info, self.d_kept,
@@ -898,7 +940,7 @@ class SearchGroup:
                       int(bt.half), int(bt.flush_stages), None, work=float(self._step_cells))
             self.score_cells += self._step_cells
             if self.reduce_scores is not None:
-                self.reduce_scores(self.d_S)             # sum of the per-rank column slices
+                self._reduce(self.d_S)                   # sum of the per-rank column slices / read shards
             be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
                       int(self.cand_cap.max()), self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S,
                       bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info, int(bt.half))
@@ -993,7 +1035,7 @@ class SearchGroup:
                 be.launch("gk_score", bt.d_table, self.d_tab, d_items, n_items, bt.d_L, self.d_P, self.d_S,
                           int(bt.half), int(bt.flush_stages), self.d_kept, work=step_cells)
                 if self.reduce_scores is not None:
-                    self.reduce_scores(self.d_S)
+                    self._reduce(self.d_S)
                 be.launch("gk_select", bt.d_table, self.d_tab, ns, self.top_n, n - 1, max(bt.max_alleles, 1),
                           int(self.cand_cap.max()), self.d_kept, self.d_ids[self.cur], self.d_cand, self.d_S,
                           bt.d_col, self.d_score[self.cur], self.d_flag, self.d_alive, self.d_info, int(bt.half))

@@ -55,6 +55,9 @@ class GenePack:
     var_is_del: np.ndarray | None = None   # bool [V]  variant.typ == "deletion"
     obs_pos: np.ndarray | None = None      # int64 [V]  positive observations after correction
     obs_neg: np.ndarray | None = None      # int64 [V]  negative observations after correction
+    # set on a read shard of a deep problem (shard_reads): the whole problem's read count / sum of K_r
+    n_reads_total: int | None = None
+    k_total: int | None = None
 
     @property
     def n_alleles(self) -> int:
@@ -341,6 +344,32 @@ def pack_synthetic(gene: SyntheticGene, variant_correction: bool = True,
     pack.var_val = ["ACGT"[v % 4] for v in range(n_var)]
     pack.var_is_del = np.zeros(n_var, dtype=bool)
     return pack
+
+
+def shard_reads(pack: GenePack, rank: int, world: int) -> GenePack:
+    """Reads ``[R * rank // world, R * (rank + 1) // world)`` of a packed problem as a problem of its own:
+    the read shard of one very deep sample on rank ``rank`` of ``world``.
+
+    Everything that depends on all reads is decided before the split and carried along: the error
+    correction (``errorCorrection`` counts observations over every read, typing_mulit_allele.py:302-338)
+    has already filtered the lists, ``obs_pos`` / ``obs_neg`` (the homozygosity tallies) stay those of
+    the whole problem, and ``n_reads_total`` / ``k_total`` hold the whole problem's read count and
+    sum of K_r - the denominators of the read fractions and the constant of the log-likelihood.
+    Partial scores, tie counts and column sums of the shards are integers and add up exactly."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    n = pack.n_reads
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    e0, e1 = int(pack.ent_off[lo]), int(pack.ent_off[hi])
+    k_eff = np.where(pack.k_obs == 0, 1, pack.k_obs).astype(np.int64)
+    part = GenePack(pack.gene, pack.allele_names, pack.variant_ids, pack.mem_words,
+                    (pack.ent_off[lo:hi + 1] - e0).astype(np.int32), pack.ent_word[e0:e1], pack.ent_pos[e0:e1],
+                    pack.ent_neg[e0:e1], pack.k_obs[lo:hi], pack.kept_reads[lo:hi],
+                    pack.csr.take(np.arange(lo, hi)) if pack.csr is not None else None,
+                    pack.var_pos, pack.var_val, pack.var_is_del, pack.obs_pos, pack.obs_neg)
+    part.n_reads_total = n if pack.n_reads_total is None else pack.n_reads_total
+    part.k_total = int(k_eff.sum()) if pack.k_total is None else pack.k_total
+    return part
 
 
 def site_tallies(pack: GenePack) -> list[dict[str, int]]:

@@ -180,7 +180,7 @@ class FakeBackend:
                 j = order[rank]
                 ids_out[s, rank, 0] = cand[j]
                 score_out[s, rank] = sc[j]
-                cnt_out[s, rank, 0] = M["n_reads"]
+                cnt_out[s, rank, 0] = M["n_reads_total"]
                 flat_out[s, rank] = j
             flags = 0
             if C > top_n and sc[order[top_n - 1]] == sc[order[top_n]]:
@@ -352,7 +352,7 @@ class FakeBackend:
             cn = cnt[int(X["cnt_off"]): int(X["cnt_off"]) + F * n * n].astype(np.int64).reshape(F, n, n)
             w = np.array([LCM[n] // q for q in range(1, n + 1)], dtype=np.int64)
             num = (cn * w[None, None, :]).sum(axis=2)
-            even = int(M["n_reads"]) * LCM[n] // n
+            even = int(M["n_reads_total"]) * LCM[n] // n
             uneven = np.abs(num - even).sum(axis=1)
             sprev = score_prev[s * top_n: (s + 1) * top_n]
             sc = np.array([self._min_sum(S, col, sprev, X, M, i // C, ids[f, -1], direct) for f, i in enumerate(flat)],
@@ -373,7 +373,7 @@ class FakeBackend:
                 flags |= 4
             best = 0
             for rank in range(k):
-                if np.all(2 * n * num[order[rank]] >= int(M["n_reads"]) * LCM[n]):
+                if np.all(2 * n * num[order[rank]] >= int(M["n_reads_total"]) * LCM[n]):
                     best = rank
                     break
             info[s]["n_kept"] = k

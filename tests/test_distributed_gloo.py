@@ -39,6 +39,19 @@ def _worker(rank, world, port, out):
         steps = [group.step(need_next=[i < 2])[0] for i in range(3)]
         cells = torch.tensor([group.score_cells], dtype=torch.int64)
         dist.all_reduce(cells)
+        # --- the same problem with its READS sharded: nothing replicated, two reductions per step ----
+        part = packing.shard_reads(pack, rank, world)
+        rbatch = engine.MatrixBatch([part], backend=be, reduce=reduce_scores)
+        rgroup = engine.SearchGroup(rbatch, [0], 40, reduce_scores=reduce_scores, read_shard=True)
+        rsteps = [rgroup.step(need_next=[i < 2])[0] for i in range(3)]
+        rcells = torch.tensor([rgroup.score_cells], dtype=torch.int64)
+        dist.all_reduce(rcells)
+        read_sharded = ([(s.ids.tolist(), s.score.tolist(), s.cnt.tolist(), s.tie_flags, s.n_unique) for s in rsteps],
+                        int(rcells.item()), rbatch.colsum(0).tolist(), part.n_reads)
+        # ... and through the batched typer (pipelined run, one read-back)
+        rcalls = cohort.BatchTyper([part], [3], top_n=40, backend=FakeBackend(), reduce_scores=reduce_scores,
+                                   read_shard=True).run()
+        read_sharded += ([(c.alleles, c.score, c.value, c.tie_flags, c.n_reads) for c in rcalls],)
         # --- cohort: samples dealt round-robin, results gathered on rank 0 -----------------
         samples = list(range(4))
         mine = cohort.shard(samples, rank, world)
@@ -54,9 +67,9 @@ def _worker(rank, world, port, out):
             merged = {}
             for part in gathered:
                 merged.update(part)
-            out.put(("ok", [(s.ids.tolist(), s.score.tolist()) for s in steps], int(cells.item()), merged))
+            out.put(("ok", [(s.ids.tolist(), s.score.tolist()) for s in steps], int(cells.item()), merged, read_sharded))
         else:
-            out.put(("ok", [(s.ids.tolist(), s.score.tolist()) for s in steps], -1, None))
+            out.put(("ok", [(s.ids.tolist(), s.score.tolist()) for s in steps], -1, None, read_sharded))
     except Exception as exc:  # pragma: no cover
         out.put(("error", repr(exc), 0, None))
     finally:
@@ -84,6 +97,20 @@ def test_column_sharding_and_cohort_sharding_world2():
     for res in results:
         for (ids, score), want in zip(res[1], ref):
             assert ids == want.allele_id.tolist() and score == want.score.tolist()
+    # read sharding: both ranks hold the complete, identical step results of the unsharded search
+    assert sorted(r[4][3] for r in results) == [pack.n_reads // 2, pack.n_reads - pack.n_reads // 2]
+    for res in results:
+        steps, cells, colsum, _, calls = res[4]
+        assert colsum == m.astype(np.int64).sum(axis=0).tolist()
+        for (ids, score, cnt, flags, n_unique), want in zip(steps, ref):
+            assert ids == want.allele_id.tolist() and score == want.score.tolist()
+            n = len(ids[0])
+            w = np.array([orc.lcm_upto(n) // q for q in range(1, n + 1)])
+            assert ((np.array(cnt).reshape(len(ids), n, n) * w[None, None, :]).sum(axis=2) == want.frac_num).all()
+            assert n_unique == want.n_unique
+        assert cells == sum(len(ref[i].score) * pack.n_alleles * pack.n_reads for i in range(2))
+        whole = cohort.BatchTyper([pack], [3], top_n=40, backend=FakeBackend()).run()
+        assert calls == [(c.alleles, c.score, c.value, c.tie_flags, c.n_reads) for c in whole]
     total_cells = max(r[2] for r in results)
     assert total_cells == sum(len(ref[i].score) * pack.n_alleles * pack.n_reads for i in range(2))
     merged = [r[3] for r in results if r[3] is not None][0]
