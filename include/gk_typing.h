@@ -41,8 +41,10 @@ extern "C" {
 
 /* Likelihood data of one gene problem.  Offsets are in elements of the pool type. */
 typedef struct GkMatrix {
-    int64_t mem_off;     /* uint32 pool: mem[w * n_alleles + a], bit b = allele a carries variant 32w+b */
-    int64_t entoff_off;  /* int32 pool : n_reads+1 entry offsets (absolute indices into the entry pools) */
+    int64_t mem_off;     /* uint32 pool: mem[w * (n_ablk * a_tile) + a], bit b = allele a carries variant 32w+b;
+                            rows are padded with zeros to whole allele blocks (aligned vector loads); a
+                            multiple of 4 */
+    int64_t entoff_off;  /* int32 pool : n_reads+1 entry offsets (absolute indices into the entry pool)  */
     int64_t L_off;       /* 4-byte pool, row-blocked: L[r_blk][a_blk][GK_RT][a_tile] with r_blk = r / GK_RT,
                             a_blk = a / a_tile, i.e. element
                             ((r_blk * n_ablk + a_blk) * GK_RT + r % GK_RT) * a_tile + a % a_tile
@@ -94,6 +96,10 @@ typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkSc
     shape = G' | log2(WK) << 4 | TA' << 8 | GK_SHAPE_WARP_SPLIT = WK * 8 G' kept sets (G' = 1..4, WK = 1, 2, 4)
     x 8 TA' alleles (TA' = 1..8) */
 #define GK_SHAPE_WARP_SPLIT (1 << 16)
+typedef struct GkExpandItem { int32_t matrix, r0, hdr_base, keep_off; uint32_t stream_off, ent_off; } GkExpandItem;
+    /* one tile of GK_LIK_READS reads of the wire format (gk_expand_reads): hdr_base = index of the matrix's
+       first read in the header pool, keep_off = offset of the gene's neg_keep words, stream_off = first
+       record of the tile (uint16 units), ent_off = index of its first entry in the entry pools */
 typedef struct GkCountItem { int32_t search, f0, r0, r1; } GkCountItem;              /* 8 alive sets from f0; r multiple of 16; */
 typedef struct GkPItem { int32_t search, k_blk, r0, r1; } GkPItem;                   /* one k-block x reads [r0, r1), multiples of 128 */
 
@@ -121,8 +127,30 @@ int gk_sizeof(const char* struct_name);     /* sizeof(GkMatrix) etc., for bindin
  *     (colsum must be zeroed by the caller). */
 int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, int n_items,
                   const uint32_t* mem_pool, const int32_t* entoff_pool,
-                  const int32_t* ent_word, const uint32_t* ent_pos, const uint32_t* ent_neg,
+                  const void* entries /* 16 bytes per observation entry: uint32 {word * row stride of mem in
+                     bytes, positive bits, negative bits, 1 << 8 (r & 3)} with r the read's index in its
+                     matrix; 16-byte aligned */,
                   float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, int half_mode, void* stream);
+
+/* Wire format of the read observations (host -> device) and its expansion; layout in csrc/gk_wire.cu.
+ *     What graphkir/hisat2.py's getPNFromVariantList (:716-800) decides per mate - the window of the
+ *     variant table whose variants are negatives unless positive or excluded - is shipped as
+ *     {lo, n, bitmap of positives, excluded offsets, outside positives} (14 B per read pair on cfg3)
+ *     instead of the 36 B of observation entries, and gk_expand_reads rebuilds the entry offsets and
+ *     the entries (the inputs of gk_likelihood) on the device.
+ * gk_wire_encode (host): off / idx = CSR lists in the order lpv, rpv, lnv, rnv; neg_keep = per word
+ *     of the gene the variants that occur as a negative in any read; ent_* = the canonical entries
+ *     (gk_pack_entries), copied into the raw records of reads the window form cannot express.
+ *     hdr gets one uint16 per read, stream the records.  With stream == NULL only the sizes are
+ *     computed.  Returns the stream length in uint16 units (or -1), *n_entries_out = entries the
+ *     expansion will emit. */
+int64_t gk_wire_encode(int64_t n_reads, const int64_t* const* off, const int32_t* const* idx,
+                       const uint32_t* neg_keep, const int32_t* ent_off, const int32_t* ent_word,
+                       const uint32_t* ent_pos, const uint32_t* ent_neg, uint16_t* hdr, uint16_t* stream,
+                       int64_t capacity, int64_t* n_entries_out);
+int gk_expand_reads(const GkMatrix* matrices, const GkExpandItem* items, int n_items, const uint16_t* hdr_pool,
+                    const uint16_t* stream_pool, const uint32_t* keep_pool, int32_t* entoff_pool,
+                    void* entries /* as gk_likelihood reads them */, void* stream);
 
 /* CN = 1 step: replaces log_probs[:, idx].sum(0) + argsort()[::-1][:top_n]
  *     (typing_mulit_allele.py:512-532).  One CTA per search.  Order: (colsum, position). */

@@ -36,6 +36,8 @@ SEARCH_DTYPE = np.dtype([
 
 LIK_ITEM_DTYPE = np.dtype([("matrix", "<i4"), ("a_blk", "<i4"), ("r0", "<i4"), ("flags", "<i4")])
 GK_LIK_COLSUM_ONLY = 1
+EXPAND_ITEM_DTYPE = np.dtype([("matrix", "<i4"), ("r0", "<i4"), ("hdr_base", "<i4"), ("keep_off", "<i4"),
+                              ("stream_off", "<u4"), ("ent_off", "<u4")])
 SCORE_ITEM_DTYPE = np.dtype([("search", "<i4"), ("k_blk", "<i4"), ("a_blk", "<i4"),
                              ("r0", "<i4"), ("r1", "<i4"), ("shape", "<i4")])
 COUNT_ITEM_DTYPE = np.dtype([("search", "<i4"), ("f0", "<i4"), ("r0", "<i4"), ("r1", "<i4")])
@@ -48,13 +50,14 @@ EM_PROBLEM_DTYPE = np.dtype([("row_off", "<i8"), ("wgt_off", "<i8"), ("len_off",
 
 _STRUCTS = {
     "GkMatrix": MATRIX_DTYPE, "GkSearch": SEARCH_DTYPE, "GkLikItem": LIK_ITEM_DTYPE,
+    "GkExpandItem": EXPAND_ITEM_DTYPE,
     "GkScoreItem": SCORE_ITEM_DTYPE, "GkCountItem": COUNT_ITEM_DTYPE, "GkPItem": P_ITEM_DTYPE,
     "GkStepInfo": STEP_INFO_DTYPE, "GkEmProblem": EM_PROBLEM_DTYPE,
 }
 
 # every symbol include/gk_typing.h declares
 EXPORTS = (
-    "gk_last_error", "gk_abi_version", "gk_sizeof", "gk_likelihood", "gk_first_step", "gk_score",
+    "gk_last_error", "gk_abi_version", "gk_sizeof", "gk_wire_encode", "gk_expand_reads", "gk_likelihood", "gk_first_step", "gk_score",
     "gk_select", "gk_rescore_count", "gk_rank", "gk_write_p", "gk_em_compat", "gk_em_squarem",
     "gk_group_reads", "gk_json_scan", "gk_json_fill", "gk_json_free", "gk_pack_entries", "gk_sam_walk",
     "gk_sam_extract", "gk_sam_extract_fill", "gk_sam_extract_free", "gk_sam_extract_json",

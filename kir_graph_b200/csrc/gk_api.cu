@@ -15,12 +15,13 @@ void gk_set_error(const char* fmt, ...) {
 
 extern "C" const char* gk_last_error(void) { return g_error; }
 
-extern "C" int gk_abi_version(void) { return 1; }
+extern "C" int gk_abi_version(void) { return 2; }
 
 extern "C" int gk_sizeof(const char* name) {
     if (!strcmp(name, "GkMatrix")) return (int)sizeof(GkMatrix);
     if (!strcmp(name, "GkSearch")) return (int)sizeof(GkSearch);
     if (!strcmp(name, "GkLikItem")) return (int)sizeof(GkLikItem);
+    if (!strcmp(name, "GkExpandItem")) return (int)sizeof(GkExpandItem);
     if (!strcmp(name, "GkScoreItem")) return (int)sizeof(GkScoreItem);
     if (!strcmp(name, "GkCountItem")) return (int)sizeof(GkCountItem);
     if (!strcmp(name, "GkPItem")) return (int)sizeof(GkPItem);

@@ -1,208 +1,236 @@
 // Kernel (a): likelihood build.
 //
 // Replaces AlleleTyping.reads2AlleleProb + np.log10 (reference:
-// graphkir/typing_mulit_allele.py:340-381, :263).  For a tile of 128 reads x up to four
-// allele blocks (128 alleles), every lane owns up to four alleles (lane, lane+32, ...) and
-// walks the read's packed observation entries:
-//     m[r, a] += popc((pos & ~mem[word, a]) | (neg & mem[word, a]))
-// The membership row mem[word, :] is word-major, so the 32 lanes of a warp read
-// 128 consecutive bytes (coalesced; a gene's table is <= 1 MB and stays in L1/L2).
-// Outputs, both written with full 128-byte lines:
-//     L  4 bytes per cell, row-blocked [r_blk][a_blk][32 reads][32] -> operand of the scoring kernel (TMA bulk tiles):
-//        float32(m) for the FP32 scoring path, the 16-bit pair (m, m) for the packed integer path
-//     LT uint8,   allele-major [a][r]         -> rescoring / P kernels stream along reads
-// and the per-allele column sums (CN=1 scores) via one 64-bit atomic per allele per CTA.
+// graphkir/typing_mulit_allele.py:340-381, :263):
+//     m[r, a] = sum over the read's observation entries e of popc(pos_e ^ ((pos_e ^ neg_e) & mem[word_e, a]))
+// (= popc((pos & ~mem) | (neg & mem)): a positive observation disagrees with an allele that lacks the
+// variant, a negative one with an allele that carries it).
 //
-// Bound: HBM writes, 5 B per cell (4 B L + 1 B LT); POPC issue is the secondary limit.
+// Work decomposition (round 2; the round-1 kernel walked one read at a time and spent ~120 warp
+// instructions per read and 32-allele group, 77 % issue-bound at 24 % of HBM):
+//   * a CTA takes 128 reads x up to 128 alleles, a warp 16 consecutive reads of them; nothing is staged
+//     in shared memory and the warps never wait for each other (the staged version of this kernel
+//     issued 40 % fewer instructions than round 1 and was no faster: 49 % issue-active, the time went
+//     into the staging phases and their barriers);
+//   * a lane owns VW = 1, 2 or 4 CONSECUTIVE alleles and loads their membership words with one 32-,
+//     64- or 128-bit load (the row stride of `mem` is padded to a multiple of 32 words for that);
+//   * the counts of four consecutive reads (a "quad") live in the four bytes of one register per allele
+//     (m <= 255) and the quad's entries are one flat run: an entry is the 16-byte record {byte offset of
+//     the membership row, pos, neg, 1 << 8 (r & 3)} (built by gk_expand_reads, or by the host for packs
+//     that arrive as entries), so per entry the warp issues one 128-bit load of the record, one
+//     vector load of the membership words and per allele LOP3 + POPC + IMAD - against 31 instructions
+//     per entry when the loop walked read by read over separate word / pos / neg arrays (ncu: IMAD
+//     24 %, LDG 12 %, POPC 6.5 % of the issue slots); the four packed registers of a
+//     warp's 16 reads are exactly the 16 bytes of the allele-major LT row, stored with one 128-bit store
+//     per allele (no shared-memory transpose); the column sums take one DP4A per quad;
+//   * genes with <= 16 (<= 8) alleles put two (four) quads side by side in a warp instead of idling
+//     half (three quarters) of the lanes.
+// Outputs, written with full lines:
+//     L  4 bytes per cell, row-blocked [r_blk][a_blk][32 reads][32] -> operand of the scoring kernel:
+//        the 16-bit pair (m, m) for the packed integer path, float32(m) for the FP32 path
+//     LT uint8, allele-major [a][r]                                  -> rescoring / P kernels
+//     colsum[a] (CN = 1 scores) via one 64-bit atomic per allele per CTA.
+//
+// Bound: HBM writes, 5 B per cell (4 B L + 1 B LT).
 #include "gk_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTilePitch = GK_LIK_READS + 16;  // bytes; keeps rows 16-byte aligned
-constexpr int kEntCap = 1024;                  // observation entries of the read tile staged in shared memory
+constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;   // 16 consecutive reads = 4 quads of four reads
 
-// Per-read work for a CTA whose allele span needs NG lane groups of 32 (uniform per CTA).
-// STAGED: every entry of the read tile sits in shared memory (one 128-bit load per entry); the
-// rare tile with more than kEntCap entries takes the variant that reads them from global memory.
-template <int NG, bool HALF, bool STAGED, bool WRITE>
-__device__ __forceinline__ void lik_reads(const GkMatrix& M, int r0, int a0, int a_span, int e_lo,
-                                          const uint32_t* __restrict__ mem, const int32_t* __restrict__ ent_word,
-                                          const uint32_t* __restrict__ ent_pos, const uint32_t* __restrict__ ent_neg,
-                                          const int* s_eoff, const int4* s_ent, float* __restrict__ L,
-                                          uint8_t* tile, unsigned int (&csum)[4]) {
-    constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;            // consecutive reads per warp
-    static_assert(GK_RT % kReadsPerWarp == 0 && kReadsPerWarp % 4 == 0, "a warp's reads lie in one row block of L");
-    const int lane = gk_lane();
-    const int warp = gk_warp();
-    bool live[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) live[g] = (lane + 32 * g < a_span) && (a0 + lane + 32 * g < M.n_alleles);
-    const uint32_t* mem_lane = mem + a0 + lane;
-    // The reads of a warp are consecutive rows of one row block of L, and group g of a lane is
-    // allele block a0 / 32 + g, column `lane`: one pointer that advances by a row per read, with
-    // the block as a constant offset.  Four byte counts at a time go to the LT tile as one word.
-    const int rl0 = warp * kReadsPerWarp;
-    float* slot = L + gk_blk_off(r0 + rl0, a0 >> 5, M.n_ablk, 32) + lane;
-#pragma unroll 1
-    for (int q = 0; q < kReadsPerWarp; q += 4) {
-        uint32_t word[NG];                                          // counts of reads q .. q + 3 as bytes
-#pragma unroll
-        for (int g = 0; g < NG; ++g) word[g] = 0u;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j, slot += 32) {
-            const int rl = rl0 + q + j;
-            const int r = r0 + rl;
-            unsigned int cnt[NG];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) cnt[g] = 0u;
-            if (r < M.n_reads) {
-                const int e0 = s_eoff[rl] - e_lo;
-                const int e1 = s_eoff[rl + 1] - e_lo;
-                for (int e = e0; e < e1; ++e) {
-                    int w;
-                    uint32_t p, n;
-                    if constexpr (STAGED) {
-                        const int4 ent = s_ent[e];
-                        w = ent.x;
-                        p = (uint32_t)ent.y;
-                        n = (uint32_t)ent.z;
-                    } else {
-                        w = __ldg(ent_word + e_lo + e);
-                        p = __ldg(ent_pos + e_lo + e);
-                        n = __ldg(ent_neg + e_lo + e);
-                    }
-                    const uint32_t* row = mem_lane + (int64_t)w * M.n_alleles;
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        const uint32_t mw = live[g] ? __ldg(row + 32 * g) : 0u;
-                        cnt[g] += __popc((p & ~mw) | (n & mw));
-                    }
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {                          // lane + 32 g < a_span = 32 NG always
-                const unsigned int c = live[g] ? cnt[g] : 0u;
-                if constexpr (WRITE) {
-                    if constexpr (HALF) {
-                        reinterpret_cast<uint32_t*>(slot)[g * (GK_RT * 32)] = c * 0x00010001u;   // (m, m) as two 16-bit lanes
-                    } else {
-                        slot[g * (GK_RT * 32)] = (float)c;
-                    }
-                    word[g] |= c << (8 * j);
-                }
-                csum[g] += c;
-            }
-        }
-        if constexpr (WRITE) {
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-                *reinterpret_cast<uint32_t*>(tile + (lane + 32 * g) * kTilePitch + rl0 + q) = word[g];
-        }
+template <int VW>
+__device__ __forceinline__ void load_words(const unsigned char* p, uint32_t (&w)[VW]) {
+    if constexpr (VW == 1) {
+        w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    } else if constexpr (VW == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        w[0] = v.x; w[1] = v.y;
+    } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+// One warp: 16 consecutive reads x (LPQ lanes x VW alleles).  With LPQ < 32 the warp's 32 / LPQ lane
+// groups take different quads of the 16 reads.  Nothing is staged and no barrier is needed: an entry
+// is one 128-bit load from the same address for all lanes of a group (a broadcast sector), and the
+// warps of an SM hide each other's load latency.  The four reads of a quad are ONE flat run of
+// entries: entry.w = 1 << 8 (r & 3) routes the popcount into the read's byte of the packed counter.
+template <int LPQ, int VW, bool HALF, bool WRITE>
+__device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int n_a, const int32_t* __restrict__ eoff,
+                                         const unsigned char* __restrict__ mem_bytes,
+                                         const uint4* __restrict__ entries, float* __restrict__ L,
+                                         uint8_t* __restrict__ LT, unsigned int* s_col) {
+    constexpr int SUBS = 32 / LPQ;                    // lane groups side by side
+    constexpr int QPS = 4 / SUBS;                     // quads per lane group
+    const int lane = gk_lane();
+    const int sub = lane / LPQ;
+    const int al = lane % LPQ;
+    const int a_rel = al * VW;                        // first allele of this lane, relative to a0
+    bool live[VW];
+#pragma unroll
+    for (int v = 0; v < VW; ++v) live[v] = a_rel + v < n_a;
+    const bool lane_on = a_rel < n_a;                 // lanes beyond the gene's alleles only keep step
+    const unsigned char* mem_lane = mem_bytes + (size_t)(a0 + (lane_on ? a_rel : 0)) * 4;     // (and stay in bounds)
+    // keep the lane's base pointer in a register pair: otherwise the compiler rebuilds it from the
+    // uniform base and the lane offset for every entry (IMAD.WIDE + IADD3 + IADD3.X per load)
+    asm volatile("" : "+l"(mem_lane));
+
+    // entry offsets at the warp's quad boundaries: lane i holds eoff[rw0 + 4 i], clipped at the last read
+    const int rw0 = r0 + gk_warp() * kReadsPerWarp;
+    int my_off = 0;
+    if (lane <= 4) {
+        const int r = rw0 + 4 * lane;
+        my_off = __ldg(eoff + (r < M.n_reads ? r : M.n_reads));
+    }
+
+    uint32_t cnt[QPS][VW];                            // byte j of cnt[q][v] = count of read 4 quad + j
+    unsigned int csum[VW];
+#pragma unroll
+    for (int v = 0; v < VW; ++v) csum[v] = 0u;
+#pragma unroll
+    for (int q = 0; q < QPS; ++q) {
+        const int quad = sub * QPS + q;               // quad of the warp's 16 reads taken by this lane group
+#pragma unroll
+        for (int v = 0; v < VW; ++v) cnt[q][v] = 0u;
+        const int e0 = __shfl_sync(0xffffffffu, my_off, quad);
+        const int e1 = __shfl_sync(0xffffffffu, my_off, quad + 1);
+        const uint4* ent_ptr = entries + e0;
+#pragma unroll 2
+        for (int i = e1 - e0; i > 0; --i, ++ent_ptr) {
+            const uint4 ent = __ldg(ent_ptr);         // {row byte offset, pos, neg, 1 << 8 (r & 3)}
+            uint32_t mw[VW];
+            load_words<VW>(mem_lane + ent.x, mw);
+#pragma unroll
+            for (int v = 0; v < VW; ++v) cnt[q][v] += (uint32_t)__popc((ent.y & ~mw[v]) | (ent.z & mw[v])) * ent.w;
+        }
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            if (!live[v]) cnt[q][v] = 0u;             // pad columns of the last allele block stay zero
+            csum[v] = __dp4a(cnt[q][v], 0x01010101u, csum[v]);
+        }
+        if constexpr (WRITE) {
+            if (lane_on) {
+                // L: rows 4 quad .. 4 quad + 3 of the row block, this lane's VW consecutive columns
+                const int a = a0 + a_rel;
+                uint32_t* slot = reinterpret_cast<uint32_t*>(L) + gk_blk_off(rw0 + 4 * quad, a >> 5, M.n_ablk, 32) + (a & 31);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t out[VW];
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) {
+                        if constexpr (HALF) {
+                            out[v] = __byte_perm(cnt[q][v], 0u, 0x4040u | j | (j << 8));    // (m, m) as two 16-bit lanes
+                        } else {
+                            out[v] = __float_as_uint((float)((cnt[q][v] >> (8 * j)) & 0xffu));
+                        }
+                    }
+                    uint32_t* dst = slot + j * 32;
+                    if constexpr (VW == 1) {
+                        dst[0] = out[0];
+                    } else if constexpr (VW == 2) {
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(out[0], out[1]);
+                    } else {
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+                    }
+                }
+            }
+        }
+    }
+    if (lane_on) {
+        if constexpr (WRITE) {
+            // LT: the lane group's 4 QPS consecutive reads of each of the lane's alleles: one 16- / 8- /
+            // 4-byte store per allele (the 8 warps of the CTA complete the 128-byte line)
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                if (!live[v]) continue;
+                uint8_t* dst = LT + (int64_t)(a0 + a_rel + v) * M.r_pad + rw0 + 4 * QPS * sub;
+                if constexpr (QPS == 4) {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(cnt[0][v], cnt[1][v], cnt[2][v], cnt[3][v]);
+                } else if constexpr (QPS == 2) {
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(cnt[0][v], cnt[1][v]);
+                } else {
+                    *reinterpret_cast<uint32_t*>(dst) = cnt[0][v];
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VW; ++v)
+            if (live[v] && csum[v]) atomicAdd(&s_col[a_rel + v], csum[v]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 5)
 gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __restrict__ items,
                      const uint32_t* __restrict__ mem_pool, const int32_t* __restrict__ entoff_pool,
-                     const int32_t* __restrict__ ent_word, const uint32_t* __restrict__ ent_pos,
-                     const uint32_t* __restrict__ ent_neg, float* __restrict__ L_pool,
+                     const uint4* __restrict__ entries, float* __restrict__ L_pool,
                      uint8_t* __restrict__ LT_pool, unsigned long long* __restrict__ col_pool, int half_mode) {
-    __shared__ __align__(16) uint8_t tile[128 * kTilePitch];
-    __shared__ unsigned int colpart[kWarps][128];
-    __shared__ int s_eoff[GK_LIK_READS + 1];
-    __shared__ __align__(16) int4 s_ent[kEntCap];
+    __shared__ unsigned int s_col[128];
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
     const bool colsum_only = (item.flags & GK_LIK_COLSUM_ONLY) != 0;
-    const int a_tile = M.a_tile;           // 32
-    const int a0 = item.a_blk * a_tile;
+    const int a0 = item.a_blk * M.a_tile;  // a_tile == 32
     const int r0 = item.r0;
     int n_blk = M.n_ablk - item.a_blk;     // allele blocks covered by this CTA (<= 4)
     n_blk = n_blk > 4 ? 4 : n_blk;
-    const int a_span = n_blk * a_tile;     // <= 128
-    const int lane = gk_lane();
-    const int warp = gk_warp();
-
-    const uint32_t* mem = mem_pool + M.mem_off;
+    int n_a = M.n_alleles - a0;            // alleles of the gene inside the span
+    n_a = n_a > 32 * n_blk ? 32 * n_blk : n_a;
+    const unsigned char* mem_bytes = reinterpret_cast<const unsigned char*>(mem_pool + M.mem_off);
     const int32_t* eoff = entoff_pool + M.entoff_off;
-    // group g of a lane is column (lane + 32 g) of the span = block (a_blk + g) when a_tile == 32
     float* L = L_pool + M.L_off;
+    uint8_t* LT = LT_pool + M.LT_off;
 
-    // stage the tile's entry offsets and entries with coalesced loads (they are shared by all lanes)
-    for (int i = threadIdx.x; i <= GK_LIK_READS; i += kThreads) {
-        const int r = r0 + i;
-        s_eoff[i] = __ldg(eoff + (r < M.n_reads ? r : M.n_reads));
-    }
-    __syncthreads();
-    const int e_lo = s_eoff[0];
-    const int e_n = s_eoff[GK_LIK_READS] - e_lo;
-    const bool staged = e_n <= kEntCap;
-    if (staged) {
-        for (int i = threadIdx.x; i < e_n; i += kThreads)
-            s_ent[i] = make_int4(__ldg(ent_word + e_lo + i), (int)__ldg(ent_pos + e_lo + i),
-                                 (int)__ldg(ent_neg + e_lo + i), 0);
-    }
+    if (threadIdx.x < 128) s_col[threadIdx.x] = 0u;
     __syncthreads();
 
-    unsigned int csum[4] = {0u, 0u, 0u, 0u};
-#define GK_LIK_ARGS M, r0, a0, a_span, e_lo, mem, ent_word, ent_pos, ent_neg, s_eoff, s_ent, L, tile, csum
-#define GK_LIK_CASE(NG)                                                    \
-    if (colsum_only) {             /* no L / LT: the layout flag is moot */   \
-        if (staged) lik_reads<NG, false, true, false>(GK_LIK_ARGS);        \
-        else lik_reads<NG, false, false, false>(GK_LIK_ARGS);              \
-    } else if (!staged) {                                                  \
-        if (half_mode) lik_reads<NG, true, false, true>(GK_LIK_ARGS);      \
-        else lik_reads<NG, false, false, true>(GK_LIK_ARGS);               \
-    } else if (half_mode) {                                                \
-        lik_reads<NG, true, true, true>(GK_LIK_ARGS);                      \
-    } else {                                                               \
-        lik_reads<NG, false, true, true>(GK_LIK_ARGS);                     \
-    }
-    switch ((a_span + 31) / 32) {
-        case 1: GK_LIK_CASE(1); break;
-        case 2: GK_LIK_CASE(2); break;
-        case 3: GK_LIK_CASE(3); break;
-        default: GK_LIK_CASE(4); break;
+#define GK_LIK_ARGS M, r0, a0, n_a, eoff, mem_bytes, entries, L, LT, s_col
+#define GK_LIK_CASE(LPQ, VW)                                             \
+    if (colsum_only) lik_warp<LPQ, VW, false, false>(GK_LIK_ARGS);       \
+    else if (half_mode) lik_warp<LPQ, VW, true, true>(GK_LIK_ARGS);      \
+    else lik_warp<LPQ, VW, false, true>(GK_LIK_ARGS);
+    if (n_a <= 8) {
+        GK_LIK_CASE(8, 1)
+    } else if (n_a <= 16) {
+        GK_LIK_CASE(16, 1)
+    } else if (n_a <= 32) {
+        GK_LIK_CASE(32, 1)
+    } else if (n_a <= 64) {
+        GK_LIK_CASE(32, 2)
+    } else {
+        GK_LIK_CASE(32, 4)
     }
 #undef GK_LIK_CASE
 #undef GK_LIK_ARGS
-#pragma unroll
-    for (int g = 0; g < 4; ++g) colpart[warp][lane + 32 * g] = csum[g];
-    __syncthreads();
 
-    unsigned long long* col = col_pool + M.col_off;
-    for (int a = threadIdx.x; a < a_span; a += kThreads) {
-        unsigned int s = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += colpart[w][a];
-        if (a0 + a < M.n_alleles && s) atomicAdd(col + a0 + a, (unsigned long long)s);
-    }
-
-    if (colsum_only) return;
-    uint8_t* LT = LT_pool + M.LT_off;
-    for (int idx = threadIdx.x; idx < a_span * (GK_LIK_READS / 16); idx += kThreads) {
-        const int a = idx / (GK_LIK_READS / 16);
-        const int seg = idx % (GK_LIK_READS / 16);
-        if (a0 + a < M.n_alleles) {
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + a * kTilePitch + seg * 16);
-            *reinterpret_cast<uint4*>(LT + (int64_t)(a0 + a) * M.r_pad + r0 + seg * 16) = v;
+    if (!colsum_only && n_a < 32 * n_blk) {
+        // L columns of the span beyond n_a (pad of the last 32-block) belong to lanes that are off (or
+        // already hold zeros): they must read as zero for the scoring kernel
+        const int a_lo = a0 + n_a, width = 32 * n_blk - n_a;
+        for (int idx = threadIdx.x; idx < width * GK_LIK_READS; idx += kThreads) {
+            const int a = a_lo + idx % width;
+            const int rl = idx / width;
+            reinterpret_cast<uint32_t*>(L)[gk_blk_off(r0 + rl, a >> 5, M.n_ablk, 32) + (a & 31)] = 0u;
         }
     }
+    __syncthreads();
+    unsigned long long* col = col_pool + M.col_off;
+    if (threadIdx.x < n_a && s_col[threadIdx.x]) atomicAdd(col + a0 + threadIdx.x, (unsigned long long)s_col[threadIdx.x]);
 }
 
 }  // namespace
 
 extern "C" int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, int n_items,
-                             const uint32_t* mem_pool, const int32_t* entoff_pool,
-                             const int32_t* ent_word, const uint32_t* ent_pos, const uint32_t* ent_neg,
+                             const uint32_t* mem_pool, const int32_t* entoff_pool, const void* entries,
                              float* L_pool, uint8_t* LT_pool, unsigned long long* col_pool, int half_mode,
                              void* stream) {
     if (n_items <= 0) return 0;
+    GK_REQUIRE(((uintptr_t)entries & 15) == 0, "gk_likelihood: the entry pool must be 16-byte aligned");
     gk_likelihood_kernel<<<n_items, kThreads, 0, (cudaStream_t)stream>>>(
-        matrices, items, mem_pool, entoff_pool, ent_word, ent_pos, ent_neg, L_pool, LT_pool, col_pool, half_mode);
+        matrices, items, mem_pool, entoff_pool, reinterpret_cast<const uint4*>(entries), L_pool, LT_pool, col_pool,
+        half_mode);
     GK_CHECK_LAUNCH("gk_likelihood");
     return 0;
 }

@@ -28,8 +28,9 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _cabi
-from ._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK_ITEM_DTYPE, MATRIX_DTYPE,
-                    P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE)
+from ._cabi import (COUNT_ITEM_DTYPE, EXPAND_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK_ITEM_DTYPE,
+                    MATRIX_DTYPE, P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE)
+from . import packing as _packing
 from .packing import GenePack
 
 import os as _os
@@ -40,6 +41,8 @@ P_READ_CHUNK = int(_os.environ.get("GK_P_CHUNK", 2048))             # reads per 
 ALIVE_SLACK = 212           # alive sets beyond top_n the rescoring grids are sized for without a read-back
 MAX_TOP_N = 2048
 
+# reads travel host -> device in the wire format of csrc/gk_wire.cu (GK_WIRE=0: as 16-byte entries)
+WIRE_DEFAULT = _os.environ.get("GK_WIRE", "1") != "0"
 # packed 16-bit integer scoring path (False: FP32 sum of absolute differences); GK_PACKED=0/1 overrides
 PACKED_DEFAULT = _os.environ.get("GK_PACKED", "1") != "0"
 SCORE_SLOTS = int(_os.environ.get("GK_SCORE_SLOTS", 444))            # resident scoring CTAs: 148 SMs x 3
@@ -253,15 +256,25 @@ class CudaBackend:
 # ---------------------------------------------------------------------------
 class HostBatch:
     """Packed problems of a batch concatenated into host pools (the "packed host arrays"
-    that the end-to-end path copies to the device)."""
+    that the end-to-end path copies to the device).
 
-    def __init__(self, packs: list[GenePack]):
+    ``wire=True`` (default when every pack carries its per-read variant lists): the reads travel in
+    the wire format of csrc/gk_wire.cu - per mate the window of the variant table, the positives as a
+    bitmap, excluded variants - 14 B per read pair on the cfg3 workload, and ``gk_expand_reads``
+    rebuilds the observation entries on the device.  ``wire=False``: the 16-byte entries themselves
+    are built here and copied (what a caller that only has packed entries can do)."""
+
+    def __init__(self, packs: list[GenePack], wire: bool | None = None):
         self.packs = packs
         self._m_max = None
+        if wire is None:
+            wire = WIRE_DEFAULT and all(p.csr is not None for p in packs)
+        self.wire = bool(wire)
         n = len(packs)
         table = np.zeros(n, dtype=MATRIX_DTYPE)
         mem_off = entoff_off = ent_base = L_off = LT_off = col_off = 0
-        entoffs = []
+        wires = [_packing.wire_encode(p) for p in packs] if self.wire else None
+        ent_bases = []
         for i, p in enumerate(packs):
             if p.n_reads and int(p.k_obs.astype(np.int64).sum()) >= 2 ** 32 - 1:
                 raise ValueError("sum of observations per problem must stay below 2^32 (32-bit score atomics)")
@@ -271,10 +284,10 @@ class HostBatch:
             n_total = getattr(p, "n_reads_total", None)        # set on a read shard (packing.shard_reads)
             table[i] = (mem_off, entoff_off, L_off, LT_off, col_off, p.n_reads, p.n_alleles, p.n_words,
                         r_pad, a_tile, n_ablk, p.n_reads if n_total is None else n_total, 0)
-            entoffs.append(p.ent_off.astype(np.int64) + ent_base)
-            mem_off += p.mem_words.size
+            ent_bases.append(ent_base)
+            mem_off += p.n_words * n_ablk * a_tile
             entoff_off += p.n_reads + 1
-            ent_base += p.n_entries
+            ent_base += wires[i].n_entries if self.wire else p.n_entries
             L_off += n_ablk * r_pad * a_tile
             LT_off += max(p.n_alleles, 1) * r_pad
             col_off += max(p.n_alleles, 1)
@@ -282,11 +295,53 @@ class HostBatch:
             raise ValueError("entry pool exceeds 2^31 entries; split the batch")
         cat = lambda xs, dt: (np.concatenate(xs).astype(dt, copy=False) if xs else np.zeros(0, dt))
         self.table = table
-        self.mem = cat([p.mem_words.reshape(-1) for p in packs], np.uint32)
-        self.entoff = cat(entoffs, np.int32)
-        self.ent_word = cat([p.ent_word for p in packs], np.int32)
-        self.ent_pos = cat([p.ent_pos for p in packs], np.uint32)
-        self.ent_neg = cat([p.ent_neg for p in packs], np.uint32)
+        self.n_entries = int(ent_base)
+        self.n_offsets = int(entoff_off)
+        # rows of the membership table are padded to whole 32-allele blocks: a lane of the likelihood
+        # kernel loads the words of 1, 2 or 4 consecutive alleles with one aligned 32- / 64- / 128-bit load
+        self.mem = np.zeros(int(mem_off), dtype=np.uint32)
+        for i, p in enumerate(packs):
+            stride = int(table["n_ablk"][i]) * int(table["a_tile"][i])
+            view = self.mem[int(table["mem_off"][i]): int(table["mem_off"][i]) + p.n_words * stride]
+            view.reshape(p.n_words, stride)[:, : p.n_alleles] = p.mem_words
+        if self.wire:
+            self.hdr = cat([w.hdr for w in wires], np.uint16)
+            self.stream = cat([w.stream for w in wires], np.uint16)
+            self.keep = cat([w.neg_keep for w in wires], np.uint32)
+            if len(self.stream) >= 2 ** 32:
+                raise ValueError("wire stream exceeds 2^32 units; split the batch")
+            hdr_base = _excl_cumsum([p.n_reads for p in packs])
+            keep_off = _excl_cumsum([len(w.neg_keep) for w in wires])
+            stream_base = _excl_cumsum([len(w.stream) for w in wires])
+            tiles = np.array([len(w.tile_stream) - 1 if p.n_reads else 1 for p, w in zip(packs, wires)], dtype=np.int64)
+            items = np.zeros(int(tiles.sum()), dtype=EXPAND_ITEM_DTYPE)
+            mat = np.repeat(np.arange(n, dtype=np.int64), tiles)
+            local = np.arange(len(items), dtype=np.int64) - np.repeat(_excl_cumsum(tiles), tiles)
+            items["matrix"] = mat
+            items["r0"] = local * GK_LIK_READS
+            items["hdr_base"] = hdr_base[mat]
+            items["keep_off"] = keep_off[mat]
+            items["stream_off"] = stream_base[mat] + cat([w.tile_stream[:max(len(w.tile_stream) - 1, 1)] for w in wires], np.int64)
+            items["ent_off"] = np.asarray(ent_bases, dtype=np.int64)[mat] + cat(
+                [w.tile_entry[:max(len(w.tile_entry) - 1, 1)] for w in wires], np.int64)
+            self.xitems = items
+        else:
+            self.entoff = cat([p.ent_off.astype(np.int64) + b for p, b in zip(packs, ent_bases)], np.int32)
+            # 16-byte entries {word * row stride of mem in bytes, pos, neg, 1 << 8 (r & 3)} (include/gk_typing.h)
+            ent = np.zeros((self.n_entries, 4), dtype=np.uint32)
+            for i, p in enumerate(packs):
+                if not p.n_entries:
+                    continue
+                stride_bytes = int(table["n_ablk"][i]) * int(table["a_tile"][i]) * 4
+                if int(p.ent_word.max(initial=0)) * stride_bytes >= 2 ** 32:
+                    raise ValueError("membership table of one gene exceeds 4 GB")
+                row = np.repeat(np.arange(p.n_reads, dtype=np.int64), np.diff(p.ent_off.astype(np.int64)))
+                blk = ent[ent_bases[i]: ent_bases[i] + p.n_entries]
+                blk[:, 0] = p.ent_word.astype(np.int64) * stride_bytes
+                blk[:, 1] = p.ent_pos
+                blk[:, 2] = p.ent_neg
+                blk[:, 3] = np.uint32(1) << (8 * (row & 3)).astype(np.uint32)
+            self.ent = ent.reshape(-1)
         self.k_max = int(max((int(p.k_obs.max()) for p in packs if p.n_reads), default=0))
         # sum of K_r over the reads of the whole problem (a read shard carries the global sum)
         self.k_total = np.array([int(np.where(p.k_obs == 0, 1, p.k_obs).astype(np.int64).sum())
@@ -302,15 +357,21 @@ class HostBatch:
             self._m_max = min(max(m, 1), 255)
         return self._m_max
 
+    @property
+    def input_names(self) -> tuple[str, ...]:
+        """Host pools that are copied to the device for every pass (besides the matrix table)."""
+        return ("mem", "hdr", "stream", "keep", "xitems") if self.wire else ("mem", "entoff", "ent")
+
     def pin(self, backend) -> "HostBatch":
-        for name in ("mem", "entoff", "ent_word", "ent_pos", "ent_neg"):
-            setattr(self, name, backend.pin(getattr(self, name)))
+        for name in self.input_names:
+            arr = getattr(self, name)
+            raw = backend.pin(arr.view(np.uint8) if arr.dtype.fields is not None else arr)
+            setattr(self, name, raw.view(arr.dtype) if arr.dtype.fields is not None else raw)
         return self
 
     @property
     def nbytes(self) -> int:
-        return sum(getattr(self, n).nbytes for n in ("mem", "entoff", "ent_word", "ent_pos", "ent_neg")) \
-            + self.table.nbytes
+        return sum(getattr(self, n).nbytes for n in self.input_names) + self.table.nbytes
 
 
 class MatrixBatch:
@@ -337,10 +398,16 @@ class MatrixBatch:
         be = self.be
         self.d_table = be.upload(host.table)
         self.d_mem = be.upload(host.mem)
-        self.d_entoff = be.upload(host.entoff)
-        self.d_ent_word = be.upload(host.ent_word)
-        self.d_ent_pos = be.upload(host.ent_pos)
-        self.d_ent_neg = be.upload(host.ent_neg)
+        if host.wire:                      # reads in the wire format: entries are rebuilt on the device
+            self.d_hdr = be.upload(host.hdr)
+            self.d_stream = be.upload(host.stream)
+            self.d_keep = be.upload(host.keep)
+            self.d_xitems = be.upload(host.xitems)
+            self.d_entoff = be.empty(host.n_offsets, np.int32)
+            self.d_ent = be.empty(4 * host.n_entries, np.uint32)
+        else:
+            self.d_entoff = be.upload(host.entoff)
+            self.d_ent = be.upload(host.ent)
         self.d_L = be.empty(host.L_size, np.float32)
         self.d_LT = be.empty(host.LT_size, np.uint8)
         self.d_col = be.zeros(host.col_size, np.uint64)
@@ -353,14 +420,12 @@ class MatrixBatch:
         if run:
             self.run_likelihood()
 
-    INPUTS = (("d_table", "table"), ("d_mem", "mem"), ("d_entoff", "entoff"), ("d_ent_word", "ent_word"),
-              ("d_ent_pos", "ent_pos"), ("d_ent_neg", "ent_neg"))
-
     def reload(self) -> None:
         """Copy the host pools into the existing device buffers again (same batch layout): device
         addresses stay put, so a recorded CUDA graph and the cached launch plan remain valid."""
-        for dev, host in self.INPUTS:
-            self.be.copy_into(getattr(self, dev), getattr(self.host, host))
+        self.be.copy_into(self.d_table, self.host.table)
+        for name in self.host.input_names:
+            self.be.copy_into(getattr(self, "d_" + name), getattr(self.host, name))
         self._colsum_host = None
 
     def lik_items(self) -> np.ndarray:
@@ -393,9 +458,12 @@ class MatrixBatch:
             per = t["r_pad"].astype(np.int64) * (t["n_ablk"].astype(np.int64) * t["a_tile"] * 4 + t["n_alleles"])
             self.bytes_out = int(per.sum() if key is None else per[~np.asarray(colsum_only, bool)].sum())
         self.be.zero_(self.d_col)
+        if self.host.wire:
+            self.be.launch("gk_expand_reads", self.d_table, self.d_xitems, len(self.host.xitems), self.d_hdr,
+                           self.d_stream, self.d_keep, self.d_entoff, self.d_ent, work=float(self.host.n_entries))
         self.be.launch("gk_likelihood", self.d_table, self.d_lik_items, self.n_lik_items, self.d_mem,
-                       self.d_entoff, self.d_ent_word, self.d_ent_pos, self.d_ent_neg, self.d_L, self.d_LT,
-                       self.d_col, int(self.half), work=float(self.n_cells))
+                       self.d_entoff, self.d_ent, self.d_L, self.d_LT, self.d_col, int(self.half),
+                       work=float(self.n_cells))
         if self.reduce is not None:
             self.reduce(self.d_col)                  # read shards: column sums of the whole problem
         self._colsum_host = None

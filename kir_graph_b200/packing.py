@@ -36,6 +36,24 @@ MAX_OBS_PER_READ = 255  # m[r, a] is stored as one byte on the device
 
 
 @dataclass
+class WirePack:
+    """The reads of a problem in the wire format of csrc/gk_wire.cu (what ``gk_expand_reads`` turns back
+    into observation entries on the device): per mate the window of the variant table, the positives
+    inside it as a bitmap, excluded variants and outside positives."""
+
+    hdr: np.ndarray          # uint16 [R]   entries the expansion emits | record length << 8 (0 = raw record)
+    stream: np.ndarray       # uint16 [U]   records
+    neg_keep: np.ndarray     # uint32 [W]   variants that occur as a negative in any read of the gene
+    n_entries: int           # entries the expansion emits in total
+    tile_stream: np.ndarray  # int64 [ceil(R / 128) + 1]  first record unit of each 128-read tile
+    tile_entry: np.ndarray   # int64 [ceil(R / 128) + 1]  first entry of each tile
+
+    @property
+    def nbytes(self) -> int:
+        return self.hdr.nbytes + self.stream.nbytes + self.neg_keep.nbytes
+
+
+@dataclass
 class GenePack:
     """Everything the device needs for one (sample, gene) typing problem."""
 
@@ -58,6 +76,7 @@ class GenePack:
     # set on a read shard of a deep problem (shard_reads): the whole problem's read count / sum of K_r
     n_reads_total: int | None = None
     k_total: int | None = None
+    wire: "WirePack | None" = None         # compact host->device form of the reads (wire_encode), cached
 
     @property
     def n_alleles(self) -> int:
@@ -344,6 +363,65 @@ def pack_synthetic(gene: SyntheticGene, variant_correction: bool = True,
     pack.var_val = ["ACGT"[v % 4] for v in range(n_var)]
     pack.var_is_del = np.zeros(n_var, dtype=bool)
     return pack
+
+
+def wire_encode(pack: GenePack) -> WirePack:
+    """Wire form of the pack's reads (cached on the pack) through ``gk_wire_encode``: 14 B per read
+    pair on the cfg3 workload against 36 B of observation entries."""
+    if pack.wire is not None:
+        return pack.wire
+    import ctypes
+    from . import _cabi
+    lib = _cabi.load()
+    csr = pack.csr
+    if csr is None:
+        raise ValueError("the wire format is encoded from the per-read variant lists (pack.csr)")
+    n = pack.n_reads
+    offs = [np.ascontiguousarray(csr.offsets[name], dtype=np.int64) for name in LIST_NAMES]
+    idxs = [np.ascontiguousarray(csr.indices[name], dtype=np.int32) for name in LIST_NAMES]
+    n_words = pack.n_words
+    keep_bits = np.zeros(n_words * 32, dtype=bool)
+    # the negatives of the gene: from the lists themselves (a read shard carries the whole problem's
+    # obs_neg, which is a superset and works as well; holes are relative to the mask that is shipped)
+    seen = pack.obs_neg if pack.obs_neg is not None else (
+        np.bincount(csr.indices["lnv"], minlength=pack.n_variants) + np.bincount(csr.indices["rnv"], minlength=pack.n_variants))
+    keep_bits[: len(seen)] = np.asarray(seen) > 0
+    neg_keep = (keep_bits.reshape(n_words, 32).astype(np.uint32) << np.arange(32, dtype=np.uint32)[None, :]) \
+        .sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    ent_off = np.ascontiguousarray(pack.ent_off, dtype=np.int32)
+    ent_word = np.ascontiguousarray(pack.ent_word, dtype=np.int32)
+    ent_pos = np.ascontiguousarray(pack.ent_pos, dtype=np.uint32)
+    ent_neg = np.ascontiguousarray(pack.ent_neg, dtype=np.uint32)
+    fn = lib.gk_wire_encode
+    fn.restype = ctypes.c_int64
+    fn.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int64, ctypes.c_void_p]
+    off_p = (ctypes.c_void_p * 4)(*[o.ctypes.data for o in offs])
+    idx_p = (ctypes.c_void_p * 4)(*[i.ctypes.data for i in idxs])
+    n_ent = ctypes.c_int64(0)
+    common = (n, off_p, idx_p, neg_keep.ctypes.data, ent_off.ctypes.data, ent_word.ctypes.data,
+              ent_pos.ctypes.data, ent_neg.ctypes.data)
+    units = fn(*common, None, None, 0, ctypes.byref(n_ent))
+    if units < 0:
+        raise ValueError(lib.gk_last_error().decode().split(": ", 1)[-1])
+    hdr = np.zeros(n, dtype=np.uint16)
+    stream = np.zeros(max(int(units), 1), dtype=np.uint16)
+    units2 = fn(*common, hdr.ctypes.data, stream.ctypes.data, int(units), ctypes.byref(n_ent))
+    if units2 != units:
+        raise ValueError(lib.gk_last_error().decode().split(": ", 1)[-1])
+    stream = stream[: int(units)]
+    # per 128-read tile: where its records and its entries start
+    length = (hdr >> 8).astype(np.int64)
+    count = (hdr & 255).astype(np.int64)
+    length = np.where(length == 0, 5 * count, length)
+    n_tiles = -(-n // 128)
+    pad = n_tiles * 128 - n
+    tile_stream = np.concatenate([[0], np.cumsum(np.pad(length, (0, pad)).reshape(n_tiles, 128).sum(axis=1))]) \
+        if n_tiles else np.zeros(1, np.int64)
+    tile_entry = np.concatenate([[0], np.cumsum(np.pad(count, (0, pad)).reshape(n_tiles, 128).sum(axis=1))]) \
+        if n_tiles else np.zeros(1, np.int64)
+    pack.wire = WirePack(hdr, stream, neg_keep, int(n_ent.value), tile_stream.astype(np.int64),
+                         tile_entry.astype(np.int64))
+    return pack.wire
 
 
 def shard_reads(pack: GenePack, rank: int, world: int) -> GenePack:

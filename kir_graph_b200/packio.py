@@ -57,6 +57,7 @@ def load_packs(path: str) -> tuple[dict[str, GenePack], dict]:
 
 
 SIDECAR_SUFFIX = ".gkpack.npz"
+PACK_FORMAT = 2        # bumped whenever the packed arrays or their meaning change: older sidecars are rebuilt
 
 
 def sidecar_path(filename_variant_json: str) -> str:
@@ -66,11 +67,15 @@ def sidecar_path(filename_variant_json: str) -> str:
 
 
 def sidecar_meta(filename_variant_json: str, variant_correction: bool = True, multiple: bool = False) -> dict:
-    """What a sidecar records about how and from what it was packed; ``json_size`` ties it to the
-    ``.json`` it sits next to (a rewritten ``.json`` of another size invalidates it)."""
+    """What a sidecar records about how and from what it was packed.  ``json_size`` and
+    ``json_mtime_ns`` tie it to the ``.json`` it sits next to: a ``.json`` that was re-extracted or
+    edited - even to the same byte size - invalidates it (a copy that does not preserve the
+    modification time merely rebuilds the sidecar); ``format`` is the packing-format version."""
     path = filename_variant_json if filename_variant_json.endswith(".json") else filename_variant_json + ".json"
+    st = os.stat(path) if os.path.exists(path) else None
     return {"variant_correction": bool(variant_correction), "multiple": bool(multiple),
-            "json_size": os.path.getsize(path) if os.path.exists(path) else -1}
+            "json_size": st.st_size if st else -1, "json_mtime_ns": st.st_mtime_ns if st else -1,
+            "format": PACK_FORMAT}
 
 
 def load_sample_packs(filename_variant_json: str, variant_correction: bool = True, multiple: bool = False

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from kir_graph_b200._cabi import (COUNT_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK_ITEM_DTYPE,
+from kir_graph_b200._cabi import (COUNT_ITEM_DTYPE, EXPAND_ITEM_DTYPE, GK_KB, GK_LIK_READS, GK_MAX_CN, GK_RT, LIK_ITEM_DTYPE,
                                   MATRIX_DTYPE, P_ITEM_DTYPE, SCORE_ITEM_DTYPE, SEARCH_DTYPE, STEP_INFO_DTYPE,
                                   EM_PROBLEM_DTYPE)
 
@@ -97,15 +97,84 @@ class FakeBackend:
         getattr(self, name)(*args)
 
     # --- kernel (a) --------------------------------------------------------------
-    def gk_likelihood(self, table, items, n_items, mem, entoff, ent_word, ent_pos, ent_neg, L, LT, col, half_mode):
+    def gk_expand_reads(self, table, items, n_items, hdr, stream, keep, entoff, ent):
+        """Wire format -> entry offsets and 16-byte entries (csrc/gk_wire.cu), read by read."""
+        table = table.view(MATRIX_DTYPE)
+        items = items.view(EXPAND_ITEM_DTYPE)[:n_items]
+        hdr, stream, keep = hdr.view(np.uint16), stream.view(np.uint16), keep.view(np.uint32)
+        ent = ent.view(np.uint32).reshape(-1, 4)
+
+        def mate(rec):
+            lo, x = int(rec[0]), int(rec[1])
+            n, n_out, n_hole = x & 255, (x >> 8) & 15, x >> 12
+            nb = (n + 15) // 16
+            pos = [lo + i for i in range(n) if (int(rec[2 + i // 16]) >> (i % 16)) & 1]
+            holes = [lo + ((int(rec[2 + nb + h // 2]) >> (8 * (h % 2))) & 255) for h in range(n_hole)]
+            outs = [int(v) for v in rec[2 + nb + (n_hole + 1) // 2: 2 + nb + (n_hole + 1) // 2 + n_out]]
+            words = {}
+            for v in range(lo, lo + n):
+                w, bit = v >> 5, 1 << (v & 31)
+                p, ng = words.setdefault(w, [0, 0])
+                if v in pos:
+                    words[w][0] |= bit
+                elif v not in holes and (int(keep_g[w]) >> (v & 31)) & 1:
+                    words[w][1] |= bit
+            return words, outs, 2 + nb + (n_hole + 1) // 2 + n_out
+
+        for it in items:
+            M = table[it["matrix"]]
+            R, stride_bytes = int(M["n_reads"]), int(M["n_ablk"]) * int(M["a_tile"]) * 4
+            keep_g = keep[int(it["keep_off"]):]
+            at, rec_at = int(it["ent_off"]), int(it["stream_off"])
+            eo = entoff[int(M["entoff_off"]):]
+            if R == 0 and int(it["r0"]) == 0:
+                eo[0] = at
+            for r in range(int(it["r0"]), min(int(it["r0"]) + GK_LIK_READS, R)):
+                h = int(hdr[int(it["hdr_base"]) + r])
+                n_ent, length = h & 255, h >> 8
+                eo[r] = at
+                out = []
+                if length == 0:                                     # raw record: the entries themselves
+                    length = 5 * n_ent
+                    rec = stream[rec_at: rec_at + length].astype(np.int64)
+                    for e in range(n_ent):
+                        out.append((int(rec[5 * e]), int(rec[5 * e + 1] | (rec[5 * e + 2] << 16)),
+                                    int(rec[5 * e + 3] | (rec[5 * e + 4] << 16))))
+                else:
+                    rec = stream[rec_at: rec_at + length]
+                    lw, louts, used = mate(rec)
+                    rw, routs, used2 = mate(rec[used:])
+                    assert used + used2 == length, "record length"
+                    for w in sorted(set(lw) | set(rw)):
+                        lp, ln = lw.get(w, (0, 0))
+                        rp, rn = rw.get(w, (0, 0))
+                        ov = (lp | ln) & (rp | rn)
+                        pp, nn = lp | (rp & ~ov), ln | (rn & ~ov)
+                        if pp | nn:
+                            out.append((w, pp, nn))
+                        if ov:
+                            out.append((w, rp & ov, rn & ov))
+                    out += [(v >> 5, 1 << (v & 31), 0) for v in louts + routs]
+                assert len(out) == n_ent, f"read {r}: {len(out)} entries emitted, header says {n_ent}"
+                for w, pp, nn in out:
+                    ent[at] = (w * stride_bytes, pp, nn, 1 << (8 * (r & 3)))
+                    at += 1
+                rec_at += length
+                if r == R - 1:
+                    eo[R] = at
+
+    def gk_likelihood(self, table, items, n_items, mem, entoff, ent, L, LT, col, half_mode):
         table = table.view(MATRIX_DTYPE)
         items = items.view(LIK_ITEM_DTYPE)[:n_items]
+        ent = ent.view(np.uint32).reshape(-1, 4)
+        ent_pos, ent_neg = ent[:, 1], ent[:, 2]
         for it in items:
             M = table[it["matrix"]]
             A, a_tile, rp, R = int(M["n_alleles"]), int(M["a_tile"]), int(M["r_pad"]), int(M["n_reads"])
             r0 = int(it["r0"])
             eo = entoff[M["entoff_off"]: M["entoff_off"] + R + 1]
-            memv = mem[M["mem_off"]: M["mem_off"] + int(M["n_words"]) * A].reshape(int(M["n_words"]), A)
+            stride = int(M["n_ablk"]) * a_tile                 # rows of mem are padded to whole allele blocks
+            memv = mem[M["mem_off"]: M["mem_off"] + int(M["n_words"]) * stride].reshape(int(M["n_words"]), stride)
             colsum_only = bool(int(it["flags"]) & 1)           # GK_LIK_COLSUM_ONLY: neither L nor LT is written
             for blk in range(int(it["a_blk"]), min(int(it["a_blk"]) + 4, int(M["n_ablk"]))):
                 a0 = blk * a_tile
@@ -116,7 +185,8 @@ class FakeBackend:
                     if r >= R:
                         continue
                     for e in range(eo[r], eo[r + 1]):
-                        mw = memv[ent_word[e], a0:a_hi]
+                        assert int(ent[e, 3]) == 1 << (8 * (r & 3)), "entry tag"
+                        mw = memv[int(ent[e, 0]) // (stride * 4), a0:a_hi]
                         x = (np.uint32(ent_pos[e]) & ~mw) | (np.uint32(ent_neg[e]) & mw)
                         tile[rl, : a_hi - a0] += popcount32(x)
                 for a in range(a0, a_hi):

@@ -22,7 +22,10 @@ def test_reference_arm_prints_one_contract_line():
     line = lines[0]
     assert line["impl"] == "reference" and line["unit"] == "GCells/s" and line["value"] > 0
     assert line["metric"] == "allele-typing read x candidate GCells/s" and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
+    from oracle import ref_loader
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert line["cpu_baseline"]["cores"] == 2
+    assert line["parity"]["genes"] == 34
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and line["gpu_launches"] == 0
@@ -36,3 +39,25 @@ def test_reference_arm_under_torchrun_rank0_only():
     assert proc.returncode == 0, proc.stderr[-2000:]
     lines = _lines(proc.stdout)
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2
+
+
+def test_reference_arm_worker_runs_the_imported_reference_without_the_cuda_library():
+    """A worker of the CPU arm types its sample with the byte-compiled reference from oracle/_ref and never
+    maps libgk_typing.so (the driver checks the arm's processes for exactly that)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        import pytest
+        pytest.skip("oracle/_ref not built (python oracle/make_ref.py where /root/reference exists)")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "cells, t_all, t_search, genes, ok = bench._cpu_type_sample((100, 0.01, 300, 'reference'))\n"
+        "import graphkir.typing_mulit_allele as tma\n"
+        "assert 'oracle/_ref' in tma.__file__.replace('\\\\', '/'), tma.__file__\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libgk_typing' not in maps and 'libcudart' not in maps, 'CUDA library mapped'\n"
+        "print(cells, genes, ok)\n" % ROOT)
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    cells, genes, ok = proc.stdout.split()
+    assert int(genes) == 17 and int(cells) > 0

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_header_symbols():
     assert names == set(_cabi.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.gk_abi_version() == 1
+    assert lib.gk_abi_version() == 2
     assert lib.gk_sizeof(b"nonsense") == -1
 
 

@@ -399,3 +399,24 @@ def test_caller_side_files_equal_the_references(cuda, tmp_path, monkeypatch):
     assert files == want["files"] and [open(f).read() for f in files] == want["tsv"]
     files = main.alleleTyping(names, cn_files, "exonfirst", _backend=cuda)
     assert [open(f).read() for f in files] == data["methods"]["exonfirst"]["tsv"]
+
+
+def test_wire_expansion_on_the_device_equals_the_numpy_statement(cuda):
+    """gk_expand_reads: entry offsets and 16-byte entries rebuilt on the GPU from the wire records, regular
+    reads and raw records, against tests/fake_backend.py; and the likelihood built from them against the
+    likelihood of host-built entries."""
+    from tests.test_wire_format import _counts_by_set_logic, _random_pack
+    rng = np.random.default_rng(12)
+    weird, member = _random_pack(rng, n_reads=900, n_var=700, n_allele=70, weird=True)
+    packs = _packs([(40, 2, 1500), (7, 1, 300), (150, 3, 700)], 55) + [weird]
+    fake = FakeBackend()
+    hb = engine.HostBatch(packs, wire=True)
+    assert int(((hb.hdr >> 8) == 0).sum()) > 0                       # raw records are exercised
+    bg, bf = engine.MatrixBatch(hb, backend=cuda), engine.MatrixBatch(hb, backend=fake)
+    assert np.array_equal(cuda.download(bg.d_entoff, np.int32)[: hb.n_offsets], bf.d_entoff[: hb.n_offsets])
+    assert np.array_equal(cuda.download(bg.d_ent, np.uint32)[: 4 * hb.n_entries], bf.d_ent[: 4 * hb.n_entries])
+    assert np.array_equal(cuda.download(bg.d_LT, np.uint8), bf.d_LT)
+    assert np.array_equal(bg.mismatch_counts(3), _counts_by_set_logic(weird, member))
+    legacy = engine.MatrixBatch(engine.HostBatch(packs, wire=False), backend=cuda)
+    for name in ("d_LT", "d_L", "d_col"):
+        assert np.array_equal(cuda.download(getattr(bg, name)), cuda.download(getattr(legacy, name))), name

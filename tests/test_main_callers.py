@@ -135,15 +135,23 @@ def test_sidecar_written_at_extraction_feeds_the_cohort_entry(tmp_path):
     for f in want_files:
         os.remove(f)
     sizes = [os.path.getsize(n + ".json") for n in names]
-    for n, size in zip(names, sizes):                       # blank the .json: only the sidecar can answer now
-        with open(n + ".json", "wb") as f:
+    stamps = [os.stat(n + ".json").st_mtime_ns for n in names]
+    for n, size, stamp in zip(names, sizes, stamps):        # blank the .json (size and time stamp kept): only
+        with open(n + ".json", "wb") as f:                  # the sidecar can answer now
             f.write(b" " * size)
+        os.utime(n + ".json", ns=(stamp, stamp))
     files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
     assert files == want_files and [open(f, "rb").read() for f in files] == want
+    # a .json rewritten to the same size at another time does not belong to the sidecar any more
+    os.utime(names[1] + ".json", ns=(stamps[1] + 10 ** 9, stamps[1] + 10 ** 9))
+    with pytest.raises(ValueError):                         # the blanked .json is what gets parsed now
+        packio.load_sample_packs(names[1] + ".json")
+    os.utime(names[1] + ".json", ns=(stamps[1], stamps[1]))
     # a .json of another size does not belong to the sidecar: the scanner is asked (and finds no reads)
     with open(names[0] + ".json", "wb") as f:
         f.write(b"{}")
     assert packio.load_sample_packs(names[0] + ".json") == {}
     side, meta = packio.load_packs(packio.sidecar_path(names[1] + ".json"))
-    assert meta == {"variant_correction": True, "multiple": False, "json_size": sizes[1]} and len(side) == 2
+    assert meta == {"variant_correction": True, "multiple": False, "json_size": sizes[1],
+                    "json_mtime_ns": stamps[1], "format": packio.PACK_FORMAT} and len(side) == 2
     assert list(packio.load_sample_packs(names[1] + ".json", variant_correction=True)) == list(side)
