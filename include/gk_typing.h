@@ -111,7 +111,10 @@ typedef struct GkStepInfo {
     int32_t cut;         /* M = max(top_n, n_unique / 5)                                                 */
     uint32_t bar;        /* score of the top_n-th unique candidate                                       */
     int32_t tie_flags;   /* bit0: tie group straddles the M cut, bit1: straddles the final top_n cut,
-                            bit2: rank 0 and rank 1 share score / column sums / evenness                 */
+                            bit2: rank 0 and rank 1 share the score, bit3: for a rank selectBest looks at,
+                            a member's fraction is below 1/(2n) counting only the reads it wins alone and
+                            reaches it counting its tied reads in full (the reference's float fractions
+                            fall anywhere in between, typing_mulit_allele.py:81-96, :575-580)            */
     int32_t best_rank;   /* first rank whose every member fraction >= 1/(2n), else 0
                             (TypingResult.selectBest, typing_mulit_allele.py:63-103), exact integers    */
     int32_t pad1;

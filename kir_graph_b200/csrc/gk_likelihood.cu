@@ -39,6 +39,14 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;   // 16 consecutive reads = 4 quads of four reads
+constexpr int kWarpEnt = 96;                           // entries of a warp's 16 reads staged in shared memory
+constexpr int kTilePitch = GK_LIK_READS + 16;          // bytes; keeps the rows of the LT tile 16-byte aligned
+
+struct LikShared {
+    uint4 ent[kWarps][kWarpEnt];                       // per warp: the entries of its 16 reads (warp-private)
+    uint8_t tile[128 * kTilePitch];                    // counts, allele-major, for the coalesced LT stores
+    unsigned int col[128];                             // column sums of the tile
+};
 
 template <int VW>
 __device__ __forceinline__ void load_words(const unsigned char* p, uint32_t (&w)[VW]) {
@@ -62,7 +70,7 @@ template <int LPQ, int VW, bool HALF, bool WRITE>
 __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int n_a, const int32_t* __restrict__ eoff,
                                          const unsigned char* __restrict__ mem_bytes,
                                          const uint4* __restrict__ entries, float* __restrict__ L,
-                                         uint8_t* __restrict__ LT, unsigned int* s_col) {
+                                         LikShared& sh) {
     constexpr int SUBS = 32 / LPQ;                    // lane groups side by side
     constexpr int QPS = 4 / SUBS;                     // quads per lane group
     const int lane = gk_lane();
@@ -85,6 +93,19 @@ __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int 
         const int r = rw0 + 4 * lane;
         my_off = __ldg(eoff + (r < M.n_reads ? r : M.n_reads));
     }
+    // The entries of the warp's 16 reads are one contiguous run: fetch them with coalesced 128-bit loads
+    // (all in flight at once: one memory round trip per warp instead of one per entry) into the warp's
+    // private staging area; the loop below then reads an entry as one broadcast shared-memory load.
+    const int e_first = __shfl_sync(0xffffffffu, my_off, 0);
+    const int n_ent = __shfl_sync(0xffffffffu, my_off, 4) - e_first;
+    const bool staged = n_ent <= kWarpEnt;
+    uint4* s_ent = sh.ent[gk_warp()];
+    if (staged) {
+#pragma unroll
+        for (int i = 0; i < kWarpEnt / 32; ++i)
+            if (lane + 32 * i < n_ent) s_ent[lane + 32 * i] = __ldg(entries + e_first + lane + 32 * i);
+        __syncwarp();
+    }
 
     uint32_t cnt[QPS][VW];                            // byte j of cnt[q][v] = count of read 4 quad + j
     unsigned int csum[VW];
@@ -97,14 +118,20 @@ __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int 
         for (int v = 0; v < VW; ++v) cnt[q][v] = 0u;
         const int e0 = __shfl_sync(0xffffffffu, my_off, quad);
         const int e1 = __shfl_sync(0xffffffffu, my_off, quad + 1);
-        const uint4* ent_ptr = entries + e0;
-#pragma unroll 2
-        for (int i = e1 - e0; i > 0; --i, ++ent_ptr) {
-            const uint4 ent = __ldg(ent_ptr);         // {row byte offset, pos, neg, 1 << 8 (r & 3)}
+        auto visit = [&](const uint4 ent) {           // {row byte offset, pos, neg, 1 << 8 (r & 3)}
             uint32_t mw[VW];
             load_words<VW>(mem_lane + ent.x, mw);
 #pragma unroll
             for (int v = 0; v < VW; ++v) cnt[q][v] += (uint32_t)__popc((ent.y & ~mw[v]) | (ent.z & mw[v])) * ent.w;
+        };
+        if (staged) {                                 // shared-memory loads (LDS), not generic ones
+            const uint4* ent_ptr = s_ent + (e0 - e_first);
+#pragma unroll 2
+            for (int i = e1 - e0; i > 0; --i, ++ent_ptr) visit(*ent_ptr);
+        } else {
+            const uint4* ent_ptr = entries + e0;
+#pragma unroll 1
+            for (int i = e1 - e0; i > 0; --i, ++ent_ptr) visit(__ldg(ent_ptr));
         }
 #pragma unroll
         for (int v = 0; v < VW; ++v) {
@@ -141,12 +168,11 @@ __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int 
     }
     if (lane_on) {
         if constexpr (WRITE) {
-            // LT: the lane group's 4 QPS consecutive reads of each of the lane's alleles: one 16- / 8- /
-            // 4-byte store per allele (the 8 warps of the CTA complete the 128-byte line)
+            // LT: the lane group's 4 QPS consecutive reads of each of the lane's alleles go to the CTA's
+            // allele-major byte tile; the CTA stores whole 128-byte rows afterwards
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
-                if (!live[v]) continue;
-                uint8_t* dst = LT + (int64_t)(a0 + a_rel + v) * M.r_pad + rw0 + 4 * QPS * sub;
+                uint8_t* dst = sh.tile + (a_rel + v) * kTilePitch + (rw0 - r0) + 4 * QPS * sub;
                 if constexpr (QPS == 4) {
                     *reinterpret_cast<uint4*>(dst) = make_uint4(cnt[0][v], cnt[1][v], cnt[2][v], cnt[3][v]);
                 } else if constexpr (QPS == 2) {
@@ -158,7 +184,7 @@ __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int 
         }
 #pragma unroll
         for (int v = 0; v < VW; ++v)
-            if (live[v] && csum[v]) atomicAdd(&s_col[a_rel + v], csum[v]);
+            if (live[v] && csum[v]) atomicAdd(&sh.col[a_rel + v], csum[v]);
     }
 }
 
@@ -167,7 +193,8 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
                      const uint32_t* __restrict__ mem_pool, const int32_t* __restrict__ entoff_pool,
                      const uint4* __restrict__ entries, float* __restrict__ L_pool,
                      uint8_t* __restrict__ LT_pool, unsigned long long* __restrict__ col_pool, int half_mode) {
-    __shared__ unsigned int s_col[128];
+    extern __shared__ __align__(16) unsigned char lik_smem[];
+    LikShared& sh = *reinterpret_cast<LikShared*>(lik_smem);
 
     const GkLikItem item = items[blockIdx.x];
     const GkMatrix M = matrices[item.matrix];
@@ -183,10 +210,10 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     float* L = L_pool + M.L_off;
     uint8_t* LT = LT_pool + M.LT_off;
 
-    if (threadIdx.x < 128) s_col[threadIdx.x] = 0u;
+    if (threadIdx.x < 128) sh.col[threadIdx.x] = 0u;
     __syncthreads();
 
-#define GK_LIK_ARGS M, r0, a0, n_a, eoff, mem_bytes, entries, L, LT, s_col
+#define GK_LIK_ARGS M, r0, a0, n_a, eoff, mem_bytes, entries, L, sh
 #define GK_LIK_CASE(LPQ, VW)                                             \
     if (colsum_only) lik_warp<LPQ, VW, false, false>(GK_LIK_ARGS);       \
     else if (half_mode) lik_warp<LPQ, VW, true, true>(GK_LIK_ARGS);      \
@@ -217,7 +244,14 @@ gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __r
     }
     __syncthreads();
     unsigned long long* col = col_pool + M.col_off;
-    if (threadIdx.x < n_a && s_col[threadIdx.x]) atomicAdd(col + a0 + threadIdx.x, (unsigned long long)s_col[threadIdx.x]);
+    if (threadIdx.x < n_a && sh.col[threadIdx.x]) atomicAdd(col + a0 + threadIdx.x, (unsigned long long)sh.col[threadIdx.x]);
+    if (colsum_only) return;
+    for (int idx = threadIdx.x; idx < n_a * (GK_LIK_READS / 16); idx += kThreads) {
+        const int a = idx / (GK_LIK_READS / 16);
+        const int seg = idx % (GK_LIK_READS / 16);
+        const uint4 v = *reinterpret_cast<const uint4*>(sh.tile + a * kTilePitch + seg * 16);
+        *reinterpret_cast<uint4*>(LT + (int64_t)(a0 + a) * M.r_pad + r0 + seg * 16) = v;
+    }
 }
 
 }  // namespace
@@ -228,7 +262,11 @@ extern "C" int gk_likelihood(const GkMatrix* matrices, const GkLikItem* items, i
                              void* stream) {
     if (n_items <= 0) return 0;
     GK_REQUIRE(((uintptr_t)entries & 15) == 0, "gk_likelihood: the entry pool must be 16-byte aligned");
-    gk_likelihood_kernel<<<n_items, kThreads, 0, (cudaStream_t)stream>>>(
+    cudaError_t err = cudaFuncSetAttribute(gk_likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(LikShared));
+    GK_REQUIRE(err == cudaSuccess, "gk_likelihood: cannot reserve %d bytes of shared memory: %s",
+               (int)sizeof(LikShared), cudaGetErrorString(err));
+    gk_likelihood_kernel<<<n_items, kThreads, sizeof(LikShared), (cudaStream_t)stream>>>(
         matrices, items, mem_pool, entoff_pool, reinterpret_cast<const uint4*>(entries), L_pool, LT_pool, col_pool,
         half_mode);
     GK_CHECK_LAUNCH("gk_likelihood");

@@ -54,6 +54,20 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def capacity_violation(n_alleles: int, cn: int, top_n: int) -> str | None:
+    """Why a problem of ``n_alleles`` alleles typed at copy number ``cn`` with ``top_n`` kept sets does not
+    fit the search kernels, or None.  (The per-read limit of 255 observations is checked when the reads
+    are packed, ``packing.CapacityError``.)  Callers check this per gene up front so that one oversized
+    gene is called ``fail`` with a warning instead of aborting a batch."""
+    if cn > GK_MAX_CN:
+        return f"copy number {cn} above {GK_MAX_CN} (GK_MAX_CN of the search kernels)"
+    if not 1 <= top_n <= MAX_TOP_N:
+        return f"top_n {top_n} outside 1..{MAX_TOP_N}"
+    if n_alleles >= 65535:
+        return f"{n_alleles} alleles exceed the 16-bit allele ids of the selection kernels"
+    return None
+
+
 # ---------------------------------------------------------------------------
 # backend: device memory + kernel launches (torch is plumbing only)
 # ---------------------------------------------------------------------------
@@ -101,7 +115,7 @@ class CudaBackend:
 
     # --- memory ---------------------------------------------------------------
     _NP2T = {"uint8": "uint8", "int32": "int32", "uint32": "int32", "float32": "float32",
-             "int64": "int64", "uint64": "int64", "float64": "float64", "uint16": "int16"}
+             "int64": "int64", "uint64": "int64", "float64": "float64", "uint16": "int16", "int16": "int16"}
 
     def _tdtype(self, dtype):
         return getattr(self.torch, self._NP2T[np.dtype(dtype).name])
@@ -630,7 +644,7 @@ class SearchGroup:
             raise ValueError("shard either the candidate columns or the reads, not both")
         self.collective_bytes = 0            # bytes handed to reduce_scores since construction
         if not 1 <= top_n <= MAX_TOP_N:
-            raise ValueError(f"top_n must be in 1..{MAX_TOP_N}")
+            raise _packing.CapacityError(f"top_n must be in 1..{MAX_TOP_N}")
         self.batch = batch
         self.be = batch.be
         self.top_n = int(top_n)
@@ -991,7 +1005,7 @@ class SearchGroup:
         be, bt = self.be, self.batch
         n = self.n + 1
         if n > GK_MAX_CN:
-            raise ValueError(f"copy number above {GK_MAX_CN} is not supported by the search kernels")
+            raise _packing.CapacityError(f"copy number above {GK_MAX_CN} is not supported by the search kernels")
         active_idx = np.flatnonzero(active)
         self._set_candidates(cands, active)
         self.d_tab = be.upload(self.tab)
@@ -1064,7 +1078,7 @@ class SearchGroup:
         self.reset()
         max_step = int(steps.max(initial=0))
         if max_step > GK_MAX_CN:
-            raise ValueError(f"copy number above {GK_MAX_CN} is not supported by the search kernels")
+            raise _packing.CapacityError(f"copy number above {GK_MAX_CN} is not supported by the search kernels")
         key = (steps.tobytes(), id(bt.host))
         if key != self._plan_key:
             self._plan_key, self._plan, self._plan_host = key, {}, bt.host     # (the reference pins the id)

@@ -152,14 +152,21 @@ def group_variants(variants: list[Variant]) -> dict[str, list[Variant]]:
 
 def packs_from_scan(sc: JsonScan, genes: list[str] | None = None, variant_correction: bool = True,
                     no_empty: bool = True, single_mapped_only: bool = True) -> dict[str, GenePack]:
+    """A gene whose reads exceed a capacity of the device path (``packing.CapacityError``) maps to the
+    exception instead of a pack: the drivers call it ``fail`` with a warning, the other genes of the
+    sample are typed."""
+    from .packing import CapacityError
     packs: dict[str, GenePack] = {}
     for gene, variants in group_variants(sc.variants).items():
         if genes is not None and gene not in genes:
             continue
         ids = list({str(v.id): None for v in variants})
         csr, _ = gene_csr(sc, gene, {vid: i for i, vid in enumerate(ids)}, single_mapped_only)
-        packs[gene] = pack_gene_csr(variants, csr, variant_correction=variant_correction, no_empty=no_empty,
-                                    gene=gene)
+        try:
+            packs[gene] = pack_gene_csr(variants, csr, variant_correction=variant_correction, no_empty=no_empty,
+                                        gene=gene)
+        except CapacityError as exc:
+            packs[gene] = exc
     return packs
 
 

@@ -16,7 +16,9 @@ from typing import Any
 
 import numpy as np
 
+from .engine import capacity_violation
 from .hisat2 import loadReadsAndVariantsData, removeMultipleMapped
+from .packing import CapacityError
 from .typing_em import hisat2TypingPerGene, preprocessHisatReads, printHisatTyping
 from .typing_mulit_allele import (AlleleTyping, AlleleTypingExonFirst, LazyAlleleProb, isHetrozygous)
 from .utils import logger
@@ -56,6 +58,7 @@ class Typing:
 
     def __init__(self) -> None:
         self._result: dict[str, Any] = {}
+        self.capacity_failures: dict[str, str] = {}      # gene -> which limit of the device path it exceeded
 
     def typingPerGene(self, gene: str, cn: int) -> tuple[list[str], int]:
         raise NotImplementedError
@@ -66,7 +69,14 @@ class Typing:
         for gene, cn in gene_cn.items():
             if not cn:
                 continue
-            called, n_reads = self.typingPerGene(gene, cn)
+            try:
+                called, n_reads = self.typingPerGene(gene, cn)
+            except CapacityError as exc:
+                # a capacity of the device path the reference does not have (255 observations per read
+                # pair, copy number 8, ...): this gene is reported as failed, the sample goes on
+                logger.warning(f"[Allele] {gene} (cn={cn}) not typed: {exc}")
+                self.capacity_failures[gene] = str(exc)
+                called, n_reads = [f"{gene.split('*')[0]}*"] * cn, 0
             alleles.extend(called)
             if n_reads < min_reads_num:
                 warning_genes.append(gene)
@@ -120,8 +130,14 @@ class TypingWithPosNegAllele(Typing):
     def typingPerGene(self, gene: str, cn: int) -> tuple[list[str], int]:
         logger.debug(f"[Allele] {gene=} {cn=}")
         force_homo = False if isHetrozygous(gene) else None
+        problem = capacity_violation(len({a for v in self._gene_variants.get(gene, []) for a in v.allele}), cn,
+                                     self._top_n)
+        if problem:
+            raise CapacityError(f"gene {gene}: {problem}")
         if self._packs is not None:
             pack = self._packs.get(gene)
+            if isinstance(pack, CapacityError):
+                raise pack
             if pack is None:                     # no variants, no reads: the reference's defaultdicts give []
                 from .packing import pack_gene
                 pack = pack_gene([], [], gene=gene)

@@ -98,7 +98,8 @@ def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: st
     if method != "full":
         raise NotImplementedError("cohortAlleleTyping covers the full-variant strategy; use alleleTyping")
     import functools
-    from . import cohort, packio
+    from . import cohort, engine, packio
+    from .packing import CapacityError
     mine = list(range(len(processed_bam)))[rank::world]
     jsons = [processed_bam[i] + ".json" for i in mine]
     # one sample's packed genes: the .gkpack.npz sidecar when it is fresh, else the .json through the scanner
@@ -118,8 +119,22 @@ def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: st
     for i, by_gene in zip(mine, packed):
         name, cn_file = processed_bam[i], cn_files[i]
         gene_cn = loadCN(cn_file)
-        # CN-file order, as Typing.typing; the flag says whether the gene goes to the device
-        plans[i] = [(g, int(c), g in by_gene) for g, c in gene_cn.items() if c]
+        # CN-file order, as Typing.typing; the flag says whether the gene goes to the device.  A gene that
+        # exceeds a capacity of the device path (255 observations in a read pair, copy number above 8,
+        # ...) is reported and called "fail"; it does not take the other genes and samples down with it.
+        plans[i] = []
+        for g, c in gene_cn.items():
+            if not c:
+                continue
+            known = g in by_gene
+            if known:
+                pack = by_gene[g]
+                problem = str(pack) if isinstance(pack, CapacityError) else \
+                    engine.capacity_violation(pack.n_alleles, int(c), top_n)
+                if problem:
+                    logger.warning(f"[Allele] {g} (cn={c}) of {name} not typed: {problem}")
+                    known = False
+            plans[i].append((g, int(c), known))
         for gene, cn, known in plans[i]:
             if known:
                 packs.append(by_gene[gene])

@@ -35,6 +35,13 @@ from .synthetic import LIST_NAMES, ReadCSR, SyntheticGene
 MAX_OBS_PER_READ = 255  # m[r, a] is stored as one byte on the device
 
 
+class CapacityError(ValueError):
+    """A gene problem exceeds a capacity of the device path that the reference does not have (more than
+    255 variant observations in one read pair, copy number above 8, ...).  Raised per gene: the drivers
+    (``kir_typing.Typing.typing``, ``main.cohortAlleleTyping``) catch it, log the sample / gene and the
+    limit, and call that gene ``fail`` instead of losing the whole sample or batch."""
+
+
 @dataclass
 class WirePack:
     """The reads of a problem in the wire format of csrc/gk_wire.cu (what ``gk_expand_reads`` turns back
@@ -273,8 +280,8 @@ def _finish(gene: str, allele_names: list[str], variant_ids: list[str], member: 
         csr = csr.take(kept)
     ent_off, ent_word, ent_pos, ent_neg, k_obs = pack_entries(csr)
     if len(k_obs) and int(k_obs.max()) > MAX_OBS_PER_READ:
-        raise ValueError(
-            f"a read pair carries {int(k_obs.max())} variant observations; the device "
+        raise CapacityError(
+            f"gene {gene}: a read pair carries {int(k_obs.max())} variant observations; the device "
             f"mismatch matrix is one byte per cell (limit {MAX_OBS_PER_READ})")
     pack = GenePack(gene, allele_names, variant_ids, pack_membership(member),
                     ent_off, ent_word, ent_pos, ent_neg, k_obs, kept, csr)

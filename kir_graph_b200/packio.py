@@ -25,6 +25,9 @@ _ARRAYS = ("mem_words", "ent_off", "ent_word", "ent_pos", "ent_neg", "k_obs", "k
 
 def save_packs(path: str, packs: dict[str, GenePack], meta: dict | None = None) -> None:
     """Write ``{gene: GenePack}`` to one compressed ``.npz``."""
+    if any(not isinstance(p, GenePack) for p in packs.values()):
+        raise ValueError("a gene exceeds a capacity of the device path (packing.CapacityError): no sidecar is "
+                         "written, the .json stays the source")
     out = {"__genes__": np.array(json.dumps(list(packs)))}
     out["__meta__"] = np.array(json.dumps(meta or {}))
     for g, p in packs.items():

@@ -39,7 +39,7 @@ C_HIT = float(np.log10(0.999))
 C_MISS = float(np.log10(0.001))
 
 
-TIE_FRACTION_NEAR_THRESHOLD = 8      # TypingResult.tie_flags bit3 (host side; bits 0-2: GkStepInfo.tie_flags)
+TIE_FRACTION_NEAR_THRESHOLD = 8      # tie_flags bit3 (set by gk_rank as well; see GkStepInfo.tie_flags)
 
 
 def _lcm_upto(n: int) -> int:

@@ -446,6 +446,14 @@ class FakeBackend:
                 if np.all(2 * n * num[order[rank]] >= int(M["n_reads_total"]) * LCM[n]):
                     best = rank
                     break
+            # bit3: selectBest's verdict on a rank it looks at hinges on how tied reads are counted
+            passing = [rank for rank in range(k) if np.all(2 * n * num[order[rank]] >= int(M["n_reads_total"]) * LCM[n])]
+            last = passing[0] + 1 if passing else k
+            reads = int(M["n_reads_total"])
+            for rank in range(last):
+                c = cn[order[rank]]
+                if np.any((2 * n * c[:, 0] < reads) & (2 * n * c.sum(axis=1) >= reads)):
+                    flags |= 8
             info[s]["n_kept"] = k
             info[s]["best_rank"] = best
             info[s]["tie_flags"] = flags

@@ -314,6 +314,10 @@ def test_fraction_near_the_select_best_threshold_is_reported():
     assert res.tie_flags & TIE_FRACTION_NEAR_THRESHOLD
     assert abs(res.fraction[0].min() - 0.25) < 0.01 and res.selectBest() == res.allele_name[1]
     assert any(r["tie_flags"] & TIE_FRACTION_NEAR_THRESHOLD for r in typ.tie_report)
+    # the batched path reads back only the called set: gk_rank reports the same bit in GkStepInfo
+    from kir_graph_b200 import cohort
+    call = cohort.BatchTyper([packing.pack_synthetic(gene)], [2], top_n=40, backend=FakeBackend()).run()[0]
+    assert call.tie_flags & TIE_FRACTION_NEAR_THRESHOLD and call.alleles == res.selectBest()
     # far from the threshold: not set
     gene = synthetic.make_gene([3, 4], "KIRY*BACKBONE", 8, 64, 2, 300)
     reads, variants = gene.to_objects()

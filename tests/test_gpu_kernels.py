@@ -242,7 +242,7 @@ def test_repeated_passes_replay_a_cuda_graph(cuda):
     for _ in range(4):
         assert key(typer.run()) == first
     assert getattr(typer, "graph_error", None) is None and typer._graph is not None
-    cuda.zero_(typer.batch.d_ent_pos)                    # wreck an input on the device ...
+    cuda.zero_(typer.batch.d_stream)                     # wreck an input on the device ...
     cuda.zero_(typer.batch.d_mem)
     assert key(typer.upload_and_run()) == first          # ... the re-upload restores it; same buffers,
     assert typer._graph is not None                      # so the recorded graph is still valid
