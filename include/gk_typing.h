@@ -110,7 +110,8 @@ typedef struct GkStepInfo {
     int32_t n_alive;     /* sets rescored                                                                */
     int32_t cut;         /* M = max(top_n, n_unique / 5)                                                 */
     uint32_t bar;        /* score of the top_n-th unique candidate                                       */
-    int32_t tie_flags;   /* bit0: tie group straddles the M cut, bit1: straddles the final top_n cut,
+    int32_t tie_flags;   /* bit0: the tie group of the top_n-th score straddles the M cut, bit1: a tie group
+                            straddles the final top_n cut,
                             bit2: rank 0 and rank 1 share the score, bit3: for a rank selectBest looks at,
                             a member's fraction is below 1/(2n) counting only the reads it wins alone and
                             reaches it counting its tied reads in full (the reference's float fractions
