@@ -417,6 +417,98 @@ def deep_leg(args, be, rank, world, timed, packed, sm_max, shard, steps=3, parit
     }
 
 
+# ---------------------------------------------------------------------------
+# cold / streaming cohort throughput: every pass types a DIFFERENT cohort
+# ---------------------------------------------------------------------------
+def cold_leg(args, be, rank, world, timed, group_size, parts, workers, n_sets=3):
+    """``e2e_cold``: each timed pass types a cohort the GPU has not seen - other samples, other read counts
+    per gene.  ``n_sets`` cohorts (other seeds than the warm benchmark's) are packed and their host pools
+    page-locked beforehand (host preparation is reported in ``host_prep``); inside the timed region every
+    pass constructs its ``CohortTyper`` from those pools - homozygosity decisions, work-item tables, device
+    buffers, every launch issued eagerly: no launch plan, CUDA graph or decision survives from another pass -
+    copies the inputs, types, and returns the calls on the host.  Two passes are in flight: the host builds
+    and enqueues pass i + 1 while the GPU runs pass i (what a streaming cohort does)."""
+    import torch
+    import torch.distributed as dist
+    from kir_graph_b200 import cohort, engine
+    sets = []
+    for k in range(n_sets):
+        seeds = list(range(5000 + 1000 * k, 5000 + 1000 * k + args.samples))[rank::world]
+        packs, cns, truth = build_cohort(seeds, args.scale, workers)
+        probe = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=parts, group_size=group_size)
+        probe.pin()
+        hosts = [p.host for p in probe.parts]
+        del probe
+        sets.append((packs, cns, truth, hosts))
+    state = {"i": 0, "pending": None}
+    results = []
+    # device buffers of a pass are slices of one of two arenas (two passes in flight), recycled as a whole
+    # when the pass two steps earlier has been read back; streams (and their staging arenas) are persistent
+    free_b, _ = torch.cuda.mem_get_info()
+    arena_bytes = int(min(0.4 * free_b, 48 * 2 ** 30))
+    arenas = [engine.DeviceArena(be, arena_bytes) for _ in range(2)]
+    stream_sets = [be.streams(parts, first=k * parts) for k in range(2)]
+
+    def step():
+        packs, cns, _, hosts = sets[state["i"] % n_sets]
+        slot = state["i"] % 2
+        arenas[slot].reset()
+        be.device_arena = arenas[slot]
+        try:
+            typer = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=parts,
+                                       group_size=group_size, own_stream=True, host_batches=hosts,
+                                       streams=stream_sets[slot])
+            token = typer.start_pass(upload=True)
+        finally:
+            be.device_arena = None
+        if state["pending"] is not None:
+            prev, prev_token, k = state["pending"]
+            results.append((k, prev.finish_pass(prev_token), prev.score_cells))
+        state["pending"] = (typer, token, state["i"] % n_sets)
+        state["i"] += 1
+
+    def finalize():
+        if state["pending"] is not None:
+            prev, prev_token, k = state["pending"]
+            results.append((k, prev.finish_pass(prev_token), prev.score_cells))
+            state["pending"] = None
+
+    for _ in range(2):                      # CUDA context, allocator pools and kernel modules are warm; no typer is
+        step()
+    finalize()
+    results.clear()
+    state["i"] = 0
+    h0 = be.h2d_bytes
+    l0 = be.launches
+    ms = timed(step, args.steps, finalize) / args.steps
+    h2d = (be.h2d_bytes - h0) / args.steps
+    launches = (be.launches - l0) / args.steps
+    ok = genes = 0
+    cells = 0.0
+    for k, calls, c in results:
+        truth = sets[k][2]
+        ok += sum(sorted(x.alleles) == t for x, t in zip(calls, truth))
+        genes += len(truth)
+        cells += c
+    agg = torch.tensor([cells / max(len(results), 1), h2d, ok, genes, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg)
+    cells_all, h2d_all, ok_all, genes_all, launches_all = [float(x) for x in agg.tolist()]
+    del sets
+    if rank != 0:
+        return None
+    return {"value": cells_all / (ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": ms,
+            "samples_per_s": args.samples / (ms * 1e-3), "h2d_bytes_per_step": h2d_all,
+            "gpu_launches_per_step": launches_all, "cohorts_rotated": n_sets, "passes_in_flight": 2,
+            "sub_batches": parts, "device_arena_gib": arena_bytes / 2 ** 30,
+            "device_arena_misses": sum(a.misses for a in arenas),
+            "parity": {"genes_matching_generator_truth": int(ok_all), "genes": int(genes_all)},
+            "timed_region": "per pass: CohortTyper constructed from page-locked packed pools of a cohort not seen "
+                            "before (homozygosity decisions, work-item tables, device buffers), host->device "
+                            "copies, every kernel launched eagerly, read-back, calls on the host; no plan, graph "
+                            "or buffer content reused"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,6 +526,8 @@ def main():
                     help="fraction of the reads of a cfg3 sample each CPU-arm process types per step")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cold", action="store_true", help="skip the e2e_cold measurement (a different cohort every pass)")
+    ap.add_argument("--no-host", action="store_true", help="skip the host_prep / api_e2e blocks (1-GPU run only)")
     ap.add_argument("--no-deep", action="store_true",
                     help="skip the nested cfg4 deep-sample measurement of the default 1-GPU cohort run")
     ap.add_argument("--deep-shard", default="reads", choices=["reads", "cols", "both"],
@@ -668,6 +762,21 @@ def main():
     d2h = (be.d2h_bytes - d0) / args.steps
     mem_e2e = torch.cuda.max_memory_allocated() / 2 ** 30
 
+    # ---- cold: a different cohort every pass ------------------------------------------------
+    cold = None
+    if args.workload == "cohort" and not args.no_cold:
+        e2e_replicas.clear()
+        e2e_typer_parts = len(e2e_typer.parts)
+        e2e_typer = typer = twin = None
+        gc.unfreeze()
+        gc.collect()
+        torch.cuda.empty_cache()
+        cold = cold_leg(args, be, rank, world, timed, group_size, min(2, e2e_typer_parts), workers)
+        gc.collect()
+        torch.cuda.empty_cache()
+    else:
+        e2e_typer_parts = len(e2e_typer.parts)
+
     # ---- aggregate over ranks --------------------------------------------------------------
     agg = torch.tensor([cells_per_step, lik_cells, launches, h2d, d2h, n_samples_local], dtype=torch.float64,
                        device="cuda")
@@ -709,7 +818,7 @@ def main():
             "vs_baseline": None, "dtype": "u16" if packed else "f32", "data": "synthetic",
             "config": {"workload": desc, "top_n": args.top_n, "l2": "inputs larger than L2 (no flush needed)",
                        "timed_region": "likelihood build + all CN steps + calls, packed inputs resident in HBM",
-                       "concurrent_sub_batches": n_parts, "e2e_sub_batches": len(e2e_typer.parts),
+                       "concurrent_sub_batches": n_parts, "e2e_sub_batches": e2e_typer_parts,
                        "passes_in_flight": depth,
                        "pipelining": ("step i+1 is enqueued on a second set of device buffers and streams before the "
                                       "host reads back step i (double-buffered passes; every step's copies, kernels, "
@@ -738,9 +847,12 @@ def main():
             "device_mem_gib": {"after_resident": mem_resident, "after_e2e": mem_e2e},
             "build_s": t_build,
         }
+        if cold is not None:
+            line["e2e_cold"] = cold
     if args.workload == "cohort" and not args.no_deep:
         # second shape of the same path: one very deep sample (cfg4) typed by all ranks together
-        del typer, e2e_typer, e2e_replicas, replicas, twin
+        typer = e2e_typer = twin = None
+        del e2e_replicas[:], replicas[:]
         gc.unfreeze()
         gc.collect()
         torch.cuda.empty_cache()
@@ -750,6 +862,10 @@ def main():
             if rank == 0:
                 line["deep" if i == 0 else "deep_" + mode] = block
     if rank == 0:
+        if world == 1 and not args.no_host:
+            from tools import host_numbers
+            line["host_prep"] = host_numbers.host_prep()
+            line["api_e2e"] = host_numbers.api_e2e(args.cpu_scale, backend=be)
         if world == 1 and not args.no_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
             arm = CpuArm(cores, args.cpu_scale, args.top_n)

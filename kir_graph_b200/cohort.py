@@ -55,65 +55,69 @@ def decide_homozygous(pack: GenePack, cn: int) -> bool:
     return _no_hetero_site(site_tallies(pack), cn)
 
 
+def _site_summary(p: GenePack):
+    """Per position of one problem, everything of isHomozygous (typing_mulit_allele.py:807-857) that does
+    not depend on the copy number: ``(second, candidate, broken)`` with ``second`` the share of the
+    runner-up allele value at the site and ``candidate`` whether the site is looked at (more than one
+    value, a positive one among them, depth >= 20, two values passing count > 3 and share > 0.1).  A
+    function of the packed observation counts alone, so it is computed once per pack and cached."""
+    cached = getattr(p, "_site_summary", None)
+    if cached is not None:
+        return cached
+    keep = ~p.var_is_del
+    _, site_id = np.unique(p.var_pos, return_inverse=True)
+    _, val_code = np.unique(np.array(p.var_val, dtype=object).astype(str), return_inverse=True)
+    site, key, pos, neg = site_id[keep], val_code[keep], p.obs_pos[keep], p.obs_neg[keep]
+    n_site = int(site_id.max()) + 1 if len(site_id) else 0
+    # one entry per (site, value, polarity) with a non-zero count; equal keys at a site add up
+    ent_site = np.concatenate([site, site])
+    ent_key = np.concatenate([key * 2, key * 2 + 1])
+    ent_cnt = np.concatenate([pos, neg])
+    nz = ent_cnt > 0
+    ent_site, ent_key, ent_cnt = ent_site[nz], ent_key[nz], ent_cnt[nz]
+    combo = ent_site * (int(ent_key.max(initial=0)) + 2) + ent_key
+    uniq, inv = np.unique(combo, return_inverse=True)
+    e_cnt = np.bincount(inv, weights=ent_cnt, minlength=len(uniq)).astype(np.int64)
+    first = np.zeros(len(uniq), dtype=np.int64)
+    first[inv] = np.arange(len(inv))
+    e_site = ent_site[first]
+    e_negative = (ent_key[first] % 2) == 1
+    n_keys = np.bincount(e_site, minlength=n_site)
+    any_pos = np.bincount(e_site, weights=(~e_negative).astype(np.float64), minlength=n_site) > 0
+    big = e_cnt > 3                                                  # drop low coverage (:844)
+    depth = np.bincount(e_site[big], weights=e_cnt[big], minlength=n_site).astype(np.int64)
+    share = e_cnt / np.maximum(depth[e_site], 1)
+    strong = big & (share > 0.1)                                     # (:850)
+    n_strong = np.bincount(e_site[strong], minlength=n_site)
+    order = np.lexsort((-e_cnt, e_site))
+    s_sorted, strong_sorted, share_sorted = e_site[order], strong[order], share[order]
+    s_strong, sh_strong = s_sorted[strong_sorted], share_sorted[strong_sorted]
+    start = np.searchsorted(s_strong, np.arange(n_site), side="left")
+    has2 = n_strong >= 2
+    second = np.zeros(n_site)                                        # runner-up share per site
+    second[has2] = sh_strong[start[has2] + 1]
+    considered = (n_keys > 1) & any_pos & (depth >= 20)
+    out = (second, considered & has2, bool(np.any(considered & (n_strong == 0))))
+    p._site_summary = out
+    return out
+
+
 class HomozygosityIndex:
     """isHomozygous (typing_mulit_allele.py:807-857) for a whole batch at once.
 
-    Static per-variant arrays are concatenated when the batch is created; ``decide`` is pure
-    array arithmetic over all variants of all problems (no per-read work: the per-variant
-    observation counts are part of the packed input)."""
+    The per-site summaries are a property of each pack (``_site_summary``, cached on it: the per-variant
+    observation counts are part of the packed input); a batch concatenates them and ``decide`` is pure
+    array arithmetic over all sites of all problems."""
 
     def __init__(self, packs: list[GenePack]):
-        site, key, pos, neg, owner = [], [], [], [], []
-        base = 0
-        for i, p in enumerate(packs):
-            keep = ~p.var_is_del
-            _, site_id = np.unique(p.var_pos, return_inverse=True)
-            _, val_code = np.unique(np.array(p.var_val, dtype=object).astype(str), return_inverse=True)
-            site.append(site_id[keep] + base)
-            key.append(val_code[keep])
-            pos.append(p.obs_pos[keep])
-            neg.append(p.obs_neg[keep])
-            n_site = int(site_id.max()) + 1 if len(site_id) else 0
-            owner.append(np.full(n_site, i, dtype=np.int64))
-            base += n_site
-        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)
-        site, key, pos, neg = cat(site), cat(key), cat(pos), cat(neg)
-        self.site_owner = cat(owner)
+        parts = [_site_summary(p) for p in packs]
+        cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+        self.second = cat([x[0] for x in parts], np.float64)
+        self.candidate = cat([x[1] for x in parts], bool)
+        self.broken = any(x[2] for x in parts)
+        self.site_owner = np.repeat(np.arange(len(packs), dtype=np.int64), [len(x[0]) for x in parts])
         self.n_pack = len(packs)
         self.forced_hetero = np.array([isHetrozygous(p.gene) for p in packs], dtype=bool)
-        # one entry per (site, value, polarity) with a non-zero count; equal keys at a site add up
-        ent_site = np.concatenate([site, site])
-        ent_key = np.concatenate([key * 2, key * 2 + 1])
-        ent_cnt = np.concatenate([pos, neg])
-        nz = ent_cnt > 0
-        ent_site, ent_key, ent_cnt = ent_site[nz], ent_key[nz], ent_cnt[nz]
-        combo = ent_site * (int(ent_key.max(initial=0)) + 2) + ent_key
-        uniq, inv = np.unique(combo, return_inverse=True)
-        e_cnt = np.bincount(inv, weights=ent_cnt, minlength=len(uniq)).astype(np.int64)
-        first = np.zeros(len(uniq), dtype=np.int64)
-        first[inv] = np.arange(len(inv))
-        e_site = ent_site[first]
-        e_negative = (ent_key[first] % 2) == 1
-
-        # per-site summary; everything except the final 1/(2 cn) comparison is independent of cn
-        n_site = len(self.site_owner)
-        n_keys = np.bincount(e_site, minlength=n_site)
-        any_pos = np.bincount(e_site, weights=(~e_negative).astype(np.float64), minlength=n_site) > 0
-        big = e_cnt > 3                                                  # drop low coverage (:844)
-        depth = np.bincount(e_site[big], weights=e_cnt[big], minlength=n_site).astype(np.int64)
-        share = e_cnt / np.maximum(depth[e_site], 1)
-        strong = big & (share > 0.1)                                     # (:850)
-        n_strong = np.bincount(e_site[strong], minlength=n_site)
-        order = np.lexsort((-e_cnt, e_site))
-        s_sorted, strong_sorted, share_sorted = e_site[order], strong[order], share[order]
-        s_strong, sh_strong = s_sorted[strong_sorted], share_sorted[strong_sorted]
-        start = np.searchsorted(s_strong, np.arange(n_site), side="left")
-        has2 = n_strong >= 2
-        self.second = np.zeros(n_site)                                   # runner-up share per site
-        self.second[has2] = sh_strong[start[has2] + 1]
-        considered = (n_keys > 1) & any_pos & (depth >= 20)
-        self.broken = bool(np.any(considered & (n_strong == 0)))
-        self.candidate = considered & has2
 
     def decide(self, cns: np.ndarray) -> np.ndarray:
         if self.broken:
@@ -357,7 +361,7 @@ class CohortTyper:
     def __init__(self, packs: list[GenePack], cns: list[int], top_n: int = 300, backend=None,
                  n_parts: int = 2, group_size: int = 1, col_shard: tuple[int, int] | None = None,
                  reduce_scores=None, own_stream: bool = False, host_batches: list | None = None,
-                 read_shard: bool = False):
+                 read_shard: bool = False, streams: list | None = None):
         """``group_size`` consecutive problems (e.g. the 17 genes of a sample) stay in one part.
         ``own_stream``: a stream of its own even for a single part (replicas of a ``PassPipeline``
         overlap on the device only if they do not share the current stream).  ``host_batches``: the
@@ -379,7 +383,9 @@ class CohortTyper:
                       for i, sl in enumerate(self.slices)]
         self.streams = None
         if (n_parts > 1 or own_stream) and not sharded and hasattr(self.be, "torch"):
-            self.streams = [self.be.torch.cuda.Stream(device=self.be.device) for _ in self.parts]
+            # ``streams``: persistent streams of the caller (``CudaBackend.streams``) for typers built per pass
+            self.streams = list(streams[: len(self.parts)]) if streams is not None else \
+                [self.be.torch.cuda.Stream(device=self.be.device) for _ in self.parts]
 
     @property
     def score_cells(self) -> int:

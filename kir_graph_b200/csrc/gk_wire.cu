@@ -308,6 +308,75 @@ __device__ void expand_pair(const uint16_t* rec, const uint32_t* __restrict__ ke
     for (int i = 0; i < r.n_out; ++i) sink.put(r.outs[i] >> 5, 1u << (r.outs[i] & 31), 0u);
 }
 
+// Fast path of expand_pair for the usual read pair: both windows of at most 32 variants, no outside
+// positives.  A mate then touches word w0 and at most w0 + 1, and its bits are two 64-bit shifts; the
+// pair's words are merged without loops.  Emits exactly the entries of expand_pair, in the same order.
+struct MateSmall {
+    int w0;                      // first word of the window (undefined when n == 0)
+    uint32_t p0, n0, p1, n1;     // positive / negative bits of words w0 and w0 + 1
+    int n, units;
+};
+
+__device__ __forceinline__ bool mate_is_small(const uint16_t* rec) {
+    const int x = rec[1];
+    return (x & 255) <= 32 && ((x >> 8) & 15) == 0;
+}
+
+__device__ __forceinline__ MateSmall open_small(const uint16_t* rec, const uint32_t* __restrict__ keep) {
+    MateSmall m;
+    const int lo = rec[0];
+    const int x = rec[1];
+    m.n = x & 255;
+    const int n_hole = x >> 12;
+    const int nb = (m.n + 15) >> 4;
+    m.units = 2 + nb + ((n_hole + 1) >> 1);
+    m.w0 = lo >> 5;
+    m.p0 = m.n0 = m.p1 = m.n1 = 0u;
+    if (m.n == 0) return m;
+    const int s = lo & 31;
+    const uint32_t bitmap = (uint32_t)rec[2] | (nb > 1 ? (uint32_t)rec[3] << 16 : 0u);
+    const unsigned long long win = (m.n == 32 ? 0xffffffffull : ((1ull << m.n) - 1ull)) << s;
+    const unsigned long long pos = ((unsigned long long)bitmap << s) & win;
+    unsigned long long hole = 0ull;
+    const uint16_t* holes = rec + 2 + nb;
+    for (int h = 0; h < n_hole; ++h) hole |= 1ull << (((holes[h >> 1] >> (8 * (h & 1))) & 255) + s);
+    const unsigned long long keep64 = (unsigned long long)__ldg(keep + m.w0) |
+                                      ((win >> 32) ? (unsigned long long)__ldg(keep + m.w0 + 1) << 32 : 0ull);
+    const unsigned long long neg = win & keep64 & ~pos & ~hole;
+    m.p0 = (uint32_t)pos;
+    m.n0 = (uint32_t)neg;
+    m.p1 = (uint32_t)(pos >> 32);
+    m.n1 = (uint32_t)(neg >> 32);
+    return m;
+}
+
+__device__ __forceinline__ void expand_pair_small(const uint16_t* rec, const uint32_t* __restrict__ keep,
+                                                  EntrySink& sink) {
+    const MateSmall l = open_small(rec, keep);
+    const MateSmall r = open_small(rec + l.units, keep);
+    // the words to visit, ascending: three consecutive ones when the windows are within a word of each
+    // other (or a mate is empty), else the two words of the lower mate followed by those of the upper
+    const bool l_on = l.n > 0, r_on = r.n > 0;
+    const int lw = l_on ? l.w0 : r.w0, rw = r_on ? r.w0 : l.w0;
+    const int a = lw < rw ? lw : rw, b = lw < rw ? rw : lw;
+    const bool close = b - a <= 1;
+    int words[4] = {a, a + 1, close ? a + 2 : b, close ? -1 : b + 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int w = words[k];
+        if (w < 0) continue;
+        uint32_t lp = 0u, ln = 0u, rp = 0u, rn = 0u;
+        if (l_on && w == l.w0) { lp = l.p0; ln = l.n0; }
+        if (l_on && w == l.w0 + 1) { lp = l.p1; ln = l.n1; }
+        if (r_on && w == r.w0) { rp = r.p0; rn = r.n0; }
+        if (r_on && w == r.w0 + 1) { rp = r.p1; rn = r.n1; }
+        const uint32_t ov = (lp | ln) & (rp | rn);
+        const uint32_t p = lp | (rp & ~ov), n = ln | (rn & ~ov);
+        if (p | n) sink.put(w, p, n);
+        if (ov) sink.put(w, rp & ov, rn & ov);
+    }
+}
+
 __global__ void __launch_bounds__(kExpandThreads)
 gk_expand_reads_kernel(const GkMatrix* __restrict__ matrices, const GkExpandItem* __restrict__ items,
                        const uint16_t* __restrict__ hdr_pool, const uint16_t* __restrict__ stream,
@@ -381,6 +450,14 @@ gk_expand_reads_kernel(const GkMatrix* __restrict__ matrices, const GkExpandItem
         return;
     }
     const uint32_t* keep = keep_pool + item.keep_off;
+    if (mate_is_small(rec)) {
+        const int x = rec[1];
+        const uint16_t* rec_r = rec + 2 + (((x & 255) + 15) >> 4) + (((x >> 12) + 1) >> 1);
+        if (mate_is_small(rec_r)) {
+            expand_pair_small(rec, keep, sink);
+            return;
+        }
+    }
     expand_pair(rec, keep, sink);
 }
 

@@ -4,9 +4,9 @@ TEST / BENCH INFRASTRUCTURE -- builds ``oracle/_ref``: the reference's own typin
 
 The reference (linnil1/KIR_graph) is pure Python, so "building" it means byte-compiling the nine modules
 of ``graphkir`` that the typing path imports, from the sources where they lie under ``/root/reference``,
-into ``oracle/_ref/graphkir/*.pyc`` (sourceless modules: no reference source text is copied into this
+into ``oracle/_ref/graphkir/*.gkref`` (byte code only: no reference source text is copied into this
 repository; ``oracle/_ref/`` is git-ignored and travels to the GPU box with the snapshot like the built
-``.so``).  ``oracle/ref_loader.py`` imports them there, with the three plotting / FASTA / MSA packages the
+``.so`` - the files do not carry the ``.pyc`` suffix because snapshot tools commonly drop ``*.pyc``).  ``oracle/ref_loader.py`` imports them there, with the three plotting / FASTA / MSA packages the
 reference imports at module top (plotly, Bio, pyhlamsa: none takes part in the typing arithmetic) stubbed.
 
 Used by: ``bench.py --impl reference`` and the ``cpu_baseline`` leg (the unmodified reference timed on the
@@ -23,6 +23,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref", "graphkir")
 # typing_mulit_allele / typing_em / kir_typing and what they import
+EXT = ".gkref"            # a .pyc by content (16-byte header + marshalled code object)
 MODULES = ("__init__", "typing_mulit_allele", "typing_em", "kir_typing", "hisat2", "msa2hisat", "utils",
            "external_tools", "pileup")
 
@@ -31,11 +32,11 @@ def build(src: str = "/root/reference", force: bool = False) -> str | None:
     """Returns the output directory, or None when the reference tree is absent (GPU box: prebuilt files)."""
     pkg = os.path.join(src, "graphkir")
     if not os.path.isdir(pkg):
-        return OUT if os.path.exists(os.path.join(OUT, "typing_mulit_allele.pyc")) else None
+        return OUT if os.path.exists(os.path.join(OUT, "typing_mulit_allele" + EXT)) else None
     os.makedirs(OUT, exist_ok=True)
     for name in MODULES:
         source = os.path.join(pkg, name + ".py")
-        target = os.path.join(OUT, name + ".pyc")
+        target = os.path.join(OUT, name + EXT)
         if force or not os.path.exists(target) or os.path.getmtime(target) < os.path.getmtime(source):
             py_compile.compile(source, cfile=target, dfile=f"graphkir/{name}.py", doraise=True,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -9,6 +9,9 @@ the MSA writers of msa2hisat.py).  Only ``tests/``, ``bench.py --impl reference`
 """
 from __future__ import annotations
 
+import importlib.abc
+import importlib.util
+import marshal
 import os
 import sys
 import types
@@ -18,8 +21,36 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 
+EXT = ".gkref"
+
+
 def available() -> bool:
-    return os.path.exists(os.path.join(REF_DIR, "graphkir", "typing_mulit_allele.pyc"))
+    return os.path.exists(os.path.join(REF_DIR, "graphkir", "typing_mulit_allele" + EXT))
+
+
+class _RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Serves the package ``graphkir`` from the byte-compiled modules under oracle/_ref/graphkir."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "graphkir" and not fullname.startswith("graphkir."):
+            return None
+        name = "__init__" if fullname == "graphkir" else fullname.split(".", 1)[1]
+        origin = os.path.join(REF_DIR, "graphkir", name + EXT)
+        if not os.path.exists(origin):
+            return None
+        return importlib.util.spec_from_loader(fullname, self, origin=origin, is_package=fullname == "graphkir")
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        with open(module.__spec__.origin, "rb") as f:
+            code = marshal.loads(f.read()[16:])           # skip the .pyc header (magic, flags, hash)
+        module.__file__ = module.__spec__.origin
+        exec(code, module.__dict__)
+
+
+_finder = _RefFinder()
 
 
 def _stubs() -> None:
@@ -42,8 +73,8 @@ def load():
     if not available():
         raise RuntimeError("oracle/_ref is not built: run `python oracle/make_ref.py` where /root/reference exists")
     _stubs()
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    if _finder not in sys.meta_path:
+        sys.meta_path.insert(0, _finder)
     import graphkir.typing_mulit_allele as tma
     import graphkir.typing_em as tem
     import graphkir.kir_typing as kt

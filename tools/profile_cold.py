@@ -1,0 +1,42 @@
+"""cProfile of cold cohort passes (bench.py's e2e_cold: a CohortTyper constructed per pass from page-locked
+pools, device buffers from an arena): where the host time of a pass that types a cohort for the first time
+goes.  Needs a GPU.
+
+    python tools/profile_cold.py [samples=96] [passes=6] [parts=2]
+"""
+import argparse
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import torch  # noqa: E402
+from kir_graph_b200 import engine  # noqa: E402
+
+n_samples = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+passes = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+parts = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+args = argparse.Namespace(samples=n_samples, scale=1.0, top_n=300, steps=passes)
+be = engine.CudaBackend(0)
+prof = cProfile.Profile()
+
+
+def timed(fn, steps, finalize=None):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prof.enable()
+    for _ in range(steps):
+        fn()
+    if finalize is not None:
+        finalize()
+    torch.cuda.synchronize()
+    prof.disable()
+    return 1e3 * (time.perf_counter() - t0)
+
+
+out = bench.cold_leg(args, be, 0, 1, timed, 17, parts, 16, n_sets=2)
+print({k: v for k, v in out.items() if k != "timed_region"})
+pstats.Stats(prof).sort_stats("cumulative").print_stats(40)
