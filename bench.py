@@ -297,12 +297,24 @@ def score_roofline(cells, ms, packed, sm_max_mhz):
     src = (f"148 SM x {{lanes}} lanes/clk x {sm_max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); not in "
            "MEASURED_PEAKS.json, which only holds HBM and bf16 tensor peaks")
     fp32 = {"achieved": 2.0 * cps / 1e12, "peak": fp32_peak, "frac": 2.0 * cps / 1e12 / fp32_peak}
+    measured = {}
+    try:                                         # the same instruction mix timed by tools/micro/mixpipe.cu on this pool
+        measured = json.load(open(os.path.join(ROOT, "profiles", "nontensor_peaks.json")))
+    except (OSError, ValueError):
+        pass
     if packed:
         peak = fp32_peak / 2.0                                                   # ALU pipe: 64 lanes/clk/SM
         ach = 0.75 * cps / 1e12
-        return {"kernel": "gk_score_packed_kernel", "bound": "alu_nontensor", "achieved": ach, "peak": peak,
-                "unit": "T ALU lane-ops/s (2 VIMNMX.U16x2 + 1 IADD3 per 4 cells)", "frac": ach / peak,
-                "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=64)}
+        out = {"kernel": "gk_score_packed_kernel", "bound": "alu_nontensor", "achieved": ach, "peak": peak,
+               "unit": "T ALU lane-ops/s (2 VIMNMX.U16x2 + 1 IADD3 per 4 cells)", "frac": ach / peak,
+               "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=64)}
+        if measured.get("u16x2_min_add_tcells_per_s"):
+            m_peak = float(measured["u16x2_min_add_tcells_per_s"])
+            out["measured_peak"] = {"achieved": cps / 1e12, "peak": m_peak, "unit": "TCells/s", "frac": cps / 1e12 / m_peak,
+                                    "source": "tools/micro/mixpipe.cu (same VIMNMX.U16x2 + IADD3 mix, operands from shared "
+                                              "memory, accumulators in registers) on a B200 of this pool: "
+                                              "profiles/r02_mixpipe.txt"}
+        return out
     return {"kernel": "gk_score_kernel", "bound": "fp32_nontensor", "achieved": fp32["achieved"], "peak": fp32_peak,
             "unit": "T FP32 ops/s (2 FADD per cell: d = p - l, acc += |d|)", "frac": fp32["frac"],
             "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=128)}
@@ -771,7 +783,7 @@ def main():
         gc.unfreeze()
         gc.collect()
         torch.cuda.empty_cache()
-        cold = cold_leg(args, be, rank, world, timed, group_size, min(2, e2e_typer_parts), workers)
+        cold = cold_leg(args, be, rank, world, timed, group_size, 1, workers)      # one sub-batch: least host work per pass
         gc.collect()
         torch.cuda.empty_cache()
     else:

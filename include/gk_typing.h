@@ -93,8 +93,9 @@ typedef struct GkScoreItem { int32_t search, k_blk, a_blk, r0, r1, shape; } GkSc
     FP32 path: shape = row mode | column mode << 8; modes: 0 = 128 wide, 1 = 64, 2 = 16, 3 = 32, 4 = 48
     (from k_blk / a_blk).  Packed path, full-width tile: rows 5..8 = 32, 64, 96, 128 kept sets, column mode 0
     (128 alleles).  Packed path, warp-split tile (small genes, ragged right edge):
-    shape = G' | log2(WK) << 4 | TA' << 8 | GK_SHAPE_WARP_SPLIT = WK * 8 G' kept sets (G' = 1..4, WK = 1, 2, 4)
-    x 8 TA' alleles (TA' = 1..8) */
+    shape = G' | log2(WK) << 4 | TA' << 8 | (row offset / 8) << 20 | GK_SHAPE_WARP_SPLIT = WK * 8 G' kept sets
+    (G' = 1..4, WK = 1, 2, 4) x 8 TA' alleles (TA' = 1..8), starting `row offset` (0, 8, .. 56) rows into
+    k-block k_blk; offset + rows <= 2 GK_KB */
 #define GK_SHAPE_WARP_SPLIT (1 << 16)
 typedef struct GkExpandItem { int32_t matrix, r0, hdr_base, keep_off; uint32_t stream_off, ent_off; } GkExpandItem;
     /* one tile of GK_LIK_READS reads of the wire format (gk_expand_reads): hdr_base = index of the matrix's

@@ -145,7 +145,7 @@ class BatchTyper:
         """``col_shard`` / ``read_shard`` + ``reduce_scores``: one very deep sample spread over several
         ranks, by candidate columns or by reads (see :class:`engine.SearchGroup`; with ``read_shard``
         the packs are this rank's ``packing.shard_reads`` parts)."""
-        self.be = backend if backend is not None else engine.CudaBackend()
+        self.be = backend if backend is not None else engine.default_backend()
         self.col_shard, self.reduce_scores, self.read_shard = col_shard, reduce_scores, bool(read_shard)
         self.packs = packs
         self.cns = np.asarray(cns, dtype=np.int64)
@@ -366,7 +366,7 @@ class CohortTyper:
         ``own_stream``: a stream of its own even for a single part (replicas of a ``PassPipeline``
         overlap on the device only if they do not share the current stream).  ``host_batches``: the
         packed host pools of another typer over the same problems and parts (shared, read only)."""
-        self.be = backend if backend is not None else engine.CudaBackend()
+        self.be = backend if backend is not None else engine.default_backend()
         sharded = read_shard or (col_shard is not None and col_shard[1] > 1)
         if sharded:
             n_parts = 1                          # one collective stream: keep the parts serial

@@ -382,6 +382,9 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
 // 2 G' rows x TA' columns (lane = 4 row pairs x 8 columns), and the 8 / WK warps that share
 // the rows split the 32 reads of every stage between them.  Granularity 8 in both dimensions,
 // same instruction mix as the full tile.  Partial sums meet in S through the atomics anyway.
+// The tile may start at any multiple of 8 rows inside its k-block (shape bits 20-22), so that a
+// ragged kept-set count is covered exactly (300 = 128 + 128 + 32 + 8 + ... instead of padding the
+// last tile to 32- or 64-row groups).
 template <int GP, int TAP>
 __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                              const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
@@ -392,14 +395,15 @@ __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMa
     constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(uint16_t);
     constexpr uint32_t kBytesLBlk = GK_RT * AT * sizeof(uint32_t);
     constexpr uint32_t kStageStride = 2 * kBytesPBlk + 2 * kBytesLBlk;
-    const int KW = ((8 * GP) << wk_log2) > GK_KB ? 2 : 1;            // k-blocks staged
+    const int row_off = ((item.shape >> 20) & 7) * 8;                // first row of the tile inside its k-block
+    const int KW = (row_off + ((8 * GP) << wk_log2)) > GK_KB ? 2 : 1;            // k-blocks staged
     const uint32_t stage_bytes = KW * kBytesPBlk + AW * kBytesLBlk;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int tk = lane >> 3;                                        // row pair inside a group of 8 rows
     const int ta = lane & 7;                                         // column inside a group of 8 columns
-    const int row0 = (warp & ((1 << wk_log2) - 1)) * (8 * GP);       // first row of this warp
+    const int row0 = row_off + (warp & ((1 << wk_log2) - 1)) * (8 * GP);       // first row of this warp
     const int reads_per_warp = 4 << wk_log2;                         // 32 reads / (8 >> wk_log2) warps
     const int rd0 = (warp >> wk_log2) * reads_per_warp;
 

@@ -308,6 +308,23 @@ class CudaBackend:
         self.launches += 1
 
 
+_default_backends: dict = {}
+
+
+def default_backend(device: int | None = None) -> CudaBackend:
+    """The process-wide backend of a device (the current one by default).  Every class that is not handed
+    a backend shares it - one page-locked staging arena and one set of read-back buffers per stream
+    instead of a new 16 MB pinned allocation per AlleleTyping / MatrixBatch / EM call."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _cabi.GkError("kir_graph_b200 needs a CUDA device (no CPU fallback)")
+    key = torch.cuda.current_device() if device is None else int(device)
+    be = _default_backends.get(key)
+    if be is None:
+        be = _default_backends[key] = CudaBackend(key)
+    return be
+
+
 # ---------------------------------------------------------------------------
 # matrices
 # ---------------------------------------------------------------------------
@@ -441,7 +458,7 @@ class MatrixBatch:
         ``reduce(tensor)``: the packs are read shards of problems whose other reads live on other
         ranks (``packing.shard_reads``); the callable sums a device array over the ranks in place and
         is applied to the column sums after the likelihood build (integer sums: order independent)."""
-        self.be = backend if backend is not None else CudaBackend()
+        self.be = backend if backend is not None else default_backend()
         self.reduce = reduce
         host = packs if isinstance(packs, HostBatch) else HostBatch(list(packs))
         self.host = host
@@ -838,6 +855,83 @@ class SearchGroup:
                 tiles.append((int(blocks[i]), MODE_S2)); i += 1
         return tiles
 
+    # --- packed scoring path: exact cover of ragged kept-set / allele counts ---------------------------
+    _W_SPANS = ((96, 3, 2), (64, 4, 1), (48, 3, 1), (32, 4, 0), (24, 3, 0), (16, 2, 0), (8, 1, 0))   # rows, G', log2 WK
+
+    @classmethod
+    def _row_pieces(cls, k: int, kind: str) -> list[tuple[int, int, int]]:
+        """Row tiles covering ``k`` kept sets as (first row, shape code without the column part, rows).
+        kind "F": under a full-width (128-allele) column tile - 128-row tiles, then the whole 32-row groups
+        of the remainder as one full-width tile; kind "H": what is left of that remainder (< 32 rows), as a
+        warp-split tile (used over the two 64-allele halves); kind "W": under a warp-split column tile -
+        128-row tiles, then the remainder cut greedily into the spans a warp-split tile offers.  Every piece
+        starts at a multiple of 8 rows; nothing is padded beyond 8 ceil(k / 8)."""
+        out = []
+        n_full, rem = divmod(k, 128)
+        if kind == "F":
+            out += [(128 * i, (4 + 4) | (MODE_F8 << 8), 128) for i in range(n_full)]
+            if rem // 32:
+                out.append((128 * n_full, (4 + rem // 32) | (MODE_F8 << 8), 32 * (rem // 32)))
+            return out
+        if kind == "H":
+            if rem % 32:
+                gp = -(-(rem % 32) // 8)
+                out.append((128 * n_full + 32 * (rem // 32), gp | SHAPE_WARP_SPLIT, 8 * gp))
+            return out
+        out += [(128 * i, 4 | (2 << 4) | SHAPE_WARP_SPLIT, 128) for i in range(n_full)]
+        at = 128 * n_full
+        rem = 8 * -(-rem // 8)
+        while rem > 0:
+            rows, gp, wk = next(sp for sp in cls._W_SPANS if sp[0] <= rem)
+            out.append((at, gp | (wk << 4) | SHAPE_WARP_SPLIT, rows))
+            at += rows
+            rem -= rows
+        return out
+
+    def _packed_tiles(self, live: np.ndarray, kept: np.ndarray):
+        """(search index into ``live``, k_blk, a_blk, shape, rows, columns) of every (row piece x column
+        tile) of the packed scoring path, vectorised over the searches."""
+        A = self.A[live]
+        a8 = -(-A // 8)
+        n128, rem8 = a8 // 16, a8 % 16
+        # column tiles: (search, first 32-column block, kind 0 = F / 1 = W / 2 = H, columns / 8)
+        cs, cb, ck, ct = [], [], [], []
+        j_all = np.arange(len(live), dtype=np.int64)
+        plain = np.array([int(s) not in self.restricted for s in live], dtype=bool)
+        jf = np.repeat(j_all[plain], n128[plain])                      # full 128-column blocks
+        bf = 4 * (np.arange(len(jf), dtype=np.int64) - np.repeat(_excl_cumsum(n128[plain]), n128[plain]))
+        cs += [jf, jf, jf]; cb += [bf, bf, bf + 2]
+        ck += [np.zeros(len(jf), np.int64), np.full(len(jf), 2), np.full(len(jf), 2)]
+        ct += [np.full(len(jf), 16), np.full(len(jf), 8), np.full(len(jf), 8)]
+        for extra, lo in ((rem8 > 0, 0), (rem8 > 8, 8)):               # one or two warp-split column tiles
+            sel = plain & extra
+            cs.append(j_all[sel]); cb.append(4 * n128[sel] + lo // 4)
+            ck.append(np.ones(int(sel.sum()), np.int64)); ct.append(np.minimum(rem8[sel] - lo, 8))
+        for j in j_all[~plain]:                                        # restricted candidates: explicit block runs
+            for a_blk, mode in self._restricted_a_tiles(int(live[j])):
+                kinds = [(0, 16, 0), (2, 8, 0), (2, 8, 2)] if mode == MODE_F8 else \
+                    [(1, 8 if mode == MODE_F4 else 4, 0)]
+                for kind, t8, shift in kinds:
+                    cs.append(np.array([j])); cb.append(np.array([a_blk + shift]))
+                    ck.append(np.array([kind])); ct.append(np.array([t8]))
+        cs, cb, ck, ct = (np.concatenate(x).astype(np.int64) for x in (cs, cb, ck, ct))
+        # row pieces per (kept count, kind), looked up from a small table
+        keys = kept[live][cs] * 3 + ck
+        uniq, inv = np.unique(keys, return_inverse=True)
+        table, base, count = [], [], []
+        for key in uniq:
+            pieces = self._row_pieces(int(key) // 3, "FWH"[int(key) % 3])
+            base.append(len(table)); count.append(len(pieces)); table += pieces
+        table = np.array(table, dtype=np.int64).reshape(-1, 3)
+        base, count = np.array(base, dtype=np.int64), np.array(count, dtype=np.int64)
+        per = count[inv]
+        col = np.repeat(np.arange(len(cs), dtype=np.int64), per)
+        piece = table[np.repeat(base[inv], per) + (np.arange(len(col), dtype=np.int64) - np.repeat(_excl_cumsum(per), per))]
+        start, code, rows = piece[:, 0], piece[:, 1], piece[:, 2]
+        split = (code & SHAPE_WARP_SPLIT) != 0
+        shape = np.where(split, code | (ct[col] << 8) | (((start % GK_KB) // 8) << 20), code)
+        return cs[col], start // GK_KB, cb[col], shape, rows, np.where(ck[col] == 0, 128, 8 * ct[col])
+
     def _score_items(self, active_idx: np.ndarray) -> np.ndarray:
         kept = self.kept.astype(np.int64)
         live = active_idx[(kept[active_idx] > 0) & (self.n_cand[active_idx] > 0)]
@@ -845,25 +939,27 @@ class SearchGroup:
         if not len(live):
             return np.zeros(0, dtype=SCORE_ITEM_DTYPE)
         half = self.batch.half
-        k16 = -(-kept[live] // 16)
-        k32 = -(-kept[live] // 32)
-        a16 = -(-self.A[live] // 16)
-        a8 = -(-self.A[live] // 8)
-        n_kt = -(-k32 // 4) if half else _tile_counts(k16)
-        # packed path: 128-column tiles, then one or two warp-split tiles of 8..64 columns
-        n_at = (a8 // 16 + (a8 % 16 > 0) + (a8 % 16 > 8)) if half else _tile_counts(a16)
         r16 = _round_up_arr(self.R[live], _cabi.GK_RT)
         custom = {}
-        for j, s in enumerate(live):
-            if int(s) in self.restricted:
-                custom[j] = self._restricted_a_tiles(int(s))
-                n_at[j] = len(custom[j])
+        if half:
+            # exact cover of the ragged kept-set and allele counts (granularity 8 x 8)
+            t_search, t_kblk, t_ablk, t_shape, t_rows, t_cols = self._packed_tiles(live, kept)
+            tiles = np.bincount(t_search, minlength=len(live)).astype(np.int64)
+        else:
+            k16 = -(-kept[live] // 16)
+            a16 = -(-self.A[live] // 16)
+            n_kt = _tile_counts(k16)
+            n_at = _tile_counts(a16)
+            for j, s in enumerate(live):
+                if int(s) in self.restricted:
+                    custom[j] = self._restricted_a_tiles(int(s))
+                    n_at[j] = len(custom[j])
+            tiles = n_kt * n_at
         # Reads per work item: a launch lasts (work per CTA slot) + (one item) at best, so large chunks
         # leave a tail when a slot holds only a few of them (one deep problem spread over 444 slots,
         # or a read shard of it), and small chunks pay the pipeline fill and the final atomics of an
         # item (about SCORE_ITEM_OVERHEAD reads' worth) more often.  Pick the candidate with the
         # smallest estimate of both.
-        tiles = n_kt * n_at
         best = None
         for cand_chunk in SCORE_CHUNK_CANDIDATES:
             if cand_chunk > SCORE_READ_CHUNK:
@@ -877,39 +973,27 @@ class SearchGroup:
         if _os.environ.get("GK_SCORE_CHUNK"):                       # sweeps (tools/sweep_params.sh)
             chunk = int(_os.environ["GK_SCORE_CHUNK"])
         n_ch = np.maximum(1, -(-r16 // chunk))
-        search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
-        items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
-        items["search"] = live[search]
         mode_span = np.array([128, 64, 16, 32, 48, 32, 64, 96, 128], dtype=np.int64)
         if half:
-            # columns: (first 32-column block, warp-split flag, columns / 8)
-            n128 = (a8 // 16)[search]
-            rem8 = (a8 % 16)[search]
-            a_blk = np.where(iat < n128, 4 * iat, 4 * n128 + 2 * (iat - n128))
-            a_w = iat >= n128
-            ta8 = np.where(iat == n128, np.minimum(rem8, 8), rem8 - 8)
-            for j, tiles in custom.items():           # restricted candidates: explicit block runs
-                sel = np.flatnonzero(search == j)
-                t = np.array(tiles, dtype=np.int64)
-                a_blk[sel] = t[iat[sel], 0]
-                a_w[sel] = t[iat[sel], 1] != MODE_F8
-                ta8[sel] = np.where(t[iat[sel], 1] == MODE_F4, 8, 4)
-            # rows: 128 per tile; the last tile of a search may be shorter
-            k_blk = 2 * ikt
-            rows = np.minimum(128, kept[live][search] - 128 * ikt)
-            g32 = -(-rows // 32)                                   # full-width tiles: 1..4 groups of 32 rows
-            rows8 = -(-rows // 8)                                  # warp-split tiles: WK warps x G' groups of 8 rows
-            wk_log2 = np.where(rows8 <= 4, 0, np.where(rows8 <= 8, 1, 2))
-            gp = -(-rows8 // (1 << wk_log2))
-            kspan = np.where(a_w, (8 * gp) << wk_log2, 32 * g32)
-            aspan = np.where(a_w, 8 * ta8, 128)
-            shape = np.where(a_w, gp | (wk_log2 << 4) | (ta8 << 8) | SHAPE_WARP_SPLIT, (4 + g32) | (MODE_F8 << 8))
+            per = n_ch[t_search]
+            tile = np.repeat(np.arange(len(t_search), dtype=np.int64), per)
+            ich = np.arange(len(tile), dtype=np.int64) - np.repeat(_excl_cumsum(per), per)
+            search, k_blk, a_blk, shape = t_search[tile], t_kblk[tile], t_ablk[tile], t_shape[tile]
+            kspan, aspan = t_rows[tile], t_cols[tile]
+            # column tile of an item (for column sharding): the 128-allele block, or the ragged tile after them
+            n128s = ((-(-self.A[live] // 8)) // 16)[search]
+            iat = np.where(a_blk < 4 * n128s, a_blk // 4, (1 << 20) | a_blk)
+            items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
+            items["search"] = live[search]
         else:
+            search, (ikt, iat, ich) = self._product_items([n_kt, n_at, n_ch])
+            items = np.zeros(len(search), dtype=SCORE_ITEM_DTYPE)
+            items["search"] = live[search]
             k_blk, k_mode = _tile_decode(k16[search], ikt, 2)
             a_blk, a_mode = _tile_decode(a16[search], iat, 4)
-            for j, tiles in custom.items():
+            for j, tiles_j in custom.items():
                 sel = np.flatnonzero(search == j)
-                t = np.array(tiles, dtype=np.int64)
+                t = np.array(tiles_j, dtype=np.int64)
                 a_blk[sel] = t[iat[sel], 0]
                 a_mode[sel] = t[iat[sel], 1]
             kspan, aspan = mode_span[k_mode], mode_span[a_mode]
@@ -927,8 +1011,8 @@ class SearchGroup:
                 sel = np.flatnonzero(search == j)
                 if not len(sel):
                     continue
-                tiles = np.unique(iat[sel])
-                width = {int(t): int(aspan[sel][iat[sel] == t][0]) for t in tiles}
+                tiles_j = np.unique(iat[sel])
+                width = {int(t): int(aspan[sel][iat[sel] == t].max()) for t in tiles_j}
                 load = [0] * world
                 assign = {}
                 for t in sorted(width, key=lambda t: (-width[t], t)):
@@ -937,7 +1021,7 @@ class SearchGroup:
                     load[r] += width[t]
                 owner[sel] = np.array([assign[int(t)] for t in iat[sel]])
             mine = owner == rank
-            k0 = k_blk * GK_KB
+            k0 = k_blk * GK_KB + (((shape >> 20) & 7) * 8 if half else 0)
             a0 = a_blk * 32
             rows_u = np.minimum(kspan, kept[live][search] - k0)
             cols_u = np.minimum(aspan, self.A[live][search] - a0)

@@ -128,7 +128,7 @@ def _membership_words(names: list[str], sets: list[tuple[str, ...]]) -> tuple[np
 
 def compatible_alleles(gene: GeneEmReads, backend=None) -> np.ndarray:
     """uint32 [R, ceil(A/32)]: per read pair the alleles of getMostFreqAllele(left + right)."""
-    be = backend if backend is not None else engine.CudaBackend()
+    be = backend if backend is not None else engine.default_backend()
     table, n_aw = _membership_words(gene.allele_names, gene.sets)
     if gene.n_reads == 0:
         return np.zeros((0, n_aw), dtype=np.uint32)
@@ -153,7 +153,7 @@ def _rows_to_names(rows: np.ndarray, names: list[str]) -> list[list[str]]:
 def em_from_rows(rows: np.ndarray, names: list[str], seq_len: dict[str, int] | None = None,
                  iter_max: int = 300, diff_threshold: float = 1e-4, backend=None) -> dict[str, float]:
     """Abundances of the alleles that occur in ``rows`` (compatibility bitsets, one per read)."""
-    be = backend if backend is not None else engine.CudaBackend()
+    be = backend if backend is not None else engine.default_backend()
     n_aw = rows.shape[1] if rows.ndim == 2 else 1
     present = np.zeros(n_aw, dtype=np.uint32)
     for w in range(n_aw):

@@ -39,6 +39,7 @@ C_HIT = float(np.log10(0.999))
 C_MISS = float(np.log10(0.001))
 
 
+INTRON_SEARCH_BUDGET_BYTES = 4 << 30     # device memory the tied exon candidates of exon-first may hold at once
 TIE_FRACTION_NEAR_THRESHOLD = 8      # tie_flags bit3 (set by gk_rank as well; see GkStepInfo.tie_flags)
 
 
@@ -615,16 +616,27 @@ class AlleleTypingExonFirst(AlleleTyping):
                 self.result.extend(steps)
                 out.append(steps[-1])
             return out
-        group = engine.SearchGroup(model._batch, [0] * n_search, model.top_n)
+        # Every search holds its own P (reads x kept sets) and score buffers, so the tied exon candidates are
+        # typed in chunks that fit a device-memory budget (the reference handles them one at a time, :774-779;
+        # exact integer ties can make them many)
+        r_pad = int(model._batch.table["r_pad"][0])
+        n_kblk = -(-model.top_n // engine.GK_KB)
+        per_search_bytes = r_pad * n_kblk * engine.GK_KB * 2 + n_kblk * engine.GK_KB * int(
+            model._batch.table["n_ablk"][0]) * 32 * 4 + model.top_n * max(len(model.id_to_allele), 1) * 8
+        chunk = int(max(1, min(n_search, INTRON_SEARCH_BUDGET_BYTES // max(per_search_bytes, 1))))
         per_search: list[list[TypingResult]] = [[] for _ in candidates]
-        for step in range(cn):
-            cands = [np.array([model.allele_to_id[a] for a in candidates[s][step]], dtype=np.int32)
-                     for s in range(n_search)]
-            outs = group.step(cands=cands, need_next=np.full(n_search, step + 1 < cn))
-            for s in range(n_search):
-                res = step_to_result(outs[s], model._batch.colsum(0), model._k_total, model._k_eff,
-                                     model.id_to_allele, lambda s=s, ids=outs[s].ids: group.materialize_p(s, ids))
-                per_search[s].append(res)
+        for lo in range(0, n_search, chunk):
+            hi = min(lo + chunk, n_search)
+            group = engine.SearchGroup(model._batch, [0] * (hi - lo), model.top_n)
+            for step in range(cn):
+                cands = [np.array([model.allele_to_id[a] for a in candidates[s][step]], dtype=np.int32)
+                         for s in range(lo, hi)]
+                outs = group.step(cands=cands, need_next=np.full(hi - lo, step + 1 < cn))
+                for s in range(lo, hi):
+                    res = step_to_result(outs[s - lo], model._batch.colsum(0), model._k_total, model._k_eff,
+                                         model.id_to_allele,
+                                         lambda g=group, j=s - lo, ids=outs[s - lo].ids: g.materialize_p(j, ids))
+                    per_search[s].append(res)
         finals = []
         for steps in per_search:
             self.result.extend(steps)

@@ -283,19 +283,22 @@ class FakeBackend:
                 gp, wk, ta8 = shape & 0xF, 1 << ((shape >> 4) & 0xF), (shape >> 8) & 0xFF
                 assert 1 <= gp <= 4 and wk in (1, 2, 4) and 1 <= ta8 <= 8
                 kspan, aspan = 8 * gp * wk, 8 * ta8
+                koff = ((shape >> 20) & 7) * 8
             else:
+                koff = 0
                 assert (shape & 0xFF >= 5) == bool(half_mode)
                 kspan = self.MODE_SPAN[shape & 0xFF]
                 aspan = self.MODE_SPAN[(shape >> 8) & 0xFF]
             assert tile == 32 and r0 % GK_RT == 0 and r1 % GK_RT == 0 and r1 <= rp and r1 > r0
-            kw, aw = -(-kspan // GK_KB), -(-aspan // tile)
+            kw, aw = -(-(koff + kspan) // GK_KB), -(-aspan // tile)
+            assert koff + kspan <= 2 * GK_KB
             assert int(it["a_blk"]) + aw <= int(M["n_ablk"])
             stride = int(X["s_stride"])
             assert int(it["k_blk"]) + kw <= int(X["n_kblk"])
             Pv = self._P_view(X, M, P)[r0 // GK_RT: r1 // GK_RT]
             Pt = np.concatenate([Pv[:, kb].reshape(r1 - r0, GK_KB)
                                  for kb in range(int(it["k_blk"]), int(it["k_blk"]) + kw)],
-                                axis=1)[:, :kspan].astype(np.float32)
+                                axis=1)[:, koff:koff + kspan].astype(np.float32)
             Lt = np.concatenate([self._L_view(M, L, half_mode)[ab, r0:r1, :]
                                  for ab in range(int(it["a_blk"]), int(it["a_blk"]) + aw)], axis=1)[:, :aspan]
             if half_mode:      # a 16-bit lane sums `flush_stages` stages of min(L, P) <= max L
@@ -306,7 +309,7 @@ class FakeBackend:
                 part = np.abs(Lt[:, None, :] - Pt[:, :, None]).sum(axis=0)      # [kspan, aspan]
             assert part.max(initial=0) < 2 ** 24
             for kl in range(kspan):
-                o = int(X["S_off"]) + (int(it["k_blk"]) * GK_KB + kl) * stride + int(it["a_blk"]) * tile
+                o = int(X["S_off"]) + (int(it["k_blk"]) * GK_KB + koff + kl) * stride + int(it["a_blk"]) * tile
                 S[o: o + aspan] += part[kl].astype(np.uint32)
 
     # --- kernel (c), part 1 ----------------------------------------------------------------

@@ -325,3 +325,22 @@ def test_fraction_near_the_select_best_threshold_is_reported():
     res = typ.typing(2)
     alone = res.frac_num is not None and typ.result[-1].fraction[0].min() > 0.3
     assert not (alone and res.tie_flags & TIE_FRACTION_NEAR_THRESHOLD and not res.fraction[0].min() < 0.35)
+
+
+def test_exon_first_candidates_typed_in_chunks_give_the_same_result(monkeypatch):
+    """The tied exon candidates of exon-first are typed in chunks bounded by a device-memory budget; one at a
+    time (budget of one search) or all together, the merged result is the same."""
+    import kir_graph_b200.typing_mulit_allele as tma
+    name = golden_names("exonfirst")[0]
+    case = load_golden(name)
+
+    def run():
+        reads, variants = objects_from_input(case["input"])
+        typ = AlleleTypingExonFirst(reads, variants, force_homo=False, top_n=case["top_n"],
+                                    candidate_set_threshold=0.0, _backend=FakeBackend())
+        res = typ.typing(case["cn"])
+        return res.allele_id.tolist(), res.value.tolist(), len(typ.result)
+
+    whole = run()
+    monkeypatch.setattr(tma, "INTRON_SEARCH_BUDGET_BYTES", 1)
+    assert run() == whole and whole[2] > case["cn"] + 1
