@@ -377,7 +377,7 @@ __device__ __forceinline__ void expand_pair_small(const uint16_t* rec, const uin
     }
 }
 
-__global__ void __launch_bounds__(kExpandThreads)
+__global__ void __launch_bounds__(kExpandThreads, 12)
 gk_expand_reads_kernel(const GkMatrix* __restrict__ matrices, const GkExpandItem* __restrict__ items,
                        const uint16_t* __restrict__ hdr_pool, const uint16_t* __restrict__ stream,
                        const uint32_t* __restrict__ keep_pool, int32_t* __restrict__ entoff_pool,
