@@ -856,7 +856,13 @@ class SearchGroup:
         return tiles
 
     # --- packed scoring path: exact cover of ragged kept-set / allele counts ---------------------------
-    _W_SPANS = ((96, 3, 2), (64, 4, 1), (48, 3, 1), (32, 4, 0), (24, 3, 0), (16, 2, 0), (8, 1, 0))   # rows, G', log2 WK
+    # Row groups (of 8 kept sets) a warp-split tile can cover -> (G', log2 WK), and how a remainder of g groups
+    # is cut: pieces that give a lane at least 6 rows where possible (a lane's shared-memory loads per minimum
+    # are (2 G' + 2 TA') / (3 G' TA'): a 16-row piece needs twice the loads per cell of a 32-row one), measured
+    # with tools/probe_score_shapes.py
+    _W_PIECE = {1: (1, 0), 2: (2, 0), 3: (3, 0), 4: (4, 0), 6: (3, 1), 8: (4, 1), 12: (3, 2), 16: (4, 2)}
+    _W_CUT = {1: (1,), 2: (2,), 3: (3,), 4: (4,), 5: (3, 2), 6: (6,), 7: (4, 3), 8: (8,), 9: (6, 3), 10: (6, 4),
+              11: (8, 3), 12: (12,), 13: (6, 4, 3), 14: (8, 6), 15: (12, 3)}
 
     @classmethod
     def _row_pieces(cls, k: int, kind: str) -> list[tuple[int, int, int]]:
@@ -864,8 +870,8 @@ class SearchGroup:
         kind "F": under a full-width (128-allele) column tile - 128-row tiles, then the whole 32-row groups
         of the remainder as one full-width tile; kind "H": what is left of that remainder (< 32 rows), as a
         warp-split tile (used over the two 64-allele halves); kind "W": under a warp-split column tile -
-        128-row tiles, then the remainder cut greedily into the spans a warp-split tile offers.  Every piece
-        starts at a multiple of 8 rows; nothing is padded beyond 8 ceil(k / 8)."""
+        128-row tiles, then the remainder cut into the spans a warp-split tile offers (``_W_CUT``).  Every
+        piece starts at a multiple of 8 rows; nothing is padded beyond 8 ceil(k / 8)."""
         out = []
         n_full, rem = divmod(k, 128)
         if kind == "F":
@@ -880,12 +886,10 @@ class SearchGroup:
             return out
         out += [(128 * i, 4 | (2 << 4) | SHAPE_WARP_SPLIT, 128) for i in range(n_full)]
         at = 128 * n_full
-        rem = 8 * -(-rem // 8)
-        while rem > 0:
-            rows, gp, wk = next(sp for sp in cls._W_SPANS if sp[0] <= rem)
-            out.append((at, gp | (wk << 4) | SHAPE_WARP_SPLIT, rows))
-            at += rows
-            rem -= rows
+        for groups in cls._W_CUT.get(-(-rem // 8), ()):
+            gp, wk = cls._W_PIECE[groups]
+            out.append((at, gp | (wk << 4) | SHAPE_WARP_SPLIT, 8 * groups))
+            at += 8 * groups
         return out
 
     def _packed_tiles(self, live: np.ndarray, kept: np.ndarray):
@@ -903,10 +907,13 @@ class SearchGroup:
         cs += [jf, jf, jf]; cb += [bf, bf, bf + 2]
         ck += [np.zeros(len(jf), np.int64), np.full(len(jf), 2), np.full(len(jf), 2)]
         ct += [np.full(len(jf), 16), np.full(len(jf), 8), np.full(len(jf), 8)]
-        for extra, lo in ((rem8 > 0, 0), (rem8 > 8, 8)):               # one or two warp-split column tiles
+        # one or two warp-split column tiles after the full blocks; two tiles start a 32-column block apart
+        # and are cut as evenly as that allows (9 groups of 8 columns = 4 + 5, not 8 + 1)
+        first = np.where(rem8 <= 8, rem8, np.where(rem8 <= 12, 4, 8))
+        for extra, lo, width in ((rem8 > 0, np.zeros_like(rem8), first), (rem8 > 8, first, rem8 - first)):
             sel = plain & extra
-            cs.append(j_all[sel]); cb.append(4 * n128[sel] + lo // 4)
-            ck.append(np.ones(int(sel.sum()), np.int64)); ct.append(np.minimum(rem8[sel] - lo, 8))
+            cs.append(j_all[sel]); cb.append(4 * n128[sel] + lo[sel] // 4)
+            ck.append(np.ones(int(sel.sum()), np.int64)); ct.append(width[sel])
         for j in j_all[~plain]:                                        # restricted candidates: explicit block runs
             for a_blk, mode in self._restricted_a_tiles(int(live[j])):
                 kinds = [(0, 16, 0), (2, 8, 0), (2, 8, 2)] if mode == MODE_F8 else \
