@@ -180,7 +180,7 @@ int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreIt
 
 /* (c) segmented selection, part 1: canonical-key dedup (uniqueAllele, :456-476, :551-563),
  *     N_uniq, the cut max(top_n, N_uniq // 5) (:567) and the list of candidates that can
- *     still reach the final top_n.  Dedup runs in slices of 8192 candidates (many CTAs per search),
+ *     still reach the final top_n.  Dedup runs in slices of 8192 (few searches: 2048) candidates (many CTAs per search),
  *     the cut and the compaction in one CTA per search. */
 int gk_select(const GkMatrix* matrices, const GkSearch* searches, int n_search, int top_n, int n_prev,
               int max_alleles, int max_cand, const int32_t* kept_count, const int32_t* ids_prev,
