@@ -102,7 +102,8 @@ class FakeBackend:
         table = table.view(MATRIX_DTYPE)
         items = items.view(EXPAND_ITEM_DTYPE)[:n_items]
         hdr, stream, keep = hdr.view(np.uint16), stream.view(np.uint16), keep.view(np.uint32)
-        ent = ent.view(np.uint32).reshape(-1, 4)
+        ent = ent.view(np.uint32)
+        ent = ent[: len(ent) // 4 * 4].reshape(-1, 4)
 
         def mate(rec):
             lo, x = int(rec[0]), int(rec[1])
@@ -166,7 +167,8 @@ class FakeBackend:
     def gk_likelihood(self, table, items, n_items, mem, entoff, ent, L, LT, col, half_mode):
         table = table.view(MATRIX_DTYPE)
         items = items.view(LIK_ITEM_DTYPE)[:n_items]
-        ent = ent.view(np.uint32).reshape(-1, 4)
+        ent = ent.view(np.uint32)
+        ent = ent[: len(ent) // 4 * 4].reshape(-1, 4)
         ent_pos, ent_neg = ent[:, 1], ent[:, 2]
         for it in items:
             M = table[it["matrix"]]

@@ -109,3 +109,16 @@ def test_wire_of_a_read_shard_and_of_an_empty_problem():
     assert empty.n_reads == 0
     batch = engine.MatrixBatch(engine.HostBatch([empty, pack], wire=True), backend=FakeBackend())
     assert np.array_equal(batch.mismatch_counts(1), whole) and batch.colsum(0).sum() == 0
+
+
+def test_reads_without_observations():
+    """no_empty=False keeps read pairs without any observation (a row of 0.999 in the reference,
+    typing_mulit_allele.py:372-374): no entries at all, counts of zero, on both input paths."""
+    member = np.random.default_rng(3).random((40, 5)) < 0.5
+    zero = np.zeros(6, dtype=np.int64)
+    csr = ReadCSR(5, {n: zero.copy() for n in LIST_NAMES}, {n: np.zeros(0, np.int32) for n in LIST_NAMES})
+    pack, _ = packing._finish("KIRE*BACKBONE", [f"KIRE*{i}" for i in range(5)], [f"hv{v}" for v in range(40)], member, csr,
+                              variant_correction=False, no_empty=False)
+    for use_wire in (True, False):
+        batch = engine.MatrixBatch(engine.HostBatch([pack], wire=use_wire), backend=FakeBackend())
+        assert batch.mismatch_counts(0).shape == (5, 5) and not batch.mismatch_counts(0).any()
