@@ -432,7 +432,20 @@ def deep_leg(args, be, rank, world, timed, packed, sm_max, shard, steps=3, parit
 # ---------------------------------------------------------------------------
 # cold / streaming cohort throughput: every pass types a DIFFERENT cohort
 # ---------------------------------------------------------------------------
-def cold_leg(args, be, rank, world, timed, group_size, parts, workers, n_sets=3):
+COLD_SETS = 3
+
+
+def build_cold_sets(args, rank, world, workers, n_sets=COLD_SETS):
+    """The cohorts of the e2e_cold measurement (other seeds than the warm benchmark's), packed on the host
+    before CUDA is initialised (the worker pool forks)."""
+    sets = []
+    for k in range(n_sets):
+        seeds = list(range(5000 + 1000 * k, 5000 + 1000 * k + args.samples))[rank::world]
+        sets.append(build_cohort(seeds, args.scale, workers))
+    return sets
+
+
+def cold_leg(args, be, rank, world, timed, group_size, parts, packed_sets):
     """``e2e_cold``: each timed pass types a cohort the GPU has not seen - other samples, other read counts
     per gene.  ``n_sets`` cohorts (other seeds than the warm benchmark's) are packed and their host pools
     page-locked beforehand (host preparation is reported in ``host_prep``); inside the timed region every
@@ -444,9 +457,8 @@ def cold_leg(args, be, rank, world, timed, group_size, parts, workers, n_sets=3)
     import torch.distributed as dist
     from kir_graph_b200 import cohort, engine
     sets = []
-    for k in range(n_sets):
-        seeds = list(range(5000 + 1000 * k, 5000 + 1000 * k + args.samples))[rank::world]
-        packs, cns, truth = build_cohort(seeds, args.scale, workers)
+    n_sets = len(packed_sets)
+    for packs, cns, truth in packed_sets:
         probe = cohort.CohortTyper(packs, cns, top_n=args.top_n, backend=be, n_parts=parts, group_size=group_size)
         probe.pin()
         hosts = [p.host for p in probe.parts]
@@ -582,6 +594,7 @@ def main():
         n_samples_total = n_samples_local = 1
         desc = f"cfg3: one synthetic 30x WGS sample, {int(200000 * args.scale)} read pairs x 900 alleles / 17 genes"
     t_build = time.perf_counter() - t_build
+    cold_sets = build_cold_sets(args, rank, world, workers) if args.workload == "cohort" and not args.no_cold else None
 
     import torch
     import torch.distributed as dist
@@ -783,7 +796,8 @@ def main():
         gc.unfreeze()
         gc.collect()
         torch.cuda.empty_cache()
-        cold = cold_leg(args, be, rank, world, timed, group_size, 1, workers)      # one sub-batch: least host work per pass
+        cold = cold_leg(args, be, rank, world, timed, group_size, 1, cold_sets)    # one sub-batch: least host work per pass
+        cold_sets = None
         gc.collect()
         torch.cuda.empty_cache()
     else:

@@ -420,3 +420,38 @@ def test_wire_expansion_on_the_device_equals_the_numpy_statement(cuda):
     legacy = engine.MatrixBatch(engine.HostBatch(packs, wire=False), backend=cuda)
     for name in ("d_LT", "d_L", "d_col"):
         assert np.array_equal(cuda.download(getattr(bg, name)), cuda.download(getattr(legacy, name))), name
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_batches_match_numpy_statement(cuda, seed):
+    """Randomised shapes through every launch: allele counts 1..260 (all lane layouts of the likelihood kernel,
+    full-width and warp-split scoring tiles with every row offset), 1..900 reads, copy numbers 1..5, ragged
+    top_n, one gene of arbitrary reads (raw wire records) - CUDA against the NumPy statement, pool by pool."""
+    from tests.test_wire_format import _random_pack
+    rng = np.random.default_rng([2024, seed])
+    n_genes = int(rng.integers(2, 6))
+    specs = [(int(rng.choice([1, 2, 5, 8, 9, 16, 17, 31, 33, 47, 64, 65, 90, 127, 129, 200, 260])),
+              int(rng.integers(1, 6)), int(rng.integers(1, 900))) for _ in range(n_genes)]
+    packs = _packs(specs, 300 + seed)
+    cns = [c for _, c, _ in specs]
+    if seed % 2:
+        weird, _ = _random_pack(rng, n_reads=int(rng.integers(50, 400)), n_var=500, n_allele=int(rng.integers(3, 80)),
+                                weird=True)
+        packs.append(weird)
+        cns.append(int(rng.integers(1, 4)))
+    top_n = int(rng.choice([5, 17, 64, 300]))
+    fake = FakeBackend()
+    bg, bf = engine.MatrixBatch(packs, backend=cuda), engine.MatrixBatch(packs, backend=fake)
+    assert np.array_equal(cuda.download(bg.d_LT, np.uint8), bf.d_LT), "LT"
+    assert np.array_equal(cuda.download(bg.d_L, np.float32).view(np.uint32), bf.d_L.view(np.uint32)), "L"
+    assert np.array_equal(cuda.download(bg.d_col, np.uint64), bf.d_col), "colsum"
+    ids = list(range(len(packs)))
+    gg, gf = engine.SearchGroup(bg, ids, top_n), engine.SearchGroup(bf, ids, top_n)
+    for step in range(max(cns)):
+        active = np.array([c > step for c in cns])
+        need = np.array([c > step + 1 for c in cns])
+        og = gg.step(active=active, need_next=need)
+        of = gf.step(active=active, need_next=need)
+        if step:
+            assert np.array_equal(cuda.download(gg.d_S, np.uint32), gf.d_S), f"S at step {step + 1}"
+        _compare_outputs(og, of)

@@ -20,6 +20,7 @@ n_samples = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 parts = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 args = argparse.Namespace(samples=n_samples, scale=1.0, top_n=300, steps=passes)
+packed_sets = bench.build_cold_sets(args, 0, 1, 16, n_sets=2)          # before CUDA is initialised (the pool forks)
 be = engine.CudaBackend(0)
 prof = cProfile.Profile()
 
@@ -37,6 +38,6 @@ def timed(fn, steps, finalize=None):
     return 1e3 * (time.perf_counter() - t0)
 
 
-out = bench.cold_leg(args, be, 0, 1, timed, 17, parts, 16, n_sets=2)
+out = bench.cold_leg(args, be, 0, 1, timed, 17, parts, packed_sets)
 print({k: v for k, v in out.items() if k != "timed_region"})
 pstats.Stats(prof).sort_stats("cumulative").print_stats(40)
