@@ -892,6 +892,7 @@ def main():
             from tools import host_numbers
             line["host_prep"] = host_numbers.host_prep()
             line["api_e2e"] = host_numbers.api_e2e(args.cpu_scale, backend=be)
+            line["cn_model"] = host_numbers.cn_model(args.samples, backend=be)
         if world == 1 and not args.no_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
             arm = CpuArm(cores, args.cpu_scale, args.top_n)

@@ -240,6 +240,16 @@ int gk_em_squarem(const GkEmProblem* problems, int n_problems, const uint32_t* r
 int gk_group_reads(const GkMatrix* matrices, int matrix, int n_reads, const int32_t* ids, int n_ids,
                    const uint8_t* LT_pool, uint32_t* pattern, void* stream);
 
+/* CN model: replaces the loop of CNgroup.fit over the candidate bases and
+ * calcCNGroupProb (graphkir/cn_model.py:124-204): likelihood[b] = sum_i log(max_n pdf_n(x[i]; bases[b]) * space
+ * + 1e-9) * density[i], with pdf_n the normal density of copy number n (n = 0 .. max_cn - 1; means n * base,
+ * deviations from base_dev, y0_dev, dev_decay, dev_decay_neg and start_base as in the reference).  float64;
+ * x, density [bin_num], bases, likelihood [n_base] are device arrays; prob_out (optional, device,
+ * [n_base][max_cn][bin_num]) receives the CN-group probabilities themselves. */
+int gk_cn_fit(const double* x, const double* density, const double* bases, int n_base, int bin_num, int max_cn,
+              int start_base, double base_dev, double y0_dev, double dev_decay, double dev_decay_neg, double space,
+              double* likelihood, double* prob_out, void* stream);
+
 /* Host-side fast path for `{prefix}.variant.json` (reference reader
  * graphkir/hisat2.py:847-866 + kir_typing.py:92-97).  No CUDA involved.  gk_json_scan walks the JSON
  * text once and keeps, for every element of "reads", backbone (interned), multiple and the four

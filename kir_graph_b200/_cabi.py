@@ -59,7 +59,7 @@ _STRUCTS = {
 EXPORTS = (
     "gk_last_error", "gk_abi_version", "gk_sizeof", "gk_wire_encode", "gk_expand_reads", "gk_likelihood", "gk_first_step", "gk_score",
     "gk_select", "gk_rescore_count", "gk_rank", "gk_write_p", "gk_em_compat", "gk_em_squarem",
-    "gk_group_reads", "gk_json_scan", "gk_json_fill", "gk_json_free", "gk_pack_entries", "gk_sam_walk",
+    "gk_group_reads", "gk_cn_fit", "gk_json_scan", "gk_json_fill", "gk_json_free", "gk_pack_entries", "gk_sam_walk",
     "gk_sam_extract", "gk_sam_extract_fill", "gk_sam_extract_free", "gk_sam_extract_json",
 )
 

@@ -2,8 +2,8 @@
 """
 TEST / BENCH INFRASTRUCTURE -- builds ``oracle/_ref``: the reference's own typing path, byte-compiled.
 
-The reference (linnil1/KIR_graph) is pure Python, so "building" it means byte-compiling the nine modules
-of ``graphkir`` that the typing path imports, from the sources where they lie under ``/root/reference``,
+The reference (linnil1/KIR_graph) is pure Python, so "building" it means byte-compiling the twelve modules
+of ``graphkir`` that the typing path and the CN model import, from the sources where they lie under ``/root/reference``,
 into ``oracle/_ref/graphkir/*.gkref`` (byte code only: no reference source text is copied into this
 repository; ``oracle/_ref/`` is git-ignored and travels to the GPU box with the snapshot like the built
 ``.so`` - the files do not carry the ``.pyc`` suffix because snapshot tools commonly drop ``*.pyc``).  ``oracle/ref_loader.py`` imports them there, with the three plotting / FASTA / MSA packages the
@@ -25,7 +25,8 @@ OUT = os.path.join(HERE, "_ref", "graphkir")
 # typing_mulit_allele / typing_em / kir_typing and what they import
 EXT = ".gkref"            # a .pyc by content (16-byte header + marshalled code object)
 MODULES = ("__init__", "typing_mulit_allele", "typing_em", "kir_typing", "hisat2", "msa2hisat", "utils",
-           "external_tools", "pileup")
+           "external_tools", "pileup",
+           "cn_model", "kir_cn", "samtools_utils")       # the CN model and its caller
 
 
 def build(src: str = "/root/reference", force: bool = False) -> str | None:

@@ -85,6 +85,14 @@ def load():
     return tma, tem, kt, h2, m2h
 
 
+def load_cn():
+    """(cn_model, kir_cn) of the reference (they import scipy, scikit-learn and pandas, which the image has)."""
+    load()
+    import graphkir.cn_model as cm
+    import graphkir.kir_cn as kc
+    return cm, kc
+
+
 def to_ref_objects(reads, variants):
     """Reads / variants of this repository's dataclasses -> the reference's own (same fields)."""
     _, _, _, h2, m2h = load()

@@ -488,6 +488,33 @@ class FakeBackend:
                     tile.reshape(128 // GK_RT, GK_RT, GK_KB)
 
     # --- read grouping (section 8f rank 3) ---------------------------------------------------------
+    def gk_cn_fit(self, x, density, bases, n_base, bin_num, max_cn, start_base, base_dev, y0_dev, dev_decay,
+                  dev_decay_neg, space, likelihood, prob_out):
+        """likelihood[b] = sum_i log(max_n pdf_n(x_i; bases[b]) * space + 1e-9) * density_i, element by element."""
+        with np.errstate(all="ignore"):
+            for b in range(n_base):
+                rows = []
+                for n in range(max_cn):
+                    if start_base == 1:
+                        loc, scale = (0.0, base_dev * y0_dev) if n == 0 else (bases[b] * n, base_dev * (dev_decay * (n - 1) + 1))
+                    else:
+                        loc = bases[b] * n
+                        scale = base_dev * (dev_decay_neg * (start_base - n) + 1) if n < start_base \
+                            else base_dev * (dev_decay * (n - start_base) + 1)
+                    if scale > 0:
+                        y = (x[:bin_num] - loc) / scale
+                        rows.append(np.exp(-(y * y) / 2.0) / 2.5066282746310002 / scale * space)
+                    else:
+                        rows.append(np.full(bin_num, np.nan))
+                rows = np.array(rows)
+                if prob_out is not None:
+                    prob_out[b * max_cn * bin_num: (b + 1) * max_cn * bin_num] = rows.reshape(-1)
+                terms = np.log(rows.max(axis=0) + 1e-9) * density[:bin_num]
+                total = 0.0
+                for t in terms:                     # plain left-to-right sum (the kernel's order differs: tests compare with a tolerance)
+                    total += t
+                likelihood[b] = total
+
     def gk_group_reads(self, table, matrix, n_reads, ids, n_ids, LT, pattern):
         M = table.view(MATRIX_DTYPE)[matrix]
         m = self._LT_view(M, LT)[np.asarray(ids[:n_ids], dtype=np.int64), :n_reads].astype(np.int64)

@@ -171,6 +171,43 @@ def api_e2e(scale: float = 0.1, backend=None) -> dict:
     return out
 
 
+def cn_model(n_samples: int = 96, backend=None) -> dict:
+    """``depthToCN`` (graphkir/kir_cn.py:41-123: CNgroup.fit over 500 candidate bases x 500 depth bins x 7 copy
+    numbers, then assignCN per gene) on the gene depths of a synthetic cohort: the mirror on the GPU beside the
+    unmodified reference on one host core, same CN calls and fitted base required."""
+    import numpy as np
+    from kir_graph_b200 import kir_cn
+    from oracle import ref_loader
+    rng = np.random.default_rng(11)
+    genes = [f"KIR{g}*BACKBONE" for g in ("2DL1", "2DL2", "2DL3", "2DL4", "2DL5", "2DP1", "2DS1", "2DS2", "2DS3", "2DS4",
+                                           "2DS5", "3DL1", "3DL2", "3DL3", "3DP1", "3DS1")]
+    depths = []
+    for _ in range(n_samples):
+        per_copy = 15.0 * rng.uniform(0.9, 1.1)
+        depths.append({g: float(max(0.0, (2 if "3DL3" in g else int(rng.choice([0, 1, 1, 2, 2, 2, 3]))) * per_copy
+                                    * (1 + 0.08 * rng.standard_normal()))) for g in genes})
+    out: dict = {"samples": n_samples, "genes": len(genes)}
+    for attempt in range(2):                         # second call warm
+        t0 = time.perf_counter()
+        cns, dist = kir_cn.depthToCN(depths, assume_3DL3_diploid=True, _backend=backend)
+        t1 = time.perf_counter()
+    out["b200_s"] = t1 - t0
+    out["base"] = float(dist.base)
+    if ref_loader.available():
+        _, kc = ref_loader.load_cn()
+        t0 = time.perf_counter()
+        ref_cns, ref_dist = kc.depthToCN(depths, assume_3DL3_diploid=True)
+        t1 = time.perf_counter()
+        out["reference_s"] = t1 - t0
+        out["same_cn_calls"] = [{k: int(v) for k, v in c.items()} for c in cns] == [{k: int(v) for k, v in c.items()} for c in ref_cns]
+        out["same_base"] = float(ref_dist.base) == float(dist.base)
+        out["likelihood_max_rel_diff"] = float(np.max(np.abs(dist.likelihood[:, 1] - ref_dist.likelihood[:, 1])
+                                                      / np.abs(ref_dist.likelihood[:, 1])))
+        out["speedup"] = out["reference_s"] / out["b200_s"]
+    out["call"] = "depthToCN(sample_gene_depths, assume_3DL3_diploid=True)  (kir_cn.py:41-123)"
+    return out
+
+
 def _per_gene(alleles: list[str], cn: dict) -> list[list[str]]:
     out, at = [], 0
     for gene, c in cn.items():
