@@ -135,6 +135,11 @@ class CNgroup(Dist):
         return [cn_max[int(depth / space)] for depth in values]
 
     def calcCNGroupProb(self, base: float) -> np.ndarray:
-        """(CN x bins) array: the probability that a normalised read depth belongs to the CN (:176-204)."""
-        _, prob = self._evaluate(np.array([base], dtype=np.float64), None, want_prob=True)
-        return prob[0]
+        """(CN x bins) array: the probability that a normalised read depth belongs to the CN (:176-204).
+        The last evaluation is kept: depthToCN calls assignCN once per sample with the same model."""
+        key = (float(base), self.x_max, self.bin_num, self.max_cn, self.base_dev, self.y0_dev, self.dev_decay,
+               self.dev_decay_neg, self.start_base)
+        if getattr(self, "_prob_cache", (None, None))[0] != key:
+            _, prob = self._evaluate(np.array([base], dtype=np.float64), None, want_prob=True)
+            self._prob_cache = (key, prob[0])
+        return self._prob_cache[1].copy()
