@@ -81,7 +81,7 @@ def main():
     ]
     path = os.path.join(HERE, "cn_model.json.gz")
     with gzip.open(path, "wt", compresslevel=9) as f:
-        json.dump(cases, f)
+        json.dump({"kind": "cn_model", "cases": cases}, f)
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
     for c in cases:
         print(c["name"], "base", round(c["base"], 4), "bins", c["bin_num"], "cn of sample 0", list(c["cns"][0].values()))

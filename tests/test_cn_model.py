@@ -14,7 +14,7 @@ from oracle import cn_oracle
 from tests.fake_backend import FakeBackend
 from tests.helpers import load_golden
 
-CASES = load_golden("cn_model")
+CASES = load_golden("cn_model")["cases"]
 NAMES = [c["name"] for c in CASES]
 
 
