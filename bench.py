@@ -288,10 +288,13 @@ def load_peaks() -> dict:
 
 def score_roofline(cells, ms, packed, sm_max_mhz):
     """Roofline entry of the scoring kernel.  Its bound is non-tensor instruction issue, not HBM or
-    the tensor cores: the packed path issues 3 ALU-pipe instructions (2 VIMNMX.U16x2 + 1 IADD3)
-    per 4 cells on the half-rate (64 lanes/clk/SM) ALU pipe, the FP32 path 2 FADD per cell on the
-    128 lanes/clk/SM FMA pipe.  The FP32-equivalent fraction (2 ops per cell against the FP32
-    non-tensor peak) is what BASELINE.json's target is stated in."""
+    the tensor cores.  The packed path spends 4 instructions on 4 cells: 2 VIMNMX.U16x2 on the ALU pipe
+    (64 lanes/clk/SM) and 2 IMAD (acc = min * 1 + acc) on the FMA pipe, i.e. ONE issue slot per cell
+    (128 lanes/clk/SM) and half an ALU-pipe instruction per cell: both limits are 128 cells/clk/SM.
+    (Until round 2 the adds were IADD3 on the ALU pipe as well: 0.75 ALU instructions per cell,
+    85.3 cells/clk/SM; ``alu_only_formulation`` keeps that denominator for comparison with round 1.)
+    The FP32 path issues 2 FADD per cell on the FMA pipe.  The FP32-equivalent fraction (2 ops per
+    cell against the FP32 non-tensor peak) is what BASELINE.json's target is stated in."""
     cps = cells / (ms * 1e-3) if ms else 0.0
     fp32_peak = SM_COUNT * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12          # T lane-ops/s
     src = (f"148 SM x {{lanes}} lanes/clk x {sm_max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); not in "
@@ -303,15 +306,20 @@ def score_roofline(cells, ms, packed, sm_max_mhz):
     except (OSError, ValueError):
         pass
     if packed:
-        peak = fp32_peak / 2.0                                                   # ALU pipe: 64 lanes/clk/SM
-        ach = 0.75 * cps / 1e12
-        out = {"kernel": "gk_score_packed_kernel", "bound": "alu_nontensor", "achieved": ach, "peak": peak,
-               "unit": "T ALU lane-ops/s (2 VIMNMX.U16x2 + 1 IADD3 per 4 cells)", "frac": ach / peak,
-               "cells_per_s": cps, "fp32_nontensor_equiv": fp32, "peak_source": src.format(lanes=64)}
-        if measured.get("u16x2_min_add_tcells_per_s"):
-            m_peak = float(measured["u16x2_min_add_tcells_per_s"])
+        peak = fp32_peak                                                         # issue: 128 lanes/clk/SM
+        ach = 1.0 * cps / 1e12
+        out = {"kernel": "gk_score_packed_kernel", "bound": "issue_nontensor", "achieved": ach, "peak": peak,
+               "unit": "T instruction lanes/s (2 VIMNMX.U16x2 on the ALU pipe + 2 IMAD on the FMA pipe per 4 cells)",
+               "frac": ach / peak, "cells_per_s": cps, "fp32_nontensor_equiv": fp32,
+               "alu_only_formulation": {"achieved": 0.75 * cps / 1e12, "peak": fp32_peak / 2.0,
+                                        "frac": 0.75 * cps / 1e12 / (fp32_peak / 2.0),
+                                        "note": "round-1 denominator: 2 VIMNMX.U16x2 + 1 IADD3 per 4 cells, all on the "
+                                                "64 lanes/clk/SM ALU pipe; above 1 means faster than that formulation can run"},
+               "peak_source": src.format(lanes=128)}
+        if measured.get("u16x2_min_imad_tcells_per_s"):
+            m_peak = float(measured["u16x2_min_imad_tcells_per_s"])
             out["measured_peak"] = {"achieved": cps / 1e12, "peak": m_peak, "unit": "TCells/s", "frac": cps / 1e12 / m_peak,
-                                    "source": "tools/micro/mixpipe.cu (same VIMNMX.U16x2 + IADD3 mix, operands from shared "
+                                    "source": "tools/micro/mixpipe.cu (same VIMNMX.U16x2 + IMAD mix, operands from shared "
                                               "memory, accumulators in registers) on a B200 of this pool: "
                                               "profiles/r02_mixpipe.txt"}
         return out

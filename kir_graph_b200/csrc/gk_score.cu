@@ -216,11 +216,22 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 // accumulator registers.  S receives the min-sum itself (not the sum of absolute differences of
 // the FP32 path).
 // Tile rows: G in {1..4} groups of 32 kept sets; columns: the same five modes as above.
+//
+// The adds do not go to the ALU pipe: acc = x * one + acc with `one` a kernel argument (so that ptxas
+// cannot fold it back into an IADD3) is an IMAD, which issues on the FMA pipe.  The minima (ALU pipe,
+// 2 clk per warp instruction) and the adds (FMA pipe) then overlap: 2 VIMNMX.U16x2 + 2 IMAD per 4 cells
+// is one issue slot per cell and 0.5 ALU-pipe instructions per cell.  tools/micro/mixpipe.cu measures
+// 106 cells/clk/SM for this mix against 83 for 2 VIMNMX + 1 IADD3 (profiles/r02_mixpipe.txt); mixes of
+// IADD3 and IMAD adds land in between.
+__device__ __forceinline__ uint32_t add_fma(uint32_t acc, uint32_t x, uint32_t one) {
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(one));
+    return acc;
+}
 template <int G, int AM>
 __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                              const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
                                              uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
-                                             uint64_t* full, uint64_t* empty, int* next, int flush) {
+                                             uint64_t* full, uint64_t* empty, int* next, int flush, uint32_t one) {
     constexpr int TA = ModeInfo<AM>::kPerThread;
     constexpr int AT = 32;
     constexpr int KW = (32 * G + GK_KB - 1) / GK_KB;                 // k-blocks staged (1 or 2)
@@ -344,7 +355,7 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
             for (int g = 0; g < G; ++g)
 #pragma unroll
                 for (int j = 0; j < TA; ++j)
-                    acc2[g][j] = acc2[g][j] + __vminu2(pv0[g], lv0[j]) + __vminu2(pv1[g], lv1[j]);
+                    acc2[g][j] = add_fma(add_fma(acc2[g][j], __vminu2(pv0[g], lv0[j]), one), __vminu2(pv1[g], lv1[j]), one);
         }
         if (++since_flush >= flush) {
             flush_acc();
@@ -389,7 +400,7 @@ template <int GP, int TAP>
 __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                              const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
                                              uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
-                                             uint64_t* full, uint64_t* empty, int* next, int flush, int wk_log2) {
+                                             uint64_t* full, uint64_t* empty, int* next, int flush, int wk_log2, uint32_t one) {
     constexpr int AT = 32;
     constexpr int AW = (8 * TAP + AT - 1) / AT;                      // a-blocks staged (1 or 2)
     constexpr uint32_t kBytesPBlk = GK_RT * GK_KB * sizeof(uint16_t);
@@ -495,7 +506,7 @@ __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMa
             for (int g = 0; g < GP; ++g)
 #pragma unroll
                 for (int j = 0; j < TAP; ++j)
-                    acc2[g][j] = acc2[g][j] + __vminu2(pv0[g], lv0[j]) + __vminu2(pv1[g], lv1[j]);
+                    acc2[g][j] = add_fma(add_fma(acc2[g][j], __vminu2(pv0[g], lv0[j]), one), __vminu2(pv1[g], lv1[j]), one);
         }
         if (++since_flush >= flush) {
             flush_acc();
@@ -512,12 +523,12 @@ __device__ __forceinline__ void score_dispatch_w(int tap, const GkScoreItem& ite
                                                  const GkSearch& X, const float* __restrict__ L_pool,
                                                  const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
                                                  unsigned char* smem, uint64_t* full, uint64_t* empty, int* next,
-                                                 int flush, int wk_log2) {
+                                                 int flush, int wk_log2, uint32_t one) {
 #define GK_W_CASE(T) \
-    case T: score_item_w<GP, T>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+    case T: score_item_w<GP, T>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
     switch (tap) {
         GK_W_CASE(1) GK_W_CASE(2) GK_W_CASE(3) GK_W_CASE(4) GK_W_CASE(5) GK_W_CASE(6) GK_W_CASE(7)
-        default: score_item_w<GP, 8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+        default: score_item_w<GP, 8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
     }
 #undef GK_W_CASE
 }
@@ -526,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, GK_PACKED_CTAS)
 gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restrict__ searches,
                      const GkScoreItem* __restrict__ items, const float* __restrict__ L_pool,
                      const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool, int flush,
-                     const int32_t* __restrict__ kept_count) {
+                     const int32_t* __restrict__ kept_count, uint32_t one) {
     if (kept_count != nullptr && items[blockIdx.x].k_blk * GK_KB >= kept_count[items[blockIdx.x].search]) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -550,19 +561,19 @@ gk_score_packed_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __
         const int tap = (item.shape >> 8) & 0xff;
         const int wk_log2 = (item.shape >> 4) & 0xf;
         switch (item.shape & 0xf) {
-            case 1: score_dispatch_w<1>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
-            case 2: score_dispatch_w<2>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
-            case 3: score_dispatch_w<3>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
-            default: score_dispatch_w<4>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2); break;
+            case 1: score_dispatch_w<1>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
+            case 2: score_dispatch_w<2>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
+            case 3: score_dispatch_w<3>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
+            default: score_dispatch_w<4>(tap, item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
         }
         return;
     }
     // full-width tile: 1..4 groups of 32 kept sets (row mode 5..8) x 128 alleles
     switch ((item.shape & 0xff) - 4) {
-        case 1: score_item_h<1, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case 2: score_item_h<2, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        case 3: score_item_h<3, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
-        default: score_item_h<4, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush); break;
+        case 1: score_item_h<1, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, one); break;
+        case 2: score_item_h<2, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, one); break;
+        case 3: score_item_h<3, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, one); break;
+        default: score_item_h<4, F8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, one); break;
     }
 }
 
@@ -645,7 +656,7 @@ extern "C" int gk_score(const GkMatrix* matrices, const GkSearch* searches, cons
                    cudaGetErrorString(err));
         gk_score_packed_kernel<<<n_items, kThreads, kSmemP, st>>>(matrices, searches, items, L_pool,
                                                                   reinterpret_cast<const uint16_t*>(P_pool), S_pool,
-                                                                  flush_stages, kept_count);
+                                                                  flush_stages, kept_count, 1u);
         GK_CHECK_LAUNCH("gk_score (packed)");
         return 0;
     }

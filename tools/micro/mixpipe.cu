@@ -3,13 +3,16 @@
 //   (0) FP32 SAD 8x8 per thread: 128 FADD (FMA pipe) per 64 cells
 //   (1) packed-u16 min-sum 8x8: k rows paired, VIMNMX.U16x2 + IADD3 (ALU pipe): 48 instr per 64 cells
 //   (2) mixed: 2 rows FP32 SAD (32 FADD) + 6 rows packed u16 (24 VIMNMX + 12 IADD3) per 64 cells
+//   (3) packed-u16 min-sum, every add an IMAD (x * one + acc, FMA pipe): 32 VIMNMX + 32 IMAD per 64 cells
+//   (4..6) packed-u16 min-sum, 1 of every 2 / 3 / 4 row pairs adds with IADD3, the others with IMAD
+//   (7) two reads per 16-bit lane pair, 32-bit sums: VIMNMX.U16x2 + IDP.2A per 2 cells
 #include <cstdio>
 #include <cuda_runtime.h>
 
 constexpr int RT = 16;
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) k(const float* gin, float* fout, unsigned* uout, int iters) {
+__global__ void __launch_bounds__(256, 2) k(const float* gin, float* fout, unsigned* uout, int iters, unsigned one) {
     __shared__ __align__(16) float sPf[RT][16 * 2 + 4];      // 2 fp32 rows per tk (16 tk)
     __shared__ __align__(16) unsigned sPu[RT][16 * 4];       // 4 packed row pairs per tk
     __shared__ __align__(16) float sLf[RT][128];
@@ -42,6 +45,38 @@ __global__ void __launch_bounds__(256, 2) k(const float* gin, float* fout, unsig
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[i * 8 + j] += fabsf(pv[i] - lv[j]);
+            } else if (MODE == 7) {
+                const uint4 pa = *reinterpret_cast<const uint4*>(&sLu[r][tk * 4]);          // stand-in P loads
+                const uint4 pb = *reinterpret_cast<const uint4*>(&sLu[r][64 + tk * 4]);
+                const uint4 l0 = *reinterpret_cast<const uint4*>(&sLu[(r + 1) % RT][ta * 4]);
+                const uint4 l1 = *reinterpret_cast<const uint4*>(&sLu[(r + 1) % RT][64 + ta * 4]);
+                const unsigned pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+                const unsigned lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                unsigned* a32 = reinterpret_cast<unsigned*>(acc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a32[i * 8 + j] = __dp2a_lo(__vminu2(pv[i], lv[j]), one, a32[i * 8 + j]);
+            } else if (MODE >= 3) {
+                const uint4 pu4 = *reinterpret_cast<const uint4*>(&sPu[r][tk * 4]);
+                const uint4 lu0 = *reinterpret_cast<const uint4*>(&sLu[r][ta * 4]);
+                const uint4 lu1 = *reinterpret_cast<const uint4*>(&sLu[r][64 + ta * 4]);
+                const unsigned pu[4] = {pu4.x, pu4.y, pu4.z, pu4.w};
+                const unsigned lu[8] = {lu0.x, lu0.y, lu0.z, lu0.w, lu1.x, lu1.y, lu1.z, lu1.w};
+                constexpr int EVERY = MODE == 3 ? 1000 : MODE - 2;     // every EVERY-th accumulator adds with IADD3
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const int idx = i * 4 + j / 2;
+                        const unsigned x = __vminu2(pu[i], lu[j]), y = __vminu2(pu[i], lu[j + 1]);
+                        if (idx % EVERY == EVERY - 1) {
+                            au[idx] += x + y;
+                        } else {
+                            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(au[idx]) : "r"(x), "r"(one));
+                            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(au[idx]) : "r"(y), "r"(one));
+                        }
+                    }
             } else {
                 const uint4 pu4 = *reinterpret_cast<const uint4*>(&sPu[r][tk * 4]);
                 const uint4 lu0 = *reinterpret_cast<const uint4*>(&sLu[r][ta * 4]);
@@ -83,12 +118,12 @@ template <int MODE> void run(const char* name) {
     cudaMalloc(&gin, 4096 * 4); cudaMalloc(&fout, 296 * 256 * 4); cudaMalloc(&uout, 296 * 256 * 4);
     cudaMemset(gin, 0, 4096 * 4);
     int iters = 1600;
-    k<MODE><<<296, 256>>>(gin, fout, uout, 10);
+    k<MODE><<<296, 256>>>(gin, fout, uout, 10, MODE == 7 ? 0x0101u : 1u);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a); k<MODE><<<296, 256>>>(gin, fout, uout, iters); cudaEventRecord(b); cudaEventSynchronize(b);
+    cudaEventRecord(a); k<MODE><<<296, 256>>>(gin, fout, uout, iters, MODE == 7 ? 0x0101u : 1u); cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
     cudaError_t e = cudaGetLastError();
-    double cells = 64.0 * RT * iters * 296 * 256;
+    double cells = (MODE == 7 ? 128.0 : 64.0) * RT * iters * 296 * 256;
     printf("%-34s %8.3f ms  %7.2f TCells/s  (%.1f cells/clk/SM at 1.965 GHz) %s\n", name, ms, cells / ms / 1e9,
            cells / (ms * 1e-3) / 148 / 1.965e9, cudaGetErrorString(e));
 }
@@ -97,5 +132,10 @@ int main() {
     run<0>("fp32 SAD 8x8 (FMA pipe)");
     run<1>("u16x2 min+add 8x8 (ALU pipe)");
     run<2>("mixed 2 rows fp32 + 6 rows u16x2");
+    run<3>("u16x2 min (ALU) + IMAD adds (FMA)");
+    run<4>("u16x2 min, adds 1/2 IADD3 1/2 IMAD");
+    run<5>("u16x2 min, adds 1/3 IADD3 2/3 IMAD");
+    run<6>("u16x2 min, adds 1/4 IADD3 3/4 IMAD");
+    run<7>("u16x2 min + IDP.2A, 32-bit sums");
     return 0;
 }
