@@ -223,6 +223,22 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 // is one issue slot per cell and 0.5 ALU-pipe instructions per cell.  tools/micro/mixpipe.cu measures
 // 106 cells/clk/SM for this mix against 83 for 2 VIMNMX + 1 IADD3 (profiles/r02_mixpipe.txt); mixes of
 // IADD3 and IMAD adds land in between.
+// N consecutive 32-bit words of shared memory with the widest load their alignment allows (the callers
+// guarantee 8-byte alignment for N = 2 and 16-byte alignment for N = 4).
+template <int N>
+__device__ __forceinline__ void lds_words(const uint32_t* src, uint32_t* out) {
+    if constexpr (N == 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else if constexpr (N == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src);
+        out[0] = v.x; out[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = src[i];
+    }
+}
+
 __device__ __forceinline__ uint32_t add_fma(uint32_t acc, uint32_t x, uint32_t one) {
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(one));
     return acc;
@@ -396,7 +412,17 @@ __device__ __forceinline__ void score_item_h(const GkScoreItem& item, const GkMa
 // The tile may start at any multiple of 8 rows inside its k-block (shape bits 20-22), so that a
 // ragged kept-set count is covered exactly (300 = 128 + 128 + 32 + 8 + ... instead of padding the
 // last tile to 32- or 64-row groups).
-template <int GP, int TAP>
+//
+// Two lane layouts.  VEC = false: rows row0 + 8 g + 2 tk, columns 8 j + ta, scalar shared loads; the eight
+// lanes that share a row pair flush eight consecutive words of S (one 32-byte sector per atomic
+// instruction and row).  VEC = true (tiles of WK = 4, where a warp has 16 reads of every stage): a lane owns
+// 2 G' consecutive rows and its TA' columns in at most two runs of consecutive ones, so its operands of a
+// read arrive with vector loads (G' = 4: one LDS.128 for P; TA' = 5: LDS.128 + LDS.32 for L) - the kernel
+// is bound by instruction issue, and this takes 18 loads per 80 arithmetic instructions down to 6.  Its
+// flush touches up to four sectors per instruction and row, which is why the tiles of fewer warps per
+// row block (fewer cells per flush) keep the first layout: measured on the shapes of a cfg3 sample, the
+// vector layout is 6-10 % faster on WK = 4 tiles and 7-18 % slower on WK <= 2 tiles.
+template <int GP, int TAP, bool VEC>
 __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMatrix& M, const GkSearch& X,
                                              const float* __restrict__ L_pool, const uint16_t* __restrict__ P_pool,
                                              uint32_t* __restrict__ S_pool, unsigned char* smem_bytes,
@@ -414,6 +440,7 @@ __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMa
     const int warp = tid >> 5;
     const int tk = lane >> 3;                                        // row pair inside a group of 8 rows
     const int ta = lane & 7;                                         // column inside a group of 8 columns
+    if constexpr (VEC) wk_log2 = 2;                                  // compile-time trip counts
     const int row0 = row_off + (warp & ((1 << wk_log2) - 1)) * (8 * GP);       // first row of this warp
     const int reads_per_warp = 4 << wk_log2;                         // 32 reads / (8 >> wk_log2) warps
     const int rd0 = (warp >> wk_log2) * reads_per_warp;
@@ -452,22 +479,29 @@ __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMa
 #pragma unroll
         for (int j = 0; j < TAP; ++j) acc2[g][j] = 0u;
 
-    // rows row0 + 8 g + 2 tk + {0, 1}: offset (in uint16) inside the staged P blocks [k_blk][r][64]
-    auto p_off = [&](int g) {
-        const int k = row0 + 8 * g + 2 * tk;
-        return (k / GK_KB) * (GK_RT * GK_KB) + (k % GK_KB);
-    };
-    // column 8 j + ta inside the staged L blocks [a_blk][r][32]
-    auto l_off = [&](int j) { return (j / 4) * (GK_RT * AT) + (j % 4) * 8 + ta; };
+    // row (relative to the k-block) and column (relative to the first a-block) of slot (g, j) of this lane
+    constexpr int TA0 = TAP < 4 ? TAP : 4;        // VEC: columns TA0 ta + j (first a-block) ...
+    constexpr int TA1 = TAP - TA0;                //      ... and 32 + TA1 ta + (j - TA0) (second a-block)
+    auto row_of = [&](int g) { return VEC ? row0 + 2 * GP * tk + 2 * g : row0 + 8 * g + 2 * tk; };
+    auto col_of = [&](int j) { return VEC ? (j < TA0 ? TA0 * ta + j : AT + TA1 * ta + (j - TA0)) : 8 * j + ta; };
+    // offset (in uint16) inside the staged P blocks [k_blk][r][64]; a lane's rows never straddle a k-block
+    // when 2 G' divides 64
+    auto p_off = [&](int g) { return (row_of(g) / GK_KB) * (GK_RT * GK_KB) + (row_of(g) % GK_KB); };
+    // offset (in words) inside the staged L blocks [a_blk][r][32]
+    auto l_off = [&](int j) { return (col_of(j) / AT) * (GK_RT * AT) + (col_of(j) % AT); };
 
-    uint32_t* S = S_pool + X.S_off + (int64_t)(item.k_blk * GK_KB + row0 + 2 * tk) * X.s_stride + item.a_blk * AT + ta;
+    // slot (0, 0) of this lane and, for the vector layout, the first slot of its second run of columns;
+    // the other slots are compile-time offsets from these
+    uint32_t* S = S_pool + X.S_off + (int64_t)(item.k_blk * GK_KB + row_of(0)) * X.s_stride + item.a_blk * AT + col_of(0);
+    uint32_t* S1 = S + (col_of(TA0 < TAP ? TA0 : 0) - col_of(0));
     auto flush_acc = [&]() {
 #pragma unroll
         for (int g = 0; g < GP; ++g)
 #pragma unroll
             for (int j = 0; j < TAP; ++j) {
                 const uint32_t v = acc2[g][j];
-                uint32_t* cell = S + (int64_t)(8 * g) * X.s_stride + 8 * j;
+                uint32_t* cell = (VEC ? (j < TA0 ? S + j : S1 + (j - TA0)) : S + 8 * j) +
+                                 (int64_t)(VEC ? 2 * g : 8 * g) * X.s_stride;
                 if (v & 0xffffu) atomicAdd(cell, v & 0xffffu);
                 if (v >> 16) atomicAdd(cell + X.s_stride, v >> 16);
                 acc2[g][j] = 0u;
@@ -492,15 +526,29 @@ __device__ __forceinline__ void score_item_w(const GkScoreItem& item, const GkMa
         for (int i = 0; i < reads_per_warp; i += 2) {
             const int r = rd0 + i;
             uint32_t pv0[GP], pv1[GP], lv0[TAP], lv1[TAP];
+            if constexpr (VEC && (GP == 4 || GP == 2)) {
+                lds_words<GP>(reinterpret_cast<const uint32_t*>(p + p_off(0) + r * GK_KB), pv0);
+                lds_words<GP>(reinterpret_cast<const uint32_t*>(p + p_off(0) + (r + 1) * GK_KB), pv1);
+            } else {
 #pragma unroll
-            for (int g = 0; g < GP; ++g) {
-                pv0[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + r * GK_KB);
-                pv1[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + (r + 1) * GK_KB);
+                for (int g = 0; g < GP; ++g) {
+                    pv0[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + r * GK_KB);
+                    pv1[g] = *reinterpret_cast<const uint32_t*>(p + p_off(g) + (r + 1) * GK_KB);
+                }
             }
+            if constexpr (VEC) {
+                lds_words<TA0>(l + l_off(0) + r * AT, lv0);
+                lds_words<TA0>(l + l_off(0) + (r + 1) * AT, lv1);
+                if constexpr (TA1 > 0) {
+                    lds_words<TA1>(l + l_off(TA0) + r * AT, lv0 + TA0);
+                    lds_words<TA1>(l + l_off(TA0) + (r + 1) * AT, lv1 + TA0);
+                }
+            } else {
 #pragma unroll
-            for (int j = 0; j < TAP; ++j) {
-                lv0[j] = l[l_off(j) + r * AT];
-                lv1[j] = l[l_off(j) + (r + 1) * AT];
+                for (int j = 0; j < TAP; ++j) {
+                    lv0[j] = l[l_off(j) + r * AT];
+                    lv1[j] = l[l_off(j) + (r + 1) * AT];
+                }
             }
 #pragma unroll
             for (int g = 0; g < GP; ++g)
@@ -524,11 +572,16 @@ __device__ __forceinline__ void score_dispatch_w(int tap, const GkScoreItem& ite
                                                  const uint16_t* __restrict__ P_pool, uint32_t* __restrict__ S_pool,
                                                  unsigned char* smem, uint64_t* full, uint64_t* empty, int* next,
                                                  int flush, int wk_log2, uint32_t one) {
-#define GK_W_CASE(T) \
-    case T: score_item_w<GP, T>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
+#define GK_W_CASE(T)                                                                                                        \
+    case T:                                                                                                                 \
+        if (wk_log2 == 2)                                                                                                   \
+            score_item_w<GP, T, true>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one);   \
+        else                                                                                                                \
+            score_item_w<GP, T, false>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one);  \
+        break;
     switch (tap) {
         GK_W_CASE(1) GK_W_CASE(2) GK_W_CASE(3) GK_W_CASE(4) GK_W_CASE(5) GK_W_CASE(6) GK_W_CASE(7)
-        default: score_item_w<GP, 8>(item, M, X, L_pool, P_pool, S_pool, smem, full, empty, next, flush, wk_log2, one); break;
+        default: GK_W_CASE(8)
     }
 #undef GK_W_CASE
 }
