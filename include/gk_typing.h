@@ -61,7 +61,9 @@ typedef struct GkMatrix {
     int32_t n_ablk;      /* ceil(n_alleles / a_tile)                                                     */
     int32_t n_reads_total; /* reads of the whole problem when its reads are sharded over ranks (the
                             denominator of the read fractions); = n_reads otherwise                      */
-    int32_t pad0;
+    int32_t m_max;       /* upper bound of every m[r, a] of this matrix (the largest K_r; m <= K_r), or 0 when
+                            unknown.  Below 128 the tie-counting and P kernels take their cheaper byte
+                            predicates (gk_rescore.cu); it never changes a result                         */
 } GkMatrix;
 
 /* State of one search.  Strides are fixed by (top_n, GK_MAX_CN). */

@@ -24,7 +24,7 @@ LIB_PATH = os.environ.get("GK_LIB") or os.path.join(os.path.dirname(os.path.absp
 MATRIX_DTYPE = np.dtype([
     ("mem_off", "<i8"), ("entoff_off", "<i8"), ("L_off", "<i8"), ("LT_off", "<i8"), ("col_off", "<i8"),
     ("n_reads", "<i4"), ("n_alleles", "<i4"), ("n_words", "<i4"), ("r_pad", "<i4"),
-    ("a_tile", "<i4"), ("n_ablk", "<i4"), ("n_reads_total", "<i4"), ("pad0", "<i4"),
+    ("a_tile", "<i4"), ("n_ablk", "<i4"), ("n_reads_total", "<i4"), ("m_max", "<i4"),
 ], align=True)
 
 SEARCH_DTYPE = np.dtype([

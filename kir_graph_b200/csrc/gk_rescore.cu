@@ -43,6 +43,41 @@ __device__ __forceinline__ uint32_t zero80(uint32_t x) {
     return ~(t | x) & 0x80808080u;
 }
 
+// Counts below 128 (m_max of the matrix, known on the host: m <= K_r) make the predicates cheap, and the
+// adds can leave the ALU pipe - the bound of both kernels of this file - for the FMA pipe:
+//     (a | 0x80..) - b        bit 7 of a byte = [a >= b], no borrow crosses a byte     LOP3 + IMAD
+//     x + 0x7f..              bit 7 = [x != 0]                                         IMAD
+//     prmt with sign replication turns bit 7 into a 0xff byte mask                     PRMT
+// acc = x * one + acc with `one` read from constant memory is an IMAD (ptxas cannot fold it into an IADD3).
+__constant__ uint32_t gk_one = 1u;
+__constant__ uint32_t gk_minus_one = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b) {        // a + b on the FMA pipe
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(gk_one), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t fma_sub(uint32_t a, uint32_t b) {        // a - b on the FMA pipe
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(gk_minus_one), "r"(a));
+    return d;
+}
+// bytes of a and b below 128: bit 7 of every byte of the result = [a >= b]
+__device__ __forceinline__ uint32_t ge7(uint32_t a, uint32_t b) { return fma_sub(a | 0x80808080u, b); }
+// bytes of x below 128: bit 7 of every byte of the result = [x != 0]
+__device__ __forceinline__ uint32_t nz7(uint32_t x) { return fma_add(x, 0x7f7f7f7fu); }
+// 0xff in the bytes whose bit 7 is set, 0x00 elsewhere
+__device__ __forceinline__ uint32_t sign_mask(uint32_t x) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xba98u));
+    return d;
+}
+// byte-wise minimum of a and b, both below 128 per byte: 3 ALU-pipe instructions + 1 IMAD
+__device__ __forceinline__ uint32_t min7(uint32_t a, uint32_t b) {
+    const uint32_t keep = sign_mask(ge7(b, a));                      // 0xff where a stays (b >= a)
+    return (a & keep) | (b & ~keep);
+}
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t c) {
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     return c;
@@ -79,12 +114,129 @@ __device__ __forceinline__ void count_pair(const uint8_t* row_a, const uint8_t* 
     }
 }
 
+// The same for counts below 128: 4 ALU-pipe and 4 FMA-pipe instructions per word pair (7 and 2 above).
+__device__ __forceinline__ void count_pair_small(const uint8_t* row_a, const uint8_t* row_b, int r0, int r1,
+                                                 int n_reads, uint32_t* __restrict__ out) {
+    const int lane = gk_lane();
+    uint32_t n_ge = 0u, n_ne = 0u, n_all = 0u;                       // n_ge, n_ne in units of 1/128 read
+#pragma unroll 2
+    for (int r = r0 + lane * 16; r < r1; r += 32 * 16) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(row_a + r));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(row_b + r));
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            n_ge = __dp4a(ge7(av[w], bv[w]) & 0x80808080u, 0x01010101u, n_ge);
+            n_ne = __dp4a(nz7(av[w] ^ bv[w]) & 0x80808080u, 0x01010101u, n_ne);
+        }
+        n_all += 16u;
+    }
+    n_ge = warp_sum(n_ge) >> 7;
+    n_ne = warp_sum(n_ne) >> 7;
+    n_all = warp_sum(n_all);
+    if (lane == 0) {
+        const int pad_lo = r0 > n_reads ? r0 : n_reads;
+        const uint32_t pad = r1 > pad_lo ? (uint32_t)(r1 - pad_lo) : 0u;
+        const uint32_t n_eq = n_all - n_ne;
+        const uint32_t lt = n_all - n_ge, gt = n_ge - n_eq, eq = n_eq - pad;
+        if (lt) atomicAdd(out + 0, lt);          // cnt[0][q=1]
+        if (eq) atomicAdd(out + 1, eq);          // cnt[0][q=2]
+        if (gt) atomicAdd(out + 2, gt);          // cnt[1][q=1]
+        if (eq) atomicAdd(out + 3, eq);          // cnt[1][q=2]
+    }
+}
+
+// Three or four members with counts below 128: count the reads of every tie PATTERN (the non-empty
+// subsets S of the members: exactly the members of S attain the minimum) and fold the patterns into
+// cnt[t][|S|] at the end.  A pattern flag is one LOP3 of the per-member flags (bit 7 of a byte = member t
+// attains the minimum), so no tie size, binary digits or selectors are formed: N = 3 needs 17 ALU-pipe
+// instructions per word where the digit form needs about 36.
+template <int N>
+__device__ __forceinline__ void count_set_small(const uint8_t* const (&rows)[N], int r0, int r1, int n_reads,
+                                                uint32_t* __restrict__ out) {
+    static_assert(N == 3 || N == 4, "pattern counting is written for three and four members");
+    constexpr int NP = (1 << N) - 1;
+    constexpr uint32_t H = 0x80808080u;
+    const int lane = gk_lane();
+    uint32_t pc[NP];                                                 // pc[S - 1], in units of 1/128 read
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pc[i] = 0u;
+    for (int r = r0 + lane * 16; r < r1; r += 32 * 16) {
+        uint4 x[N];
+#pragma unroll
+        for (int t = 0; t < N; ++t) x[t] = __ldg(reinterpret_cast<const uint4*>(rows[t] + r));
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t v[N];
+#pragma unroll
+            for (int t = 0; t < N; ++t) v[t] = w == 0 ? x[t].x : w == 1 ? x[t].y : w == 2 ? x[t].z : x[t].w;
+            uint32_t mn = v[0];
+#pragma unroll
+            for (int t = 1; t < N; ++t) mn = min7(mn, v[t]);
+            uint32_t e[N];                                           // bit 7 of a byte: member t attains the minimum
+#pragma unroll
+            for (int t = 0; t < N; ++t) {
+                e[t] = ge7(mn, v[t]) & H;                            // mn >= v[t] means v[t] attains the minimum
+                // keep the masked flag in a register: folded into the pattern expressions the mask becomes
+                // a fourth input of every one of them, i.e. a second LOP3 per pattern
+                asm volatile("" : "+r"(e[t]));
+            }
+            if constexpr (N == 3) {
+#pragma unroll
+                for (int S = 1; S <= NP; ++S) {
+                    const uint32_t f = ((S & 1) ? e[0] : ~e[0]) & ((S & 2) ? e[1] : ~e[1]) & ((S & 4) ? e[2] : ~e[2]);
+                    pc[S - 1] = __dp4a(f, 0x01010101u, pc[S - 1]);
+                }
+            } else {
+                // the four combinations of members 0 and 1 first (bits outside bit 7 may be set in the
+                // negated ones; every pattern has a member, whose flag clears them - except through the
+                // pair (not 0, not 1), which is masked here)
+                uint32_t p01[4] = {~e[0] & ~e[1] & H, e[0] & ~e[1], ~e[0] & e[1], e[0] & e[1]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) asm volatile("" : "+r"(p01[i]));
+#pragma unroll
+                for (int S = 1; S <= NP; ++S) {
+                    const uint32_t f = p01[S & 3] & ((S & 4) ? e[2] : ~e[2]) & ((S & 8) ? e[3] : ~e[3]);
+                    pc[S - 1] = __dp4a(f, 0x01010101u, pc[S - 1]);
+                }
+            }
+        }
+    }
+    const int pad_lo = r0 > n_reads ? r0 : n_reads;
+    const uint32_t pad = r1 > pad_lo ? (uint32_t)(r1 - pad_lo) : 0u;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pc[i] = warp_sum(pc[i]) >> 7;
+    pc[NP - 1] -= pad;                                               // pad reads are all-zero rows: every member ties
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            uint32_t c[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) c[q] = 0u;
+#pragma unroll
+            for (int S = 1; S <= NP; ++S)
+                if (S & (1 << t)) c[__popc(S) - 1] += pc[S - 1];
+#pragma unroll
+            for (int q = 0; q < N; ++q)
+                if (c[q]) atomicAdd(out + t * N + q, c[q]);
+        }
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void count_set(const uint8_t* const (&rows)[N], int r0, int r1, int n_reads,
-                                          uint32_t* __restrict__ out) {
+                                          uint32_t* __restrict__ out, bool small) {
     if constexpr (N == 2) {
-        count_pair(rows[0], rows[1], r0, r1, n_reads, out);
+        if (small) count_pair_small(rows[0], rows[1], r0, r1, n_reads, out);
+        else count_pair(rows[0], rows[1], r0, r1, n_reads, out);
         return;
+    }
+    if constexpr (N == 3 || N == 4) {
+        if (small) {
+            count_set_small<N>(rows, r0, r1, n_reads, out);
+            return;
+        }
     }
     const int lane = gk_lane();
     uint32_t cnt[N][N];
@@ -167,7 +319,8 @@ gk_rescore_count_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* _
 #pragma unroll
     for (int t = 0; t < N - 1; ++t) rows[t] = LT + (int64_t)prev[t] * M.r_pad;
     rows[N - 1] = LT + (int64_t)a * M.r_pad;
-    count_set<N>(rows, item.r0, item.r1, M.n_reads, cnt_pool + X.cnt_off + (int64_t)f * N * N);
+    count_set<N>(rows, item.r0, item.r1, M.n_reads, cnt_pool + X.cnt_off + (int64_t)f * N * N,
+                 M.m_max > 0 && M.m_max < 128);
 }
 
 // P tiles: one k-block (GK_KB = 64 kept sets) x 512 reads at a time, over the item's read range.
@@ -193,6 +346,7 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
     const int K = kept_count[item.search];
     const int lane = gk_lane();
     const int warp = gk_warp();
+    const bool small = M.m_max > 0 && M.m_max < 128;
     // member ids of the 64 sets of this k-block
     for (int i = threadIdx.x; i < GK_KB * GK_MAX_CN; i += kThreads) {
         const int k = item.k_blk * GK_KB + i / GK_MAX_CN;
@@ -208,13 +362,23 @@ gk_write_p_kernel(const GkMatrix* __restrict__ matrices, const GkSearch* __restr
         for (int kl = warp; kl < GK_KB; kl += kWarps) {
             uint4 mn = make_uint4(0u, 0u, 0u, 0u);
             if (in_range && item.k_blk * GK_KB + kl < K) {
-                mn = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                for (int t = 0; t < n_set; ++t) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(LT + (int64_t)s_ids[kl * GK_MAX_CN + t] * M.r_pad));
-                    mn.x = __vminu4(mn.x, v.x);
-                    mn.y = __vminu4(mn.y, v.y);
-                    mn.z = __vminu4(mn.z, v.z);
-                    mn.w = __vminu4(mn.w, v.w);
+                mn = __ldg(reinterpret_cast<const uint4*>(LT + (int64_t)s_ids[kl * GK_MAX_CN] * M.r_pad));
+                if (small) {                  // counts below 128: 3 ALU-pipe instructions per byte-wise minimum
+                    for (int t = 1; t < n_set; ++t) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(LT + (int64_t)s_ids[kl * GK_MAX_CN + t] * M.r_pad));
+                        mn.x = min7(mn.x, v.x);
+                        mn.y = min7(mn.y, v.y);
+                        mn.z = min7(mn.z, v.z);
+                        mn.w = min7(mn.w, v.w);
+                    }
+                } else {
+                    for (int t = 1; t < n_set; ++t) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(LT + (int64_t)s_ids[kl * GK_MAX_CN + t] * M.r_pad));
+                        mn.x = __vminu4(mn.x, v.x);
+                        mn.y = __vminu4(mn.y, v.y);
+                        mn.z = __vminu4(mn.z, v.z);
+                        mn.w = __vminu4(mn.w, v.w);
+                    }
                 }
             }
             *reinterpret_cast<uint4*>(tile + kl * kPWords + 4 * (lane ^ ((kl >> 2) & 15))) = mn;

@@ -357,7 +357,8 @@ class HostBatch:
             r_pad = max(128, _round_up(p.n_reads, 128))
             n_total = getattr(p, "n_reads_total", None)        # set on a read shard (packing.shard_reads)
             table[i] = (mem_off, entoff_off, L_off, LT_off, col_off, p.n_reads, p.n_alleles, p.n_words,
-                        r_pad, a_tile, n_ablk, p.n_reads if n_total is None else n_total, 0)
+                        r_pad, a_tile, n_ablk, p.n_reads if n_total is None else n_total,
+                        min(int(p.k_obs.max(initial=0)), 255))
             ent_bases.append(ent_base)
             mem_off += p.n_words * n_ablk * a_tile
             entoff_off += p.n_reads + 1

@@ -316,6 +316,49 @@ def test_many_observations_per_read(cuda, packed):
         assert np.array_equal(out.ids, ref.allele_id) and np.array_equal(out.score, ref.score)
 
 
+def _cap_observations(csr, cap):
+    """The reads with their lists cut from the end (rnv, lnv, rpv, lpv) to at most ``cap`` observations."""
+    names = ("lpv", "rpv", "lnv", "rnv")
+    lens = {n: np.diff(csr.offsets[n]) for n in names}
+    excess = np.maximum(sum(lens.values()) - cap, 0)
+    for n in reversed(names):
+        cut = np.minimum(excess, lens[n])
+        lens[n] = lens[n] - cut
+        excess = excess - cut
+    offsets, indices = {}, {}
+    for n in names:
+        off = np.zeros(csr.n_reads + 1, dtype=np.int64)
+        np.cumsum(lens[n], out=off[1:])
+        row = np.repeat(np.arange(csr.n_reads), lens[n])
+        indices[n] = csr.indices[n][csr.offsets[n][:-1][row] + (np.arange(off[-1]) - off[:-1][row])]
+        offsets[n] = off
+    return type(csr)(csr.n_reads, offsets, indices)
+
+
+@pytest.mark.parametrize("cap", [127, 128, 255])
+def test_tie_counts_and_p_on_both_byte_predicate_paths(cuda, cap):
+    """The tie-counting and P kernels take cheaper byte predicates when every count of the matrix is below
+    128 (GkMatrix.m_max): reads with at most 127 observations take that path with the largest value it
+    allows, 128 and 255 take the general one; two, three and four members, ids / scores / fraction
+    numerators / P against the oracle's integer search."""
+    import dataclasses
+    gene = synthetic.make_gene([92, 0], "KIRWIDE*BACKBONE", 30, 400, 4, 2500, w=100)
+    pack = packing.pack_synthetic(dataclasses.replace(gene, reads=_cap_observations(gene.reads, cap)))
+    assert pack.k_obs.max() == min(cap, 200)          # the generator's reads carry about 200 observations
+    batch = engine.MatrixBatch([pack], backend=cuda)
+    assert int(batch.host.table["m_max"][0]) == int(pack.k_obs.max())
+    m = batch.mismatch_counts(0)
+    search = orc.IntSearch(m.astype(np.int64), pack.k_obs, top_n=40)
+    group = engine.SearchGroup(batch, [0], 40)
+    for step in range(4):
+        out = group.step(need_next=[step < 3])[0]
+        ref = search.add_candidate()
+        assert np.array_equal(out.ids, ref.allele_id) and np.array_equal(out.score, ref.score)
+        w = np.array([orc.lcm_upto(out.n) // q for q in range(1, out.n + 1)])
+        assert np.array_equal((out.cnt * w[None, None, :]).sum(axis=2), ref.frac_num)
+    assert np.array_equal(group.materialize_p(0, out.ids), ref.allele_prob)
+
+
 def test_scattered_observations_overflow_the_staged_entries(cuda):
     """Reads whose observations are scattered over the variant table produce more than 1024 entries per
     64-read tile, which takes the likelihood kernel's unstaged path."""
