@@ -861,9 +861,16 @@ class SearchGroup:
     # is cut: pieces that give a lane at least 6 rows where possible (a lane's shared-memory loads per minimum
     # are (2 G' + 2 TA') / (3 G' TA'): a 16-row piece needs twice the loads per cell of a 32-row one), measured
     # with tools/probe_score_shapes.py
-    _W_PIECE = {1: (1, 0), 2: (2, 0), 3: (3, 0), 4: (4, 0), 6: (3, 1), 8: (4, 1), 12: (3, 2), 16: (4, 2)}
-    _W_CUT = {1: (1,), 2: (2,), 3: (3,), 4: (4,), 5: (3, 2), 6: (6,), 7: (4, 3), 8: (8,), 9: (6, 3), 10: (6, 4),
-              11: (8, 3), 12: (12,), 13: (6, 4, 3), 14: (8, 6), 15: (12, 3)}
+    # _W_CUT[g] = the pieces (G', log2 WK) that cover a remainder of g row groups, in order; a piece spans
+    # (8 G') << log2 WK rows and the last one may reach beyond the kept sets (P and S are allocated in whole
+    # 64-row blocks and rows >= the kept count are never read back).
+    # Measured per remainder size with tools/tune_row_cuts.py (profiles/r02_row_cuts.txt): one piece of four
+    # (or two) warps per row block beats an exact cover by smaller pieces even when it computes up to 37 %
+    # padding rows - a warp of a narrow piece has a quarter of the reads of every stage and pays the
+    # per-stage overhead four times as often.
+    _W_CUT = {1: ((1, 0),), 2: ((2, 0),), 3: ((3, 0),), 4: ((4, 0),), 5: ((3, 1),), 6: ((3, 1),), 7: ((2, 2),),
+              8: ((4, 1),), 9: ((3, 1), (3, 0)), 10: ((3, 2),), 11: ((3, 2),), 12: ((3, 2),), 13: ((4, 2),),
+              14: ((4, 2),), 15: ((4, 2),)}
 
     @classmethod
     def _row_pieces(cls, k: int, kind: str) -> list[tuple[int, int, int]]:
@@ -872,7 +879,9 @@ class SearchGroup:
         of the remainder as one full-width tile; kind "H": what is left of that remainder (< 32 rows), as a
         warp-split tile (used over the two 64-allele halves); kind "W": under a warp-split column tile -
         128-row tiles, then the remainder cut into the spans a warp-split tile offers (``_W_CUT``).  Every
-        piece starts at a multiple of 8 rows; nothing is padded beyond 8 ceil(k / 8)."""
+        piece starts at a multiple of 8 rows; kinds "F" and "H" pad nothing beyond 8 ceil(k / 8), kind "W"
+        may pad the remainder up to the next multiple of 32 rows where that is faster (never beyond the
+        64-row blocks P and S are allocated in)."""
         out = []
         n_full, rem = divmod(k, 128)
         if kind == "F":
@@ -887,10 +896,9 @@ class SearchGroup:
             return out
         out += [(128 * i, 4 | (2 << 4) | SHAPE_WARP_SPLIT, 128) for i in range(n_full)]
         at = 128 * n_full
-        for groups in cls._W_CUT.get(-(-rem // 8), ()):
-            gp, wk = cls._W_PIECE[groups]
-            out.append((at, gp | (wk << 4) | SHAPE_WARP_SPLIT, 8 * groups))
-            at += 8 * groups
+        for gp, wk in cls._W_CUT.get(-(-rem // 8), ()):
+            out.append((at, gp | (wk << 4) | SHAPE_WARP_SPLIT, (8 * gp) << wk))
+            at += (8 * gp) << wk
         return out
 
     def _packed_tiles(self, live: np.ndarray, kept: np.ndarray):
