@@ -5,7 +5,7 @@ samples/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cohort|wgs30x|deep]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # CPU arm: the oracle's float64 NumPy restatement
+    python bench.py --impl reference ...      # CPU arm: the unmodified reference (oracle/_ref) on every host core
 
 One step = one pass of the hot path over the whole batch: likelihood build (kernel a), every
 copy-number step of the greedy search (kernels b, c) and the allele calls.
@@ -23,7 +23,12 @@ copy-number step of the greedy search (kernels b, c) and the allele calls.
   warm-up pass afterwards (``parity.every_timed_pass_equals_warmup_calls``).
   roofline        dominant kernel (gk_score), CUDA events around every launch of extra passes run
                   right after the timed region (eager launches, one stream)
-  cpu_baseline    the oracle (kind "port": reference NumPy expressions, read-chunked) on host cores
+  roofline        ... bound "issue_nontensor": one issue slot per cell (2 VIMNMX.U16x2 on the ALU pipe + 2 IMAD on
+                  the FMA pipe per 4 cells), with the fraction of the measured peak of that mix and of round 1's
+                  ALU-only denominator beside it (score_roofline below)
+  cpu_baseline    the reference itself (kind "reference": oracle/_ref, the byte-compiled graphkir typing path,
+                  likelihood build included, one process per sample on every host core) over a bounded
+                  sample; kind "port" (the oracle's NumPy restatement) only where oracle/_ref is absent
 
 Workloads: cohort = cfg5 (96 x cfg3, sample-sharded over the ranks, strong
 scaling), wgs30x = cfg3 (one sample, 17 genes), deep = cfg4 (2M reads x 1000 alleles, CN 6).
