@@ -38,6 +38,13 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+#ifndef GK_LIK_UNROLL
+#define GK_LIK_UNROLL 2       // entries of a quad in flight per warp (each is a dependent LDS -> LDG -> LOP3 / POPC chain)
+#endif
+#ifndef GK_LIK_CTAS
+#define GK_LIK_CTAS 5         // resident CTAs per SM the register budget is cut for
+#endif
+constexpr int kEntUnroll = GK_LIK_UNROLL;
 constexpr int kReadsPerWarp = GK_LIK_READS / kWarps;   // 16 consecutive reads = 4 quads of four reads
 constexpr int kWarpEnt = 96;                           // entries of a warp's 16 reads staged in shared memory
 constexpr int kTilePitch = GK_LIK_READS + 16;          // bytes; keeps the rows of the LT tile 16-byte aligned
@@ -126,7 +133,7 @@ __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int 
         };
         if (staged) {                                 // shared-memory loads (LDS), not generic ones
             const uint4* ent_ptr = s_ent + (e0 - e_first);
-#pragma unroll 2
+#pragma unroll kEntUnroll
             for (int i = e1 - e0; i > 0; --i, ++ent_ptr) visit(*ent_ptr);
         } else {
             const uint4* ent_ptr = entries + e0;
@@ -188,7 +195,7 @@ __device__ __forceinline__ void lik_warp(const GkMatrix& M, int r0, int a0, int 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, GK_LIK_CTAS)
 gk_likelihood_kernel(const GkMatrix* __restrict__ matrices, const GkLikItem* __restrict__ items,
                      const uint32_t* __restrict__ mem_pool, const int32_t* __restrict__ entoff_pool,
                      const uint4* __restrict__ entries, float* __restrict__ L_pool,
