@@ -870,7 +870,7 @@ class SearchGroup:
     # per-stage overhead four times as often.
     _W_CUT = {1: ((1, 0),), 2: ((2, 0),), 3: ((3, 0),), 4: ((4, 0),), 5: ((3, 1),), 6: ((3, 1),), 7: ((2, 2),),
               8: ((4, 1),), 9: ((3, 1), (3, 0)), 10: ((3, 2),), 11: ((3, 2),), 12: ((3, 2),), 13: ((4, 2),),
-              14: ((4, 2),), 15: ((4, 2),)}
+              14: ((4, 2),), 15: ((4, 2),), 16: ((4, 2),)}
 
     @classmethod
     def _row_pieces(cls, k: int, kind: str) -> list[tuple[int, int, int]]:

@@ -40,6 +40,9 @@ def check_steps(group_out, ref):
     dict(seed=[7, 2], n_allele=70, n_var=560, cn=2, n_reads=300, top_n=40),
     dict(seed=[7, 3], n_allele=150, n_var=600, cn=2, n_reads=140, top_n=130),
     dict(seed=[7, 4], n_allele=14, n_var=64, cn=7, n_reads=120, top_n=20),
+    # 125 kept sets at the second step: a remainder of 16 row groups (121..127 rows) had no tile at all
+    dict(seed=[7, 5], n_allele=125, n_var=500, cn=2, n_reads=120, top_n=300),
+    dict(seed=[7, 6], n_allele=40, n_var=160, cn=3, n_reads=100, top_n=250),
 ])
 @pytest.mark.parametrize("half", [False, True])
 def test_search_group_equals_int_oracle(spec, half):
@@ -344,3 +347,25 @@ def test_exon_first_candidates_typed_in_chunks_give_the_same_result(monkeypatch)
     whole = run()
     monkeypatch.setattr(tma, "INTRON_SEARCH_BUDGET_BYTES", 1)
     assert run() == whole and whole[2] > case["cn"] + 1
+
+
+def test_row_pieces_cover_every_kept_set_once_inside_the_allocated_blocks():
+    """Row tiles of the packed scoring path (SearchGroup._row_pieces): for every kept-set count the pieces
+    under a warp-split column tile ("W") and under a full-width tile plus its halves ("F" + "H") cover rows
+    0 .. k-1 exactly once, start at multiples of 8, may pad only beyond k, stay inside the 64-row blocks P
+    and S are allocated in for top_n = k, and span at most two k-blocks each (what a stage copies)."""
+    from kir_graph_b200.engine import SHAPE_WARP_SPLIT, SearchGroup
+    for k in range(1, 700):
+        alloc = 64 * -(-k // 64)
+        for kinds in (("W",), ("F", "H")):
+            cover = np.zeros(alloc, dtype=np.int64)
+            for kind in kinds:
+                for start, code, rows in SearchGroup._row_pieces(k, kind):
+                    assert start % 8 == 0 and rows > 0 and start + rows <= alloc, (k, kind, start, rows)
+                    assert (start % 64) + rows <= 128, (k, kind, start, rows)
+                    if code & SHAPE_WARP_SPLIT:
+                        gp, wk = code & 0xf, (code >> 4) & 0xf
+                        assert rows == (8 * gp) << wk and 1 <= gp <= 4 and wk <= 2
+                    cover[start:start + rows] += 1
+            assert (cover[:k] == 1).all(), (k, kinds)
+            assert (cover[k:] <= 1).all(), (k, kinds)

@@ -81,7 +81,8 @@ def test_every_launch_matches_numpy_statement(cuda, specs, top_n, cns, half):
 
 
 @pytest.mark.parametrize("half", [False, True])
-@pytest.mark.parametrize("a,cn,r,top_n", [(120, 3, 6000, 300), (200, 2, 12000, 300), (45, 4, 3000, 64)])
+@pytest.mark.parametrize("a,cn,r,top_n", [(120, 3, 6000, 300), (200, 2, 12000, 300), (45, 4, 3000, 64),
+                                          (125, 2, 4000, 300), (40, 3, 3000, 250)])
 def test_search_equals_oracle(cuda, a, cn, r, top_n, half):
     gene = synthetic.make_gene([77, a], "KIRO*BACKBONE", a, 8 * a, cn, r)
     pack = packing.pack_synthetic(gene)
