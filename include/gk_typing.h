@@ -172,7 +172,7 @@ int gk_first_step(const GkMatrix* matrices, const GkSearch* searches, int n_sear
  *     S_pool (zeroed by the caller); the min-sum score is (colsum[a] + score_prev[k] - D[k, a]) / 2,
  *     formed by gk_select / gk_rank (score_prev = score_out of the previous step = sum_r P[r, k]).
  *     Packed path (half_mode = 1: L as 16-bit pairs, P as uint16): accumulates the min-sum itself
- *     with VIMNMX.U16x2 + IADD3 on 16-bit lanes that are added to S_pool every flush_stages stages
+ *     with VIMNMX.U16x2 + IMAD on 16-bit lanes that are added to S_pool every flush_stages stages
  *     of GK_RT reads: flush_stages * GK_RT * (largest m of the batch) must be <= 65535.  Pass
  *     s_is_minsum = 1 to gk_select / gk_rank. */
 int gk_score(const GkMatrix* matrices, const GkSearch* searches, const GkScoreItem* items, int n_items,

@@ -7,8 +7,8 @@
 // Reads are the reduction dimension.  No tensor cores: max-then-sum is not a multiply-accumulate.
 //
 // Two kernels share the tiling and the pipeline:
-//   gk_score_packed_kernel (default)  16-bit integer lanes: 2 VIMNMX.U16x2 + 1 IADD3 per 4 cells on
-//       the ALU pipe, the min-sum itself goes to S (see score_item_h / score_item_w below);
+//   gk_score_packed_kernel (default)  16-bit integer lanes: 2 VIMNMX.U16x2 on the ALU pipe + 2 IMAD (the
+//       adds) on the FMA pipe per 4 cells, the min-sum itself goes to S (see score_item_h / score_item_w);
 //   gk_score_kernel                   FP32: D[k, a] += sum_r |L[r, a] - P[r, k]| with two FADDs per
 //       cell; the consumers recover sum_r min(L, P) = (colsum_L[a] + colsum_P[k] - D[k, a]) / 2
 //       (colsum_L = the CN=1 column sums, colsum_P[k] = the previous step's score of set k).  The
@@ -29,8 +29,8 @@
 // (granularity 8).
 //
 // Bound: non-tensor instruction issue.  FP32 path: 2 FADD per cell on the 128 lanes/clk/SM FMA pipe
-// = 148 SM x 64 cells/clk x f_clk; packed path: 0.75 instructions per cell on the 64 lanes/clk/SM
-// ALU pipe = 148 SM x 85.3 cells/clk x f_clk.
+// = 148 SM x 64 cells/clk x f_clk; packed path: one issue slot per cell (half an ALU-pipe and half an
+// FMA-pipe instruction) = 148 SM x 128 cells/clk x f_clk, 106 cells/clk/SM measured for the mix.
 #include "gk_common.cuh"
 
 namespace {
@@ -201,15 +201,16 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 }
 
 // ---------------------------------------------------------------------------------------
-// Packed 16-bit integer path (ALU pipe): 0.75 instructions per cell instead of 2.
+// Packed 16-bit integer path: one instruction per cell instead of 2, split over the ALU and FMA pipes.
 //
 // P is stored as uint16 [k_blk][r][64], L as the pair (m, m) in one 32-bit word [a_blk][r][32].
 // A thread owns row pairs (2 tk, 2 tk + 1) of every 32-row group g < G of the tile, so one 32-bit
 // word of P holds two rows and pairs with the duplicated L value:
-//     acc2 += min.u16x2(p2(r), l2(r)) + min.u16x2(p2(r+1), l2(r+1))
-// = 2 VIMNMX.U16x2 + 1 IADD3 for 4 cells (two reads are folded into one 3-input add).  These
-// issue on the half-rate ALU pipe (1.5 clk per cell against 2 clk for the two FADDs of the FP32
-// path; tools/micro/mixpipe.cu measures 83 against 55 cells/clk/SM).  Everything is integer, so
+//     acc2 += min.u16x2(p2(r), l2(r))
+// = 1 VIMNMX.U16x2 + 1 add for 2 cells.  (Until the middle of round 2 two reads were folded into one
+// 3-input IADD3: 0.75 instructions per cell, but all of them on the half-rate ALU pipe -
+// tools/micro/mixpipe.cu measures 83 cells/clk/SM for that, 55 for the two FADDs of the FP32 path; see
+// add_fma below for what replaced it.)  Everything is integer, so
 // it is exact for every supported input (counts <= 255).  A 16-bit lane holds 65535 / m_max reads
 // (m_max = the largest count of the batch, <= 255), so every `flush` stages (the host derives it
 // from m_max) the packed sums are added to S with integer atomics; there are no 32-bit
@@ -223,6 +224,7 @@ __device__ __forceinline__ void score_item(const GkScoreItem& item, const GkMatr
 // is one issue slot per cell and 0.5 ALU-pipe instructions per cell.  tools/micro/mixpipe.cu measures
 // 106 cells/clk/SM for this mix against 83 for 2 VIMNMX + 1 IADD3 (profiles/r02_mixpipe.txt); mixes of
 // IADD3 and IMAD adds land in between.
+
 // N consecutive 32-bit words of shared memory with the widest load their alignment allows (the callers
 // guarantee 8-byte alignment for N = 2 and 16-byte alignment for N = 4).
 template <int N>

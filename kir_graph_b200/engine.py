@@ -453,9 +453,9 @@ class MatrixBatch:
     """Likelihood data of a batch of gene problems, resident on one GPU."""
 
     def __init__(self, packs, backend=None, run: bool = True, packed: bool = PACKED_DEFAULT, reduce=None):
-        """``packed``: score on 16-bit integer lanes (VIMNMX.U16x2 + IADD3 on the ALU pipe, 1.5 clk per
-        cell; ``L`` holds the pair (m, m), ``P`` is uint16) instead of FP32 (two FADDs, 2 clk per
-        cell).  Both are exact for every supported input (counts <= 255).
+        """``packed``: score on 16-bit integer lanes (VIMNMX.U16x2 on the ALU pipe + IMAD on the FMA pipe,
+        one issue slot per cell; ``L`` holds the pair (m, m), ``P`` is uint16) instead of FP32 (two FADDs
+        per cell).  Both are exact for every supported input (counts <= 255).
         ``reduce(tensor)``: the packs are read shards of problems whose other reads live on other
         ranks (``packing.shard_reads``); the callable sums a device array over the ranks in place and
         is applied to the column sums after the likelihood build (integer sums: order independent)."""
