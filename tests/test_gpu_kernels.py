@@ -466,6 +466,27 @@ def test_wire_expansion_on_the_device_equals_the_numpy_statement(cuda):
         assert np.array_equal(cuda.download(getattr(bg, name)), cuda.download(getattr(legacy, name))), name
 
 
+@pytest.mark.parametrize("a", [36, 52, 100])
+def test_every_row_remainder_of_the_packed_tiles(cuda, a):
+    """Kept-set counts 8 g - 3 for g = 1 .. 16 row groups (every entry of SearchGroup._W_CUT, padded pieces
+    included) under one (36, 52 alleles) or two (100) warp-split column tiles: scores and kept sets of the
+    third step against the oracle's integer search."""
+    gene = synthetic.make_gene([93, a], "KIRROW*BACKBONE", a, 4 * a, 3, 1500)
+    pack = packing.pack_synthetic(gene)
+    batch = engine.MatrixBatch([pack], backend=cuda)
+    m = batch.mismatch_counts(0).astype(np.int64)
+    for g in range(1, 17):
+        top_n = 8 * g - 3
+        search = orc.IntSearch(m, pack.k_obs, top_n=top_n)
+        group = engine.SearchGroup(batch, [0], top_n)
+        for step in range(3):
+            out = group.step(need_next=[step < 2])[0]
+            ref = search.add_candidate()
+            assert np.array_equal(out.ids, ref.allele_id), (a, g, step)
+            assert np.array_equal(out.score, ref.score), (a, g, step)
+        assert len(ref.score) == top_n
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_random_batches_match_numpy_statement(cuda, seed):
     """Randomised shapes through every launch: allele counts 1..260 (all lane layouts of the likelihood kernel,
