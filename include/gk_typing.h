@@ -326,6 +326,27 @@ void gk_sam_extract_free(void* handle);
 int gk_sam_extract_json(void* handle, const char* sam, const int64_t* id_off, const char* id_bytes,
                         int32_t novel_id, const char** out, int64_t* out_len);
 
+/* Host: work-item tables of the search kernels (csrc/gk_plan.cu; no CUDA calls).  They restate what
+ * kir_graph_b200/engine.py builds with NumPy per copy-number step (the definition, and the fallback for the
+ * FP32 scoring path, restricted candidate lists and candidate-column sharding), row for row, for hosts that
+ * type a new cohort every pass.
+ * gk_plan_score_tiles / gk_plan_score_items: packed scoring path.  A / kept / r16 (reads rounded up to GK_RT)
+ *     per live search; cut = int32 [17][3][2]: for a remainder of g = 1..16 row groups of 8 kept sets up to
+ *     three warp-split pieces (G', log2 WK), G' = 0 ends the list (engine.SearchGroup._W_CUT).  _tiles counts
+ *     the (row piece x column tile) pairs per search (the caller picks the read chunk from them); _items
+ *     writes every tile x every chunk of `chunk` reads as GkScoreItem with .search = search_id[j], largest
+ *     item first (stable).
+ * gk_plan_grid_items: rows {search_id[j], i * scale, r0, r1} for i < count[j] and the chunks [r0, r1) of
+ *     `chunk` reads over extent[j], the chunk varying fastest: GkCountItem (count = ceil(alive / 8), scale 8,
+ *     extent = reads rounded up to 16) and GkPItem (count = k-blocks, scale 1, extent = r_pad).
+ * _items / _grid_items return the number of rows, or -(rows needed) when `cap` is too small. */
+int64_t gk_plan_score_tiles(int n, const int64_t* A, const int64_t* kept, const int32_t* cut,
+                            int64_t* tiles_per_search);
+int64_t gk_plan_score_items(int n, const int32_t* search_id, const int64_t* A, const int64_t* kept,
+                            const int64_t* r16, int64_t chunk, const int32_t* cut, GkScoreItem* out, int64_t cap);
+int64_t gk_plan_grid_items(int n, const int32_t* search_id, const int64_t* count, int32_t scale,
+                           const int64_t* extent, int64_t chunk, int32_t* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,7 @@ EXPORTS = (
     "gk_select", "gk_rescore_count", "gk_rank", "gk_write_p", "gk_em_compat", "gk_em_squarem",
     "gk_group_reads", "gk_cn_fit", "gk_json_scan", "gk_json_fill", "gk_json_free", "gk_pack_entries", "gk_sam_walk",
     "gk_sam_extract", "gk_sam_extract_fill", "gk_sam_extract_free", "gk_sam_extract_json",
+    "gk_plan_score_tiles", "gk_plan_score_items", "gk_plan_grid_items",
 )
 
 _lib = None
@@ -86,6 +87,13 @@ def load(path: str | None = None) -> ctypes.CDLL:
             raise GkError(f"{path} does not export {name}")
     lib.gk_last_error.restype = ctypes.c_char_p
     lib.gk_sizeof.argtypes = [ctypes.c_char_p]
+    _vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    lib.gk_plan_score_tiles.restype = _i64
+    lib.gk_plan_score_tiles.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp]
+    lib.gk_plan_score_items.restype = _i64
+    lib.gk_plan_score_items.argtypes = [ctypes.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64]
+    lib.gk_plan_grid_items.restype = _i64
+    lib.gk_plan_grid_items.argtypes = [ctypes.c_int, _vp, _vp, _i32, _vp, _i64, _vp, _i64]
     for name, dtype in _STRUCTS.items():
         size = lib.gk_sizeof(name.encode())
         if size != dtype.itemsize:

@@ -48,6 +48,9 @@ PACKED_DEFAULT = _os.environ.get("GK_PACKED", "1") != "0"
 SCORE_SLOTS = int(_os.environ.get("GK_SCORE_SLOTS", 444))            # resident scoring CTAs: 148 SMs x 3
 SCORE_ITEM_OVERHEAD = int(_os.environ.get("GK_SCORE_ITEM_OVERHEAD", 48))   # fixed cost of a work item, in reads
 SCORE_CHUNK_CANDIDATES = (8192, 6144, 4096, 3072, 2048, 1536, 1024)
+# Work-item tables from the C++ host routines of csrc/gk_plan.cu (row for row what the NumPy statements
+# below produce; GK_PLAN=numpy keeps the NumPy path, which also serves the cases the routines do not cover)
+PLAN_NATIVE = _os.environ.get("GK_PLAN", "native") != "numpy"
 
 
 def _round_up(x: int, m: int) -> int:
@@ -872,6 +875,20 @@ class SearchGroup:
               8: ((4, 1),), 9: ((3, 1), (3, 0)), 10: ((3, 2),), 11: ((3, 2),), 12: ((3, 2),), 13: ((4, 2),),
               14: ((4, 2),), 15: ((4, 2),), 16: ((4, 2),)}
 
+    _cut_cache = None
+
+    @classmethod
+    def _cut_table(cls) -> np.ndarray:
+        """``_W_CUT`` as the int32 [17][3][2] array of csrc/gk_plan.cu (rebuilt when the table is replaced)."""
+        key = tuple(sorted(cls._W_CUT.items()))
+        if cls._cut_cache is None or cls._cut_cache[0] != key:
+            table = np.zeros((17, 3, 2), dtype=np.int32)
+            for g, pieces in cls._W_CUT.items():
+                for i, (gp, wk) in enumerate(pieces):
+                    table[g, i] = (gp, wk)
+            cls._cut_cache = (key, table)
+        return cls._cut_cache[1]
+
     @classmethod
     def _row_pieces(cls, k: int, kind: str) -> list[tuple[int, int, int]]:
         """Row tiles covering ``k`` kept sets as (first row, shape code without the column part, rows).
@@ -957,7 +974,16 @@ class SearchGroup:
         half = self.batch.half
         r16 = _round_up_arr(self.R[live], _cabi.GK_RT)
         custom = {}
-        if half:
+        native = (PLAN_NATIVE and half and not self.restricted
+                  and (self.col_shard is None or self.col_shard[1] <= 1))
+        if native:
+            lib = _cabi.load()
+            A_l = np.ascontiguousarray(self.A[live], dtype=np.int64)
+            kept_l = np.ascontiguousarray(kept[live], dtype=np.int64)
+            cut = self._cut_table()
+            tiles = np.zeros(len(live), dtype=np.int64)
+            lib.gk_plan_score_tiles(len(live), A_l.ctypes.data, kept_l.ctypes.data, cut.ctypes.data, tiles.ctypes.data)
+        elif half:
             # exact cover of the ragged kept-set and allele counts (granularity 8 x 8)
             t_search, t_kblk, t_ablk, t_shape, t_rows, t_cols = self._packed_tiles(live, kept)
             tiles = np.bincount(t_search, minlength=len(live)).astype(np.int64)
@@ -989,6 +1015,15 @@ class SearchGroup:
         if _os.environ.get("GK_SCORE_CHUNK"):                       # sweeps (tools/sweep_params.sh)
             chunk = int(_os.environ["GK_SCORE_CHUNK"])
         n_ch = np.maximum(1, -(-r16 // chunk))
+        if native:
+            r16_l = np.ascontiguousarray(r16, dtype=np.int64)
+            ids = np.ascontiguousarray(live, dtype=np.int32)
+            items = np.zeros(int((tiles * n_ch).sum()), dtype=SCORE_ITEM_DTYPE)
+            got = lib.gk_plan_score_items(len(live), ids.ctypes.data, A_l.ctypes.data, kept_l.ctypes.data,
+                                          r16_l.ctypes.data, int(chunk), cut.ctypes.data, items.ctypes.data, len(items))
+            if got != len(items):
+                raise RuntimeError(f"gk_plan_score_items wrote {got} rows, {len(items)} expected")
+            return items
         mode_span = np.array([128, 64, 16, 32, 48, 32, 64, 96, 128], dtype=np.int64)
         if half:
             per = n_ch[t_search]
@@ -1049,12 +1084,30 @@ class SearchGroup:
                            kind="stable")
         return items[order]
 
+    @staticmethod
+    def _grid_items(idx, count, scale: int, extent, chunk: int, dtype) -> np.ndarray:
+        """{search, index * scale, r0, r1} rows through gk_plan_grid_items (see the NumPy statements in
+        ``_p_items`` / ``_count_items``)."""
+        lib = _cabi.load()
+        ids = np.ascontiguousarray(idx, dtype=np.int32)
+        count = np.ascontiguousarray(count, dtype=np.int64)
+        extent = np.ascontiguousarray(extent, dtype=np.int64)
+        n_rows = int((count * np.maximum(1, -(-extent // chunk))).sum())
+        items = np.zeros(n_rows, dtype=dtype)
+        got = lib.gk_plan_grid_items(len(ids), ids.ctypes.data, count.ctypes.data, int(scale), extent.ctypes.data,
+                                     int(chunk), items.ctypes.data, n_rows)
+        if got != n_rows:
+            raise RuntimeError(f"gk_plan_grid_items wrote {got} rows, {n_rows} expected")
+        return items
+
     def _p_items(self, idx: np.ndarray) -> np.ndarray:
         kept = self.kept.astype(np.int64)
         idx = idx[kept[idx] > 0]
         if not len(idx):
             return np.zeros(0, dtype=P_ITEM_DTYPE)
         n_k64 = -(-kept[idx] // GK_KB)
+        if PLAN_NATIVE:
+            return self._grid_items(idx, n_k64, 1, self.r_pad[idx], P_READ_CHUNK, P_ITEM_DTYPE)
         n_rt = -(-self.r_pad[idx] // P_READ_CHUNK)
         search, (ik, ir) = self._product_items([n_k64, n_rt])
         items = np.zeros(len(search), dtype=P_ITEM_DTYPE)
@@ -1070,6 +1123,8 @@ class SearchGroup:
             return np.zeros(0, dtype=COUNT_ITEM_DTYPE)
         n_f = -(-n_alive[idx] // 8)
         r16 = _round_up_arr(self.R[idx], 16)
+        if PLAN_NATIVE:
+            return self._grid_items(idx, n_f, 8, r16, COUNT_READ_CHUNK, COUNT_ITEM_DTYPE)
         n_ch = np.maximum(1, -(-r16 // COUNT_READ_CHUNK))
         search, (jf, ich) = self._product_items([n_f, n_ch])
         items = np.zeros(len(search), dtype=COUNT_ITEM_DTYPE)
