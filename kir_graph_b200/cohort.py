@@ -97,7 +97,10 @@ def _site_summary(p: GenePack):
     second = np.zeros(n_site)                                        # runner-up share per site
     second[has2] = sh_strong[start[has2] + 1]
     considered = (n_keys > 1) & any_pos & (depth >= 20)
-    out = (second, considered & has2, bool(np.any(considered & (n_strong == 0))))
+    candidate = considered & has2
+    # the fourth element is all a batch needs: the runner-up shares of the sites that are looked at (about a
+    # tenth of the sites of a 30x sample)
+    out = (second, candidate, bool(np.any(considered & (n_strong == 0))), second[candidate])
     p._site_summary = out
     return out
 
@@ -111,19 +114,19 @@ class HomozygosityIndex:
 
     def __init__(self, packs: list[GenePack]):
         parts = [_site_summary(p) for p in packs]
-        cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
-        self.second = cat([x[0] for x in parts], np.float64)
-        self.candidate = cat([x[1] for x in parts], bool)
+        # only the sites isHomozygous looks at take part (``second`` of the candidate sites of every problem)
+        shares = [x[3] for x in parts]
+        self.second = np.concatenate(shares) if shares else np.zeros(0, np.float64)
         self.broken = any(x[2] for x in parts)
-        self.site_owner = np.repeat(np.arange(len(packs), dtype=np.int64), [len(x[0]) for x in parts])
+        self.site_owner = np.repeat(np.arange(len(packs), dtype=np.int64), [len(x) for x in shares])
         self.n_pack = len(packs)
         self.forced_hetero = np.array([isHetrozygous(p.gene) for p in packs], dtype=bool)
 
     def decide(self, cns: np.ndarray) -> np.ndarray:
         if self.broken:
             raise IndexError("list index out of range")                  # the reference fails here too
-        cn_site = cns[self.site_owner]
-        hetero_site = self.candidate & (self.second > 1 / (np.maximum(cn_site, 1) * 2))
+        threshold = 1 / (np.maximum(cns, 1) * 2)
+        hetero_site = self.second > threshold[self.site_owner]
         hits = np.bincount(self.site_owner[hetero_site], minlength=self.n_pack)
         return (hits == 0) & (cns > 1) & ~self.forced_hetero
 
@@ -151,11 +154,17 @@ class BatchTyper:
         self.cns = np.asarray(cns, dtype=np.int64)
         self.top_n = top_n
         self.host = host_batch if host_batch is not None else engine.HostBatch(packs)
-        self.homo_index = HomozygosityIndex(packs)
-        # reads of the whole problem (a read shard may hold none of them and still takes part)
-        self.n_reads = np.array([p.n_reads if p.n_reads_total is None else p.n_reads_total for p in packs],
-                                dtype=np.int64)
-        typable = (self.n_reads > 0) & np.array([p.n_alleles > 0 for p in packs], dtype=bool)
+        # Functions of the packed input alone live on the host batch (like its pools): a typer that is built
+        # per pass from prepared host batches (a cohort stream) does not redo them.
+        # (``host_batch`` holds the same problems by contract.)
+        static = getattr(self.host, "_typer_static", None)
+        if static is None or len(static[0]) != len(packs):
+            n_reads = np.array([p.n_reads if p.n_reads_total is None else p.n_reads_total for p in packs],
+                               dtype=np.int64)       # reads of the whole problem (a read shard may hold none)
+            typable = (n_reads > 0) & np.array([p.n_alleles > 0 for p in packs], dtype=bool)
+            static = (packs, HomozygosityIndex(packs), n_reads, typable)
+            self.host._typer_static = static
+        _, self.homo_index, self.n_reads, typable = static
         self.live = np.flatnonzero((self.cns > 0) & typable)
         # per problem: what the call phase needs without attribute look-ups in its loop
         self._static = [(p.gene, p.allele_names, int(r), int(c)) for p, r, c in zip(packs, self.n_reads, self.cns)]

@@ -80,3 +80,24 @@ def test_too_many_observations_is_loud():
     gene = synthetic.make_gene([5, 2], "KIRW*BACKBONE", 8, 600, 1, 4, w=140)
     with pytest.raises(ValueError):
         packing.pack_synthetic(gene, variant_correction=False)
+
+
+def test_batched_homozygosity_decisions_equal_the_per_gene_rule():
+    """cohort.HomozygosityIndex (candidate sites of all problems in one array) against decide_homozygous per
+    problem (isHomozygous, typing_mulit_allele.py:807-857), for every copy number 1..4."""
+    from kir_graph_b200 import cohort
+    packs = []
+    for i in range(24):
+        gene = synthetic.make_gene([61, i], f"KIRHZ{i}*BACKBONE", 6 + 3 * (i % 7), 96, 2 + i % 3, 600 + 40 * i,
+                                   homo_prob=0.5)
+        packs.append(packing.pack_synthetic(gene))
+    index = cohort.HomozygosityIndex(packs)
+    seen = set()
+    for cn in (1, 2, 3, 4):
+        got = index.decide(np.full(len(packs), cn, dtype=np.int64))
+        want = np.array([cohort.decide_homozygous(p, cn) for p in packs])
+        assert np.array_equal(got, want), cn
+        seen |= set(want.tolist())
+    assert seen == {True, False}
+    mixed = np.array([1 + i % 4 for i in range(len(packs))], dtype=np.int64)
+    assert np.array_equal(index.decide(mixed), np.array([cohort.decide_homozygous(p, int(c)) for p, c in zip(packs, mixed)]))
