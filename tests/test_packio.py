@@ -2,7 +2,7 @@ import os
 
 import numpy as np
 
-from kir_graph_b200 import cohort, packio
+from kir_graph_b200 import cohort, packing, packio
 from kir_graph_b200.hisat2 import writeReadsAndVariantsData
 from tests.fake_backend import FakeBackend
 from tests.helpers import load_golden, objects_from_input
@@ -21,10 +21,37 @@ def test_sidecar_roundtrip_and_cohort_calls(tmp_path):
     for g in packs:
         for name in ("mem_words", "ent_off", "ent_word", "ent_pos", "ent_neg", "k_obs", "obs_pos", "obs_neg"):
             assert np.array_equal(getattr(packs[g], name), getattr(back[g], name))
-        assert packs[g].allele_names == back[g].allele_names
+        assert packs[g].allele_names == back[g].allele_names and packs[g].var_val == back[g].var_val
+        # the wire form of the reads travels with the sidecar: equal to a fresh encoding of the same lists
+        stored, packs[g].wire = back[g].wire, None
+        fresh = packing.wire_encode(packs[g])
+        for name in ("hdr", "stream", "neg_keep", "tile_stream", "tile_entry"):
+            assert np.array_equal(getattr(stored, name), getattr(fresh, name)), (g, name)
+        assert stored.n_entries == fresh.n_entries
+        for name in ("lpv", "rpv", "lnv", "rnv"):
+            assert np.array_equal(packs[g].csr.indices[name], back[g].csr.indices[name])
+            assert np.array_equal(packs[g].csr.offsets[name], back[g].csr.offsets[name])
     genes = [g for g, cn in sample["gene_cn"].items() if cn and g in back]
     typer = cohort.BatchTyper([back[g] for g in genes], [sample["gene_cn"][g] for g in genes], top_n=60,
                               backend=FakeBackend())
     calls = typer.run()
     got = [a for c in calls for a in c.alleles]
     assert got == sample["calls"]["full"]["alleles"] or any(c.tie_flags for c in calls)
+
+
+def test_sidecar_of_another_format_or_stale_json_is_not_used(tmp_path):
+    """A sidecar without the format-3 index (older layout), or one whose meta no longer matches the .json,
+    is ignored: the packs come from the .json."""
+    sample = load_golden("sample_small")
+    reads, variants = objects_from_input(sample["input"])
+    path = os.path.join(tmp_path, "s.variant.json")
+    writeReadsAndVariantsData({"reads": reads, "variants": variants}, path)
+    want = packio.pack_variant_json(path, variant_correction=True)
+    side = packio.sidecar_path(path)
+    np.savez_compressed(side, __genes__=np.array("[]"), __meta__=np.array("{}"))     # format-2 style file
+    got = packio.load_sample_packs(path)
+    assert list(got) == list(want) and all(np.array_equal(got[g].ent_pos, want[g].ent_pos) for g in want)
+    packio.save_packs(side, want, packio.sidecar_meta(path))
+    assert all(p.wire is not None for p in packio.load_sample_packs(path).values())       # fresh: used
+    os.utime(path, ns=(1, 1))                                                               # .json touched
+    assert all(p.wire is None for p in packio.load_sample_packs(path).values())           # stale: rebuilt from .json
