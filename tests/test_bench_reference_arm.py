@@ -61,3 +61,21 @@ def test_reference_arm_worker_runs_the_imported_reference_without_the_cuda_libra
     assert proc.returncode == 0, proc.stderr[-2000:]
     cells, genes, ok = proc.stdout.split()
     assert int(genes) == 17 and int(cells) > 0
+
+
+def test_score_roofline_entries():
+    """The roofline block of the GPU arm: the packed kernel is reported against one issue slot per cell
+    (148 SM x 128 lanes), with the measured peak of its instruction mix and round 1's ALU-only denominator
+    beside it; the FP32 kernel against the FP32 non-tensor peak."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cells, ms = 168.6e9, 7.62
+    r = bench.score_roofline(cells, ms, True, 1965.0)
+    peak = 148 * 128 * 1965e6 / 1e12
+    assert r["bound"] == "issue_nontensor" and abs(r["peak"] - peak) < 1e-9
+    assert abs(r["achieved"] - cells / (ms * 1e-3) / 1e12) < 1e-9 and abs(r["frac"] - r["achieved"] / peak) < 1e-12
+    assert abs(r["alu_only_formulation"]["frac"] - 0.75 * r["achieved"] / (peak / 2)) < 1e-12
+    assert abs(r["fp32_nontensor_equiv"]["frac"] - 2 * r["frac"]) < 1e-12
+    assert r["measured_peak"]["peak"] > 25 and 0 < r["measured_peak"]["frac"] < 1
+    f = bench.score_roofline(cells, ms, False, 1965.0)
+    assert f["bound"] == "fp32_nontensor" and abs(f["frac"] - 2 * cells / (ms * 1e-3) / 1e12 / peak) < 1e-12
