@@ -154,9 +154,11 @@ class BatchTyper:
         self.cns = np.asarray(cns, dtype=np.int64)
         self.top_n = top_n
         self.host = host_batch if host_batch is not None else engine.HostBatch(packs)
+        if len(self.host.packs) != len(packs) or any(a is not b for a, b in zip(self.host.packs, packs)):
+            raise ValueError("host_batch was packed from other problems than the ones to type")
         # Functions of the packed input alone live on the host batch (like its pools): a typer that is built
         # per pass from prepared host batches (a cohort stream) does not redo them.
-        # (``host_batch`` holds the same problems by contract.)
+        # (``host_batch`` holds the same problems: checked above.)
         static = getattr(self.host, "_typer_static", None)
         if static is None or len(static[0]) != len(packs):
             n_reads = np.array([p.n_reads if p.n_reads_total is None else p.n_reads_total for p in packs],

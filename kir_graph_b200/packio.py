@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import json
 import os
+import zipfile
 
 import numpy as np
 
@@ -133,8 +134,8 @@ def load_sample_packs(filename_variant_json: str, variant_correction: bool = Tru
             packs, meta = load_packs(side)
             if meta == sidecar_meta(filename_variant_json, variant_correction, multiple):
                 return packs
-        except (OSError, ValueError, KeyError):
-            pass                                  # unreadable sidecar: fall through to the .json
+        except (OSError, ValueError, KeyError, EOFError, zipfile.BadZipFile):
+            pass                                  # unreadable / truncated sidecar: fall through to the .json
     from . import fastjson
     return fastjson.load_packs(filename_variant_json, variant_correction=variant_correction,
                                single_mapped_only=not multiple)

@@ -282,6 +282,23 @@ def test_pass_pipeline_equals_serial_passes():
     assert [key(c) for c in pipe.drain()] == [want, want]
 
 
+def test_host_batch_of_other_problems_is_refused():
+    """A prepared host batch carries state derived from its packs (pools, homozygosity index): handing it
+    to a typer of other problems - even of the same number - is an error, not a silent wrong call."""
+    import pytest
+    from kir_graph_b200 import cohort
+    genes = [g for g in synthetic.make_wgs30x_sample(seed=21, total_reads=600) if g.n_alleles <= 40][:4]
+    packs = [packing.pack_synthetic(g) for g in genes]
+    cns = [g.cn for g in genes]
+    first = cohort.BatchTyper(packs, cns, top_n=25, backend=FakeBackend())
+    again = cohort.BatchTyper(packs, cns, top_n=25, backend=FakeBackend(), host_batch=first.host)
+    assert again.homo_index is first.homo_index
+    with pytest.raises(ValueError, match="other problems"):
+        cohort.BatchTyper(packs[::-1], cns[::-1], top_n=25, backend=FakeBackend(), host_batch=first.host)
+    with pytest.raises(ValueError, match="other problems"):
+        cohort.BatchTyper(packs[:3], cns[:3], top_n=25, backend=FakeBackend(), host_batch=first.host)
+
+
 def test_exon_first_with_top_n_below_five_follows_the_reference():
     """top_n < 5 leaves the restricted model of exon-first with top_n // 5 == 0 kept sets
     (typing_mulit_allele.py:716): the reference then answers "fail" for one step and raises IndexError

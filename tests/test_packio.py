@@ -55,3 +55,22 @@ def test_sidecar_of_another_format_or_stale_json_is_not_used(tmp_path):
     assert all(p.wire is not None for p in packio.load_sample_packs(path).values())       # fresh: used
     os.utime(path, ns=(1, 1))                                                               # .json touched
     assert all(p.wire is None for p in packio.load_sample_packs(path).values())           # stale: rebuilt from .json
+
+
+def test_truncated_or_garbled_sidecar_falls_back_to_json(tmp_path):
+    """A sidecar cut short (a crashed writer, a full disk) or overwritten with other bytes is not an error:
+    the packs come from the .json."""
+    sample = load_golden("sample_small")
+    reads, variants = objects_from_input(sample["input"])
+    path = os.path.join(tmp_path, "s.variant.json")
+    writeReadsAndVariantsData({"reads": reads, "variants": variants}, path)
+    want = packio.pack_variant_json(path, variant_correction=True)
+    side = packio.sidecar_path(path)
+    packio.save_packs(side, want, packio.sidecar_meta(path))
+    whole = open(side, "rb").read()
+    for damaged in (whole[: len(whole) // 2], whole[:100], b"", b"PK\x03\x04" + b"\0" * 64, b"not a zip file"):
+        with open(side, "wb") as f:
+            f.write(damaged)
+        got = packio.load_sample_packs(path)
+        assert list(got) == list(want) and all(p.wire is None for p in got.values())
+        assert all(np.array_equal(got[g].ent_pos, want[g].ent_pos) for g in want)
