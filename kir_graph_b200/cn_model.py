@@ -143,3 +143,12 @@ class CNgroup(Dist):
             _, prob = self._evaluate(np.array([base], dtype=np.float64), None, want_prob=True)
             self._prob_cache = (key, prob[0])
         return self._prob_cache[1].copy()
+
+
+def loadCNModel(filename: str) -> Dist:
+    """Model of a saved parameter file (cn_model.py:382-390); only ``CNgroup`` files are read here."""
+    with open(filename) as f:
+        method = json.load(f)["method"]
+    if method == "CNgroup":
+        return CNgroup.load(filename)
+    raise NotImplementedError("KDEcut models (scikit-learn) stay in the reference" if method == "KDEcut" else method)

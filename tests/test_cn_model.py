@@ -82,3 +82,96 @@ def test_parameters_round_trip_and_errors(tmp_path):
 def test_mirror_on_cuda(name, tmp_path):
     from kir_graph_b200 import engine
     _run_mirror(_case(name), engine.default_backend(), tmp_path)
+
+
+# --- the callers: samtools depth tables -> .cn.tsv files (kir_cn.py:126-231, cn_model.py:382-390) -----------
+PREDICT = load_golden("cn_predict")
+PREDICT_NAMES = [c["name"] for c in PREDICT["cases"]]
+
+
+def _slim(params):
+    if isinstance(params, list):
+        return [_slim(p) for p in params]
+    return {k: (len(v) if k == "likelihood" else v) for k, v in params.items()}
+
+
+def _run_predict(c, backend, d):
+    d = str(d)
+    depth_files, cn_files = [], []
+    for i, text in enumerate(c["tables"]):
+        depth_files.append(os.path.join(d, f"s{i}.depth.tsv"))
+        cn_files.append(os.path.join(d, f"s{i}.cn.tsv"))
+        open(depth_files[-1], "w").write(text)
+    path = ""
+    if c["diploid"] is not None:
+        path = os.path.join(d, "dp")
+        json.dump({"mean": c["diploid"][0], "std": c["diploid"][1]}, open(path + ".json", "w"))
+    model_path = os.path.join(d, "model.json")
+    kir_cn.predictSamplesCN(depth_files, cn_files, diploid_depth=path, save_cn_model_path=model_path,
+                            _backend=backend, **c["kwargs"])
+    assert [open(f).read() for f in cn_files] == c["cn_tsv"]                # byte for byte what the reference wrote
+    models = {f[len("model.json"):]: _slim(json.loads(open(os.path.join(d, f)).read().replace(d, "@DIR@")))
+              for f in sorted(os.listdir(d)) if f.startswith("model.json")}
+    assert list(models) == list(c["models"])
+    for suffix, want in c["models"].items():
+        got = models[suffix]
+        pairs = zip(got, want) if isinstance(want, list) else [(got, want)]
+        for g, w in pairs:
+            assert list(g) == list(w)                                       # same keys in the same order
+            assert g == w                                                   # base, x_max, data, raw_df, gene ...
+    if c["loaded"] is not None:
+        dist = cn_model.loadCNModel(model_path)
+        dist._backend = backend
+        data = json.loads(open(model_path).read())["data"][:8]
+        assert dist.base == c["loaded"]["base"]
+        assert [int(x) for x in dist.assignCN([float(v) for v in data])] == c["loaded"]["cn_of_first"]
+    assert main_mod.loadCN(cn_files[0]) == {k: int(v) for k, v in (line.split("\t")[:2] for line in
+                                                                   c["cn_tsv"][0].splitlines()[1:])}
+
+
+from kir_graph_b200 import main as main_mod  # noqa: E402
+
+
+@pytest.mark.parametrize("name", PREDICT_NAMES)
+def test_predict_samples_cn_writes_the_reference_files(name, tmp_path):
+    _run_predict(PREDICT["cases"][PREDICT_NAMES.index(name)], FakeBackend(), tmp_path)
+
+
+def test_filter_depth_and_aggregation_modes(tmp_path):
+    f = PREDICT["filter"]
+    src, dst = str(tmp_path / "a.tsv"), str(tmp_path / "b.tsv")
+    open(src, "w").write(f["table"])
+    kir_cn.filterDepth(src, dst, {k: [tuple(r) for r in v] for k, v in f["regions"].items()})
+    assert open(dst).read() == f["filtered"]
+    table = kir_cn.readSamtoolsDepth(src)
+    assert list(table.columns) == ["gene", "pos", "depth"]
+    with pytest.raises(NotImplementedError):
+        kir_cn.aggrDepths(table, "max")
+    with pytest.raises(ValueError):                                         # no region at all (pd.concat of nothing)
+        kir_cn.selectSamtoolsDepth(table, {})
+    kde = str(tmp_path / "kde.json")
+    json.dump({"method": "KDEcut"}, open(kde, "w"))
+    with pytest.raises(NotImplementedError):
+        cn_model.loadCNModel(kde)
+
+
+def test_per_gene_prediction_with_a_dash_in_the_file_names(tmp_path):
+    """The reference splits its ``{gene}-{file}`` keys at every ``-`` and fails on such paths; the mirror splits
+    at the first one only and gives what it gives for the same tables under other names."""
+    c = PREDICT["cases"][PREDICT_NAMES.index("cohort6_per_gene")]
+    d = tmp_path / "run-2"
+    d.mkdir()
+    depth_files, cn_files = [], []
+    for i, text in enumerate(c["tables"]):
+        depth_files.append(str(d / f"s-{i}.depth.tsv"))
+        cn_files.append(str(d / f"s-{i}.cn.tsv"))
+        open(depth_files[-1], "w").write(text)
+    kir_cn.predictSamplesCN(depth_files, cn_files, per_gene=True, _backend=FakeBackend())
+    assert [open(f).read() for f in cn_files] == c["cn_tsv"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PREDICT_NAMES)
+def test_predict_samples_cn_on_cuda(name, tmp_path):
+    from kir_graph_b200 import engine
+    _run_predict(PREDICT["cases"][PREDICT_NAMES.index(name)], engine.default_backend(), tmp_path)
