@@ -6,7 +6,8 @@ cohort entry that types every sample's genes as one GPU batch.
 ``selectKirTypingModel(method, name + ".json", top_n=600, variant_correction=True)``, ``loadCN``,
 ``typing``, then ``{name}{suffix}.tsv`` (name / alleles / warnings) and ``.possible.tsv``; file names,
 columns and formatting come from the same pandas calls, so the files are interchangeable.
-``mergeAllele`` (utils.py:161-165) concatenates them into ``cohort.allele.tsv``.
+``mergeAllele`` (utils.py:161-165) concatenates them into ``cohort.allele.tsv``; ``mergeCN`` (utils.py:168-180)
+pivots the ``.cn.tsv`` files into ``cohort.cn.tsv``.
 
 ``cohortAlleleTyping`` is new: the (sample, gene) problems of all samples of
 this rank go through ``cohort.CohortTyper`` in one pass - samples are independent, so ranks take
@@ -18,8 +19,8 @@ gene with copy number >= 2 and no usable reads is called ``<gene>*`` (fail) here
 - and the per-sample mirror - end in numpy's AxisError (``createHomoResult`` on the empty first-step
 result, typing_mulit_allele.py:441) unless the gene is one of the always-heterozygous ones.
 
-Everything upstream (mapping, BAM handling, copy-number estimation) stays in the reference; the CLI
-itself is not rebuilt.
+Mapping and BAM handling stay in the reference (copy-number estimation from depth tables:
+:mod:`kir_graph_b200.kir_cn`); the CLI itself is not rebuilt.
 """
 from __future__ import annotations
 
@@ -52,6 +53,19 @@ def mergeAllele(allele_result_files: list[str], final_result_file: str) -> pd.Da
     df = pd.concat(pd.read_csv(f, sep="\t") for f in allele_result_files)
     df.to_csv(final_result_file, index=False, sep="\t")
     return df
+
+
+def mergeCN(cn_result_files: list[str], final_result_file: str) -> pd.DataFrame:
+    """Gene x sample table of the copy numbers of several ``.cn.tsv`` files, columns named by file, a gene a
+    sample does not list counted as 0 (utils.py:168-180; what the reference's CLI writes as ``cohort.cn.tsv``)."""
+    tables = []
+    for f in cn_result_files:
+        one = pd.read_csv(f, sep="\t")
+        one["name"] = f
+        tables.append(one)
+    merged = pd.pivot_table(pd.concat(tables), values="cn", index="gene", columns=["name"]).fillna(0).astype(int)
+    merged.to_csv(final_result_file, sep="\t")
+    return merged
 
 
 def _suffix(name: str, cn_file: str, method: str) -> str:

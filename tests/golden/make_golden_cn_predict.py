@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """
 Golden fixtures of the CN callers (the callers of the model) from the UNMODIFIED
-reference: ``graphkir.kir_cn.predictSamplesCN`` (kir_cn.py:148-231), ``filterDepth`` (:126-145) and
-``graphkir.cn_model.loadCNModel`` (cn_model.py:382-390) on synthetic ``samtools depth`` tables.
+reference: ``graphkir.kir_cn.predictSamplesCN`` (kir_cn.py:148-231), ``filterDepth`` (:126-145),
+``graphkir.cn_model.loadCNModel`` (cn_model.py:382-390) and ``graphkir.utils.mergeCN`` (utils.py:168-180) on synthetic ``samtools depth`` tables.
 
 Build container only (needs /root/reference):    python tests/golden/make_golden_cn_predict.py
 Writes tests/golden/cn_predict.json.gz: per case the depth tables (file texts), the arguments, and what the
@@ -26,6 +26,7 @@ from make_golden import import_reference  # noqa: E402  (installs the plotly / B
 import_reference()
 import graphkir.cn_model as cm  # noqa: E402
 import graphkir.kir_cn as kc  # noqa: E402
+import graphkir.utils as gu  # noqa: E402
 from make_golden_cn import GENES  # noqa: E402
 
 
@@ -70,8 +71,11 @@ def run(name, tables, diploid=None, **kw):
                 [float(v) for v in json.loads(open(model_path).read())["data"][:8]])]}
         models = {f[len("model.json"):]: slim(json.loads(open(os.path.join(d, f)).read().replace(d, "@DIR@")))
                   for f in sorted(os.listdir(d)) if f.startswith("model.json")}
+        merged = os.path.join(d, "cohort.cn.tsv")
+        gu.mergeCN(cn_files, merged)                                   # utils.py:168-180 (main.py:592)
         return {"name": name, "tables": tables, "diploid": diploid, "kwargs": kw,
-                "cn_tsv": [open(f).read() for f in cn_files], "models": models, "loaded": loaded}
+                "cn_tsv": [open(f).read() for f in cn_files], "models": models, "loaded": loaded,
+                "merged_cn": open(merged).read().replace(d, "@DIR@")}
 
 
 def run_filter(tables):
@@ -96,7 +100,9 @@ def main():
         run("cohort6_per_gene", six, per_gene=True),
         run("cohort6_lcnd_kwargs", six, cluster_method="lcnd", cluster_method_kwargs={"base_dev": 0.1}),
     ]
-    out = {"kind": "cn_predict", "cases": cases, "filter": run_filter(five)}
+    names = ["KIR3DP1*0010101", "KIR2DL1*0320102N", "KIR3DP1*BACKBONE", "KIR2DS4", "KIR2DL5A*0010101e2", "KIR2DL1*new7", ""]
+    fields = [[n, r, gu.getAlleleField(n, r), gu.limitAlleleField(n, r), gu.getGeneName(n)] for n in names for r in (3, 5, 7)]
+    out = {"kind": "cn_predict", "cases": cases, "filter": run_filter(five), "allele_fields": fields}
     path = os.path.join(HERE, "cn_predict.json.gz")
     with gzip.open(path, "wt", compresslevel=9) as f:
         json.dump(out, f)

@@ -125,6 +125,9 @@ def _run_predict(c, backend, d):
         data = json.loads(open(model_path).read())["data"][:8]
         assert dist.base == c["loaded"]["base"]
         assert [int(x) for x in dist.assignCN([float(v) for v in data])] == c["loaded"]["cn_of_first"]
+    merged = os.path.join(d, "cohort.cn.tsv")
+    main_mod.mergeCN(cn_files, merged)
+    assert open(merged).read().replace(d, "@DIR@") == c["merged_cn"]
     assert main_mod.loadCN(cn_files[0]) == {k: int(v) for k, v in (line.split("\t")[:2] for line in
                                                                    c["cn_tsv"][0].splitlines()[1:])}
 
@@ -175,3 +178,11 @@ def test_per_gene_prediction_with_a_dash_in_the_file_names(tmp_path):
 def test_predict_samples_cn_on_cuda(name, tmp_path):
     from kir_graph_b200 import engine
     _run_predict(PREDICT["cases"][PREDICT_NAMES.index(name)], engine.default_backend(), tmp_path)
+
+
+def test_allele_name_helpers_against_the_reference():
+    from kir_graph_b200 import utils
+    for name, resolution, field, limited, gene in PREDICT["allele_fields"]:
+        assert utils.getAlleleField(name, resolution) == field
+        assert utils.limitAlleleField(name, resolution) == limited
+        assert utils.getGeneName(name) == gene
