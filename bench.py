@@ -22,10 +22,10 @@ copy-number step of the greedy search (kernels b, c) and the allele calls.
   and host-side calls, complete inside the timed region, and every step's calls are compared with the
   warm-up pass afterwards (``parity.every_timed_pass_equals_warmup_calls``).
   roofline        dominant kernel (gk_score), CUDA events around every launch of extra passes run
-                  right after the timed region (eager launches, one stream)
-  roofline        ... bound "issue_nontensor": one issue slot per cell (2 VIMNMX.U16x2 on the ALU pipe + 2 IMAD on
-                  the FMA pipe per 4 cells), with the fraction of the measured peak of that mix and of round 1's
-                  ALU-only denominator beside it (score_roofline below)
+                  right after the timed region (eager launches, one stream); bound "issue_nontensor": one
+                  issue slot per cell (2 VIMNMX.U16x2 on the ALU pipe + 2 IMAD on the FMA pipe per 4 cells),
+                  with the fraction of the measured peak of that mix and of round 1's ALU-only denominator
+                  beside it (score_roofline below)
   cpu_baseline    the reference itself (kind "reference": oracle/_ref, the byte-compiled graphkir typing path,
                   likelihood build included, one process per sample on every host core) over a bounded
                   sample; kind "port" (the oracle's NumPy restatement) only where oracle/_ref is absent
