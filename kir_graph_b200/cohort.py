@@ -164,12 +164,13 @@ class BatchTyper:
             n_reads = np.array([p.n_reads if p.n_reads_total is None else p.n_reads_total for p in packs],
                                dtype=np.int64)       # reads of the whole problem (a read shard may hold none)
             typable = (n_reads > 0) & np.array([p.n_alleles > 0 for p in packs], dtype=bool)
-            static = (packs, HomozygosityIndex(packs), n_reads, typable)
+            static = (packs, HomozygosityIndex(packs), n_reads, typable,
+                      [(p.gene, p.allele_names, r) for p, r in zip(packs, n_reads.tolist())])
             self.host._typer_static = static
-        _, self.homo_index, self.n_reads, typable = static
+        _, self.homo_index, self.n_reads, typable, per_problem = static
         self.live = np.flatnonzero((self.cns > 0) & typable)
         # per problem: what the call phase needs without attribute look-ups in its loop
-        self._static = [(p.gene, p.allele_names, int(r), int(c)) for p, r, c in zip(packs, self.n_reads, self.cns)]
+        self._static = [(gene, names, r, c) for (gene, names, r), c in zip(per_problem, self.cns.tolist())]
         self.batch: engine.MatrixBatch | None = None
         self.group: engine.SearchGroup | None = None
         self.score_cells = 0

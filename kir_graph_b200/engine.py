@@ -344,6 +344,7 @@ class HostBatch:
     def __init__(self, packs: list[GenePack], wire: bool | None = None):
         self.packs = packs
         self._m_max = None
+        self._lik_items = None
         if wire is None:
             wire = WIRE_DEFAULT and all(p.csr is not None for p in packs)
         self.wire = bool(wire)
@@ -440,11 +441,31 @@ class HostBatch:
         """Host pools that are copied to the device for every pass (besides the matrix table)."""
         return ("mem", "hdr", "stream", "keep", "xitems") if self.wire else ("mem", "entoff", "ent")
 
+    def lik_items(self) -> np.ndarray:
+        """Work items of the likelihood build (128-read tiles x groups of 4 allele blocks per problem): a
+        function of the batch layout alone, built once per host batch - ``pin`` does it, so a typer built
+        per pass from a prepared host batch finds it there."""
+        if self._lik_items is None:
+            t = self.table
+            tiles = (t["r_pad"] // GK_LIK_READS).astype(np.int64)
+            groups = -(-t["n_ablk"].astype(np.int64) // 4)          # 4 allele blocks per CTA
+            per = tiles * groups
+            total = int(per.sum())
+            items = np.zeros(total, dtype=LIK_ITEM_DTYPE)
+            mat = np.repeat(np.arange(len(t), dtype=np.int64), per)
+            local = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(per) - per, per)
+            items["matrix"] = mat
+            items["a_blk"] = (local // tiles[mat]) * 4
+            items["r0"] = (local % tiles[mat]) * GK_LIK_READS
+            self._lik_items = items
+        return self._lik_items
+
     def pin(self, backend) -> "HostBatch":
         for name in self.input_names:
             arr = getattr(self, name)
             raw = backend.pin(arr.view(np.uint8) if arr.dtype.fields is not None else arr)
             setattr(self, name, raw.view(arr.dtype) if arr.dtype.fields is not None else raw)
+        self.lik_items()
         return self
 
     @property
@@ -507,18 +528,8 @@ class MatrixBatch:
         self._colsum_host = None
 
     def lik_items(self) -> np.ndarray:
-        t = self.table
-        tiles = (t["r_pad"] // GK_LIK_READS).astype(np.int64)
-        groups = -(-t["n_ablk"].astype(np.int64) // 4)          # 4 allele blocks per CTA
-        per = tiles * groups
-        total = int(per.sum())
-        items = np.zeros(total, dtype=LIK_ITEM_DTYPE)
-        mat = np.repeat(np.arange(len(t), dtype=np.int64), per)
-        local = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(per) - per, per)
-        items["matrix"] = mat
-        items["a_blk"] = (local // tiles[mat]) * 4
-        items["r0"] = (local % tiles[mat]) * GK_LIK_READS
-        return items
+        """Work items of the likelihood build: a copy of the host batch's table (the caller sets flags)."""
+        return self.host.lik_items().copy()
 
     def run_likelihood(self, colsum_only: np.ndarray | None = None) -> None:
         """Kernel (a) over every problem of the batch.  ``colsum_only`` (bool per problem): only the

@@ -71,18 +71,27 @@ def main():
 
     for i in range(2):
         one_pass(i)
+    if os.environ.get("GK_GC_FREEZE", "1") != "0":      # as bench.py: the packed cohorts leave the collector's view
+        import gc
+        gc.collect()
+        gc.freeze()
     prof = cProfile.Profile()
     l0 = be.launches
     t0 = time.perf_counter()
     if profiling:
         prof.enable()
+    each = []
     for i in range(passes):
+        t1 = time.perf_counter()
         calls = one_pass(i)
+        each.append(1e3 * (time.perf_counter() - t1))
     if profiling:
         prof.disable()
     ms = 1e3 * (time.perf_counter() - t0) / passes
-    print(f"host time per cold pass of {n_samples} samples: {ms:.1f} ms ({(be.launches - l0) / passes:.0f} launches, "
-          f"{len(calls)} calls; cProfile {'on' if profiling else 'off'})")
+    each.sort()
+    print(f"host time per cold pass of {n_samples} samples: mean {ms:.1f} ms, median {each[len(each) // 2]:.1f}, "
+          f"min {each[0]:.1f} ({(be.launches - l0) / passes:.0f} launches, {len(calls)} calls; "
+          f"cProfile {'on' if profiling else 'off'})")
     if profiling:
         pstats.Stats(prof).sort_stats("cumulative").print_stats(45)
 
