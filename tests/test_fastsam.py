@@ -322,3 +322,44 @@ exit 1
     monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
     with pytest.raises(FileNotFoundError):
         hisat2.extractVariantFromBam(table, str(tmp_path / "in.bam"), str(tmp_path / "out"), error_correction=False)
+
+
+def _mask_first_mismatch(record: str):
+    """The read base of the first MD mismatch replaced by N (records aligned without indels only)."""
+    import re
+    cols = record.split("\t")
+    if len(cols) < 12 or not re.fullmatch(r"\d+M", cols[5]):
+        return None
+    md = next((c[5:] for c in cols[11:] if c.startswith("MD:Z:")), None)
+    m = re.match(r"(\d+)[ACGT]", md or "")
+    if m is None:
+        return None
+    k = int(m.group(1))
+    cols[9] = cols[9][:k] + "N" + cols[9][k + 1:]
+    return "\t".join(cols)
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_bases_masked_with_n_exclude_every_alternative(seed):
+    """A read base masked as N (what the reference's pileup error correction writes) becomes a novel variant
+    with val N, and none of A / T / C / G at that position counts as a negative (hisat2.py:758-768): native
+    loop against the Python statement."""
+    table, pairs = _multi_gene(seed)
+    masked, n_masked = [], 0
+    for left, right in pairs:
+        new = [_mask_first_mismatch(r) for r in (left, right)]
+        n_masked += sum(x is not None for x in new)
+        masked.append(tuple(x if x is not None else r for x, r in zip(new, (left, right))))
+    assert n_masked > 10
+    sam = _sam_text(masked)
+    Variant.novel_id = 0
+    got = fastsam.extract(sam, table, num_editdist=9).reads_data()
+    Variant.novel_id = 0
+    want = _python_path(sam, copy.deepcopy(table), 9)
+    assert _as_dicts(got) == _as_dicts(want)
+    n_variants = [v for v in got["variants"] if v.val == "N"]
+    assert n_variants and all(v.id.startswith("nv") for v in n_variants)
+    # the masking changes the lists: the unmasked text gives other negatives for some pair
+    Variant.novel_id = 0
+    plain = fastsam.extract(_sam_text(pairs), table, num_editdist=9).reads_data()
+    assert _as_dicts(plain)[1] != _as_dicts(got)[1]

@@ -138,3 +138,25 @@ def test_index_readers_match_reference(tmp_path):
         got = hisat2.getVariants(index)
         assert [asdict(v) for v in got] == case["variants"]
         assert got == sorted(got) and any(v.in_exon for v in got) and any(not v.allele for v in got)
+
+
+def test_record_with_more_segments_than_the_reusable_buffer():
+    """A long read with 90 mismatches and 12 indels walks into 200+ segments: the native walk reports that its
+    reusable 64-segment buffer is too small and is called again with a buffer sized from the record."""
+    md, cigar, seq = [], [], []
+    for i in range(12):                                   # 12 x (20M 1I 20M 2D) with 7 mismatches per block
+        cigar.append("20M1I20M2D")
+        md.append("2C2C2C2C2C2C2C5" + "^GG")             # 26 + ... : first 20M + second 20M = 40 aligned bases
+        seq.append("A" * 41)
+    # MD above covers 7 * 3 + 5 = 26 bases per block; pad the blocks to 40 aligned bases
+    md = [m.replace("5^GG", "19^GG") for m in md]
+    cigar.append("30M")
+    md.append("2T" * 6 + "12")
+    seq.append("A" * 30)
+    line = "\t".join(["long", "99", "KIRX*BACKBONE", "101", "60", "".join(cigar), "=", "400", "700", "".join(seq),
+                      "F" * sum(len(s) for s in seq), "NM:i:126", "MD:Z:" + "".join(md)])
+    native, python = _outcome(hisat2.recordToRawVariant, line), _outcome(hisat2.recordToRawVariantPy, line)
+    assert native == python and not isinstance(native, str)
+    assert len(native[0]) > 64
+    short = load_golden("sam_walk")["kats"]["k1"]["line"]  # the reusable buffer still serves the next record
+    assert _outcome(hisat2.recordToRawVariant, short) == _outcome(hisat2.recordToRawVariantPy, short)
