@@ -117,14 +117,20 @@ class HomozygosityIndex:
         # only the sites isHomozygous looks at take part (``second`` of the candidate sites of every problem)
         shares = [x[3] for x in parts]
         self.second = np.concatenate(shares) if shares else np.zeros(0, np.float64)
-        self.broken = any(x[2] for x in parts)
+        self.broken = np.array([x[2] for x in parts], dtype=bool)
+        self.genes = [p.gene for p in packs]
         self.site_owner = np.repeat(np.arange(len(packs), dtype=np.int64), [len(x) for x in shares])
         self.n_pack = len(packs)
         self.forced_hetero = np.array([isHetrozygous(p.gene) for p in packs], dtype=bool)
 
     def decide(self, cns: np.ndarray) -> np.ndarray:
-        if self.broken:
-            raise IndexError("list index out of range")                  # the reference fails here too
+        # a site that is looked at without any value passing the share filter: the reference indexes an empty
+        # list there (:853) - for the problems it runs isHomozygous on, i.e. copy number > 1 and not one of the
+        # always-heterozygous genes
+        failing = self.broken & (cns > 1) & ~self.forced_hetero
+        if failing.any():
+            raise IndexError("list index out of range (isHomozygous: " +
+                             ", ".join(self.genes[i] for i in np.flatnonzero(failing)[:5]) + ")")
         threshold = 1 / (np.maximum(cns, 1) * 2)
         hetero_site = self.second > threshold[self.site_owner]
         hits = np.bincount(self.site_owner[hetero_site], minlength=self.n_pack)

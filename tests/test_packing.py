@@ -101,3 +101,41 @@ def test_batched_homozygosity_decisions_equal_the_per_gene_rule():
     assert seen == {True, False}
     mixed = np.array([1 + i % 4 for i in range(len(packs))], dtype=np.int64)
     assert np.array_equal(index.decide(mixed), np.array([cohort.decide_homozygous(p, int(c)) for p, c in zip(packs, mixed)]))
+
+
+def _gene_with_an_undecidable_site(name: str):
+    """Ten insertions at one position, each seen four times: the site is looked at by isHomozygous (depth 40,
+    a positive value) but no value passes share > 0.1, and the reference indexes an empty list (:853)."""
+    from kir_graph_b200.hisat2 import PairRead
+    from kir_graph_b200.msa2hisat import Variant
+    vals = ["A", "C", "G", "T", "AA", "CC", "GG", "TT", "AC", "AG"]
+    variants = [Variant(pos=100, typ="insertion", ref=name, val=v, id=f"hv{i}", allele=[f"{name[:-9]}*{i % 3:03d}"])
+                for i, v in enumerate(vals)]
+    variants.append(Variant(pos=300, typ="single", ref=name, val="A", id="hv90", allele=[f"{name[:-9]}*000"]))
+    reads = [PairRead(backbone=name, lpv=[f"hv{i % 10}"], rnv=["hv90"]) for i in range(40)]
+    return reads, variants
+
+
+def test_undecidable_site_fails_like_the_reference_only_where_it_is_looked_at():
+    """The batched homozygosity index raises IndexError for a problem with such a site exactly when the per-gene
+    rule does: copy number above 1 and not a gene that is heterozygous by name."""
+    import pytest
+    from kir_graph_b200 import cohort
+    from kir_graph_b200.typing_mulit_allele import isHomozygous
+    reads, variants = _gene_with_an_undecidable_site("KIR3DL9*BACKBONE")
+    with pytest.raises(IndexError):                                             # the mirror of the reference's rule
+        isHomozygous(reads, {v.id: v for v in variants}, 2)
+    bad = packing.pack_gene(reads, variants, variant_correction=False, gene="KIR3DL9*BACKBONE")
+    reads2, variants2 = _gene_with_an_undecidable_site("KIR2DL5*BACKBONE")       # heterozygous by name: never asked
+    named = packing.pack_gene(reads2, variants2, variant_correction=False, gene="KIR2DL5*BACKBONE")
+    good = packing.pack_synthetic(synthetic.make_gene([61, 3], "KIRHZ3*BACKBONE", 9, 96, 2, 600))
+    index = cohort.HomozygosityIndex([good, bad, named])
+    assert index.broken.tolist() == [False, True, True]
+    for cn in (2, 3):
+        with pytest.raises(IndexError, match="KIR3DL9"):
+            index.decide(np.array([2, cn, 2]))
+        with pytest.raises(IndexError):
+            cohort.decide_homozygous(bad, cn)
+    for cns in ([2, 1, 2], [2, 0, 3]):                                          # not asked for that problem: no failure
+        got = index.decide(np.array(cns))
+        assert got.tolist() == [cohort.decide_homozygous(p, c) for p, c in zip([good, bad, named], cns)]
