@@ -105,6 +105,12 @@ def _site_summary(p: GenePack):
     return out
 
 
+def undecidable_homozygosity(pack: GenePack, cn: int) -> bool:
+    """isHomozygous would index an empty list for this problem (a site that is looked at without any value
+    passing the share filter, typing_mulit_allele.py:850-853): copy number above 1, not heterozygous by name."""
+    return bool(cn > 1 and not isHetrozygous(pack.gene) and _site_summary(pack)[2])
+
+
 class HomozygosityIndex:
     """isHomozygous (typing_mulit_allele.py:807-857) for a whole batch at once.
 

@@ -17,7 +17,9 @@ that needs no per-gene Python objects) and writes no ``.possible.tsv`` (only the
 back from the device); other strategies go through ``alleleTyping``.  One deliberate difference: a
 gene with copy number >= 2 and no usable reads is called ``<gene>*`` (fail) here, where the reference
 - and the per-sample mirror - end in numpy's AxisError (``createHomoResult`` on the empty first-step
-result, typing_mulit_allele.py:441) unless the gene is one of the always-heterozygous ones.
+result, typing_mulit_allele.py:441) unless the gene is one of the always-heterozygous ones; likewise a
+gene on which ``isHomozygous`` ends in IndexError (:853, a site with ten or more equally frequent values)
+is reported and called fail instead of stopping every sample of the batch.
 
 Mapping and BAM handling stay in the reference (copy-number estimation from depth tables:
 :mod:`kir_graph_b200.kir_cn`); the CLI itself is not rebuilt.
@@ -145,6 +147,10 @@ def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: st
                 pack = by_gene[g]
                 problem = str(pack) if isinstance(pack, CapacityError) else \
                     engine.capacity_violation(pack.n_alleles, int(c), top_n)
+                if not problem and cohort.undecidable_homozygosity(pack, int(c)):
+                    # the reference (and the per-sample mirror) end in IndexError inside isHomozygous here,
+                    # which would take the whole batch down
+                    problem = "isHomozygous cannot decide (a site without any value above the share filter)"
                 if problem:
                     logger.warning(f"[Allele] {g} (cn={c}) of {name} not typed: {problem}")
                     known = False

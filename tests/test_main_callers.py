@@ -155,3 +155,32 @@ def test_sidecar_written_at_extraction_feeds_the_cohort_entry(tmp_path):
     assert meta == {"variant_correction": True, "multiple": False, "json_size": sizes[1],
                     "json_mtime_ns": stamps[1], "format": packio.PACK_FORMAT} and len(side) == 2
     assert list(packio.load_sample_packs(names[1] + ".json", variant_correction=True)) == list(side)
+
+
+def test_cohort_entry_survives_a_gene_the_homozygosity_rule_cannot_decide(tmp_path, caplog):
+    """One gene of one sample with a site on which isHomozygous indexes an empty list (the reference's
+    IndexError): the per-sample path raises like the reference, the cohort entry reports the gene, calls it
+    fail and types everything else as before."""
+    import json
+    from tests.test_packing import _gene_with_an_undecidable_site
+    names, cn_files = _cohort(tmp_path)
+    want = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    rows_before = [pd.read_csv(f, sep="\t").fillna("") for f in want]
+    reads, variants = _gene_with_an_undecidable_site("KIR3DL9*BACKBONE")
+    data = json.load(open(names[1] + ".json"))
+    from dataclasses import asdict
+    data["reads"] += [asdict(r) for r in reads]
+    data["variants"] += [asdict(v) for v in variants]
+    json.dump(data, open(names[1] + ".json", "w"))
+    cn = pd.read_csv(cn_files[1], sep="\t")
+    cn = pd.concat([cn, pd.DataFrame({"gene": ["KIR3DL9*BACKBONE"], "cn": [2]})])
+    cn.to_csv(cn_files[1], sep="\t", index=False)
+    with pytest.raises(IndexError):
+        main.alleleTyping(names[1:2], cn_files[1:2], "full", _backend=FakeBackend())
+    with caplog.at_level("WARNING", logger="graphkir"):
+        files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    assert any("KIR3DL9" in r.getMessage() and "isHomozygous" in r.getMessage() for r in caplog.records)
+    rows = [pd.read_csv(f, sep="\t").fillna("") for f in files]
+    assert rows[0].equals(rows_before[0]) and rows[2].equals(rows_before[2])
+    assert rows[1]["alleles"][0] == rows_before[1]["alleles"][0] + "_KIR3DL9*_KIR3DL9*"
+    assert "KIR3DL9*BACKBONE" in rows[1]["warnings"][0]
