@@ -74,3 +74,9 @@ def test_em_report_writer(tmp_path, monkeypatch):
     out = io.StringIO()
     typing_em.printHisatTyping({"KIRX*BACKBONE": []}, file=out)
     assert out.getvalue() == "KIRX*BACKBONE\n"
+
+
+def test_most_frequent_allele_and_empty_em():
+    assert typing_em.getMostFreqAllele(["a", "b", "b", "c", "c"]) == ["b", "c"]
+    assert typing_em.getMostFreqAllele([]) == []
+    assert typing_em.hisatEMnp([], _backend=FakeBackend()) == {}

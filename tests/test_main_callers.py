@@ -184,3 +184,53 @@ def test_cohort_entry_survives_a_gene_the_homozygosity_rule_cannot_decide(tmp_pa
     assert rows[0].equals(rows_before[0]) and rows[2].equals(rows_before[2])
     assert rows[1]["alleles"][0] == rows_before[1]["alleles"][0] + "_KIR3DL9*_KIR3DL9*"
     assert "KIR3DL9*BACKBONE" in rows[1]["warnings"][0]
+
+
+def _gene_with_a_read_pair_beyond_the_capacity(name: str, n_obs: int = 256):
+    """A gene whose last read pairs carry ``n_obs`` variant observations each (the device path counts mismatches
+    per read pair in a byte: at most 255)."""
+    variants = [Variant(pos=10 + 3 * i, typ="single", ref=name, val="A", id=f"hw{i}",
+                        allele=[f"{name[:-9]}*{j:03d}" for j in range(4) if (i + j) % 3])
+                for i in range(n_obs + 4)]
+    reads = [PairRead(backbone=name, lpv=[f"hw{i % 7}"], rnv=[f"hw{7 + i % 5}"]) for i in range(40)]
+    for _ in range(3):                                    # three of them: the observations survive errorCorrection
+        reads.append(PairRead(backbone=name, lnv=[f"hw{i}" for i in range(n_obs // 2)],
+                              rnv=[f"hw{i}" for i in range(n_obs // 2, n_obs)]))
+    return reads, variants
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_a_gene_beyond_a_capacity_fails_alone(tmp_path, caplog, fast):
+    """A read pair with 256 observations exceeds a capacity the reference does not have: every entry point
+    reports that gene and calls it fail, the other genes and samples are typed as before (the per-sample
+    driver on the object and the fast path, and the cohort entry)."""
+    import json
+    from dataclasses import asdict
+    from kir_graph_b200 import kir_typing
+    names, cn_files = _cohort(tmp_path)
+    before = [pd.read_csv(f, sep="\t").fillna("") for f in
+              main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())]
+    reads, variants = _gene_with_a_read_pair_beyond_the_capacity("KIRWIDE*BACKBONE")
+    data = json.load(open(names[0] + ".json"))
+    data["reads"] += [asdict(r) for r in reads]
+    data["variants"] += [asdict(v) for v in variants]
+    json.dump(data, open(names[0] + ".json", "w"))
+    cn = pd.concat([pd.read_csv(cn_files[0], sep="\t"), pd.DataFrame({"gene": ["KIRWIDE*BACKBONE"], "cn": [2]})])
+    cn.to_csv(cn_files[0], sep="\t", index=False)
+    with caplog.at_level("WARNING", logger="graphkir"):
+        t = kir_typing.selectKirTypingModel("full", names[0] + ".json", top_n=600, variant_correction=True,
+                                            _backend=FakeBackend(), **({"_fast": True} if fast else {}))
+        alleles, warnings = t.typing(main.loadCN(cn_files[0]))
+    assert alleles[-2:] == ["KIRWIDE*", "KIRWIDE*"] and "KIRWIDE*BACKBONE" in warnings
+    assert "KIRWIDE*BACKBONE" in t.capacity_failures and "255" in t.capacity_failures["KIRWIDE*BACKBONE"]
+    assert any("KIRWIDE" in r.getMessage() and "not typed" in r.getMessage() for r in caplog.records)
+    files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    rows = [pd.read_csv(f, sep="\t").fillna("") for f in files]
+    assert rows[1].equals(before[1]) and rows[2].equals(before[2])
+    assert rows[0]["alleles"][0] == before[0]["alleles"][0] + "_KIRWIDE*_KIRWIDE*"
+    # one observation fewer fits: the gene is typed
+    reads, variants = _gene_with_a_read_pair_beyond_the_capacity("KIRWIDE*BACKBONE", 254)
+    data["reads"] = [r for r in data["reads"] if r["backbone"] != "KIRWIDE*BACKBONE"] + [asdict(r) for r in reads]
+    json.dump(data, open(names[0] + ".json", "w"))
+    files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    assert "KIRWIDE*0" in pd.read_csv(files[0], sep="\t")["alleles"][0]
