@@ -558,6 +558,21 @@ def cold_leg(args, be, rank, world, timed, group_size, parts, packed_sets):
                             "frozen out of the garbage collector's view (gc.freeze) as in the warm legs"}
 
 
+def guarded(world, fn, *a, **kw):
+    """A secondary block of the line (cold, deep, host_prep, api_e2e, cn_model, cpu_baseline) must not cost the
+    headline numbers measured before it: on one GPU its failure is recorded in the block ({"error": ...}, traceback
+    on stderr) and the line is still printed.  With several ranks a block may hold collectives, where a rank that
+    went on alone would leave the others waiting: there the failure stays fatal."""
+    if world > 1:
+        return fn(*a, **kw)
+    try:
+        return fn(*a, **kw)
+    except Exception as exc:                                          # noqa: BLE001 - recorded, not swallowed
+        import traceback
+        traceback.print_exc()
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -821,7 +836,8 @@ def main():
         gc.unfreeze()
         gc.collect()
         torch.cuda.empty_cache()
-        cold = cold_leg(args, be, rank, world, timed, group_size, 1, cold_sets)    # one sub-batch: least host work per pass
+        cold = guarded(world, cold_leg, args, be, rank, world, timed, group_size, 1, cold_sets)   # one sub-batch: least host work per pass
+        be.device_arena = None
         cold_sets = None
         gc.collect()
         torch.cuda.empty_cache()
@@ -909,24 +925,28 @@ def main():
         torch.cuda.empty_cache()
         modes = ["reads", "cols"] if args.deep_shard == "both" else [args.deep_shard]
         for i, mode in enumerate(modes if world > 1 else modes[:1]):
-            block = deep_leg(args, be, rank, world, timed, packed, sm_max, mode)
+            block = guarded(world, deep_leg, args, be, rank, world, timed, packed, sm_max, mode)
+            be.timing = None
             if rank == 0:
                 line["deep" if i == 0 else "deep_" + mode] = block
     if rank == 0:
         if world == 1 and not args.no_host:
             from tools import host_numbers
-            line["host_prep"] = host_numbers.host_prep()
-            line["api_e2e"] = host_numbers.api_e2e(args.cpu_scale, backend=be)
-            line["cn_model"] = host_numbers.cn_model(args.samples, backend=be)
+            line["host_prep"] = guarded(world, host_numbers.host_prep)
+            line["api_e2e"] = guarded(world, host_numbers.api_e2e, args.cpu_scale, backend=be)
+            line["cn_model"] = guarded(world, host_numbers.cn_model, args.samples, backend=be)
         if world == 1 and not args.no_cpu_baseline:
-            cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
-            arm = CpuArm(cores, args.cpu_scale, args.top_n)
-            c_cells, c_wall, c_search, c_n, _, _ = arm.step()
-            arm.close()
-            line["cpu_baseline"] = {
-                "value": c_cells / c_wall / 1e9, "unit": "GCells/s", "cores": cores, "kind": arm.kind,
-                "samples_per_s": c_n * args.cpu_scale / c_wall,
-                "search_only_value": c_cells / c_search / 1e9 if c_search else None, "sample": arm.describe()}
+            def cpu_baseline():
+                cores = max(1, min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1), 64))
+                arm = CpuArm(cores, args.cpu_scale, args.top_n)
+                try:
+                    c_cells, c_wall, c_search, c_n, _, _ = arm.step()
+                finally:
+                    arm.close()
+                return {"value": c_cells / c_wall / 1e9, "unit": "GCells/s", "cores": cores, "kind": arm.kind,
+                        "samples_per_s": c_n * args.cpu_scale / c_wall,
+                        "search_only_value": c_cells / c_search / 1e9 if c_search else None, "sample": arm.describe()}
+            line["cpu_baseline"] = guarded(world, cpu_baseline)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
