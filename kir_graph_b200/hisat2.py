@@ -369,7 +369,15 @@ def _write_sidecar(ext, output_prefix: str) -> None:
     cohort does not parse the ``.json`` again."""
     from . import fastjson, packio
     packs = fastjson.packs_from_scan(ext.scan(), variant_correction=True, single_mapped_only=True)
-    packio.save_packs(packio.sidecar_path(output_prefix), packs, packio.sidecar_meta(output_prefix))
+    side = packio.sidecar_path(output_prefix)
+    try:
+        packio.save_packs(side, packs, packio.sidecar_meta(output_prefix))
+    except ValueError as exc:
+        # the sidecar is a cache: a gene beyond a capacity of the device path is reported per gene when the
+        # sample is typed from its .json; the extraction itself goes on (and leaves no older sidecar behind)
+        logger.warning(f"[Graph] No packed sidecar for {output_prefix}: {exc}")
+        if os.path.exists(side):
+            os.remove(side)
 
 
 def extractVariantFromSam(index: str | list[Variant], sam_file: str, output_prefix: str | None,

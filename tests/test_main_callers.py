@@ -234,3 +234,31 @@ def test_a_gene_beyond_a_capacity_fails_alone(tmp_path, caplog, fast):
     json.dump(data, open(names[0] + ".json", "w"))
     files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
     assert "KIRWIDE*0" in pd.read_csv(files[0], sep="\t")["alleles"][0]
+
+
+def test_extraction_goes_on_when_no_sidecar_can_be_written(tmp_path, monkeypatch, caplog):
+    """The sidecar is a cache: when a gene exceeds a capacity of the device path no sidecar is written (and an
+    older one is removed), the extraction still returns with its .json in place."""
+    from kir_graph_b200 import fastjson, hisat2, packio
+    from kir_graph_b200.packing import CapacityError
+    from tests import sam_sim
+    table, pairs = sam_sim.multi_gene(95, n_pairs=60, novel=0.0)
+    name = str(tmp_path / "c.variant")
+    with open(name + ".sam", "w") as f:
+        f.write(sam_sim.sam_text(pairs))
+    Variant.novel_id = 0
+    hisat2.extractVariantFromSam(table, name + ".sam", name, num_editdist=9, write_pack=True)
+    assert os.path.exists(packio.sidecar_path(name))
+    real = fastjson.packs_from_scan
+
+    def one_gene_too_wide(scan, **kw):
+        packs = real(scan, **kw)
+        packs[next(iter(packs))] = CapacityError("a read pair carries 256 variant observations (limit 255)")
+        return packs
+
+    monkeypatch.setattr(fastjson, "packs_from_scan", one_gene_too_wide)
+    Variant.novel_id = 0
+    with caplog.at_level("WARNING", logger="graphkir"):
+        ext = hisat2.extractVariantFromSam(table, name + ".sam", name, num_editdist=9, write_pack=True)
+    assert ext.n_reads > 0 and os.path.exists(name + ".json") and not os.path.exists(packio.sidecar_path(name))
+    assert any("No packed sidecar" in r.getMessage() for r in caplog.records)
