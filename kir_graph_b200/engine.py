@@ -458,6 +458,7 @@ class HostBatch:
             items["a_blk"] = (local // tiles[mat]) * 4
             items["r0"] = (local % tiles[mat]) * GK_LIK_READS
             self._lik_items = items
+            self.lik_matrix = mat                   # problem of every item (contiguous: per-pass flags are one gather)
         return self._lik_items
 
     def pin(self, backend) -> "HostBatch":
@@ -537,9 +538,11 @@ class MatrixBatch:
         not written for them - they must not be read back or searched beyond the first step."""
         key = None if colsum_only is None or not np.any(colsum_only) else np.asarray(colsum_only, bool).tobytes()
         if self.d_lik_items is None or key != self._lik_key:
-            items = self.lik_items()
+            items = self.host.lik_items()             # read only: copied when this pass sets flags
             if key is not None:
-                items["flags"] = np.where(np.asarray(colsum_only, bool)[items["matrix"]], _cabi.GK_LIK_COLSUM_ONLY, 0)
+                items = items.copy()
+                flag = np.where(np.asarray(colsum_only, bool), _cabi.GK_LIK_COLSUM_ONLY, 0).astype(items.dtype["flags"])
+                items["flags"] = flag[self.host.lik_matrix]
             self.n_lik_items = len(items)
             self.d_lik_items = self.be.upload(items)
             self._lik_key = key
