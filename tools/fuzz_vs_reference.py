@@ -3,7 +3,7 @@ tests/golden/make_golden.py - build container only): random small genes through 
 AlleleTypingExonFirst of both implementations (ours on the NumPy test double of the kernels), called
 alleles or exception type compared; differences covered by tie flags are counted, others printed.
 
-    python tools/fuzz_vs_reference.py <seed> <seconds>
+    python tools/fuzz_vs_reference.py <seed> <seconds> [size factor]
 """
 import sys, time, copy, logging
 import numpy as np
@@ -17,9 +17,10 @@ from kir_graph_b200 import synthetic
 from kir_graph_b200.typing_mulit_allele import AlleleTyping, AlleleTypingExonFirst
 from tests.fake_backend import FakeBackend
 rng = np.random.default_rng(int(sys.argv[1])); T = float(sys.argv[2])
+BIG = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # 4: genes of up to 110 alleles x 880 reads, top_n up to 300
 t0 = time.time(); n = 0; bad = 0; tie = 0; order = 0
 while time.time() - t0 < T:
-    a = int(rng.integers(2, 28)); cn = int(rng.integers(1, 5)); r = int(rng.integers(5, 220)); top_n = int(rng.choice([3, 10, 30, 60]))
+    a = int(rng.integers(2, 28 * BIG)); cn = int(rng.integers(1, 5)); r = int(rng.integers(5, 220 * BIG)); top_n = int(rng.choice([3, 10, 30, 60] if BIG == 1 else [30, 60, 150, 300]))
     seed = int(rng.integers(1 << 30)); hier = bool(rng.integers(2)); mode = rng.choice(["full", "exon", "exon_thr"])
     gene = synthetic.make_gene([seed, 0], "KIRQ*BACKBONE", a, max(64, 8 * a), cn, r, hierarchical=hier)
     reads, variants = gene.to_objects()
