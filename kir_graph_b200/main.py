@@ -104,19 +104,32 @@ def alleleTyping(processed_bam: list[str], cn_files: list[str], method: str = "f
 
 def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: str = "full", top_n: int = 600,
                        min_reads_num: int = 100, rank: int = 0, world: int = 1, n_parts: int = 6,
-                       workers: int = 0, _backend=None) -> list[str]:
+                       workers: int = 0, batch_samples: int = 96, _backend=None) -> list[str]:
     """The samples ``rank, rank + world, ...`` typed as one batch on this rank's GPU; writes the
     ``{name}{suffix}.tsv`` of each (same bytes as ``alleleTyping``) and returns the names of ALL
     samples' files in input order, so that rank 0 can ``mergeAllele`` them once every rank is done.
     ``workers``: processes that scan and pack the samples' ``.json`` files in parallel (the host
     preparation is seconds per 200k-pair sample, the typing itself a fraction of a millisecond);
-    0 packs them one after the other in this process."""
+    0 packs them one after the other in this process.  ``batch_samples``: at most that many samples are
+    loaded and typed per GPU pass (96 samples of 200 k read pairs take 58 GB of device memory and 0.46 G of the
+    2^31 observation entries a batch can address), so a rank's share of a large cohort goes through in several
+    passes instead of failing; the files do not depend on it."""
     if method != "full":
         raise NotImplementedError("cohortAlleleTyping covers the full-variant strategy; use alleleTyping")
+    mine = list(range(len(processed_bam)))[rank::world]
+    step = max(1, int(batch_samples))
+    for at in range(0, len(mine), step):
+        _type_samples(mine[at:at + step], processed_bam, cn_files, method, top_n, min_reads_num, n_parts, workers,
+                      _backend)
+    return [n + _suffix(n, c, method) + ".tsv" for n, c in zip(processed_bam, cn_files)]
+
+
+def _type_samples(mine: list[int], processed_bam: list[str], cn_files: list[str], method: str, top_n: int,
+                  min_reads_num: int, n_parts: int, workers: int, _backend) -> None:
+    """One GPU pass over the samples ``mine`` (indices into ``processed_bam``) and their ``.tsv`` files."""
     import functools
     from . import cohort, engine, packio
     from .packing import CapacityError
-    mine = list(range(len(processed_bam)))[rank::world]
     jsons = [processed_bam[i] + ".json" for i in mine]
     # one sample's packed genes: the .gkpack.npz sidecar when it is fresh, else the .json through the scanner
     load = functools.partial(packio.load_sample_packs, variant_correction=True)
@@ -183,4 +196,3 @@ def cohortAlleleTyping(processed_bam: list[str], cn_files: list[str], method: st
         name = processed_bam[i] + _suffix(processed_bam[i], cn_files[i], method)
         logger.info(f"[Allele] {alleles} ({processed_bam[i]})")
         _write_sample(name, alleles, warnings)
-    return [n + _suffix(n, c, method) + ".tsv" for n, c in zip(processed_bam, cn_files)]

@@ -84,6 +84,12 @@ def test_cohort_entry_writes_the_same_files(tmp_path):
     assert files == per_sample and [open(f, "rb").read() for f in files] == want
     for f in per_sample:
         os.remove(f)
+    # a rank's samples in several GPU passes of bounded size: same files
+    for step in (1, 2):
+        files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend(), batch_samples=step)
+        assert files == per_sample and [open(f, "rb").read() for f in files] == want
+        for f in per_sample:
+            os.remove(f)
     # host preparation in worker processes
     files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend(), workers=2)
     assert files == per_sample and [open(f, "rb").read() for f in files] == want
