@@ -174,7 +174,18 @@ def _type_samples(mine: list[int], processed_bam: list[str], cn_files: list[str]
                 cns.append(cn)
     calls = []
     if packs:
-        typer = cohort.CohortTyper(packs, cns, top_n=top_n, backend=_backend, n_parts=n_parts)
+        try:
+            typer = cohort.CohortTyper(packs, cns, top_n=top_n, backend=_backend, n_parts=n_parts)
+        except ValueError as exc:
+            # more observation entries (or wire units) than a batch addresses - samples far deeper than the
+            # 200 k pairs ``batch_samples`` is sized for: type the two halves on their own
+            if "split the batch" not in str(exc) or len(mine) < 2:
+                raise
+            logger.info(f"[Allele] {len(mine)} samples do not fit one batch ({exc}): typing them in two")
+            del packs, packed
+            for half in (mine[: len(mine) // 2], mine[len(mine) // 2:]):
+                _type_samples(half, processed_bam, cn_files, method, top_n, min_reads_num, n_parts, workers, _backend)
+            return
         calls = typer.upload_and_run()
     at = 0
     for i in mine:

@@ -90,6 +90,25 @@ def test_cohort_entry_writes_the_same_files(tmp_path):
         assert files == per_sample and [open(f, "rb").read() for f in files] == want
         for f in per_sample:
             os.remove(f)
+    # a batch that exceeds the entry range of the device tables is typed in halves
+    from kir_graph_b200 import cohort as cohort_mod
+    real_typer, built = cohort_mod.CohortTyper, []
+
+    def small_batches_only(packs, cns, **kw):
+        built.append(len(packs))
+        if len(packs) > 3:
+            raise ValueError("entry pool exceeds 2^31 entries; split the batch")
+        return real_typer(packs, cns, **kw)
+
+    cohort_mod.CohortTyper = small_batches_only
+    try:
+        files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend())
+    finally:
+        cohort_mod.CohortTyper = real_typer
+    assert files == per_sample and [open(f, "rb").read() for f in files] == want
+    assert built[0] > 3 and len(built) >= 3 and all(n <= 3 for n in built[-2:])
+    for f in per_sample:
+        os.remove(f)
     # host preparation in worker processes
     files = main.cohortAlleleTyping(names, cn_files, "full", _backend=FakeBackend(), workers=2)
     assert files == per_sample and [open(f, "rb").read() for f in files] == want
