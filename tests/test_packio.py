@@ -74,3 +74,41 @@ def test_truncated_or_garbled_sidecar_falls_back_to_json(tmp_path):
         got = packio.load_sample_packs(path)
         assert list(got) == list(want) and all(p.wire is None for p in got.values())
         assert all(np.array_equal(got[g].ent_pos, want[g].ent_pos) for g in want)
+
+
+def test_sidecar_round_trip_over_ragged_and_empty_genes(tmp_path):
+    """Format 3 stores the arrays of all genes back to back per array name: genes without reads, with a single
+    read, with reads that observe nothing after correction, and of very different sizes come back array for
+    array, and type to the same calls."""
+    from kir_graph_b200 import synthetic
+    from kir_graph_b200.hisat2 import PairRead
+    specs = [(4, 64, 1, 0), (9, 72, 2, 1), (30, 240, 3, 400), (2, 64, 1, 3), (17, 136, 2, 90), (6, 64, 2, 0)]
+    packs = {}
+    for i, (a, v, cn, r) in enumerate(specs):
+        gene = synthetic.make_gene([81, i], f"KIRR{i}*BACKBONE", a, v, cn, max(r, 1), hierarchical=bool(i % 2))
+        reads, variants = gene.to_objects()
+        if r == 0:
+            reads = []
+        if i == 3:                                               # reads that carry nothing
+            reads = [PairRead(backbone=gene.gene) for _ in range(3)]
+        packs[gene.gene] = packing.pack_gene(reads, variants, variant_correction=bool(i % 2), gene=gene.gene,
+                                             no_empty=i != 3)
+    side = os.path.join(tmp_path, "r.gkpack.npz")
+    packio.save_packs(side, packs, {"k": 1})
+    back, meta = packio.load_packs(side)
+    assert meta == {"k": 1} and list(back) == list(packs)
+    for g, p in packs.items():
+        q = back[g]
+        assert (q.n_reads, q.n_alleles, q.n_variants, q.n_words) == (p.n_reads, p.n_alleles, p.n_variants, p.n_words)
+        for name in packio._ARRAYS:
+            a, b = np.asarray(getattr(p, name)), np.asarray(getattr(q, name))
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (g, name)
+        for name in packio._WIRE_ARRAYS:
+            a, b = np.asarray(getattr(p.wire, name)), np.asarray(getattr(q.wire, name))
+            assert a.dtype == b.dtype and np.array_equal(a, b), (g, name)
+        assert q.wire.n_entries == p.wire.n_entries and q.allele_names == p.allele_names and q.variant_ids == p.variant_ids
+    cns = [c for (_, _, c, _) in specs]
+    key = lambda calls: [(c.gene, c.alleles, c.score, c.tie_flags, c.n_reads) for c in calls]
+    want = key(cohort.BatchTyper(list(packs.values()), cns, top_n=20, backend=FakeBackend()).run())
+    got = key(cohort.BatchTyper(list(back.values()), cns, top_n=20, backend=FakeBackend()).run())
+    assert got == want and any(c[1][0] == "fail" for c in got) and any(c[1][0] != "fail" for c in got)
