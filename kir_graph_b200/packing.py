@@ -199,7 +199,7 @@ def pack_entries(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.n
     idxs = [np.ascontiguousarray(csr.indices[name], dtype=np.int32) for name in LIST_NAMES]
     total = int(sum(int(o[-1]) for o in offs))
     if total and (max(int(i.max(initial=0)) for i in idxs) >= 1 << 30 or n >= 1 << 30):
-        raise ValueError("problem too large for the 64-bit packing keys")
+        raise CapacityError("problem too large for the 64-bit packing keys (2^30 reads or variants per gene)")
     pol = np.array([1 if name in ("lpv", "rpv") else 0 for name in LIST_NAMES], dtype=np.int32)
     ent_off = np.zeros(n + 1, dtype=np.int32)
     ent_word = np.zeros(max(total, 1), dtype=np.int32)
@@ -238,7 +238,7 @@ def pack_entries_numpy(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray
     # occurrence rank of identical (read, polarity, variant) observations
     # (single 64-bit sort keys: row < 2^31, variant index < 2^30)
     if len(row) and (int(vid.max()) >= 1 << 30 or n >= 1 << 30):
-        raise ValueError("problem too large for the 64-bit packing keys")
+        raise CapacityError("problem too large for the 64-bit packing keys (2^30 reads or variants per gene)")
     key = (row << 31) | (pol << 30) | vid
     order = np.argsort(key)
     key = key[order]
@@ -248,7 +248,7 @@ def pack_entries_numpy(csr: ReadCSR) -> tuple[np.ndarray, np.ndarray, np.ndarray
     run_start = np.maximum.accumulate(np.where(new_run, np.arange(len(row)), 0))
     rank = np.arange(len(row)) - run_start
     if len(rank) and int(rank.max()) >= 256:
-        raise ValueError("an observation is repeated more than 255 times in one read pair")
+        raise CapacityError("an observation is repeated more than 255 times in one read pair")
 
     word = vid >> 5
     bit = (np.uint32(1) << (vid & 31).astype(np.uint32)).astype(np.uint32)
