@@ -79,3 +79,21 @@ def test_score_roofline_entries():
     assert r["measured_peak"]["peak"] > 25 and 0 < r["measured_peak"]["frac"] < 1
     f = bench.score_roofline(cells, ms, False, 1965.0)
     assert f["bound"] == "fp32_nontensor" and abs(f["frac"] - 2 * cells / (ms * 1e-3) / 1e12 / peak) < 1e-12
+
+
+def test_secondary_blocks_are_guarded_on_one_gpu_only(capsys):
+    """bench.guarded: on one GPU a failing secondary block becomes {"error": ...} (the headline line is still
+    printed); with several ranks the failure stays fatal (a rank going on alone would leave the others in a
+    collective)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import pytest
+
+    def boom(x, y=0):
+        raise RuntimeError(f"no {x}{y}")
+
+    assert bench.guarded(1, lambda a, b=1: a + b, 2, b=3) == 5
+    block = bench.guarded(1, boom, "gpu", y=7)
+    assert block == {"error": "RuntimeError: no gpu7"} and "RuntimeError" in capsys.readouterr().err
+    with pytest.raises(RuntimeError):
+        bench.guarded(2, boom, "gpu")
